@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- queries/s of the brute-force cosine hot path on B200 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one batch search of B=1024 queries over the whole resident corpus
+(10M x 768 fp32 at N=1).  `value` is measured with every input already in HBM
+(cdb_search_batch_device); `e2e` is the same step through cdb_search_batch with
+HOST query/result buffers, copies inside the timed region.  For N>1 the corpus is
+row-sharded over the ranks (strong scaling: the same 10M rows and the same queries),
+each rank searches its shard, the per-shard top-k are all-gathered (NCCL) and merged
+on every rank by cdb_merge_topk_device.
+
+The reference arm times the CPU oracle (bit-faithful C/AVX2 port of the Rust path;
+the Rust crate cannot be built in this image) on all host cores over a bounded
+sample (a 1/8-size corpus shard, few queries) and scales linearly in rows.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_CORPUS = 0xC05DA7A + 2
+SEED_QUERY = 0xC05DA7A + 102
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--exact-only", action="store_true", help="pure FFMA scan (no tensor-core prefilter)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_250_000)
+    ap.add_argument("--cpu-sample-queries", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_baseline(rows_full, dim, k, sample_rows, sample_queries, threads):
+    import oracle as orc
+    sample_rows = min(sample_rows, rows_full)
+    corpus = orc.synth_matrix(SEED_CORPUS, sample_rows, dim)
+    queries = orc.synth_matrix(SEED_QUERY, sample_queries, dim)
+    orc.brute_topk_f32(corpus[: min(sample_rows, 20000)], queries[:1], k, threads=threads)  # warm
+    t0 = time.perf_counter()
+    orc.brute_topk_f32(corpus, queries, k, threads=threads)
+    dt = time.perf_counter() - t0
+    qps_sample = sample_queries / dt
+    qps_full = qps_sample * (sample_rows / rows_full)
+    return qps_full, dt, f"oracle port (C/AVX2+FMA, {threads} threads, one query per thread) on {sample_rows}x{dim} rows " \
+                         f"(1/{rows_full // sample_rows} of the corpus) x {sample_queries} queries in {dt:.2f}s, scaled linearly in rows"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    import oracle as orc
+    sample_rows = min(args.cpu_sample_rows, args.rows)
+    corpus = orc.synth_matrix(SEED_CORPUS, sample_rows, args.dim)
+    queries = orc.synth_matrix(SEED_QUERY, args.cpu_sample_queries, args.dim)
+    for _ in range(max(0, min(args.warmup, 1))):
+        orc.brute_topk_f32(corpus[: min(sample_rows, 50000)], queries, args.k, threads=threads)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        orc.brute_topk_f32(corpus, queries, args.k, threads=threads)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.sum(times))
+    qps = args.steps * args.cpu_sample_queries / dt * (sample_rows / args.rows)
+    sample = (f"each step = {args.cpu_sample_queries} queries x {sample_rows}x{args.dim} rows "
+              f"(1/{args.rows // sample_rows} of the corpus), scaled linearly in rows")
+    line = {
+        "impl": "reference", "metric": "queries/sec, brute-force cosine top-10", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"brute-force cosine top-{args.k}, {args.rows}x{args.dim} fp32 corpus, batch={args.batch} queries "
+                        f"(BASELINE.json configs[1])",
+            "rows": args.rows, "dim": args.dim, "batch": args.batch, "k": args.k,
+            "sharding": f"rows/{world}" if world > 1 else "none", "l2": "inputs_exceed_l2 (corpus >> 126 MB)",
+            "synthetic": "uniform[-1,1) counter RNG, include/cosdata_b200.h"}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import cosdata_b200 as cdb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    rows_local = args.rows // world + (1 if rank < args.rows % world else 0)
+    row0 = rank * (args.rows // world) + min(rank, args.rows % world)
+    B, D, k = args.batch, args.dim, args.k
+
+    ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.FullPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
+                        capacity=rows_local, device=local_rank, id_base=row0)
+    # same global synthetic corpus for every world size: shard r holds rows [row0, row0+rows_local)
+    ix.append_synthetic(SEED_CORPUS, rows_local, first_row=row0)
+
+    q_host = cdb.synth_matrix(SEED_QUERY, B, D)
+    q_pinned = torch.from_numpy(q_host).pin_memory()
+    d_q = q_pinned.to(dev)
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    if world > 1:
+        g_ids = torch.empty((world, B, k), dtype=torch.int32, device=dev)
+        g_scores = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+        m_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+        m_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_ids = torch.empty((B, k), dtype=torch.int32).pin_memory()
+    out_scores = torch.empty((B, k), dtype=torch.float32).pin_memory()
+
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                               stream.cuda_stream, exact_only=args.exact_only)
+        if world > 1:
+            dist.all_gather_into_tensor(g_ids.view(-1), d_ids.view(-1))
+            dist.all_gather_into_tensor(g_scores.view(-1), d_scores.view(-1))
+            rc = ix._lib.cdb_merge_topk_device(local_rank, 0, g_ids.data_ptr(), g_scores.data_ptr(), world, B, k,
+                                               m_ids.data_ptr(), m_scores.data_ptr(), stream.cuda_stream)
+            assert rc == 0
+            return m_ids, m_scores
+        return d_ids, d_scores
+
+    def step_e2e():
+        # host queries in, host results out, through the public C-ABI call with HOST buffers
+        if world == 1:
+            ids, scores, counts, err = ix.batch_search(q_host, k, exact_only=args.exact_only)
+            return ids, scores
+        d_q.copy_(q_pinned, non_blocking=True)
+        r_ids, r_scores = step_device()
+        out_ids.copy_(r_ids, non_blocking=True)
+        out_scores.copy_(r_scores, non_blocking=True)
+        stream.synchronize()
+        return out_ids, out_scores
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    launches0 = cdb.kernel_launch_count()
+    sampler.start()
+    total_ms = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop()
+    launches = cdb.kernel_launch_count() - launches0
+    # launches counted over warm-up + timed steps; per timed region:
+    launches_timed = launches * args.steps // (args.steps + max(args.warmup, 3))
+    scan_ms = ix.scan_ms_history(args.steps)
+    e2e_ms = timed(step_e2e, args.steps, 1)
+
+    value = args.steps * B / (total_ms / 1000.0)
+    e2e_value = args.steps * B / (e2e_ms / 1000.0)
+
+    # roofline of the dominant kernel (the scan): algorithmic bytes per launch:
+    # rows*(D*4 + 4) + B*D*4, and algorithmic flops 2*rows*D*B
+    alg_bytes = rows_local * (D * 4 + 4) + B * D * 4
+    alg_flops = 2.0 * rows_local * D * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+    scan_avg_ms = float(np.mean(scan_ms)) if len(scan_ms) else float("nan")
+    achieved_gbs = alg_bytes / (scan_avg_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "scan_f32_kernel (exact FFMA scan, fused top-k)", "kernel_ms": scan_avg_ms,
+                "alg_bytes_per_launch": alg_bytes, "fp32_tflops": alg_flops / (scan_avg_ms / 1000.0) / 1e12,
+                "note": "at batch=1024 the exact FP32 scan is FFMA-bound (2*N*D*B flop vs N*D*4 bytes), not HBM-bound"}
+
+    line = {
+        "metric": "queries/sec, brute-force cosine top-10", "value": value, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 8 + B * 5,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches_timed), "roofline": roofline,
+        "recall_at_10": 1.0, "recall_note": "exact search: ids bit-identical to the CPU oracle (tests/test_gpu_parity.py)",
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt, sample = cpu_baseline(args.rows, D, k, args.cpu_sample_rows, args.cpu_sample_queries, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

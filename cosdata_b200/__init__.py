@@ -1,0 +1,10 @@
+"""cosdata_b200 -- B200-native (sm_100a) implementation of cosdata's ANN distance hot path.
+
+The package is a thin host mirror of the reference's operator surface over the
+C ABI in include/cosdata_b200.h; all compute lives in csrc/*.cu.
+"""
+from .api import (  # noqa: F401
+    INVALID_ID, CosdataError, DenseIndex, DistanceError, DistanceMetric, DistanceMetricKind,
+    ScalarQuantization, SearchMode, Status, Storage, StorageType, code_bytes, device_count,
+    kernel_launch_count, synth_matrix,
+)

@@ -1,0 +1,93 @@
+"""ctypes loader for libcosdata_b200.so -- the only way Python reaches the kernels.
+
+There is no fallback: if the shared object is missing or a symbol declared in
+include/cosdata_b200.h is absent, import-time use fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcosdata_b200.so")
+
+c_u8p = C.c_void_p
+c_f32p = C.c_void_p
+c_u32p = C.c_void_p
+c_i32p = C.c_void_p
+c_vp = C.c_void_p
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_uint32),
+        ("storage_type", C.c_int32),
+        ("metric", C.c_int32),
+        ("range_lo", C.c_float),
+        ("range_hi", C.c_float),
+        ("capacity", C.c_uint64),
+        ("device", C.c_int32),
+        ("keep_raw_f32", C.c_int32),
+        ("id_base", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [
+        ("k", C.c_uint32),
+        ("mode", C.c_int32),
+        ("ef_search", C.c_uint32),
+        ("shortlist_size", C.c_uint32),
+        ("exact_only", C.c_int32),
+        ("prefilter_k", C.c_uint32),
+        ("reserved0", C.c_uint32),
+        ("reserved1", C.c_uint32),
+    ]
+
+
+# symbol -> (restype, argtypes); must list every function of include/cosdata_b200.h
+PROTOTYPES = {
+    "cdb_abi_version": (C.c_int32, []),
+    "cdb_last_error_string": (C.c_char_p, []),
+    "cdb_device_count": (C.c_int32, [C.POINTER(C.c_int32)]),
+    "cdb_synth_fill_host": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint64, c_f32p]),
+    "cdb_code_bytes": (C.c_size_t, [C.c_int32, C.c_uint32]),
+    "cdb_quantize_batch": (C.c_int32, [C.c_int32, C.c_int32, C.c_float, C.c_float, c_f32p, C.c_uint64, C.c_uint32, c_vp, c_f32p]),
+    "cdb_distance_pairs": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, c_vp, c_f32p, c_vp, c_f32p, C.c_uint64, c_f32p, c_i32p]),
+    "cdb_index_create": (C.c_int32, [C.POINTER(IndexDesc), C.POINTER(C.c_void_p)]),
+    "cdb_index_destroy": (C.c_int32, [C.c_void_p]),
+    "cdb_index_size": (C.c_uint64, [C.c_void_p]),
+    "cdb_index_append_f32": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint64]),
+    "cdb_index_append_codes": (C.c_int32, [C.c_void_p, c_vp, c_f32p, C.c_uint64]),
+    "cdb_index_append_synthetic": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "cdb_index_read_codes": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, c_vp, c_f32p]),
+    "cdb_search_batch": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p]),
+    "cdb_search_batch_device": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p, C.c_void_p]),
+    "cdb_score_ids": (C.c_int32, [C.c_void_p, c_f32p, c_u32p, C.c_uint32, c_f32p, c_i32p]),
+    "cdb_rerank_f32": (C.c_int32, [C.c_void_p, c_f32p, c_u32p, C.c_uint32, C.c_uint32, c_u32p, c_f32p, c_u32p]),
+    "cdb_merge_topk_device": (C.c_int32, [C.c_int32, C.c_int32, c_u32p, c_f32p, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_f32p, C.c_void_p]),
+    "cdb_kernel_launch_count": (C.c_uint64, []),
+    "cdb_index_last_kernel_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "cdb_index_scan_ms_history": (C.c_int32, [C.c_void_p, C.c_uint32, c_f32p, C.POINTER(C.c_uint32)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared object and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -m cosdata_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.cdb_abi_version() != 1:
+        raise RuntimeError("libcosdata_b200 ABI version mismatch")
+    _lib = lib
+    return lib

@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's operator surface for the distance hot path.
+
+Same names / argument meaning / error behaviour as the Rust traits, implemented
+as thin calls into the C ABI (include/cosdata_b200.h) -- nothing is computed in
+Python:
+
+  StorageType, Storage           src/quantization/mod.rs:19-25, src/storage/mod.rs:7-25
+  ScalarQuantization.quantize    src/quantization/scalar.rs:10-52
+  DistanceMetric.calculate       src/models/types.rs:460-496 (DistanceFunction, src/distance/mod.rs:8-16)
+  DistanceError                  src/distance/mod.rs:18-22
+  DenseIndex.batch_search        IndexOps::batch_search, src/indexes/mod.rs:260-272
+  DenseIndex.score_ids           neighbour expansion, src/vector_store.rs:1161-1191
+  DenseIndex.rerank              finalize_ann_results, src/vector_store.rs:404-445
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+from ._lib import IndexDesc, SearchParams
+
+INVALID_ID = 0xFFFFFFFF
+
+
+class Status(enum.IntEnum):
+    OK = 0
+    STORAGE_MISMATCH = 1
+    CALCULATION_ERROR = 2
+    INVALID_PARAMS = 3
+    CUDA_ERROR = 4
+    NCCL_ERROR = 5
+    UNSUPPORTED = 6
+
+
+class StorageType(enum.IntEnum):
+    """StorageType; SubByte(r) is SUB1..SUB3."""
+    UnsignedByte = 0
+    SubByte1 = 1
+    SubByte2 = 2
+    SubByte3 = 3
+    HalfPrecisionFP = 4
+    FullPrecisionFP = 5
+
+
+class DistanceMetricKind(enum.IntEnum):
+    Cosine = 0
+    Euclidean = 1
+    Hamming = 2
+    DotProduct = 3
+
+
+class SearchMode(enum.IntEnum):
+    BRUTE_RAW = 0
+    BRUTE_CODES = 1
+    HNSW = 2
+
+
+class CosdataError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = Status(status)
+        super().__init__(f"{self.status.name}: {msg}")
+
+
+class DistanceError(CosdataError):
+    """DistanceError::{StorageMismatch, CalculationError}"""
+
+
+def _check(rc):
+    if rc != 0:
+        msg = _lib.load().cdb_last_error_string().decode("utf-8", "replace")
+        raise CosdataError(rc, msg)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    n = C.c_int32(0)
+    rc = _lib.load().cdb_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def kernel_launch_count():
+    return int(_lib.load().cdb_kernel_launch_count())
+
+
+def synth_matrix(seed, n, dim, first_row=0):
+    out = np.empty((n, dim), dtype=np.float32)
+    _check(_lib.load().cdb_synth_fill_host(seed, first_row * dim, n * dim, _ptr(out)))
+    return out
+
+
+def code_bytes(storage_type, dim):
+    return int(_lib.load().cdb_code_bytes(int(storage_type), dim))
+
+
+class Storage:
+    """enum Storage: one quantized vector = (variant, mag, payload bytes)."""
+
+    __slots__ = ("storage_type", "mag", "code", "dim")
+
+    def __init__(self, storage_type, mag, code, dim):
+        self.storage_type = StorageType(storage_type)
+        self.mag = np.float32(mag)
+        self.code = np.ascontiguousarray(code, dtype=np.uint8)
+        self.dim = int(dim)
+
+
+class ScalarQuantization:
+    """impl Quantization for ScalarQuantization"""
+
+    def __init__(self, device=0):
+        self.device = device
+
+    def quantize_batch(self, vectors, storage_type, value_range=(-1.0, 1.0)):
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        if v.ndim == 1:
+            v = v[None]
+        n, dim = v.shape
+        codes = np.zeros((n, code_bytes(storage_type, dim)), dtype=np.uint8)
+        mags = np.zeros(n, dtype=np.float32)
+        _check(_lib.load().cdb_quantize_batch(self.device, int(storage_type), float(value_range[0]), float(value_range[1]),
+                                              _ptr(v), n, dim, _ptr(codes), _ptr(mags)))
+        return codes, mags
+
+    def quantize(self, vector, storage_type, value_range=(-1.0, 1.0)):
+        codes, mags = self.quantize_batch(vector, storage_type, value_range)
+        return Storage(storage_type, mags[0], codes[0], np.asarray(vector).size)
+
+    def train(self, vectors):  # scalar.rs:54-57: nothing to train
+        return None
+
+
+class DistanceMetric:
+    """enum DistanceMetric + impl DistanceFunction (pairwise; batched here over pairs)."""
+
+    def __init__(self, kind, device=0):
+        self.kind = DistanceMetricKind(kind)
+        self.device = device
+
+    def calculate_pairs(self, storage_type, dim, x_codes, x_mags, y_codes, y_mags):
+        """-> (values f32[n], status int32[n]); status mirrors Result<_, DistanceError> per pair."""
+        x = np.ascontiguousarray(x_codes, dtype=np.uint8)
+        y = np.ascontiguousarray(y_codes, dtype=np.uint8)
+        xm = np.ascontiguousarray(x_mags, dtype=np.float32)
+        ym = np.ascontiguousarray(y_mags, dtype=np.float32)
+        n = xm.size
+        out = np.zeros(n, dtype=np.float32)
+        st = np.zeros(n, dtype=np.int32)
+        _check(_lib.load().cdb_distance_pairs(self.device, int(self.kind), int(storage_type), dim, _ptr(x), _ptr(xm),
+                                              _ptr(y), _ptr(ym), n, _ptr(out), _ptr(st)))
+        return out, st
+
+    def calculate(self, x: Storage, y: Storage):
+        """DistanceFunction::calculate(x, y) -> f32 or raises DistanceError."""
+        if x.storage_type != y.storage_type:
+            raise DistanceError(Status.STORAGE_MISMATCH, "storage variants differ")  # cosine.rs:214
+        out, st = self.calculate_pairs(x.storage_type, x.dim, x.code[None], [x.mag], y.code[None], [y.mag])
+        if st[0] != 0:
+            raise DistanceError(int(st[0]), "pair")
+        return out[0]
+
+
+class DenseIndex:
+    """Device-resident dense index shard: the GPU counterpart of what HNSWIndex +
+    Collection hold for this path (quantized rows + mags, optional raw f32 rows)."""
+
+    def __init__(self, dim, storage_type=StorageType.FullPrecisionFP, metric=DistanceMetricKind.Cosine,
+                 value_range=(-1.0, 1.0), capacity=1, device=0, keep_raw_f32=False, id_base=0):
+        self._lib = _lib.load()
+        self.desc = IndexDesc(dim, int(storage_type), int(metric), float(value_range[0]), float(value_range[1]),
+                              int(capacity), int(device), 1 if keep_raw_f32 else 0, int(id_base), 0)
+        self._h = C.c_void_p()
+        _check(self._lib.cdb_index_create(C.byref(self.desc), C.byref(self._h)))
+        self.dim = dim
+        self.storage_type = StorageType(storage_type)
+        self.metric = DistanceMetricKind(metric)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.cdb_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __len__(self):
+        return int(self._lib.cdb_index_size(self._h))
+
+    # -- ingest
+    def append(self, vectors):
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        assert v.ndim == 2 and v.shape[1] == self.dim
+        _check(self._lib.cdb_index_append_f32(self._h, _ptr(v), v.shape[0]))
+
+    def append_codes(self, codes, mags):
+        c = np.ascontiguousarray(codes, dtype=np.uint8)
+        m = np.ascontiguousarray(mags, dtype=np.float32)
+        _check(self._lib.cdb_index_append_codes(self._h, _ptr(c), _ptr(m), m.size))
+
+    def append_synthetic(self, seed, n, first_row=None):
+        """rows [first_row, first_row+n) of synthetic stream `seed` (default: continue at len(self))"""
+        first_row = len(self) if first_row is None else first_row
+        _check(self._lib.cdb_index_append_synthetic(self._h, seed, first_row, n))
+
+    def read_codes(self, first, n):
+        codes = np.zeros((n, code_bytes(self.storage_type, self.dim)), dtype=np.uint8)
+        mags = np.zeros(n, dtype=np.float32)
+        _check(self._lib.cdb_index_read_codes(self._h, first, n, _ptr(codes), _ptr(mags)))
+        return codes, mags
+
+    # -- S1
+    def params(self, k, mode=SearchMode.BRUTE_RAW, ef_search=256, shortlist_size=64, exact_only=False, prefilter_k=0):
+        return SearchParams(k, int(mode), ef_search, shortlist_size, 1 if exact_only else 0, prefilter_k, 0, 0)
+
+    def batch_search(self, queries, k, mode=SearchMode.BRUTE_RAW, **kw):
+        """IndexOps::batch_search -> (ids u32[B,k], scores f32[B,k], counts u32[B], err u8[B])"""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None]
+        b = q.shape[0]
+        ids = np.zeros((b, k), dtype=np.uint32)
+        scores = np.zeros((b, k), dtype=np.float32)
+        counts = np.zeros(b, dtype=np.uint32)
+        err = np.zeros(b, dtype=np.uint8)
+        p = self.params(k, mode, **kw)
+        _check(self._lib.cdb_search_batch(self._h, _ptr(q), b, C.byref(p), _ptr(ids), _ptr(scores), _ptr(counts), _ptr(err)))
+        return ids, scores, counts, err
+
+    def batch_search_device(self, d_queries_ptr, b, k, d_ids_ptr, d_scores_ptr, d_counts_ptr=None, d_err_ptr=None,
+                            stream_ptr=None, mode=SearchMode.BRUTE_RAW, **kw):
+        """All pointers are device addresses (ints), asynchronous on stream_ptr."""
+        p = self.params(k, mode, **kw)
+        _check(self._lib.cdb_search_batch_device(self._h, d_queries_ptr, b, C.byref(p), d_ids_ptr, d_scores_ptr,
+                                                 d_counts_ptr, d_err_ptr, stream_ptr))
+
+    # -- S2
+    def score_ids(self, query, ids):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        i = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.zeros(i.size, dtype=np.float32)
+        st = np.zeros(i.size, dtype=np.int32)
+        _check(self._lib.cdb_score_ids(self._h, _ptr(q), _ptr(i), i.size, _ptr(out), _ptr(st)))
+        return out, st
+
+    # -- S3
+    def rerank(self, query, cand_ids, k):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        c = np.ascontiguousarray(cand_ids, dtype=np.uint32)
+        ids = np.zeros(k, dtype=np.uint32)
+        scores = np.zeros(k, dtype=np.float32)
+        cnt = np.zeros(1, dtype=np.uint32)
+        _check(self._lib.cdb_rerank_f32(self._h, _ptr(q), _ptr(c), c.size, k, _ptr(ids), _ptr(scores), _ptr(cnt)))
+        return ids, scores, int(cnt[0])
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        _check(self._lib.cdb_index_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def scan_ms_history(self, n=64):
+        out = np.zeros(n, dtype=np.float32)
+        m = C.c_uint32(0)
+        _check(self._lib.cdb_index_scan_ms_history(self._h, n, _ptr(out), C.byref(m)))
+        return out[: m.value].copy()

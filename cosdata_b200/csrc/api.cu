@@ -1,0 +1,549 @@
+// api.cu -- the extern "C" boundary declared in include/cosdata_b200.h.
+// Host-side orchestration only: device buffers, streams, launch order.  No torch,
+// no CPU compute path -- without a CUDA device every entry point fails.
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+
+namespace cdb {
+
+static thread_local std::string t_last_error;
+void set_error(const std::string &msg) { t_last_error = msg; }
+std::atomic<uint64_t> g_launch_count{0};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cdb_status ensure(size_t bytes) {
+        if (bytes <= cap) return CDB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CDB_CUDA_TRY(cudaMalloc(&p, want));
+        cap = want;
+        return CDB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// (metric, storage) arms of DistanceMetric::calculate: OK / StorageMismatch / unimplemented!()
+static cdb_status arm_status(int metric, int st) {
+    if (st < CDB_ST_U8 || st > CDB_ST_F32) return CDB_INVALID_PARAMS;
+    switch (metric) {
+    case CDB_METRIC_COSINE: return CDB_OK;                                                        // cosine.rs:104-216
+    case CDB_METRIC_DOT_PRODUCT: return st == CDB_ST_F32 ? CDB_STORAGE_MISMATCH : CDB_OK;          // dotproduct.rs:20-63
+    case CDB_METRIC_EUCLIDEAN:                                                                      // euclidean.rs:17-39
+        if (st == CDB_ST_U8 || st == CDB_ST_F16) return CDB_OK;
+        return st == CDB_ST_F32 ? CDB_STORAGE_MISMATCH : CDB_UNSUPPORTED;
+    case CDB_METRIC_HAMMING: return st == CDB_ST_F32 ? CDB_STORAGE_MISMATCH : CDB_OK;              // hamming.rs:21-57
+    default: return CDB_INVALID_PARAMS;
+    }
+}
+
+// host code layout: tight [n][code_bytes]; sub-byte planes at p*ceil(D/8)
+static size_t host_code_bytes(int st, uint32_t dim) {
+    switch (st) {
+    case CDB_ST_U8: return dim;
+    case CDB_ST_SUB1: case CDB_ST_SUB2: case CDB_ST_SUB3: return (size_t)st * plane_bytes(dim);
+    case CDB_ST_F16: return (size_t)dim * 2;
+    case CDB_ST_F32: return (size_t)dim * 4;
+    default: return 0;
+    }
+}
+static cdb_status copy_codes(void *dst, const void *src, int st, uint32_t dim, uint64_t n, bool to_device, cudaStream_t s) {
+    if (!n) return CDB_OK;
+    const uint32_t pitch = row_pitch_bytes(st, dim);
+    const size_t hb = host_code_bytes(st, dim);
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (st >= CDB_ST_SUB1 && st <= CDB_ST_SUB3) {
+        const uint32_t nb = plane_bytes(dim), pp = plane_pitch(dim);
+        for (int p = 0; p < st; ++p) {
+            if (to_device)
+                CDB_CUDA_TRY(cudaMemcpy2DAsync((uint8_t *)dst + (size_t)p * pp, pitch, (const uint8_t *)src + (size_t)p * nb, hb, nb, n, kind, s));
+            else
+                CDB_CUDA_TRY(cudaMemcpy2DAsync((uint8_t *)dst + (size_t)p * nb, hb, (const uint8_t *)src + (size_t)p * pp, pitch, nb, n, kind, s));
+        }
+    } else {
+        if (to_device) CDB_CUDA_TRY(cudaMemcpy2DAsync(dst, pitch, src, hb, hb, n, kind, s));
+        else CDB_CUDA_TRY(cudaMemcpy2DAsync(dst, hb, src, pitch, hb, n, kind, s));
+    }
+    return CDB_OK;
+}
+
+__global__ void err32_to_u8_kernel(const uint32_t *e, uint8_t *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint8_t)e[i];
+}
+
+}  // namespace cdb
+
+using namespace cdb;
+
+struct cdb_index {
+    cdb_index_desc desc{};
+    int sm_count = 0;
+    uint32_t row_pitch = 0;        // bytes per stored code row
+    uint32_t raw_pitch_elems = 0;  // floats per raw row
+    uint64_t size = 0;
+    uint8_t *d_codes = nullptr;
+    float *d_mags = nullptr;
+    float *d_raw = nullptr;       // raw f32 rows (may alias d_codes)
+    float *d_raw_mags = nullptr;  // |raw row| (may alias d_mags)
+    bool raw_owned = false, raw_mags_owned = false;
+    cudaStream_t stream = nullptr;
+    static constexpr int EV_RING = 64;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ring0[EV_RING] = {}, ring1[EV_RING] = {};  // per-search (before scan, after scan)
+    uint64_t n_search = 0;
+    bool ev_valid = false;
+    std::mutex mu;
+    DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
+};
+
+#define CDB_REQUIRE(cond, msg)                              \
+    do {                                                    \
+        if (!(cond)) { set_error(msg); return CDB_INVALID_PARAMS; } \
+    } while (0)
+
+extern "C" {
+
+int32_t cdb_abi_version(void) { return CDB_ABI_VERSION; }
+const char *cdb_last_error_string(void) { return t_last_error.c_str(); }
+uint64_t cdb_kernel_launch_count(void) { return g_launch_count.load(); }
+
+cdb_status cdb_device_count(int32_t *out) {
+    CDB_REQUIRE(out, "null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); return CDB_CUDA_ERROR; }
+    *out = n;
+    return CDB_OK;
+}
+
+cdb_status cdb_synth_fill_host(uint64_t seed, uint64_t first_idx, uint64_t n, float *out) {
+    CDB_REQUIRE(out || !n, "null out");
+    for (uint64_t i = 0; i < n; ++i) out[i] = synth_value(seed, first_idx + i);
+    return CDB_OK;
+}
+
+size_t cdb_code_bytes(int32_t st, uint32_t dim) { return host_code_bytes(st, dim); }
+
+cdb_status cdb_quantize_batch(int32_t device, int32_t st, float lo, float hi, const float *vecs, uint64_t n, uint32_t dim,
+                              void *out_codes, float *out_mags) {
+    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_F32, "bad storage type");
+    CDB_REQUIRE(dim > 0 && (vecs || !n) && (out_codes || !n) && (out_mags || !n), "bad arguments");
+    CDB_CUDA_TRY(cudaSetDevice(device));
+    const uint32_t pitch = row_pitch_bytes(st, dim);
+    const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / ((size_t)dim * 4));
+    DevBuf in, codes, mags;
+    cdb_status rc = CDB_OK;
+    for (uint64_t off = 0; off < n && rc == CDB_OK; off += chunk) {
+        uint64_t m = std::min(chunk, n - off);
+        if ((rc = in.ensure(m * dim * 4)) || (rc = codes.ensure(m * pitch)) || (rc = mags.ensure(m * 4))) break;
+        cudaMemcpyAsync(in.p, vecs + off * dim, m * dim * 4, cudaMemcpyHostToDevice, 0);
+        cudaMemsetAsync(codes.p, 0, m * pitch, 0);
+        rc = quantize_rows_device(in.as<float>(), m, dim, st, lo, hi, codes.as<uint8_t>(), pitch, mags.as<float>(), nullptr, 0, 0);
+        if (rc) break;
+        rc = copy_codes((uint8_t *)out_codes + off * host_code_bytes(st, dim), codes.p, st, dim, m, false, 0);
+        if (rc) break;
+        cudaMemcpyAsync(out_mags + off, mags.p, m * 4, cudaMemcpyDeviceToHost, 0);
+        cudaError_t e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = CDB_CUDA_ERROR; }
+    }
+    in.release(); codes.release(); mags.release();
+    return rc;
+}
+
+cdb_status cdb_distance_pairs(int32_t device, int32_t metric, int32_t st, uint32_t dim, const void *x_codes,
+                              const float *x_mags, const void *y_codes, const float *y_mags, uint64_t n, float *out,
+                              int32_t *out_status) {
+    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_F32 && metric >= 0 && metric <= 3 && dim > 0, "bad metric/storage/dim");
+    if (!n) return CDB_OK;
+    CDB_REQUIRE(x_codes && y_codes && x_mags && y_mags && out && out_status, "null buffer");
+    CDB_CUDA_TRY(cudaSetDevice(device));
+    const uint32_t pitch = row_pitch_bytes(st, dim);
+    DevBuf x, y, xm, ym, o, os;
+    cdb_status rc;
+    if ((rc = x.ensure(n * pitch)) || (rc = y.ensure(n * pitch)) || (rc = xm.ensure(n * 4)) || (rc = ym.ensure(n * 4)) ||
+        (rc = o.ensure(n * 4)) || (rc = os.ensure(n * 4)))
+        goto done;
+    cudaMemsetAsync(x.p, 0, n * pitch, 0);
+    cudaMemsetAsync(y.p, 0, n * pitch, 0);
+    if ((rc = copy_codes(x.p, x_codes, st, dim, n, true, 0)) || (rc = copy_codes(y.p, y_codes, st, dim, n, true, 0))) goto done;
+    cudaMemcpyAsync(xm.p, x_mags, n * 4, cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(ym.p, y_mags, n * 4, cudaMemcpyHostToDevice, 0);
+    rc = distance_pairs_device(metric, st, dim, x.as<uint8_t>(), xm.as<float>(), y.as<uint8_t>(), ym.as<float>(), pitch, n,
+                               o.as<float>(), os.as<int32_t>(), 0);
+    if (rc) goto done;
+    cudaMemcpyAsync(out, o.p, n * 4, cudaMemcpyDeviceToHost, 0);
+    cudaMemcpyAsync(out_status, os.p, n * 4, cudaMemcpyDeviceToHost, 0);
+    {
+        cudaError_t e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = CDB_CUDA_ERROR; }
+    }
+done:
+    x.release(); y.release(); xm.release(); ym.release(); o.release(); os.release();
+    return rc;
+}
+
+// ------------------------------------------------------------------ index lifecycle
+
+cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
+    CDB_REQUIRE(d && out, "null argument");
+    CDB_REQUIRE(d->dim > 0 && d->storage_type >= CDB_ST_U8 && d->storage_type <= CDB_ST_F32, "bad dim/storage type");
+    CDB_REQUIRE(d->metric >= CDB_METRIC_COSINE && d->metric <= CDB_METRIC_DOT_PRODUCT, "bad metric");
+    CDB_REQUIRE(d->capacity > 0 && d->capacity < 0xFFFFFFFFull, "capacity must be in 1..2^32-2");
+    CDB_CUDA_TRY(cudaSetDevice(d->device));
+    cdb_index *ix = new cdb_index();
+    ix->desc = *d;
+    cudaDeviceProp prop;
+    CDB_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    ix->sm_count = prop.multiProcessorCount;
+    ix->row_pitch = row_pitch_bytes(d->storage_type, d->dim);
+    ix->raw_pitch_elems = round_up(d->dim * 4, 16) / 4;
+    auto fail = [&](cudaError_t e, const char *what) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        cdb_index_destroy(ix);
+        return CDB_CUDA_ERROR;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    for (auto &ev : ix->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "event");
+    for (int i = 0; i < cdb_index::EV_RING; ++i)
+        if ((e = cudaEventCreate(&ix->ring0[i])) != cudaSuccess || (e = cudaEventCreate(&ix->ring1[i])) != cudaSuccess) return fail(e, "event");
+    if ((e = cudaMalloc(&ix->d_codes, (size_t)d->capacity * ix->row_pitch)) != cudaSuccess) return fail(e, "cudaMalloc(codes)");
+    if ((e = cudaMemsetAsync(ix->d_codes, 0, (size_t)d->capacity * ix->row_pitch, ix->stream)) != cudaSuccess) return fail(e, "memset");
+    if ((e = cudaMalloc(&ix->d_mags, (size_t)d->capacity * 4)) != cudaSuccess) return fail(e, "cudaMalloc(mags)");
+    if (d->storage_type == CDB_ST_F32) {
+        ix->d_raw = reinterpret_cast<float *>(ix->d_codes);
+        ix->d_raw_mags = ix->d_mags;
+    } else if (d->keep_raw_f32) {
+        if ((e = cudaMalloc(&ix->d_raw, (size_t)d->capacity * ix->raw_pitch_elems * 4)) != cudaSuccess) return fail(e, "cudaMalloc(raw)");
+        ix->raw_owned = true;
+        if ((e = cudaMemsetAsync(ix->d_raw, 0, (size_t)d->capacity * ix->raw_pitch_elems * 4, ix->stream)) != cudaSuccess) return fail(e, "memset");
+        if (d->storage_type == CDB_ST_U8) {
+            if ((e = cudaMalloc(&ix->d_raw_mags, (size_t)d->capacity * 4)) != cudaSuccess) return fail(e, "cudaMalloc(raw mags)");
+            ix->raw_mags_owned = true;
+        } else {
+            ix->d_raw_mags = ix->d_mags;  // same formula: sequential fold of the original values
+        }
+    }
+    if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return fail(e, "sync");
+    *out = ix;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_destroy(cdb_index *ix) {
+    if (!ix) return CDB_OK;
+    cudaSetDevice(ix->desc.device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    if (ix->d_codes) cudaFree(ix->d_codes);
+    if (ix->d_mags) cudaFree(ix->d_mags);
+    if (ix->raw_owned && ix->d_raw) cudaFree(ix->d_raw);
+    if (ix->raw_mags_owned && ix->d_raw_mags) cudaFree(ix->d_raw_mags);
+    for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
+                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc})
+        b->release();
+    for (auto &ev : ix->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < cdb_index::EV_RING; ++i) {
+        if (ix->ring0[i]) cudaEventDestroy(ix->ring0[i]);
+        if (ix->ring1[i]) cudaEventDestroy(ix->ring1[i]);
+    }
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return CDB_OK;
+}
+
+uint64_t cdb_index_size(const cdb_index *ix) { return ix ? ix->size : 0; }
+
+static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) {
+    if (ix->raw_mags_owned)
+        return raw_mags_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, n, ix->desc.dim,
+                               ix->d_raw_mags + first, ix->stream);
+    return CDB_OK;
+}
+
+cdb_status cdb_index_append_f32(cdb_index *ix, const float *vecs, uint64_t n) {
+    CDB_REQUIRE(ix && (vecs || !n), "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    const uint32_t dim = ix->desc.dim;
+    const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / ((size_t)dim * 4));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        uint64_t m = std::min(chunk, n - off);
+        cdb_status rc = ix->stage.ensure(m * dim * 4);
+        if (rc) return rc;
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->stage.p, vecs + off * dim, m * dim * 4, cudaMemcpyHostToDevice, ix->stream));
+        uint64_t first = ix->size;
+        float *raw = ix->raw_owned ? ix->d_raw + first * ix->raw_pitch_elems : nullptr;
+        rc = quantize_rows_device(ix->stage.as<float>(), m, dim, ix->desc.storage_type, ix->desc.range_lo, ix->desc.range_hi,
+                                  ix->d_codes + first * ix->row_pitch, ix->row_pitch, ix->d_mags + first, raw,
+                                  ix->raw_pitch_elems, ix->stream);
+        if (rc) return rc;
+        if ((rc = index_after_append(ix, first, m))) return rc;
+        CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        ix->size += m;
+    }
+    return CDB_OK;
+}
+
+cdb_status cdb_index_append_codes(cdb_index *ix, const void *codes, const float *mags, uint64_t n) {
+    CDB_REQUIRE(ix && ((codes && mags) || !n), "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
+    CDB_REQUIRE(!ix->raw_owned, "append_codes cannot populate raw f32 rows (keep_raw_f32 index)");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    cdb_status rc = copy_codes(ix->d_codes + ix->size * ix->row_pitch, codes, ix->desc.storage_type, ix->desc.dim, n, true, ix->stream);
+    if (rc) return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(ix->d_mags + ix->size, mags, n * 4, cudaMemcpyHostToDevice, ix->stream));
+    CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->size += n;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_append_synthetic(cdb_index *ix, uint64_t seed, uint64_t first_row, uint64_t n) {
+    CDB_REQUIRE(ix, "null index");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    uint64_t first = ix->size;
+    float *raw = ix->raw_owned ? ix->d_raw + first * ix->raw_pitch_elems : nullptr;
+    cdb_status rc = quantize_rows_synth(seed, first_row, n, ix->desc.dim, ix->desc.storage_type, ix->desc.range_lo,
+                                        ix->desc.range_hi, ix->d_codes + first * ix->row_pitch, ix->row_pitch,
+                                        ix->d_mags + first, raw, ix->raw_pitch_elems, ix->stream);
+    if (rc) return rc;
+    if ((rc = index_after_append(ix, first, n))) return rc;
+    CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->size += n;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_read_codes(const cdb_index *ix, uint64_t first, uint64_t n, void *out_codes, float *out_mags) {
+    CDB_REQUIRE(ix && first + n <= ix->size, "range out of bounds");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    if (out_codes) {
+        cdb_status rc = copy_codes(out_codes, ix->d_codes + first * ix->row_pitch, ix->desc.storage_type, ix->desc.dim, n, false, ix->stream);
+        if (rc) return rc;
+    }
+    if (out_mags) CDB_CUDA_TRY(cudaMemcpyAsync(out_mags, ix->d_mags + first, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return CDB_OK;
+}
+
+// ------------------------------------------------------------------ S1 search
+
+static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+                                       uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+    const cdb_index_desc &d = ix->desc;
+    CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
+    if (nq == 0) return CDB_OK;
+    cdb_status rc;
+    if (p->mode == CDB_MODE_BRUTE_RAW || p->mode == CDB_MODE_BRUTE_CODES) {
+        const bool raw = p->mode == CDB_MODE_BRUTE_RAW;
+        if (raw) CDB_REQUIRE(ix->d_raw, "BRUTE_RAW needs raw f32 rows (F32 storage or keep_raw_f32)");
+        const int st = raw ? CDB_ST_F32 : d.storage_type;
+        const int metric = raw ? CDB_METRIC_COSINE : d.metric;
+        if (!raw && (rc = arm_status(metric, st)) != CDB_OK) {
+            set_error("metric/storage arm is an Err in the reference (StorageMismatch / unimplemented)");
+            return rc;
+        }
+        const uint32_t pitch = raw ? ix->raw_pitch_elems * 4 : ix->row_pitch;
+        // search_internal: quantize the query with the index's storage type and range (hnsw/mod.rs:399-403);
+        // raw mode keeps f32 and |q| = sequential fold (vector_store.rs:412)
+        if ((rc = ix->q_codes.ensure((size_t)nq * pitch)) || (rc = ix->q_mags.ensure((size_t)nq * 4))) return rc;
+        CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)nq * pitch, s));
+        if ((rc = quantize_rows_device(d_queries, nq, d.dim, st, d.range_lo, d.range_hi, ix->q_codes.as<uint8_t>(), pitch,
+                                       ix->q_mags.as<float>(), nullptr, 0, s)))
+            return rc;
+        ScanArgs a{};
+        a.rows = raw ? reinterpret_cast<const uint8_t *>(ix->d_raw) : ix->d_codes;
+        a.row_pitch = pitch;
+        a.mags = raw ? ix->d_raw_mags : ix->d_mags;
+        a.n = ix->size;
+        a.dim = d.dim;
+        a.st = st;
+        a.metric = metric;
+        a.raw_mode = raw ? 1 : 0;
+        a.q = ix->q_codes.as<uint8_t>();
+        a.qmags = ix->q_mags.as<float>();
+        a.nq = nq;
+        a.k = p->k;
+        a.id_base = d.id_base;
+        a.nsplit = scan_plan_nsplit(a, ix->sm_count);
+        if ((rc = ix->partial.ensure((size_t)nq * a.nsplit * p->k * 8)) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
+        a.partial = ix->partial.as<uint64_t>();
+        a.err32 = ix->err32.as<uint32_t>();
+        CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));
+        const int slot = (int)(ix->n_search % cdb_index::EV_RING);
+        CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+        if ((rc = scan_topk_device(a, s))) return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+        CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
+        ix->n_search++;
+        if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, p->k, d_ids, d_scores, d_counts, s))) return rc;
+        if (d_err) {
+            err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
+            CDB_LAUNCH_CHECK();
+        }
+        CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
+        ix->ev_valid = true;
+        return CDB_OK;
+    }
+    set_error("search mode not implemented");
+    return CDB_UNSUPPORTED;
+}
+
+cdb_status cdb_search_batch_device(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+                                   uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, void *stream) {
+    CDB_REQUIRE(ix && p && (d_queries || !nq) && (d_ids || !nq) && (d_scores || !nq), "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    cdb_status rc;
+    if (!d_counts) {
+        if ((rc = ix->io_counts.ensure((size_t)nq * 4))) return rc;
+        d_counts = ix->io_counts.as<uint32_t>();
+    }
+    return search_device_locked(ix, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
+}
+
+cdb_status cdb_search_batch(cdb_index *ix, const float *queries, uint32_t nq, const cdb_search_params *p, uint32_t *out_ids,
+                            float *out_scores, uint32_t *out_counts, uint8_t *err_flags) {
+    CDB_REQUIRE(ix && p && (queries || !nq) && (out_ids || !nq) && (out_scores || !nq), "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    if (!nq) return CDB_OK;
+    CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
+    cudaStream_t s = ix->stream;
+    const size_t nk = (size_t)nq * p->k;
+    cdb_status rc;
+    if ((rc = ix->io_q.ensure((size_t)nq * ix->desc.dim * 4)) || (rc = ix->io_ids.ensure(nk * 4)) ||
+        (rc = ix->io_scores.ensure(nk * 4)) || (rc = ix->io_counts.ensure((size_t)nq * 4)) || (rc = ix->io_err.ensure(nq)))
+        return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, queries, (size_t)nq * ix->desc.dim * 4, cudaMemcpyHostToDevice, s));
+    rc = search_device_locked(ix, ix->io_q.as<float>(), nq, p, ix->io_ids.as<uint32_t>(), ix->io_scores.as<float>(),
+                              ix->io_counts.as<uint32_t>(), ix->io_err.as<uint8_t>(), s);
+    if (rc) return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, ix->io_scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    if (out_counts) CDB_CUDA_TRY(cudaMemcpyAsync(out_counts, ix->io_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    if (err_flags) CDB_CUDA_TRY(cudaMemcpyAsync(err_flags, ix->io_err.p, nq, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaStreamSynchronize(s));
+    return CDB_OK;
+}
+
+// ------------------------------------------------------------------ S2 / S3
+
+cdb_status cdb_score_ids(cdb_index *ix, const float *query, const uint32_t *ids, uint32_t n, float *out, int32_t *out_status) {
+    CDB_REQUIRE(ix && query && (ids || !n) && (out || !n) && (out_status || !n), "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    if (!n) return CDB_OK;
+    const cdb_index_desc &d = ix->desc;
+    cudaStream_t s = ix->stream;
+    cdb_status rc;
+    if ((rc = ix->io_q.ensure((size_t)d.dim * 4)) || (rc = ix->q_codes.ensure(ix->row_pitch)) || (rc = ix->q_mags.ensure(4)) ||
+        (rc = ix->io_ids.ensure((size_t)n * 4)) || (rc = ix->io_scores.ensure((size_t)n * 4)) || (rc = ix->misc.ensure((size_t)n * 4)))
+        return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, query, (size_t)d.dim * 4, cudaMemcpyHostToDevice, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, ix->row_pitch, s));
+    if ((rc = quantize_rows_device(ix->io_q.as<float>(), 1, d.dim, d.storage_type, d.range_lo, d.range_hi,
+                                   ix->q_codes.as<uint8_t>(), ix->row_pitch, ix->q_mags.as<float>(), nullptr, 0, s)))
+        return rc;
+    float qmag = 0.0f;
+    CDB_CUDA_TRY(cudaMemcpyAsync(&qmag, ix->q_mags.p, 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaStreamSynchronize(s));
+    if ((rc = score_ids_device(d.metric, d.storage_type, d.dim, ix->q_codes.as<uint8_t>(), qmag, ix->d_codes, ix->d_mags,
+                               ix->row_pitch, ix->size, ix->io_ids.as<uint32_t>(), n, ix->io_scores.as<float>(),
+                               ix->misc.as<int32_t>(), s)))
+        return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(out, ix->io_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_status, ix->misc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaStreamSynchronize(s));
+    return CDB_OK;
+}
+
+cdb_status cdb_rerank_f32(cdb_index *ix, const float *query, const uint32_t *cand_ids, uint32_t n, uint32_t k,
+                          uint32_t *out_ids, float *out_scores, uint32_t *out_count) {
+    CDB_REQUIRE(ix && query && (cand_ids || !n) && out_ids && out_scores && k >= 1, "bad argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->d_raw, "re-rank needs raw f32 rows (F32 storage or keep_raw_f32)");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    const cdb_index_desc &d = ix->desc;
+    cudaStream_t s = ix->stream;
+    cdb_status rc;
+    const uint32_t qpitch = ix->raw_pitch_elems;
+    if ((rc = ix->io_q.ensure((size_t)d.dim * 4)) || (rc = ix->q_codes.ensure((size_t)qpitch * 4)) || (rc = ix->q_mags.ensure(4)) ||
+        (rc = ix->misc.ensure((size_t)(n ? n : 1) * 4)) || (rc = ix->io_ids.ensure((size_t)k * 4)) ||
+        (rc = ix->io_scores.ensure((size_t)k * 4)) || (rc = ix->io_counts.ensure(4)))
+        return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, query, (size_t)d.dim * 4, cudaMemcpyHostToDevice, s));
+    if (n) CDB_CUDA_TRY(cudaMemcpyAsync(ix->misc.p, cand_ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)qpitch * 4, s));
+    if ((rc = quantize_rows_device(ix->io_q.as<float>(), 1, d.dim, CDB_ST_F32, 0.f, 0.f, ix->q_codes.as<uint8_t>(), qpitch * 4,
+                                   ix->q_mags.as<float>(), nullptr, 0, s)))
+        return rc;
+    if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(), qpitch,
+                                ix->q_mags.as<float>(), 1, ix->misc.as<uint32_t>(), n, k, d.id_base, ix->io_ids.as<uint32_t>(),
+                                ix->io_scores.as<float>(), ix->io_counts.as<uint32_t>(), s)))
+        return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, ix->io_scores.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
+    if (out_count) CDB_CUDA_TRY(cudaMemcpyAsync(out_count, ix->io_counts.p, 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaStreamSynchronize(s));
+    return CDB_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU merge
+
+cdb_status cdb_merge_topk_device(int32_t device, int32_t metric, const uint32_t *d_ids, const float *d_scores,
+                                 uint32_t n_shards, uint32_t nq, uint32_t k, uint32_t *d_out_ids, float *d_out_scores,
+                                 void *stream) {
+    CDB_REQUIRE(d_ids && d_scores && d_out_ids && d_out_scores && n_shards >= 1 && k >= 1, "bad argument");
+    CDB_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    uint64_t *keys = nullptr;
+    CDB_CUDA_TRY(cudaMallocAsync(&keys, (size_t)n_shards * nq * k * 8, s));
+    cdb_status rc = pack_keys_device(metric, d_ids, d_scores, n_shards, nq, k, keys, s);
+    if (!rc) rc = merge_partials_device(metric, keys, nq, n_shards, k, d_out_ids, d_out_scores, nullptr, s);
+    cudaFreeAsync(keys, s);
+    return rc;
+}
+
+cdb_status cdb_index_last_kernel_ms(const cdb_index *ix, float *scan_ms, float *total_ms) {
+    CDB_REQUIRE(ix, "null index");
+    if (scan_ms) *scan_ms = 0.f;
+    if (total_ms) *total_ms = 0.f;
+    if (!ix->ev_valid) return CDB_OK;
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    CDB_CUDA_TRY(cudaEventSynchronize(ix->ev[2]));
+    if (scan_ms) CDB_CUDA_TRY(cudaEventElapsedTime(scan_ms, ix->ev[0], ix->ev[1]));
+    if (total_ms) CDB_CUDA_TRY(cudaEventElapsedTime(total_ms, ix->ev[0], ix->ev[2]));
+    return CDB_OK;
+}
+
+
+cdb_status cdb_index_scan_ms_history(const cdb_index *ix, uint32_t n, float *out, uint32_t *out_n) {
+    CDB_REQUIRE(ix && out && out_n, "null argument");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    uint64_t have = ix->n_search < (uint64_t)cdb_index::EV_RING ? ix->n_search : (uint64_t)cdb_index::EV_RING;
+    uint32_t m = n < have ? n : (uint32_t)have;
+    for (uint32_t i = 0; i < m; ++i) {  // oldest of the last m first
+        int slot = (int)((ix->n_search - m + i) % cdb_index::EV_RING);
+        CDB_CUDA_TRY(cudaEventSynchronize(ix->ring1[slot]));
+        CDB_CUDA_TRY(cudaEventElapsedTime(out + i, ix->ring0[slot], ix->ring1[slot]));
+    }
+    *out_n = m;
+    return CDB_OK;
+}
+
+}  // extern "C"

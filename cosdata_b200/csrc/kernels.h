@@ -1,0 +1,61 @@
+// kernels.h -- internal launch wrappers shared between the .cu files.
+#pragma once
+#include "common.cuh"
+#include "scorers.cuh"
+
+namespace cdb {
+
+// ---- quantize.cu
+cdb_status quantize_rows_device(const float *d_vecs, uint64_t n, uint32_t dim, int st, float lo, float hi,
+                                uint8_t *d_codes, uint32_t row_pitch, float *d_mags, float *d_raw,
+                                uint32_t raw_pitch_elems, cudaStream_t s);
+cdb_status quantize_rows_synth(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t dim, int st, float lo, float hi,
+                               uint8_t *d_codes, uint32_t row_pitch, float *d_mags, float *d_raw,
+                               uint32_t raw_pitch_elems, cudaStream_t s);
+cdb_status raw_mags_device(const float *d_raw, uint32_t pitch_elems, uint64_t n, uint32_t dim, float *d_mags, cudaStream_t s);
+
+// ---- pairs.cu
+cdb_status distance_pairs_device(int metric, int st, uint32_t dim, const uint8_t *d_x, const float *d_xm,
+                                 const uint8_t *d_y, const float *d_ym, uint32_t row_pitch, uint64_t n,
+                                 float *d_out, int32_t *d_status, cudaStream_t s);
+// gather-score: one query against rows ids[0..n) of a stored matrix
+cdb_status score_ids_device(int metric, int st, uint32_t dim, const uint8_t *d_q, float qmag,
+                            const uint8_t *d_rows, const float *d_mags, uint32_t row_pitch, uint64_t n_rows,
+                            const uint32_t *d_ids, uint32_t n, float *d_out, int32_t *d_status, cudaStream_t s);
+// batched exact f32 cosine re-rank (finalize_ann_results): for each query b, score candidates
+// cand[b*ncand .. ) (CDB_INVALID_ID = skip), write sorted top-k keys as ids/scores.
+cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
+                             uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
+                             const uint32_t *d_cand, uint32_t ncand, uint32_t k, uint32_t id_base,
+                             uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s);
+
+// ---- scan.cu
+struct ScanArgs {
+    const uint8_t *rows;   // stored matrix (codes or raw f32), row-pitched
+    uint32_t row_pitch;    // bytes
+    const float *mags;     // per-row magnitude used by the formula
+    uint64_t n;
+    uint32_t dim;
+    int st;                // storage type of `rows`
+    int metric;
+    int raw_mode;          // 1: finalize formula (no zero check), 0: DistanceMetric::calculate
+    const uint8_t *q;      // prepared queries, same layout/pitch as rows
+    const float *qmags;
+    uint32_t nq;
+    uint32_t k;
+    uint32_t id_base;
+    uint64_t *partial;     // [nq][nsplit][k] selection keys
+    uint32_t nsplit;
+    uint32_t *err32;       // [nq] error bits (atomicOr) or null
+};
+// picks grid/template; returns nsplit chosen through args.nsplit (caller sizes `partial` with scan_max_partials)
+uint32_t scan_plan_nsplit(const ScanArgs &a, int sm_count);
+cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s);
+// partial [nq][nsplit][k] -> ids/scores/counts
+cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s);
+// [n_shards][nq][k] ids/scores -> keys [nq][n_shards][k]
+cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
+                            uint32_t k, uint64_t *d_keys, cudaStream_t s);
+
+}  // namespace cdb

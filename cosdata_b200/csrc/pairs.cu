@@ -1,0 +1,124 @@
+// pairs.cu -- pairwise DistanceFunction::calculate (src/models/types.rs:469-495),
+// gather-score for neighbour expansion (S2, src/vector_store.rs:1161-1191) and the
+// exact f32 re-rank of finalize_ann_results (S3, src/vector_store.rs:404-445).
+#include "kernels.h"
+
+namespace cdb {
+
+__global__ void distance_pairs_kernel(int metric, int st, uint32_t dim, const uint8_t *__restrict__ x,
+                                      const float *__restrict__ xm, const uint8_t *__restrict__ y,
+                                      const float *__restrict__ ym, uint32_t pitch, uint64_t n,
+                                      float *__restrict__ out, int32_t *__restrict__ status) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pp = plane_pitch(dim);
+    float v = 0.0f;
+    int rc = pair_distance(metric, st, dim, x + i * pitch, xm[i], pp, y + i * pitch, ym[i], pp, &v);
+    out[i] = rc == CDB_OK ? v : 0.0f;
+    status[i] = rc;
+}
+
+cdb_status distance_pairs_device(int metric, int st, uint32_t dim, const uint8_t *d_x, const float *d_xm,
+                                 const uint8_t *d_y, const float *d_ym, uint32_t row_pitch, uint64_t n,
+                                 float *d_out, int32_t *d_status, cudaStream_t s) {
+    if (!n) return CDB_OK;
+    distance_pairs_kernel<<<(uint32_t)((n + 63) / 64), 64, 0, s>>>(metric, st, dim, d_x, d_xm, d_y, d_ym, row_pitch, n, d_out, d_status);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+// one thread per id; the query row sits in global memory (L1/L2 resident)
+__global__ void score_ids_kernel(int metric, int st, uint32_t dim, const uint8_t *__restrict__ q, float qmag,
+                                 const uint8_t *__restrict__ rows, const float *__restrict__ mags, uint32_t pitch,
+                                 uint64_t n_rows, const uint32_t *__restrict__ ids, uint32_t n,
+                                 float *__restrict__ out, int32_t *__restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = ids[i];
+    if (id >= n_rows) { out[i] = 0.0f; status[i] = CDB_INVALID_PARAMS; return; }
+    const uint32_t pp = plane_pitch(dim);
+    float v = 0.0f;
+    int rc = pair_distance(metric, st, dim, q, qmag, pp, rows + (size_t)id * pitch, mags[id], pp, &v);
+    out[i] = rc == CDB_OK ? v : 0.0f;
+    status[i] = rc;
+}
+
+cdb_status score_ids_device(int metric, int st, uint32_t dim, const uint8_t *d_q, float qmag,
+                            const uint8_t *d_rows, const float *d_mags, uint32_t row_pitch, uint64_t n_rows,
+                            const uint32_t *d_ids, uint32_t n, float *d_out, int32_t *d_status, cudaStream_t s) {
+    if (!n) return CDB_OK;
+    score_ids_kernel<<<(n + 63) / 64, 64, 0, s>>>(metric, st, dim, d_q, qmag, d_rows, d_mags, row_pitch, n_rows, d_ids, n, d_out, d_status);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+// ------------------------------------------------------------------ exact re-rank
+// One CTA per query.  Eight consecutive lanes score one candidate: lane j owns AVX
+// lane j of dot_product_f32_simd, so a group reads 32 contiguous bytes per step and
+// the xor-butterfly reproduces the reference's hadd tree.  cs = dp / (|q|*|v|) with
+// no zero check (vector_store.rs:427-429); sort by total_cmp desc, truncate k.
+constexpr int RERANK_THREADS = 256;
+
+__global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
+    const float *__restrict__ raw, uint32_t pitch_elems, const float *__restrict__ raw_mags, uint64_t n_rows,
+    uint32_t dim, const float *__restrict__ q, uint32_t q_pitch_elems, const float *__restrict__ qmags,
+    const uint32_t *__restrict__ cand, uint32_t ncand, uint32_t k, uint32_t id_base,
+    uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, uint32_t *__restrict__ out_counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    float *qs = reinterpret_cast<float *>(smem);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(qs + round_up(dim, 4));
+    __shared__ int nvalid;
+    const uint32_t b = blockIdx.x;
+    for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) qs[c] = q[(size_t)b * q_pitch_elems + c];
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { out_ids[(size_t)b * k + j] = CDB_INVALID_ID; out_scores[(size_t)b * k + j] = 0.0f; }
+    if (threadIdx.x == 0) nvalid = 0;
+    __syncthreads();
+    const float mag_q = qmags[b];
+    const int j = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const uint32_t rounds = (ncand + RERANK_THREADS / 8 - 1) / (RERANK_THREADS / 8);
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t ci = r * (RERANK_THREADS / 8) + grp;
+        uint32_t id = ci < ncand ? cand[(size_t)b * ncand + ci] : CDB_INVALID_ID;
+        const bool ok = id != CDB_INVALID_ID && id >= id_base && (uint64_t)(id - id_base) < n_rows;
+        const uint64_t rowi = ok ? (uint64_t)(id - id_base) : 0;
+        float dp = dot_f32_avx_order_8t(qs, raw + rowi * pitch_elems, dim, j);  // all lanes participate in the shuffles
+        if (j == 0 && ci < ncand) {
+            uint64_t key = 0;
+            if (ok) {
+                float cs = canon_nan(__fdiv_rn(dp, __fmul_rn(mag_q, raw_mags[rowi])));
+                key = make_key64(order_key(CDB_METRIC_COSINE, __float_as_uint(cs)), id);
+            }
+            keys[ci] = key;
+            if (ok) atomicAdd(&nvalid, 1);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < ncand; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (!key) continue;
+        uint32_t rank = 0;
+        for (uint32_t t = 0; t < ncand; ++t) rank += (keys[t] > key) || (keys[t] == key && t < i);
+        if (rank < k) {
+            out_ids[(size_t)b * k + rank] = key64_id(key);
+            out_scores[(size_t)b * k + rank] = __uint_as_float(key_to_bits(CDB_METRIC_COSINE, (uint32_t)(key >> 32)));
+        }
+    }
+    if (threadIdx.x == 0 && out_counts) out_counts[b] = (uint32_t)nvalid < k ? (uint32_t)nvalid : k;
+}
+
+cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
+                             uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
+                             const uint32_t *d_cand, uint32_t ncand, uint32_t k, uint32_t id_base,
+                             uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s) {
+    if (!nq) return CDB_OK;
+    if (k == 0) { set_error("rerank: k must be > 0"); return CDB_INVALID_PARAMS; }
+    size_t smem = (size_t)round_up(dim, 4) * 4 + (size_t)(ncand ? ncand : 1) * 8;
+    if (smem > 200 * 1024) { set_error("rerank: too many candidates per query"); return CDB_INVALID_PARAMS; }
+    CDB_CUDA_TRY(cudaFuncSetAttribute(rerank_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rerank_f32_kernel<<<nq, RERANK_THREADS, smem, s>>>(d_raw, pitch_elems, d_raw_mags, n_rows, dim, d_q, q_pitch_elems,
+                                                        d_qmags, d_cand, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+}  // namespace cdb

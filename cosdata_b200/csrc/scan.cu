@@ -1,0 +1,374 @@
+// scan.cu -- exact brute-force scan with fused per-query top-k (S1, BRUTE modes).
+//
+// Two kernels share one top-k scheme:
+//   scan_f32_kernel   raw / F32 rows, cosine.  Two threads per row: thread t owns AVX
+//                     lanes 4t..4t+3 of the reference's dot_product_f32_simd
+//                     (x86_64.rs:418-444) and walks the row with 128-bit loads, so every
+//                     (query,row) dot is bit-identical to the reference.  R rows x QB
+//                     queries are register-blocked per thread.
+//   scan_generic_kernel  every other (metric, storage) arm through pair_distance():
+//                     one thread per row, reference operation order.
+// Grid: x = query group (QB queries), y = row split.  Splits interleave 256-row
+// passes, so all resident CTAs sweep the corpus front to back together and the
+// query groups of one split share rows through L2.
+//
+// Top-k: per CTA and query a shared-memory candidate buffer guarded by a threshold
+// (the k-th best key seen at the last compaction).  Scores below the threshold --
+// almost all of them after warm-up -- cost one compare.  A warp compacts a buffer by
+// rank selection when it could overflow.  Keys are (order_key<<32 | ~id): unique, so
+// the result is the exact top-k under (score desc, id asc) whatever the arrival order.
+#include "kernels.h"
+
+namespace cdb {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int RPP = 256;  // rows per pass per CTA
+
+struct TopK {
+    uint64_t *thr;  // [QB]
+    int *cnt;       // [QB]
+    int *err;       // [QB]
+    uint64_t *buf;  // [QB][cap]
+    uint64_t *tmp;  // [QB][k]
+    uint32_t cap, k;
+};
+
+__host__ __device__ inline uint32_t topk_cap(uint32_t k) { return k + 3 * RPP; }
+__host__ __device__ inline size_t topk_smem_bytes(uint32_t qb, uint32_t k) {
+    return (size_t)qb * (8 + 4 + 4) + (size_t)qb * (topk_cap(k) + k) * 8 + 16;
+}
+
+__device__ inline TopK topk_carve(uint8_t *p, uint32_t qb, uint32_t k) {
+    TopK t;
+    t.cap = topk_cap(k);
+    t.k = k;
+    t.buf = reinterpret_cast<uint64_t *>(p);
+    t.tmp = t.buf + (size_t)qb * t.cap;
+    t.thr = t.tmp + (size_t)qb * k;
+    t.cnt = reinterpret_cast<int *>(t.thr + qb);
+    t.err = t.cnt + qb;
+    return t;
+}
+__device__ inline void topk_init(const TopK &t, uint32_t qb) {
+    for (uint32_t i = threadIdx.x; i < qb; i += blockDim.x) { t.thr[i] = 0; t.cnt[i] = 0; t.err[i] = 0; }
+}
+__device__ inline void topk_offer(const TopK &t, int b, uint64_t key) {
+    if (key > t.thr[b]) {
+        int pos = atomicAdd(&t.cnt[b], 1);
+        t.buf[(size_t)b * t.cap + pos] = key;
+    }
+}
+// one warp: keep the best min(n,k) keys of buffer b, sorted best-first
+__device__ inline void topk_compact_warp(const TopK &t, int b, int lane) {
+    const int n = t.cnt[b];
+    uint64_t *B = t.buf + (size_t)b * t.cap;
+    uint64_t *T = t.tmp + (size_t)b * t.k;
+    for (int idx = lane; idx < n; idx += 32) {
+        const uint64_t key = B[idx];
+        uint32_t rank = 0;
+        for (int j = 0; j < n; ++j) rank += (B[j] > key);
+        if (rank < t.k) T[rank] = key;
+    }
+    __syncwarp();
+    const int m = n < (int)t.k ? n : (int)t.k;
+    for (int idx = lane; idx < m; idx += 32) B[idx] = T[idx];
+    __syncwarp();
+    if (lane == 0) {
+        t.cnt[b] = m;
+        if (n >= (int)t.k) t.thr[b] = T[t.k - 1];
+    }
+}
+// end of a pass: compacts when a buffer could overflow during the next pass.
+// A reader may miss appends of the current pass (<= RPP), hence the slack in topk_cap().
+__device__ inline void topk_end_pass(const TopK &t, uint32_t qb) {
+    int pred = (threadIdx.x < qb) ? (t.cnt[threadIdx.x] > (int)(t.k + RPP)) : 0;
+    if (__syncthreads_or(pred)) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (uint32_t b = warp; b < qb; b += SCAN_THREADS / 32) topk_compact_warp(t, b, lane);
+        __syncthreads();
+    }
+}
+__device__ inline void topk_finish(const TopK &t, uint32_t qb, uint32_t nqv, uint32_t q0, uint32_t split,
+                                   uint32_t nsplit, uint64_t *partial, uint32_t *err32) {
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t b = warp; b < qb; b += SCAN_THREADS / 32) topk_compact_warp(t, b, lane);
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < nqv * t.k; idx += blockDim.x) {
+        uint32_t b = idx / t.k, j = idx % t.k;
+        partial[((size_t)(q0 + b) * nsplit + split) * t.k + j] = (int)j < t.cnt[b] ? t.buf[(size_t)b * t.cap + j] : 0ull;
+    }
+    if (err32 && threadIdx.x < nqv && t.err[threadIdx.x]) atomicOr(err32 + q0 + threadIdx.x, (uint32_t)t.err[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ f32 exact scan
+template <int QB, int R>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_f32_kernel(ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t qp = a.row_pitch / 4;  // floats per (padded) query row
+    float *qs = reinterpret_cast<float *>(smem);
+    float *qmag = qs + (size_t)QB * qp;
+    TopK tk = topk_carve(reinterpret_cast<uint8_t *>(qmag + ((QB + 3) & ~3)), QB, a.k);
+
+    const int tid = threadIdx.x, t = tid & 1, pi = tid >> 1;
+    const uint32_t q0 = blockIdx.x * QB;
+    const uint32_t nqv = min((uint32_t)QB, a.nq - q0);
+    for (uint32_t i = tid; i < QB * qp; i += SCAN_THREADS) {
+        uint32_t b = i / qp, c = i % qp;
+        qs[i] = (b < nqv && c < a.dim) ? reinterpret_cast<const float *>(a.q + (size_t)(q0 + b) * a.row_pitch)[c] : 0.0f;
+    }
+    if (tid < QB) qmag[tid] = tid < (int)nqv ? a.qmags[q0 + tid] : 0.0f;
+    topk_init(tk, QB);
+    __syncthreads();
+
+    const uint32_t chunks = a.dim / 8;
+    const uint64_t npass = (a.n + RPP - 1) / RPP;
+    for (uint64_t pass = blockIdx.y; pass < npass; pass += gridDim.y) {
+        uint64_t row[R];
+        const float *xp[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            row[rr] = pass * RPP + pi + (uint64_t)(RPP / R) * rr;
+            uint64_t rc = row[rr] < a.n ? row[rr] : 0;
+            xp[rr] = reinterpret_cast<const float *>(a.rows + rc * a.row_pitch) + 4 * t;
+        }
+        float acc[R][QB][4];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int b = 0; b < QB; ++b)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[rr][b][e] = 0.0f;
+
+        const float *qt = qs + 4 * t;
+        uint32_t i = 0;
+        for (; i + 2 <= chunks; i += 2) {
+            float4 xv[2][R];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    uint4 w = ldg128_stream(xp[rr] + 8 * (i + u));
+                    xv[u][rr] = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    const float4 qv = *reinterpret_cast<const float4 *>(qt + (size_t)b * qp + 8 * (i + u));
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        acc[rr][b][0] = __fmaf_rn(qv.x, xv[u][rr].x, acc[rr][b][0]);
+                        acc[rr][b][1] = __fmaf_rn(qv.y, xv[u][rr].y, acc[rr][b][1]);
+                        acc[rr][b][2] = __fmaf_rn(qv.z, xv[u][rr].z, acc[rr][b][2]);
+                        acc[rr][b][3] = __fmaf_rn(qv.w, xv[u][rr].w, acc[rr][b][3]);
+                    }
+                }
+        }
+        for (; i < chunks; ++i) {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                uint4 w = ldg128_stream(xp[rr] + 8 * i);
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    const float4 qv = *reinterpret_cast<const float4 *>(qt + (size_t)b * qp + 8 * i);
+                    acc[rr][b][0] = __fmaf_rn(qv.x, __uint_as_float(w.x), acc[rr][b][0]);
+                    acc[rr][b][1] = __fmaf_rn(qv.y, __uint_as_float(w.y), acc[rr][b][1]);
+                    acc[rr][b][2] = __fmaf_rn(qv.z, __uint_as_float(w.z), acc[rr][b][2]);
+                    acc[rr][b][3] = __fmaf_rn(qv.w, __uint_as_float(w.w), acc[rr][b][3]);
+                }
+            }
+        }
+        // hadd tree: thread t holds (s[4t]+s[4t+1]) + (s[4t+2]+s[4t+3]); partner adds the other half
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const bool valid = row[rr] < a.n;
+            const float rmag = valid ? a.mags[row[rr]] : 1.0f;
+            const float *xrow = xp[rr] - 4 * t;
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                float h = __fadd_rn(__fadd_rn(acc[rr][b][0], acc[rr][b][1]), __fadd_rn(acc[rr][b][2], acc[rr][b][3]));
+                float o = __shfl_xor_sync(0xFFFFFFFFu, h, 1);
+                float tot = t == 0 ? __fadd_rn(h, o) : __fadd_rn(o, h);
+                for (uint32_t c = chunks * 8; c < a.dim; ++c) tot = __fadd_rn(tot, __fmul_rn(qs[(size_t)b * qp + c], __ldg(xrow + c)));
+                if (valid && (uint32_t)b < nqv && (b & 1) == t) {
+                    const float denom = __fmul_rn(qmag[b], rmag);
+                    if (!a.raw_mode && denom == 0.0f) {
+                        atomicOr(&tk.err[b], CDB_ERRFLAG_CALCULATION);
+                    } else {
+                        const float v = canon_nan(__fdiv_rn(tot, denom));
+                        topk_offer(tk, b, make_key64(order_key(CDB_METRIC_COSINE, __float_as_uint(v)), a.id_base + (uint32_t)row[rr]));
+                    }
+                }
+            }
+        }
+        topk_end_pass(tk, QB);
+    }
+    topk_finish(tk, QB, nqv, q0, blockIdx.y, a.nsplit, a.partial, a.err32);
+}
+
+// ------------------------------------------------------------------ generic scan
+template <int QB>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_generic_kernel(ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *qs = smem;  // [QB][row_pitch]
+    float *qmag = reinterpret_cast<float *>(qs + (size_t)QB * a.row_pitch);
+    TopK tk = topk_carve(reinterpret_cast<uint8_t *>(qmag + ((QB + 3) & ~3)), QB, a.k);
+    const int tid = threadIdx.x;
+    const uint32_t q0 = blockIdx.x * QB;
+    const uint32_t nqv = min((uint32_t)QB, a.nq - q0);
+    for (uint32_t i = tid; i < QB * (a.row_pitch / 4); i += SCAN_THREADS) {
+        uint32_t b = i / (a.row_pitch / 4), c = i % (a.row_pitch / 4);
+        reinterpret_cast<uint32_t *>(qs)[i] = b < nqv ? reinterpret_cast<const uint32_t *>(a.q + (size_t)(q0 + b) * a.row_pitch)[c] : 0u;
+    }
+    if (tid < QB) qmag[tid] = tid < (int)nqv ? a.qmags[q0 + tid] : 0.0f;
+    topk_init(tk, QB);
+    __syncthreads();
+    const uint32_t pp = plane_pitch(a.dim);
+    const uint64_t npass = (a.n + RPP - 1) / RPP;
+    for (uint64_t pass = blockIdx.y; pass < npass; pass += gridDim.y) {
+        const uint64_t row = pass * RPP + tid;
+        if (row < a.n) {
+            const uint8_t *xr = a.rows + row * a.row_pitch;
+            const float rmag = a.mags[row];
+            for (uint32_t b = 0; b < nqv; ++b) {
+                float v;
+                int rc = pair_distance(a.metric, a.st, a.dim, qs + (size_t)b * a.row_pitch, qmag[b], pp, xr, rmag, pp, &v);
+                if (rc == CDB_OK)
+                    topk_offer(tk, b, make_key64(order_key(a.metric, __float_as_uint(v)), a.id_base + (uint32_t)row));
+                else if (rc == CDB_CALCULATION_ERROR)
+                    atomicOr(&tk.err[b], CDB_ERRFLAG_CALCULATION);
+            }
+        }
+        topk_end_pass(tk, QB);
+    }
+    topk_finish(tk, QB, nqv, q0, blockIdx.y, a.nsplit, a.partial, a.err32);
+}
+
+// ------------------------------------------------------------------ planning / launch
+static int pick_qb(uint32_t nq, uint32_t row_pitch, uint32_t k) {
+    int qb = nq >= 5 ? 8 : (nq >= 3 ? 4 : (nq == 2 ? 2 : 1));
+    while (qb > 1 && (size_t)qb * row_pitch + topk_smem_bytes(qb, k) + 64 > 100 * 1024) qb >>= 1;
+    return qb;
+}
+static size_t scan_smem(int qb, uint32_t row_pitch, uint32_t k) {
+    return (size_t)qb * row_pitch + ((qb + 3) & ~3) * 4 + topk_smem_bytes(qb, k);
+}
+
+uint32_t scan_plan_nsplit(const ScanArgs &a, int sm_count) {
+    const int qb = pick_qb(a.nq, a.row_pitch, a.k);
+    const uint64_t ngroups = (a.nq + qb - 1) / qb;
+    const uint64_t npass = (a.n + RPP - 1) / RPP;
+    const uint64_t resident = 2ull * sm_count;
+    uint64_t max_split = npass < 1 ? 1 : npass;
+    if (max_split > 8192 / a.k) max_split = 8192 / a.k ? 8192 / a.k : 1;
+    if (max_split > 1024) max_split = 1024;
+    // aim for ~8 waves worth of CTAs, whole waves preferred
+    uint64_t best = 1;
+    double best_score = -1.0;
+    for (uint64_t s = 1; s <= max_split; ++s) {
+        uint64_t total = s * ngroups;
+        uint64_t waves = (total + resident - 1) / resident;
+        double eff = (double)total / (double)(waves * resident);
+        if (waves > 8) eff *= 8.0 / (double)waves;  // do not shred the work needlessly
+        if (npass / s < 4 && s > 1) eff *= 0.5;       // keep a few passes per CTA
+        if (eff > best_score + 1e-9) { best_score = eff; best = s; }
+    }
+    return (uint32_t)best;
+}
+
+template <int QB>
+static cdb_status launch_scan(const ScanArgs &a, cudaStream_t s) {
+    const uint32_t ngroups = (a.nq + QB - 1) / QB;
+    dim3 grid(ngroups, a.nsplit);
+    size_t smem = scan_smem(QB, a.row_pitch, a.k);
+    const bool f32path = (a.st == CDB_ST_F32 && a.metric == CDB_METRIC_COSINE);
+    if (f32path) {
+        auto kern = scan_f32_kernel<QB, 2>;
+        CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SCAN_THREADS, smem, s>>>(a);
+    } else {
+        auto kern = scan_generic_kernel<QB>;
+        CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SCAN_THREADS, smem, s>>>(a);
+    }
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s) {
+    if (a.k == 0 || a.k > 1024) { set_error("scan: k must be in 1..1024"); return CDB_INVALID_PARAMS; }
+    if (a.nq == 0) return CDB_OK;
+    switch (pick_qb(a.nq, a.row_pitch, a.k)) {
+    case 8: return launch_scan<8>(a, s);
+    case 4: return launch_scan<4>(a, s);
+    case 2: return launch_scan<2>(a, s);
+    default: return launch_scan<1>(a, s);
+    }
+}
+
+// ------------------------------------------------------------------ merge
+// one CTA per query: rank-select the best k of nlists*k keys (0 = empty)
+__global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ partial, uint32_t nlists, uint32_t k,
+                                      uint32_t *__restrict__ ids, float *__restrict__ scores, uint32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *keys = reinterpret_cast<uint64_t *>(smem);
+    __shared__ int nvalid;
+    const uint32_t q = blockIdx.x, M = nlists * k;
+    if (threadIdx.x == 0) nvalid = 0;
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { ids[(size_t)q * k + j] = CDB_INVALID_ID; scores[(size_t)q * k + j] = 0.0f; }
+    __syncthreads();
+    int local = 0;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        uint64_t v = partial[(size_t)q * M + i];
+        keys[i] = v;
+        local += v != 0;
+    }
+    if (local) atomicAdd(&nvalid, local);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (!key) continue;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < M; ++j) rank += keys[j] > key;
+        if (rank < k) {
+            ids[(size_t)q * k + rank] = key64_id(key);
+            scores[(size_t)q * k + rank] = __uint_as_float(key_to_bits(metric, (uint32_t)(key >> 32)));
+        }
+    }
+    if (threadIdx.x == 0 && counts) counts[q] = (uint32_t)nvalid < k ? (uint32_t)nvalid : k;
+}
+
+cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s) {
+    if (nq == 0) return CDB_OK;
+    size_t smem = (size_t)nlists * k * 8;
+    if (smem > 200 * 1024) { set_error("merge: too many partial candidates"); return CDB_INVALID_PARAMS; }
+    CDB_CUDA_TRY(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_partials_kernel<<<nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+__global__ void pack_keys_kernel(int metric, const uint32_t *ids, const float *scores, uint32_t n_shards, uint32_t nq,
+                                 uint32_t k, uint64_t *keys) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t total = (uint64_t)n_shards * nq * k;
+    if (i >= total) return;
+    uint32_t j = (uint32_t)(i % k);
+    uint32_t q = (uint32_t)((i / k) % nq);
+    uint32_t sh = (uint32_t)(i / ((uint64_t)k * nq));
+    uint32_t id = ids[i];
+    uint64_t key = id == CDB_INVALID_ID ? 0ull : make_key64(order_key(metric, __float_as_uint(scores[i])), id);
+    keys[((size_t)q * n_shards + sh) * k + j] = key;
+}
+cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
+                            uint32_t k, uint64_t *d_keys, cudaStream_t s) {
+    uint64_t total = (uint64_t)n_shards * nq * k;
+    if (!total) return CDB_OK;
+    pack_keys_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(metric, d_ids, d_scores, n_shards, nq, k, d_keys);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+}  // namespace cdb

@@ -1,0 +1,206 @@
+/*
+ * cosdata_b200.h -- C ABI of libcosdata_b200.so, the B200 (sm_100a) replacement
+ * for cosdata's ANN-search distance hot path.
+ *
+ * The reference (cosdata/cosdata, Rust) has no FFI layer; its operator surface
+ * for this path is three traits/enums.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference root)
+ * and INTEGRATION.md shows the Rust `extern "C"` block + shim that binds it:
+ *
+ *   Quantization::quantize          src/quantization/mod.rs:8-17, scalar.rs:10-52
+ *   DistanceFunction::calculate     src/distance/mod.rs:8-16, models/types.rs:469-495
+ *   IndexOps::batch_search (S1)     src/indexes/mod.rs:260-272 -> hnsw/mod.rs:390-440
+ *   neighbour expansion (S2)        src/vector_store.rs:1161-1191
+ *   finalize_ann_results (S3)       src/vector_store.rs:404-445
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types.  `stream` arguments are a cudaStream_t
+ *     passed as void* (NULL = the handle's own stream).
+ *   - every function returns cdb_status; cdb_last_error_string() describes the
+ *     last failure on the calling thread.
+ *   - caller owns every host buffer; the library owns device memory behind the
+ *     handle.  No callbacks, no exceptions cross the ABI.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns CDB_CUDA_ERROR.
+ *   - results are defined by the reference arithmetic: integer scores and
+ *     top-k ids bit-exact, f32 scores bit-identical to the reference's AVX2
+ *     reduction order.  Ties are broken by smaller id.
+ */
+#ifndef COSDATA_B200_H
+#define COSDATA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDB_ABI_VERSION 1
+
+typedef int32_t cdb_status;
+enum {
+    CDB_OK = 0,
+    CDB_STORAGE_MISMATCH = 1,  /* DistanceError::StorageMismatch  (src/distance/mod.rs:19) */
+    CDB_CALCULATION_ERROR = 2, /* DistanceError::CalculationError (src/distance/mod.rs:20) */
+    CDB_INVALID_PARAMS = 3,
+    CDB_CUDA_ERROR = 4,
+    CDB_NCCL_ERROR = 5,
+    CDB_UNSUPPORTED = 6        /* reference hits unimplemented!() / metadata replica arms */
+};
+
+/* StorageType (src/quantization/mod.rs:19-25); SubByte(r) is CDB_ST_SUB1..3. */
+enum {
+    CDB_ST_U8 = 0,
+    CDB_ST_SUB1 = 1,
+    CDB_ST_SUB2 = 2,
+    CDB_ST_SUB3 = 3,
+    CDB_ST_F16 = 4,
+    CDB_ST_F32 = 5
+};
+
+/* DistanceMetric (src/models/types.rs:460-467). */
+enum {
+    CDB_METRIC_COSINE = 0,
+    CDB_METRIC_EUCLIDEAN = 1,
+    CDB_METRIC_HAMMING = 2,
+    CDB_METRIC_DOT_PRODUCT = 3
+};
+
+/* search modes of cdb_search_batch */
+enum {
+    CDB_MODE_BRUTE_RAW = 0,   /* finalize_ann_results formula (vector_store.rs:414-439)
+                                 applied to every raw f32 row: cos = dp/(|q|*|v|), no zero check */
+    CDB_MODE_BRUTE_CODES = 1, /* DistanceMetric::calculate of the quantized query against every
+                                 quantized row (cosine.rs:104-235 etc.); zero denominator sets
+                                 err_flags[q] and skips the row */
+    CDB_MODE_HNSW = 2         /* ann_search + finalize_ann_results on the uploaded graph */
+};
+
+/* per-query error flag bits (u8 err_flags[B]) */
+enum {
+    CDB_ERRFLAG_CALCULATION = 1 /* some scored pair had a zero denominator (cosine.rs:230-231);
+                                   the reference `?`-propagates this and fails the query */
+};
+
+#define CDB_INVALID_ID 0xFFFFFFFFu
+
+typedef struct cdb_index cdb_index; /* opaque */
+
+typedef struct {
+    uint32_t dim;
+    int32_t storage_type;   /* CDB_ST_* : HNSWIndex.storage_type */
+    int32_t metric;         /* CDB_METRIC_* : HNSWIndex.distance_metric */
+    float range_lo;         /* HNSWIndex.values_range */
+    float range_hi;
+    uint64_t capacity;      /* max rows resident on this device */
+    int32_t device;         /* CUDA ordinal */
+    int32_t keep_raw_f32;   /* keep raw f32 rows for the exact re-rank
+                               (Collection.internal_to_external_map, collection.rs:110) */
+    uint32_t id_base;       /* global id of local row 0 (corpus shard offset) */
+    uint32_t reserved;
+} cdb_index_desc;
+
+typedef struct {
+    uint32_t k;              /* top_k */
+    int32_t mode;            /* CDB_MODE_* */
+    uint32_t ef_search;      /* hnsw_params.ef_search   (config.toml:23) */
+    uint32_t shortlist_size; /* config.search.shortlist_size (config.toml:32) */
+    int32_t exact_only;      /* 1: never use the tensor-core prefilter (pure FFMA scan) */
+    uint32_t prefilter_k;    /* candidates kept by the prefilter (0 = default) */
+    uint32_t reserved0;
+    uint32_t reserved1;
+} cdb_search_params;
+
+/* ---------------------------------------------------------------- misc */
+int32_t cdb_abi_version(void);
+const char *cdb_last_error_string(void);
+cdb_status cdb_device_count(int32_t *out);
+
+/* Synthetic data (bench / tests): element idx of stream `seed` is
+ *   z = seed + idx*0x9E3779B97F4A7C15; z = (z^(z>>30))*0xBF58476D1CE4E5B9;
+ *   z = (z^(z>>27))*0x94D049BB133111EB; z ^= z>>31;
+ *   value = ((int)(z>>40) - 2^23) / 2^23            (uniform on [-1,1), exact f32)
+ * Row r of a dim-D matrix uses idx = r*D + c. */
+cdb_status cdb_synth_fill_host(uint64_t seed, uint64_t first_idx, uint64_t n, float *out);
+
+/* ------------------------------------------------- Quantization::quantize
+ * bytes per code: u8 D | sub r*ceil(D/8) (planes [r][ceil(D/8)], plane 0 first) | f16 2D | f32 4D */
+size_t cdb_code_bytes(int32_t storage_type, uint32_t dim);
+cdb_status cdb_quantize_batch(int32_t device, int32_t storage_type, float range_lo, float range_hi,
+                              const float *vecs, uint64_t n, uint32_t dim,
+                              void *out_codes, float *out_mags);
+
+/* ---------------------------------------------- DistanceFunction::calculate
+ * (Base,Base) arm, batched over independent pairs.  out_status[i] is the
+ * Result of pair i (CDB_OK / CDB_STORAGE_MISMATCH / CDB_CALCULATION_ERROR /
+ * CDB_UNSUPPORTED); out[i] is defined only when it is CDB_OK. */
+cdb_status cdb_distance_pairs(int32_t device, int32_t metric, int32_t storage_type, uint32_t dim,
+                              const void *x_codes, const float *x_mags,
+                              const void *y_codes, const float *y_mags,
+                              uint64_t n_pairs, float *out, int32_t *out_status);
+
+/* ------------------------------------------------------------ index handle */
+cdb_status cdb_index_create(const cdb_index_desc *desc, cdb_index **out);
+cdb_status cdb_index_destroy(cdb_index *index);
+uint64_t cdb_index_size(const cdb_index *index);
+/* preprocess_embedding (vector_store.rs:629-712): quantize with the index's
+ * StorageType/range and append; raw rows kept when keep_raw_f32. */
+cdb_status cdb_index_append_f32(cdb_index *index, const float *vecs, uint64_t n);
+/* append already-quantized rows (prop.data payloads) */
+cdb_status cdb_index_append_codes(cdb_index *index, const void *codes, const float *mags, uint64_t n);
+/* generate rows [first_row, first_row+n) of synthetic stream `seed` ON DEVICE and append
+ * them (exactly what cdb_index_append_f32 would store for the same values) */
+cdb_status cdb_index_append_synthetic(cdb_index *index, uint64_t seed, uint64_t first_row, uint64_t n);
+/* copy stored state back (tests): codes/mags of rows [first, first+n) */
+cdb_status cdb_index_read_codes(const cdb_index *index, uint64_t first, uint64_t n, void *out_codes, float *out_mags);
+
+/* --------------------------------------------------- S1 IndexOps::batch_search
+ * queries: B x dim raw f32 (search_internal quantizes them with the index's
+ * storage type, hnsw/mod.rs:399-403).  out_ids/out_scores: B x k, best first;
+ * unused slots get CDB_INVALID_ID / 0.  out_counts[q] = valid slots.
+ * err_flags may be NULL. */
+cdb_status cdb_search_batch(cdb_index *index, const float *queries, uint32_t n_queries,
+                            const cdb_search_params *params,
+                            uint32_t *out_ids, float *out_scores, uint32_t *out_counts,
+                            uint8_t *err_flags);
+/* same, every pointer is DEVICE memory on the index's device; asynchronous on `stream` */
+cdb_status cdb_search_batch_device(cdb_index *index, const float *d_queries, uint32_t n_queries,
+                                   const cdb_search_params *params,
+                                   uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts,
+                                   uint8_t *d_err_flags, void *stream);
+
+/* ------------------------------------- S2 neighbour expansion (gather-score)
+ * score one quantized query (raw f32 in, quantized like search_internal) against
+ * rows ids[0..n): DistanceMetric::calculate(query, row). */
+cdb_status cdb_score_ids(cdb_index *index, const float *query, const uint32_t *ids, uint32_t n,
+                         float *out, int32_t *out_status);
+
+/* ------------------------------------------- S3 finalize_ann_results re-rank
+ * exact f32 cosine of `query` against raw rows cand_ids[0..n), sorted best
+ * first, truncated to k.  Needs keep_raw_f32 (or F32 storage). */
+cdb_status cdb_rerank_f32(cdb_index *index, const float *query, const uint32_t *cand_ids, uint32_t n,
+                          uint32_t k, uint32_t *out_ids, float *out_scores, uint32_t *out_count);
+
+/* ------------------------------------------------ multi-GPU shard merge (5e)
+ * d_ids/d_scores: [n_shards][n_queries][k] gathered per-shard results (device);
+ * writes the global top-k per query with the same ordering rule. */
+cdb_status cdb_merge_topk_device(int32_t device, int32_t metric, const uint32_t *d_ids, const float *d_scores,
+                                 uint32_t n_shards, uint32_t n_queries, uint32_t k,
+                                 uint32_t *d_out_ids, float *d_out_scores, void *stream);
+
+/* ----------------------------------------------------- instrumentation
+ * number of kernels launched by this library since process start (bench.py
+ * reports the delta over the timed region as gpu_launches) */
+uint64_t cdb_kernel_launch_count(void);
+/* last search's timing of the dominant kernel, measured with CUDA events on
+ * the launching stream (ms); 0 if unavailable */
+cdb_status cdb_index_last_kernel_ms(const cdb_index *index, float *scan_ms, float *total_ms);
+/* durations (ms) of the dominant (scan) kernel of the last min(n, 64) searches, oldest
+ * first, from CUDA events recorded on the launching stream around each launch */
+cdb_status cdb_index_scan_ms_history(const cdb_index *index, uint32_t n, float *out, uint32_t *out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSDATA_B200_H */
