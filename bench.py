@@ -190,7 +190,8 @@ def run_ours(args, rank, world, local_rank):
     out_ids = torch.empty((B, k), dtype=torch.int32).pin_memory()
     out_scores = torch.empty((B, k), dtype=torch.float32).pin_memory()
 
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)   # a real (non-default) stream: the ABI treats NULL as "use the handle's own stream"
+    torch.cuda.set_stream(stream)
 
     def step_device():
         ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
