@@ -27,7 +27,7 @@ class IndexDesc(C.Structure):
         ("device", C.c_int32),
         ("keep_raw_f32", C.c_int32),
         ("id_base", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("tensor_prefilter", C.c_uint32),
     ]
 
 
@@ -67,6 +67,8 @@ PROTOTYPES = {
     "cdb_merge_topk_device": (C.c_int32, [C.c_int32, C.c_int32, c_u32p, c_f32p, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_f32p, C.c_void_p]),
     "cdb_kernel_launch_count": (C.c_uint64, []),
     "cdb_index_last_kernel_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "cdb_index_stats": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "cdb_index_last_candidate_counts": (C.c_int32, [C.c_void_p, C.c_uint32, c_u32p]),
     "cdb_index_scan_ms_history": (C.c_int32, [C.c_void_p, C.c_uint32, c_f32p, C.POINTER(C.c_uint32)]),
 }
 

@@ -168,10 +168,12 @@ class DenseIndex:
     Collection hold for this path (quantized rows + mags, optional raw f32 rows)."""
 
     def __init__(self, dim, storage_type=StorageType.FullPrecisionFP, metric=DistanceMetricKind.Cosine,
-                 value_range=(-1.0, 1.0), capacity=1, device=0, keep_raw_f32=False, id_base=0):
+                 value_range=(-1.0, 1.0), capacity=1, device=0, keep_raw_f32=False, id_base=0,
+                 tensor_prefilter=True):
         self._lib = _lib.load()
         self.desc = IndexDesc(dim, int(storage_type), int(metric), float(value_range[0]), float(value_range[1]),
-                              int(capacity), int(device), 1 if keep_raw_f32 else 0, int(id_base), 0)
+                              int(capacity), int(device), 1 if keep_raw_f32 else 0, int(id_base),
+                              1 if tensor_prefilter else 0)
         self._h = C.c_void_p()
         _check(self._lib.cdb_index_create(C.byref(self.desc), C.byref(self._h)))
         self.dim = dim
@@ -264,3 +266,13 @@ class DenseIndex:
         m = C.c_uint32(0)
         _check(self._lib.cdb_index_scan_ms_history(self._h, n, _ptr(out), C.byref(m)))
         return out[: m.value].copy()
+
+    def stats(self):
+        out = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.cdb_index_stats(self._h, _ptr(out)))
+        return {"tensor_searches": int(out[0]), "fallbacks": int(out[1]), "zero_rows": int(out[2]), "has_shadow": bool(out[3])}
+
+    def last_candidate_counts(self, n):
+        out = np.zeros(n, dtype=np.uint32)
+        _check(self._lib.cdb_index_last_candidate_counts(self._h, n, _ptr(out)))
+        return out

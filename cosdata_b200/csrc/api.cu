@@ -94,6 +94,11 @@ struct cdb_index {
     float *d_raw = nullptr;       // raw f32 rows (may alias d_codes)
     float *d_raw_mags = nullptr;  // |raw row| (may alias d_mags)
     bool raw_owned = false, raw_mags_owned = false;
+    void *d_xh = nullptr;          // fp16 L2-normalised rows for the tcgen05 prefilter (tensor_scan.cu)
+    uint32_t xh_pitch = 0;         // halfs per shadow row
+    uint64_t n_zero_rows = 0;      // rows with |v| == 0 (their exact score is NaN)
+    uint32_t *h_flags = nullptr;   // pinned host copy of d_flags
+    uint64_t stat_tensor_searches = 0, stat_fallbacks = 0, stat_candidates = 0;
     cudaStream_t stream = nullptr;
     static constexpr int EV_RING = 64;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -102,6 +107,7 @@ struct cdb_index {
     bool ev_valid = false;
     std::mutex mu;
     DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
+    DevBuf qh, gthr, cand, cand_cnt, flags;
 };
 
 #define CDB_REQUIRE(cond, msg)                              \
@@ -233,6 +239,14 @@ cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
             ix->d_raw_mags = ix->d_mags;  // same formula: sequential fold of the original values
         }
     }
+    if (d->tensor_prefilter && ix->d_raw) {
+        ix->xh_pitch = round_up(d->dim * 2, 16) / 2;
+        if ((e = cudaMalloc(&ix->d_xh, (size_t)d->capacity * ix->xh_pitch * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp16 shadow)");
+        if ((e = cudaMemsetAsync(ix->d_xh, 0, (size_t)d->capacity * ix->xh_pitch * 2, ix->stream)) != cudaSuccess) return fail(e, "memset");
+    }
+    if ((e = cudaMallocHost(&ix->h_flags, 16)) != cudaSuccess) return fail(e, "cudaMallocHost");
+    if (ix->flags.ensure(16) != CDB_OK) return fail(cudaErrorMemoryAllocation, "flags");
+    if ((e = cudaMemsetAsync(ix->flags.p, 0, 16, ix->stream)) != cudaSuccess) return fail(e, "memset");
     if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return fail(e, "sync");
     *out = ix;
     return CDB_OK;
@@ -246,8 +260,10 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     if (ix->d_mags) cudaFree(ix->d_mags);
     if (ix->raw_owned && ix->d_raw) cudaFree(ix->d_raw);
     if (ix->raw_mags_owned && ix->d_raw_mags) cudaFree(ix->d_raw_mags);
+    if (ix->d_xh) cudaFree(ix->d_xh);
+    if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
-                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc})
+                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags})
         b->release();
     for (auto &ev : ix->ev)
         if (ev) cudaEventDestroy(ev);
@@ -263,9 +279,21 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
 uint64_t cdb_index_size(const cdb_index *ix) { return ix ? ix->size : 0; }
 
 static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) {
-    if (ix->raw_mags_owned)
-        return raw_mags_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, n, ix->desc.dim,
-                               ix->d_raw_mags + first, ix->stream);
+    cdb_status rc;
+    if (ix->raw_mags_owned &&
+        (rc = raw_mags_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, n, ix->desc.dim,
+                              ix->d_raw_mags + first, ix->stream)))
+        return rc;
+    if (ix->d_xh) {
+        // flags[1] accumulates the number of zero-norm rows
+        if ((rc = normalize_f16_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, ix->d_raw_mags + first, n,
+                                       ix->desc.dim, (uint8_t *)ix->d_xh + first * ix->xh_pitch * 2, ix->xh_pitch,
+                                       ix->flags.as<uint32_t>() + 1, ix->stream)))
+            return rc;
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags + 1, ix->flags.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, ix->stream));
+        CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        ix->n_zero_rows = ix->h_flags[1];
+    }
     return CDB_OK;
 }
 
@@ -339,66 +367,118 @@ cdb_status cdb_index_read_codes(const cdb_index *ix, uint64_t first, uint64_t n,
 
 // ------------------------------------------------------------------ S1 search
 
+// prepared (quantized) queries live in ix->q_codes / ix->q_mags
+static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric, uint32_t pitch, uint32_t nq, uint32_t k,
+                                    uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+    const cdb_index_desc &d = ix->desc;
+    cdb_status rc;
+    ScanArgs a{};
+    a.rows = raw ? reinterpret_cast<const uint8_t *>(ix->d_raw) : ix->d_codes;
+    a.row_pitch = pitch;
+    a.mags = raw ? ix->d_raw_mags : ix->d_mags;
+    a.n = ix->size;
+    a.dim = d.dim;
+    a.st = st;
+    a.metric = metric;
+    a.raw_mode = raw ? 1 : 0;
+    a.q = ix->q_codes.as<uint8_t>();
+    a.qmags = ix->q_mags.as<float>();
+    a.nq = nq;
+    a.k = k;
+    a.id_base = d.id_base;
+    a.nsplit = scan_plan_nsplit(a, ix->sm_count);
+    if ((rc = ix->partial.ensure((size_t)nq * a.nsplit * k * 8)) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
+    a.partial = ix->partial.as<uint64_t>();
+    a.err32 = ix->err32.as<uint32_t>();
+    CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));
+    if ((rc = scan_topk_device(a, s))) return rc;
+    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s))) return rc;
+    if (d_err) {
+        err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
+        CDB_LAUNCH_CHECK();
+    }
+    return CDB_OK;
+}
+
+// rigorous bound on |approximate cosine - reference cosine| of the fp16 tensor-core prefilter
+// (two fp16 roundings, fp32 tensor accumulation, f32 norms)
+static float prefilter_eps(uint32_t dim) { return 1.0e-3f + 8.0e-7f * (float)dim; }
+static const uint32_t PREFILTER_CAP = 4096;
+
 static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                        uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
     const cdb_index_desc &d = ix->desc;
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
     if (nq == 0) return CDB_OK;
     cdb_status rc;
-    if (p->mode == CDB_MODE_BRUTE_RAW || p->mode == CDB_MODE_BRUTE_CODES) {
-        const bool raw = p->mode == CDB_MODE_BRUTE_RAW;
-        if (raw) CDB_REQUIRE(ix->d_raw, "BRUTE_RAW needs raw f32 rows (F32 storage or keep_raw_f32)");
-        const int st = raw ? CDB_ST_F32 : d.storage_type;
-        const int metric = raw ? CDB_METRIC_COSINE : d.metric;
-        if (!raw && (rc = arm_status(metric, st)) != CDB_OK) {
-            set_error("metric/storage arm is an Err in the reference (StorageMismatch / unimplemented)");
-            return rc;
-        }
-        const uint32_t pitch = raw ? ix->raw_pitch_elems * 4 : ix->row_pitch;
-        // search_internal: quantize the query with the index's storage type and range (hnsw/mod.rs:399-403);
-        // raw mode keeps f32 and |q| = sequential fold (vector_store.rs:412)
-        if ((rc = ix->q_codes.ensure((size_t)nq * pitch)) || (rc = ix->q_mags.ensure((size_t)nq * 4))) return rc;
-        CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)nq * pitch, s));
-        if ((rc = quantize_rows_device(d_queries, nq, d.dim, st, d.range_lo, d.range_hi, ix->q_codes.as<uint8_t>(), pitch,
-                                       ix->q_mags.as<float>(), nullptr, 0, s)))
-            return rc;
-        ScanArgs a{};
-        a.rows = raw ? reinterpret_cast<const uint8_t *>(ix->d_raw) : ix->d_codes;
-        a.row_pitch = pitch;
-        a.mags = raw ? ix->d_raw_mags : ix->d_mags;
-        a.n = ix->size;
-        a.dim = d.dim;
-        a.st = st;
-        a.metric = metric;
-        a.raw_mode = raw ? 1 : 0;
-        a.q = ix->q_codes.as<uint8_t>();
-        a.qmags = ix->q_mags.as<float>();
-        a.nq = nq;
-        a.k = p->k;
-        a.id_base = d.id_base;
-        a.nsplit = scan_plan_nsplit(a, ix->sm_count);
-        if ((rc = ix->partial.ensure((size_t)nq * a.nsplit * p->k * 8)) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
-        a.partial = ix->partial.as<uint64_t>();
-        a.err32 = ix->err32.as<uint32_t>();
-        CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));
-        const int slot = (int)(ix->n_search % cdb_index::EV_RING);
-        CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
-        CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-        if ((rc = scan_topk_device(a, s))) return rc;
-        CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
-        CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
-        ix->n_search++;
-        if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, p->k, d_ids, d_scores, d_counts, s))) return rc;
-        if (d_err) {
-            err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
-            CDB_LAUNCH_CHECK();
-        }
-        CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
-        ix->ev_valid = true;
-        return CDB_OK;
+    if (p->mode != CDB_MODE_BRUTE_RAW && p->mode != CDB_MODE_BRUTE_CODES) {
+        set_error("search mode not implemented");
+        return CDB_UNSUPPORTED;
     }
-    set_error("search mode not implemented");
-    return CDB_UNSUPPORTED;
+    const bool raw = p->mode == CDB_MODE_BRUTE_RAW;
+    if (raw) CDB_REQUIRE(ix->d_raw, "BRUTE_RAW needs raw f32 rows (F32 storage or keep_raw_f32)");
+    const int st = raw ? CDB_ST_F32 : d.storage_type;
+    const int metric = raw ? CDB_METRIC_COSINE : d.metric;
+    if (!raw && (rc = arm_status(metric, st)) != CDB_OK) {
+        set_error("metric/storage arm is an Err in the reference (StorageMismatch / unimplemented)");
+        return rc;
+    }
+    const uint32_t pitch = raw ? ix->raw_pitch_elems * 4 : ix->row_pitch;
+    // search_internal: quantize the query with the index's storage type and range (hnsw/mod.rs:399-403);
+    // raw mode keeps f32 and |q| = sequential fold (vector_store.rs:412)
+    if ((rc = ix->q_codes.ensure((size_t)nq * pitch)) || (rc = ix->q_mags.ensure((size_t)nq * 4))) return rc;
+    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)nq * pitch, s));
+    if ((rc = quantize_rows_device(d_queries, nq, d.dim, st, d.range_lo, d.range_hi, ix->q_codes.as<uint8_t>(), pitch,
+                                   ix->q_mags.as<float>(), nullptr, 0, s)))
+        return rc;
+    const int slot = (int)(ix->n_search % cdb_index::EV_RING);
+    ix->n_search++;
+    CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
+
+    // ---- tcgen05 prefilter + exact re-rank: identical results, far fewer exact dot products
+    const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 128 &&
+                           ix->size - ix->n_zero_rows >= p->k && tensor_scan_smem_bytes(p->k) <= 227 * 1024;
+    bool done = false;
+    if (tensor_ok) {
+        const uint32_t mt = (nq + 127) / 128;
+        const uint32_t cap = p->prefilter_k ? p->prefilter_k : PREFILTER_CAP;
+        if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)nq * 4)) ||
+            (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)))
+            return rc;
+        uint32_t *flags = ix->flags.as<uint32_t>();  // [0] overflowed queries, [2] zero-norm queries
+        CDB_CUDA_TRY(cudaMemsetAsync(flags, 0, 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(flags + 2, 0, 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * ix->xh_pitch * 2, s));
+        if ((rc = normalize_f16_device(ix->q_codes.as<float>(), pitch / 4, ix->q_mags.as<float>(), nq, d.dim, ix->qh.p,
+                                       ix->xh_pitch, flags + 2, s)))
+            return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+        if ((rc = tensor_scan_device(ix->d_xh, ix->qh.p, ix->xh_pitch, ix->size, nq, d.dim, p->k, 2.0f * prefilter_eps(d.dim),
+                                     d.id_base, ix->gthr.as<int>(), ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), cap,
+                                     ix->sm_count, s)))
+            return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(),
+                                    pitch / 4, ix->q_mags.as<float>(), nq, ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(),
+                                    cap, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
+            return rc;
+        if ((rc = overflow_check_device(ix->cand_cnt.as<uint32_t>(), cap, nq, flags, s))) return rc;
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags, flags, 12, cudaMemcpyDeviceToHost, s));
+        CDB_CUDA_TRY(cudaStreamSynchronize(s));  // the fallback decision needs the flags on the host
+        ix->stat_tensor_searches++;
+        done = ix->h_flags[0] == 0 && ix->h_flags[2] == 0;
+        if (!done) ix->stat_fallbacks++;
+        else if (d_err) CDB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nq, s));
+    }
+    if (!done) {
+        if (!tensor_ok) CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+        if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s))) return rc;
+        if (!tensor_ok) CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+    }
+    CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
+    CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
+    ix->ev_valid = true;
+    return CDB_OK;
 }
 
 cdb_status cdb_search_batch_device(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
@@ -493,7 +573,7 @@ cdb_status cdb_rerank_f32(cdb_index *ix, const float *query, const uint32_t *can
                                    ix->q_mags.as<float>(), nullptr, 0, s)))
         return rc;
     if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(), qpitch,
-                                ix->q_mags.as<float>(), 1, ix->misc.as<uint32_t>(), n, k, d.id_base, ix->io_ids.as<uint32_t>(),
+                                ix->q_mags.as<float>(), 1, ix->misc.as<uint32_t>(), nullptr, n, k, d.id_base, ix->io_ids.as<uint32_t>(),
                                 ix->io_scores.as<float>(), ix->io_counts.as<uint32_t>(), s)))
         return rc;
     CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
@@ -531,6 +611,23 @@ cdb_status cdb_index_last_kernel_ms(const cdb_index *ix, float *scan_ms, float *
     return CDB_OK;
 }
 
+
+cdb_status cdb_index_stats(const cdb_index *ix, uint64_t *out4) {
+    CDB_REQUIRE(ix && out4, "null argument");
+    out4[0] = ix->stat_tensor_searches;
+    out4[1] = ix->stat_fallbacks;
+    out4[2] = ix->n_zero_rows;
+    out4[3] = ix->d_xh ? 1 : 0;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_last_candidate_counts(const cdb_index *ix, uint32_t n, uint32_t *out) {
+    CDB_REQUIRE(ix && out, "null argument");
+    CDB_REQUIRE(ix->cand_cnt.p && (size_t)n * 4 <= ix->cand_cnt.cap, "no prefilter search of that size has run");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    CDB_CUDA_TRY(cudaMemcpy(out, ix->cand_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
 
 cdb_status cdb_index_scan_ms_history(const cdb_index *ix, uint32_t n, float *out, uint32_t *out_n) {
     CDB_REQUIRE(ix && out && out_n, "null argument");

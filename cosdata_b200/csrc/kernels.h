@@ -26,7 +26,7 @@ cdb_status score_ids_device(int metric, int st, uint32_t dim, const uint8_t *d_q
 // cand[b*ncand .. ) (CDB_INVALID_ID = skip), write sorted top-k keys as ids/scores.
 cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
                              uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
-                             const uint32_t *d_cand, uint32_t ncand, uint32_t k, uint32_t id_base,
+                             const uint32_t *d_cand, const uint32_t *d_cand_counts, uint32_t ncand, uint32_t k, uint32_t id_base,
                              uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s);
 
 // ---- scan.cu
@@ -57,5 +57,14 @@ cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t
 // [n_shards][nq][k] ids/scores -> keys [nq][n_shards][k]
 cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
                             uint32_t k, uint64_t *d_keys, cudaStream_t s);
+
+// ---- tensor_scan.cu (tcgen05 prefilter)
+cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
+                                void *d_out, uint32_t out_pitch_halfs, uint32_t *d_zero_count, cudaStream_t s);
+size_t tensor_scan_smem_bytes(uint32_t k);
+cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
+                              uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_gthr, uint32_t *d_cand,
+                              uint32_t *d_cand_cnt, uint32_t cand_cap, int sm_count, cudaStream_t s);
+cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s);
 
 }  // namespace cdb

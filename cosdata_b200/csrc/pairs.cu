@@ -62,13 +62,14 @@ constexpr int RERANK_THREADS = 256;
 __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
     const float *__restrict__ raw, uint32_t pitch_elems, const float *__restrict__ raw_mags, uint64_t n_rows,
     uint32_t dim, const float *__restrict__ q, uint32_t q_pitch_elems, const float *__restrict__ qmags,
-    const uint32_t *__restrict__ cand, uint32_t ncand, uint32_t k, uint32_t id_base,
+    const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_counts, uint32_t cand_stride, uint32_t k, uint32_t id_base,
     uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, uint32_t *__restrict__ out_counts) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *qs = reinterpret_cast<float *>(smem);
     uint64_t *keys = reinterpret_cast<uint64_t *>(qs + round_up(dim, 4));
     __shared__ int nvalid;
     const uint32_t b = blockIdx.x;
+    const uint32_t ncand = cand_counts ? min(cand_counts[b], cand_stride) : cand_stride;
     for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) qs[c] = q[(size_t)b * q_pitch_elems + c];
     for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { out_ids[(size_t)b * k + j] = CDB_INVALID_ID; out_scores[(size_t)b * k + j] = 0.0f; }
     if (threadIdx.x == 0) nvalid = 0;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
     const uint32_t rounds = (ncand + RERANK_THREADS / 8 - 1) / (RERANK_THREADS / 8);
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t ci = r * (RERANK_THREADS / 8) + grp;
-        uint32_t id = ci < ncand ? cand[(size_t)b * ncand + ci] : CDB_INVALID_ID;
+        uint32_t id = ci < ncand ? cand[(size_t)b * cand_stride + ci] : CDB_INVALID_ID;
         const bool ok = id != CDB_INVALID_ID && id >= id_base && (uint64_t)(id - id_base) < n_rows;
         const uint64_t rowi = ok ? (uint64_t)(id - id_base) : 0;
         float dp = dot_f32_avx_order_8t(qs, raw + rowi * pitch_elems, dim, j);  // all lanes participate in the shuffles
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
 
 cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
                              uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
-                             const uint32_t *d_cand, uint32_t ncand, uint32_t k, uint32_t id_base,
+                             const uint32_t *d_cand, const uint32_t *d_cand_counts, uint32_t ncand, uint32_t k, uint32_t id_base,
                              uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s) {
     if (!nq) return CDB_OK;
     if (k == 0) { set_error("rerank: k must be > 0"); return CDB_INVALID_PARAMS; }
@@ -116,7 +117,7 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
     if (smem > 200 * 1024) { set_error("rerank: too many candidates per query"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(rerank_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_f32_kernel<<<nq, RERANK_THREADS, smem, s>>>(d_raw, pitch_elems, d_raw_mags, n_rows, dim, d_q, q_pitch_elems,
-                                                        d_qmags, d_cand, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts);
+                                                        d_qmags, d_cand, d_cand_counts, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

@@ -1,0 +1,397 @@
+// tensor_scan.cu -- tcgen05 prefilter for the batched brute-force cosine scan (S1, large B).
+//
+// The dense query x corpus product of configs C2/C5 genuinely is a contraction, so it runs
+// on the 5th-gen tensor cores: fp16 copies of the L2-normalised rows ("shadow", built at
+// append time) and of the normalised queries are multiplied with tcgen05.mma.kind::f16
+// (fp32 accumulators in TMEM).  The result is an APPROXIMATE cosine a(q,x) with a rigorous
+// error bound eps; it is used only to discard rows that provably
+// cannot be in the exact top-k:
+//     every epilogue thread owns one query (one TMEM lane) and keeps, in shared memory,
+//     the k best approximate scores it has seen (A_k = the k-th).  k rows with a >= A_k
+//     exist, so the exact k-th best score is >= A_k - eps, so a row can be in the exact
+//     top-k only if a >= A_k - 2*eps.  Rows passing that test are appended to the query's
+//     candidate list; A_k is shared between CTAs through a global atomicMax.
+// The candidates are then re-scored by rerank_f32_kernel with the reference's exact
+// arithmetic, so the final ids/scores are bit-identical to the exact scan.
+//
+// Kernel anatomy (one CTA per SM, 192 threads):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-stage mbarrier ring
+//   warp 1      MMA issuer     tcgen05.mma cta_group::1 M128 x N256 x K16, commit -> mbarrier
+//   warps 2..5  epilogue       tcgen05.ld 32x32b.x32 from a double-buffered TMEM accumulator
+// Tile: 128 queries (A, K-major) x 256 corpus rows (B, K-major), K block = 64 halfs (128 B).
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace cdb {
+
+constexpr int TS_BLOCK_M = 128;
+constexpr int TS_BLOCK_N = 256;
+constexpr int TS_BLOCK_K = 64;  // fp16 elements = one 128-byte swizzle row
+constexpr int TS_STAGES = 4;
+constexpr int TS_THREADS = 192;
+constexpr uint32_t TS_A_BYTES = TS_BLOCK_M * TS_BLOCK_K * 2;  // 16 KB
+constexpr uint32_t TS_B_BYTES = TS_BLOCK_N * TS_BLOCK_K * 2;  // 32 KB
+constexpr uint32_t TS_STAGE_BYTES = TS_A_BYTES + TS_B_BYTES;
+constexpr uint32_t TS_TMEM_COLS = 512;  // 2 accumulator stages x 256 fp32 columns
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) |
+//   [32,46) SBO >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1 |
+//   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N >> 3, M >> 4
+constexpr uint32_t TS_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TS_BLOCK_N >> 3) << 17) | ((uint32_t)(TS_BLOCK_M >> 4) << 24);
+
+// order-preserving float <-> int (for atomicMax on thresholds)
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+struct TensorScanArgs {
+    uint64_t n_rows;
+    uint32_t n_queries;
+    uint32_t k;
+    uint32_t kblocks, mtiles, ntiles;
+    float two_eps;
+    uint32_t id_base;
+    int *gthr;           // [n_queries] shared lower bound of A_k (ordered int), init INT_MIN
+    uint32_t *cand;      // [n_queries][cand_cap] global ids
+    uint32_t *cand_cnt;  // [n_queries]
+    uint32_t cand_cap;
+};
+
+// min-heap of the k best approximate scores of one query (root = k-th best)
+__device__ __forceinline__ void heap_push(float *h, uint32_t &cnt, uint32_t k, float v) {
+    if (cnt < k) {
+        uint32_t i = cnt++;
+        h[i] = v;
+        while (i > 0) {
+            uint32_t p = (i - 1) >> 1;
+            if (h[p] <= h[i]) break;
+            float t = h[p]; h[p] = h[i]; h[i] = t;
+            i = p;
+        }
+    } else {
+        h[0] = v;
+        uint32_t i = 0;
+        for (;;) {
+            uint32_t l = 2 * i + 1, r = l + 1, m = i;
+            if (l < k && h[l] < h[m]) m = l;
+            if (r < k && h[r] < h[m]) m = r;
+            if (m == i) break;
+            float t = h[m]; h[m] = h[i]; h[i] = t;
+            i = m;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TensorScanArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *tiles = smem;
+    float *heaps = reinterpret_cast<float *>(tiles + TS_STAGES * TS_STAGE_BYTES);  // [128][k]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(heaps + (size_t)TS_BLOCK_M * a.k + ((TS_BLOCK_M * a.k) & 1));
+    uint64_t *full_bar = bars, *empty_bar = bars + TS_STAGES, *tfull_bar = bars + 2 * TS_STAGES, *tempty_bar = bars + 2 * TS_STAGES + 2;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TS_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // work assignment: CTA c owns query tile c % mtiles and every G-th corpus tile
+    const uint32_t mt = blockIdx.x % a.mtiles;
+    const uint32_t g = blockIdx.x / a.mtiles;
+    const uint32_t G = (gridDim.x - mt + a.mtiles - 1) / a.mtiles;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        for (int s = 0; s < TS_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TS_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t s = 0, phase = 0;
+            for (uint32_t nt = g; nt < a.ntiles; nt += G) {
+                for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(fb, TS_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * TS_STAGE_BYTES);
+                    tma_load_2d(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
+                    tma_load_2d(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N));
+                    if (++s == TS_STAGES) { s = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t s = 0, phase = 0, as = 0, aphase = 0;
+            for (uint32_t nt = g; nt < a.ntiles; nt += G) {
+                mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * TS_BLOCK_N;
+                for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[s]), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * TS_STAGE_BYTES);
+                    const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TS_A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < TS_BLOCK_K / 16; ++kk)  // +32 bytes along K = +2 in the encoded start address
+                        tcgen05_mma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, TS_IDESC, (kb | kk) != 0);
+                    tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the smem stage when these MMAs retire
+                    if (++s == TS_STAGES) { s = 0; phase ^= 1; }
+                }
+                tcgen05_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: threshold filter =====================
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const uint32_t ql = lane_base + lane;                  // query within the tile == TMEM lane
+        const uint32_t qi = mt * TS_BLOCK_M + ql;
+        const bool qvalid = qi < a.n_queries;
+        float *h = heaps + (size_t)ql * a.k;
+        uint32_t hcnt = 0;
+        float local_min = -INFINITY;  // A_k of this CTA's share once the heap is full
+        uint32_t as = 0, aphase = 0;
+        for (uint32_t nt = g; nt < a.ntiles; nt += G) {
+            float bound = local_min;
+            if (qvalid) bound = fmaxf(bound, ord2f(*reinterpret_cast<volatile int *>(a.gthr + qi)));
+            float thr = bound - a.two_eps;
+            mbar_wait(smem_u32(&tfull_bar[as]), aphase);
+            tcgen05_fence_after();
+            const uint64_t row0 = (uint64_t)nt * TS_BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < TS_BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                // refresh the shared bound every 32 rows (issued before the TMEM load so the latencies overlap):
+                // other CTAs tighten it continuously, which keeps the candidate lists short
+                int gnow = (int)0x807FFFFF;
+                if (qvalid) gnow = *reinterpret_cast<volatile int *>(a.gthr + qi);
+                tmem_ld_32x32(tmem_base + (lane_base << 16) + as * TS_BLOCK_N + c * 32, r);
+                tmem_ld_wait();
+                {
+                    const float gb = ord2f(gnow);
+                    if (gb > bound) { bound = gb; thr = bound - a.two_eps; }
+                }
+                if (qvalid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (v >= thr) {
+                            const uint64_t row = row0 + c * 32 + j;
+                            if (row < a.n_rows) {
+                                const uint32_t pos = atomicAdd(a.cand_cnt + qi, 1u);
+                                if (pos < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos] = a.id_base + (uint32_t)row;
+                                if (hcnt < a.k || v > local_min) {
+                                    heap_push(h, hcnt, a.k, v);
+                                    if (hcnt == a.k) {
+                                        local_min = h[0];
+                                        atomicMax(a.gthr + qi, f2ord(local_min));
+                                        if (local_min > bound) { bound = local_min; thr = bound - a.two_eps; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(&tempty_bar[as]));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ fp16 normalised copies
+// x_hat = x / |x| (IEEE), rounded to fp16; zero-norm rows become zero rows.
+__global__ void normalize_f16_kernel(const float *__restrict__ raw, uint32_t pitch_elems, const float *__restrict__ mags,
+                                     uint64_t n, uint32_t dim, __half *__restrict__ out, uint32_t out_pitch, uint32_t *zero_flag) {
+    const uint32_t groups = (dim + 7) / 8;
+    uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n * groups) return;
+    uint64_t row = gid / groups;
+    uint32_t c0 = (uint32_t)(gid % groups) * 8;
+    const float m = mags[row];
+    if (m == 0.0f && zero_flag && c0 == 0) atomicAdd(zero_flag, 1u);
+    for (uint32_t e = 0; e < 8 && c0 + e < dim; ++e) {
+        float v = raw[row * pitch_elems + c0 + e];
+        out[row * out_pitch + c0 + e] = __float2half_rn(m == 0.0f ? 0.0f : __fdiv_rn(v, m));
+    }
+}
+
+cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
+                                void *d_out, uint32_t out_pitch_halfs, uint32_t *d_zero_count, cudaStream_t s) {
+    if (!n) return CDB_OK;
+    uint64_t total = n * ((dim + 7) / 8);
+    normalize_f16_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(d_raw, pitch_elems, d_mags, n, dim,
+                                                                          reinterpret_cast<__half *>(d_out), out_pitch_halfs, d_zero_count);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+__global__ void fill_i32_kernel(int *p, int v, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// counts queries whose candidate list overflowed (or whose norm is zero) -> flag[0]
+__global__ void overflow_check_kernel(const uint32_t *cnt, uint32_t cap, uint32_t n, uint32_t *flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && cnt[i] > cap) atomicAdd(flag, 1u);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static cdb_status make_map_f16(CUtensorMap *map, const void *base, uint64_t rows, uint32_t dim, uint32_t pitch_halfs, uint32_t box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CDB_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return CDB_CUDA_ERROR; }
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t gdim[2] = {dim, rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch_halfs * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TS_BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return CDB_CUDA_ERROR; }
+    return CDB_OK;
+}
+
+size_t tensor_scan_smem_bytes(uint32_t k) {
+    return 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + ((size_t)TS_BLOCK_M * k + 1) * 4 + (2 * TS_STAGES + 4) * 8 + 16;
+}
+
+// d_xh: fp16 normalised corpus [n_rows][pitch_halfs]; d_qh: fp16 normalised queries, padded with zero
+// rows to a multiple of 128 [mtiles*128][pitch_halfs].
+cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
+                              uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_gthr, uint32_t *d_cand,
+                              uint32_t *d_cand_cnt, uint32_t cand_cap, int sm_count, cudaStream_t s) {
+    TensorScanArgs a{};
+    a.n_rows = n_rows;
+    a.n_queries = nq;
+    a.k = k;
+    a.kblocks = (dim + TS_BLOCK_K - 1) / TS_BLOCK_K;
+    a.mtiles = (nq + TS_BLOCK_M - 1) / TS_BLOCK_M;
+    a.ntiles = (uint32_t)((n_rows + TS_BLOCK_N - 1) / TS_BLOCK_N);
+    a.two_eps = two_eps;
+    a.id_base = id_base;
+    a.gthr = d_gthr;
+    a.cand = d_cand;
+    a.cand_cnt = d_cand_cnt;
+    a.cand_cap = cand_cap;
+    CUtensorMap mq, mx;
+    cdb_status rc;
+    if ((rc = make_map_f16(&mq, d_qh, (uint64_t)a.mtiles * TS_BLOCK_M, dim, pitch_halfs, TS_BLOCK_M))) return rc;
+    if ((rc = make_map_f16(&mx, d_xh, n_rows, dim, pitch_halfs, TS_BLOCK_N))) return rc;
+    fill_i32_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_gthr, (int)0x807FFFFF /* f2ord(-inf) */, nq);
+    CDB_LAUNCH_CHECK();
+    CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
+    const size_t smem = tensor_scan_smem_bytes(k);
+    if (smem > 227 * 1024) { set_error("tensor scan: k too large for shared memory"); return CDB_INVALID_PARAMS; }
+    CDB_CUDA_TRY(cudaFuncSetAttribute(tensor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // every CTA should own several corpus tiles: its first tile emits ~k(1+ln(256/k)) candidates before
+    // the thresholds bite, so tiny corpora must not be shredded over all SMs
+    uint64_t total_tiles = (uint64_t)a.mtiles * a.ntiles;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count, std::max<uint64_t>(1, total_tiles / 4));
+    if (grid < a.mtiles) grid = a.mtiles;  // every query tile needs at least one CTA
+    tensor_scan_kernel<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s) {
+    overflow_check_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cnt, cap, n, d_flag);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+}  // namespace cdb

@@ -98,7 +98,8 @@ typedef struct {
     int32_t keep_raw_f32;   /* keep raw f32 rows for the exact re-rank
                                (Collection.internal_to_external_map, collection.rs:110) */
     uint32_t id_base;       /* global id of local row 0 (corpus shard offset) */
-    uint32_t reserved;
+    uint32_t tensor_prefilter; /* 1: also keep an fp16 copy of the L2-normalised raw rows so that large
+                                  batches use the tcgen05 prefilter + exact re-rank (results identical) */
 } cdb_index_desc;
 
 typedef struct {
@@ -199,6 +200,11 @@ cdb_status cdb_index_last_kernel_ms(const cdb_index *index, float *scan_ms, floa
 /* durations (ms) of the dominant (scan) kernel of the last min(n, 64) searches, oldest
  * first, from CUDA events recorded on the launching stream around each launch */
 cdb_status cdb_index_scan_ms_history(const cdb_index *index, uint32_t n, float *out, uint32_t *out_n);
+/* out4 = {searches that took the tcgen05 prefilter path, of those how many fell back to the exact
+ * scan (candidate overflow / zero-norm query), zero-norm rows, 1 if an fp16 shadow exists} */
+cdb_status cdb_index_stats(const cdb_index *index, uint64_t *out4);
+/* candidates the prefilter emitted for each of the first n queries of the last prefilter search */
+cdb_status cdb_index_last_candidate_counts(const cdb_index *index, uint32_t n, uint32_t *out);
 
 #ifdef __cplusplus
 }
