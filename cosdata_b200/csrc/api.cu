@@ -441,7 +441,8 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
     bool done = false;
     if (tensor_ok) {
         const uint32_t mt = (nq + 127) / 128;
-        const uint32_t cap = p->prefilter_k ? p->prefilter_k : PREFILTER_CAP;
+        // candidate slots per query (power of two; ~32 MB in total): long lists only arise for few queries
+        const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 8192u : PREFILTER_CAP));
         if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)nq * 4)) ||
             (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)))
             return rc;

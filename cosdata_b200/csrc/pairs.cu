@@ -93,18 +93,30 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
             if (ok) atomicAdd(&nvalid, 1);
         }
     }
+    // bitonic sort (descending) of the keys, zero-padded to a power of two; 0 = empty sorts last
+    uint32_t P = 1;
+    while (P < ncand) P <<= 1;
+    for (uint32_t i = ncand + threadIdx.x; i < P; i += blockDim.x) keys[i] = 0ull;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < ncand; i += blockDim.x) {
-        const uint64_t key = keys[i];
-        if (!key) continue;
-        uint32_t rank = 0;
-        for (uint32_t t = 0; t < ncand; ++t) rank += (keys[t] > key) || (keys[t] == key && t < i);
-        if (rank < k) {
-            out_ids[(size_t)b * k + rank] = key64_id(key);
-            out_scores[(size_t)b * k + rank] = __uint_as_float(key_to_bits(CDB_METRIC_COSINE, (uint32_t)(key >> 32)));
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
+                const uint32_t hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t x = keys[lo], y = keys[hi];
+                if ((x < y) == desc) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
         }
     }
-    if (threadIdx.x == 0 && out_counts) out_counts[b] = (uint32_t)nvalid < k ? (uint32_t)nvalid : k;
+    const uint32_t nout = (uint32_t)nvalid < k ? (uint32_t)nvalid : k;
+    for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        out_ids[(size_t)b * k + i] = key64_id(key);
+        out_scores[(size_t)b * k + i] = __uint_as_float(key_to_bits(CDB_METRIC_COSINE, (uint32_t)(key >> 32)));
+    }
+    if (threadIdx.x == 0 && out_counts) out_counts[b] = nout;
 }
 
 cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
@@ -113,7 +125,9 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
                              uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s) {
     if (!nq) return CDB_OK;
     if (k == 0) { set_error("rerank: k must be > 0"); return CDB_INVALID_PARAMS; }
-    size_t smem = (size_t)round_up(dim, 4) * 4 + (size_t)(ncand ? ncand : 1) * 8;
+    uint32_t pcap = 1;
+    while (pcap < ncand) pcap <<= 1;
+    size_t smem = (size_t)round_up(dim, 4) * 4 + (size_t)pcap * 8;
     if (smem > 200 * 1024) { set_error("rerank: too many candidates per query"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(rerank_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_f32_kernel<<<nq, RERANK_THREADS, smem, s>>>(d_raw, pitch_elems, d_raw_mags, n_rows, dim, d_q, q_pitch_elems,

@@ -109,53 +109,88 @@ __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); retur
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
 struct TensorScanArgs {
-    uint64_t n_rows;
+    uint64_t n_rows;     // rows visible to this launch (the seeding pass sees a prefix)
     uint32_t n_queries;
     uint32_t k;
     uint32_t kblocks, mtiles, ntiles;
     float two_eps;
     uint32_t id_base;
-    int *gthr;           // [n_queries] shared lower bound of A_k (ordered int), init INT_MIN
+    uint32_t emit;       // 0: seeding pass (only tightens gthr), 1: emit candidates
+    int *gthr;           // [n_queries] shared lower bound of A_k (ordered int), init f2ord(-inf)
     uint32_t *cand;      // [n_queries][cand_cap] global ids
     uint32_t *cand_cnt;  // [n_queries]
     uint32_t cand_cap;
 };
 
-// min-heap of the k best approximate scores of one query (root = k-th best)
-__device__ __forceinline__ void heap_push(float *h, uint32_t &cnt, uint32_t k, float v) {
-    if (cnt < k) {
-        uint32_t i = cnt++;
-        h[i] = v;
-        while (i > 0) {
-            uint32_t p = (i - 1) >> 1;
-            if (h[p] <= h[i]) break;
-            float t = h[p]; h[p] = h[i]; h[i] = t;
-            i = p;
+constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory)
+
+// per-thread (= per-query) epilogue state
+struct EpiState {
+    float *heap;          // [k] min-heap of the k best approximate scores seen by this CTA
+    uint32_t *stage;      // [TS_LSTAGE] staged candidate ids
+    uint32_t hcnt, scnt;
+    float local_min;      // A_k of this CTA's share once the heap is full
+    float bound, thr;     // current lower bound of the global A_k, thr = bound - 2 eps
+};
+
+__device__ __forceinline__ void epi_flush(const TensorScanArgs &a, EpiState &st, uint32_t qi) {
+    if (!st.scnt) return;
+    const uint32_t pos = atomicAdd(a.cand_cnt + qi, st.scnt);
+    for (uint32_t i = 0; i < st.scnt; ++i)
+        if (pos + i < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos + i] = st.stage[i];
+    st.scnt = 0;
+}
+
+// slow path: a score passed the threshold test (rare after warm-up)
+__device__ __noinline__ void epi_accept(const TensorScanArgs &a, EpiState &st, uint32_t qi, float v, uint64_t row) {
+    if (row >= a.n_rows) return;  // TMA zero-fill rows past the end
+    if (a.emit) {
+        st.stage[st.scnt++] = a.id_base + (uint32_t)row;
+        if (st.scnt == TS_LSTAGE) epi_flush(a, st, qi);
+    }
+    if (st.hcnt < a.k || v > st.local_min) {
+        float *h = st.heap;
+        if (st.hcnt < a.k) {
+            uint32_t i = st.hcnt++;
+            h[i] = v;
+            while (i > 0) {
+                uint32_t p = (i - 1) >> 1;
+                if (h[p] <= h[i]) break;
+                float t = h[p]; h[p] = h[i]; h[i] = t;
+                i = p;
+            }
+        } else {
+            h[0] = v;
+            uint32_t i = 0;
+            for (;;) {
+                uint32_t l = 2 * i + 1, r = l + 1, m = i;
+                if (l < a.k && h[l] < h[m]) m = l;
+                if (r < a.k && h[r] < h[m]) m = r;
+                if (m == i) break;
+                float t = h[m]; h[m] = h[i]; h[i] = t;
+                i = m;
+            }
         }
-    } else {
-        h[0] = v;
-        uint32_t i = 0;
-        for (;;) {
-            uint32_t l = 2 * i + 1, r = l + 1, m = i;
-            if (l < k && h[l] < h[m]) m = l;
-            if (r < k && h[r] < h[m]) m = r;
-            if (m == i) break;
-            float t = h[m]; h[m] = h[i]; h[i] = t;
-            i = m;
+        if (st.hcnt == a.k) {
+            st.local_min = h[0];
+            atomicMax(a.gthr + qi, f2ord(st.local_min));  // result unused -> RED, does not stall
+            if (st.local_min > st.bound) { st.bound = st.local_min; st.thr = st.bound - a.two_eps; }
         }
     }
 }
 
+template <int STAGES>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TensorScanArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *tiles = smem;
-    float *heaps = reinterpret_cast<float *>(tiles + TS_STAGES * TS_STAGE_BYTES);  // [128][k]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(heaps + (size_t)TS_BLOCK_M * a.k + ((TS_BLOCK_M * a.k) & 1));
-    uint64_t *full_bar = bars, *empty_bar = bars + TS_STAGES, *tfull_bar = bars + 2 * TS_STAGES, *tempty_bar = bars + 2 * TS_STAGES + 2;
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * TS_STAGES + 4);
+    uint32_t *lstage = reinterpret_cast<uint32_t *>(tiles + STAGES * TS_STAGE_BYTES);       // [128][TS_LSTAGE]
+    float *heaps = reinterpret_cast<float *>(lstage + TS_BLOCK_M * TS_LSTAGE);               // [128][k]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(heaps + (size_t)TS_BLOCK_M * a.k);          // 128*k floats: 8B aligned
+    uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -167,7 +202,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-        for (int s = 0; s < TS_STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -192,7 +227,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     const uint32_t sa = smem_u32(tiles + (size_t)s * TS_STAGE_BYTES);
                     tma_load_2d(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
                     tma_load_2d(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N));
-                    if (++s == TS_STAGES) { s = 0; phase ^= 1; }
+                    if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
             }
         }
@@ -213,7 +248,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     for (int kk = 0; kk < TS_BLOCK_K / 16; ++kk)  // +32 bytes along K = +2 in the encoded start address
                         tcgen05_mma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, TS_IDESC, (kb | kk) != 0);
                     tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the smem stage when these MMAs retire
-                    if (++s == TS_STAGES) { s = 0; phase ^= 1; }
+                    if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
                 tcgen05_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
                 if (++as == 2) { as = 0; aphase ^= 1; }
@@ -225,56 +260,55 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t ql = lane_base + lane;                  // query within the tile == TMEM lane
         const uint32_t qi = mt * TS_BLOCK_M + ql;
         const bool qvalid = qi < a.n_queries;
-        float *h = heaps + (size_t)ql * a.k;
-        uint32_t hcnt = 0;
-        float local_min = -INFINITY;  // A_k of this CTA's share once the heap is full
+        EpiState st;
+        st.heap = heaps + (size_t)ql * a.k;
+        st.stage = lstage + (size_t)ql * TS_LSTAGE;
+        st.hcnt = 0;
+        st.scnt = 0;
+        st.local_min = -INFINITY;
+        st.bound = -INFINITY;
+        st.thr = -INFINITY;
         uint32_t as = 0, aphase = 0;
         for (uint32_t nt = g; nt < a.ntiles; nt += G) {
-            float bound = local_min;
-            if (qvalid) bound = fmaxf(bound, ord2f(*reinterpret_cast<volatile int *>(a.gthr + qi)));
-            float thr = bound - a.two_eps;
+            // pick up what the other CTAs have learnt (the load overlaps the wait for the accumulator)
+            int gnow = (int)0x807FFFFF;
+            if (qvalid) gnow = *reinterpret_cast<volatile int *>(a.gthr + qi);
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tcgen05_fence_after();
+            {
+                const float gb = ord2f(gnow);
+                if (gb > st.bound) { st.bound = gb; st.thr = st.bound - a.two_eps; }
+            }
             const uint64_t row0 = (uint64_t)nt * TS_BLOCK_N;
 #pragma unroll 1
-            for (int c = 0; c < TS_BLOCK_N / 32; ++c) {
-                uint32_t r[32];
-                // refresh the shared bound every 32 rows (issued before the TMEM load so the latencies overlap):
-                // other CTAs tighten it continuously, which keeps the candidate lists short
-                int gnow = (int)0x807FFFFF;
-                if (qvalid) gnow = *reinterpret_cast<volatile int *>(a.gthr + qi);
-                tmem_ld_32x32(tmem_base + (lane_base << 16) + as * TS_BLOCK_N + c * 32, r);
+            for (int c = 0; c < TS_BLOCK_N / 64; ++c) {
+                uint32_t r0[32], r1[32];
+                const uint32_t taddr = tmem_base + (lane_base << 16) + as * TS_BLOCK_N + c * 64;
+                tmem_ld_32x32(taddr, r0);
+                tmem_ld_32x32(taddr + 32, r1);
                 tmem_ld_wait();
-                {
-                    const float gb = ord2f(gnow);
-                    if (gb > bound) { bound = gb; thr = bound - a.two_eps; }
-                }
-                if (qvalid) {
+                // fast path: one predicate per value, no memory traffic
+                uint32_t m0 = 0, m1 = 0;
+                const float thr = st.thr;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float v = __uint_as_float(r[j]);
-                        if (v >= thr) {
-                            const uint64_t row = row0 + c * 32 + j;
-                            if (row < a.n_rows) {
-                                const uint32_t pos = atomicAdd(a.cand_cnt + qi, 1u);
-                                if (pos < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos] = a.id_base + (uint32_t)row;
-                                if (hcnt < a.k || v > local_min) {
-                                    heap_push(h, hcnt, a.k, v);
-                                    if (hcnt == a.k) {
-                                        local_min = h[0];
-                                        atomicMax(a.gthr + qi, f2ord(local_min));
-                                        if (local_min > bound) { bound = local_min; thr = bound - a.two_eps; }
-                                    }
-                                }
-                            }
-                        }
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    m0 |= (__uint_as_float(r0[j]) >= thr ? 1u : 0u) << j;
+                    m1 |= (__uint_as_float(r1[j]) >= thr ? 1u : 0u) << j;
+                }
+                if (qvalid && (m0 | m1)) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if ((m0 >> j) & 1u) { const float v = __uint_as_float(r0[j]); if (v >= st.thr) epi_accept(a, st, qi, v, row0 + c * 64 + j); }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if ((m1 >> j) & 1u) { const float v = __uint_as_float(r1[j]); if (v >= st.thr) epi_accept(a, st, qi, v, row0 + c * 64 + 32 + j); }
                 }
             }
             tcgen05_fence_before();
             mbar_arrive(smem_u32(&tempty_bar[as]));
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (qvalid && a.emit) epi_flush(a, st, qi);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -346,8 +380,29 @@ static cdb_status make_map_f16(CUtensorMap *map, const void *base, uint64_t rows
     return CDB_OK;
 }
 
+static int tensor_scan_stages(uint32_t k) {
+    auto bytes = [&](int stages) {
+        return 1024 + (size_t)stages * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * TS_LSTAGE * 4 + (size_t)TS_BLOCK_M * k * 4 +
+               (2 * stages + 4) * 8 + 16;
+    };
+    if (bytes(4) <= 227 * 1024) return 4;
+    if (bytes(3) <= 227 * 1024) return 3;
+    return 0;
+}
 size_t tensor_scan_smem_bytes(uint32_t k) {
-    return 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + ((size_t)TS_BLOCK_M * k + 1) * 4 + (2 * TS_STAGES + 4) * 8 + 16;
+    int st = tensor_scan_stages(k);
+    if (!st) return (size_t)1 << 30;
+    return 1024 + (size_t)st * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * TS_LSTAGE * 4 + (size_t)TS_BLOCK_M * k * 4 + (2 * st + 4) * 8 + 16;
+}
+
+template <int STAGES>
+static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
+                                     size_t smem, cudaStream_t s) {
+    auto kern = tensor_scan_kernel<STAGES>;
+    CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
 }
 
 // d_xh: fp16 normalised corpus [n_rows][pitch_halfs]; d_qh: fp16 normalised queries, padded with zero
@@ -368,6 +423,9 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     a.cand = d_cand;
     a.cand_cnt = d_cand_cnt;
     a.cand_cap = cand_cap;
+    const int stages = tensor_scan_stages(k);
+    if (!stages) { set_error("tensor scan: k too large for shared memory"); return CDB_INVALID_PARAMS; }
+    const size_t smem = tensor_scan_smem_bytes(k);
     CUtensorMap mq, mx;
     cdb_status rc;
     if ((rc = make_map_f16(&mq, d_qh, (uint64_t)a.mtiles * TS_BLOCK_M, dim, pitch_halfs, TS_BLOCK_M))) return rc;
@@ -375,17 +433,28 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     fill_i32_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_gthr, (int)0x807FFFFF /* f2ord(-inf) */, nq);
     CDB_LAUNCH_CHECK();
     CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
-    const size_t smem = tensor_scan_smem_bytes(k);
-    if (smem > 227 * 1024) { set_error("tensor scan: k too large for shared memory"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(tensor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // every CTA should own several corpus tiles: its first tile emits ~k(1+ln(256/k)) candidates before
-    // the thresholds bite, so tiny corpora must not be shredded over all SMs
+
+    // 1. seeding pass over a prefix of the corpus: a few CTAs per query tile, no emission, only gthr.
+    //    Afterwards every CTA of the main pass starts from the k-th best of ~16K rows instead of from
+    //    -inf, which removes the per-CTA warm-up bursts from the candidate lists.
+    const uint32_t seed_tiles = std::min<uint32_t>(a.ntiles, 64);
+    if (a.ntiles > 8) {
+        TensorScanArgs sa = a;
+        sa.emit = 0;
+        sa.ntiles = seed_tiles;
+        sa.n_rows = std::min<uint64_t>(n_rows, (uint64_t)seed_tiles * TS_BLOCK_N);
+        uint32_t per_m = std::max<uint32_t>(1, std::min<uint32_t>(8, (uint32_t)sm_count / a.mtiles));
+        per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 8));
+        const uint32_t sgrid = a.mtiles * per_m;
+        rc = stages == 4 ? launch_tensor_scan<4>(mq, mx, sa, sgrid, smem, s) : launch_tensor_scan<3>(mq, mx, sa, sgrid, smem, s);
+        if (rc) return rc;
+    }
+    // 2. main pass.  Every CTA should own several corpus tiles, so tiny corpora are not shredded over all SMs.
+    a.emit = 1;
     uint64_t total_tiles = (uint64_t)a.mtiles * a.ntiles;
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count, std::max<uint64_t>(1, total_tiles / 4));
     if (grid < a.mtiles) grid = a.mtiles;  // every query tile needs at least one CTA
-    tensor_scan_kernel<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
-    CDB_LAUNCH_CHECK();
-    return CDB_OK;
+    return stages == 4 ? launch_tensor_scan<4>(mq, mx, a, grid, smem, s) : launch_tensor_scan<3>(mq, mx, a, grid, smem, s);
 }
 
 cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s) {
