@@ -107,7 +107,7 @@ struct cdb_index {
     bool ev_valid = false;
     std::mutex mu;
     DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
-    DevBuf qh, gthr, cand, cand_cnt, flags;
+    DevBuf qh, gthr, cand, cand_cnt, flags, progress;
 };
 
 #define CDB_REQUIRE(cond, msg)                              \
@@ -263,7 +263,7 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     if (ix->d_xh) cudaFree(ix->d_xh);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
-                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags})
+                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress})
         b->release();
     for (auto &ev : ix->ev)
         if (ev) cudaEventDestroy(ev);
@@ -437,14 +437,15 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
 
     // ---- tcgen05 prefilter + exact re-rank: identical results, far fewer exact dot products
     const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 128 &&
-                           ix->size - ix->n_zero_rows >= p->k && tensor_scan_smem_bytes(p->k) <= 227 * 1024;
+                           ix->size - ix->n_zero_rows >= p->k && tensor_scan_smem_bytes(p->k) <= 227 * 1024 &&
+                           (nq + 127) / 128 <= (uint32_t)ix->sm_count;
     bool done = false;
     if (tensor_ok) {
         const uint32_t mt = (nq + 127) / 128;
         // candidate slots per query (power of two; ~32 MB in total): long lists only arise for few queries
         const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 8192u : PREFILTER_CAP));
         if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)nq * 4)) ||
-            (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)))
+            (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) || (rc = ix->progress.ensure(4096)))
             return rc;
         uint32_t *flags = ix->flags.as<uint32_t>();  // [0] overflowed queries, [2] zero-norm queries
         CDB_CUDA_TRY(cudaMemsetAsync(flags, 0, 4, s));
@@ -456,7 +457,7 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
         CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
         if ((rc = tensor_scan_device(ix->d_xh, ix->qh.p, ix->xh_pitch, ix->size, nq, d.dim, p->k, 2.0f * prefilter_eps(d.dim),
                                      d.id_base, ix->gthr.as<int>(), ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), cap,
-                                     ix->sm_count, s)))
+                                     ix->progress.as<uint32_t>(), ix->sm_count, s)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(),

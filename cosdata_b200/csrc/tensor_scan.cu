@@ -120,6 +120,8 @@ struct TensorScanArgs {
     uint32_t *cand;      // [n_queries][cand_cap] global ids
     uint32_t *cand_cnt;  // [n_queries]
     uint32_t cand_cap;
+    uint32_t *progress;  // [groups] tiles completed by the CTAs of a group (bounded-drift window), zeroed per launch
+    uint32_t window;     // a CTA may run at most `window` tiles ahead of the slowest CTA of its group
 };
 
 constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory)
@@ -195,9 +197,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // work assignment: CTA c owns query tile c % mtiles and every G-th corpus tile
+    // gridDim.x is a multiple of mtiles: the mtiles CTAs of group g walk the same corpus tiles g, g+G, ...
+    // and are kept within `window` tiles of each other, so a corpus tile is fetched from HBM once and
+    // served to the other query tiles from L2.
     const uint32_t mt = blockIdx.x % a.mtiles;
     const uint32_t g = blockIdx.x / a.mtiles;
-    const uint32_t G = (gridDim.x - mt + a.mtiles - 1) / a.mtiles;
+    const uint32_t G = gridDim.x / a.mtiles;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -218,8 +223,14 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t s = 0, phase = 0;
-            for (uint32_t nt = g; nt < a.ntiles; nt += G) {
+            uint32_t s = 0, phase = 0, t = 0;
+            for (uint32_t nt = g; nt < a.ntiles; nt += G, ++t) {
+                if (a.mtiles > 1 && t >= a.window) {
+                    // bounded drift: every CTA of the group must have issued tile t - window
+                    const uint32_t need = (t - a.window + 1) * a.mtiles;
+                    // bounded spin: if a peer CTA is not resident (GPU shared with another stream) we only lose locality
+                    for (int spin = 0; spin < 20000 && *reinterpret_cast<volatile uint32_t *>(a.progress + g) < need; ++spin) __nanosleep(64);
+                }
                 for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full_bar[s]);
@@ -251,6 +262,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
                 tcgen05_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
+                if (a.mtiles > 1) atomicAdd(a.progress + g, 1u);  // all loads of this tile have landed in smem
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -409,8 +421,10 @@ static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &m
 // rows to a multiple of 128 [mtiles*128][pitch_halfs].
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
                               uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_gthr, uint32_t *d_cand,
-                              uint32_t *d_cand_cnt, uint32_t cand_cap, int sm_count, cudaStream_t s) {
+                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, int sm_count, cudaStream_t s) {
     TensorScanArgs a{};
+    a.progress = d_progress;
+    a.window = 3;
     a.n_rows = n_rows;
     a.n_queries = nq;
     a.k = k;
@@ -446,6 +460,7 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
         uint32_t per_m = std::max<uint32_t>(1, std::min<uint32_t>(8, (uint32_t)sm_count / a.mtiles));
         per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 8));
         const uint32_t sgrid = a.mtiles * per_m;
+        CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 4096, s));
         rc = stages == 4 ? launch_tensor_scan<4>(mq, mx, sa, sgrid, smem, s) : launch_tensor_scan<3>(mq, mx, sa, sgrid, smem, s);
         if (rc) return rc;
     }
@@ -453,7 +468,9 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     a.emit = 1;
     uint64_t total_tiles = (uint64_t)a.mtiles * a.ntiles;
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count, std::max<uint64_t>(1, total_tiles / 4));
-    if (grid < a.mtiles) grid = a.mtiles;  // every query tile needs at least one CTA
+    grid = std::max<uint32_t>(1, grid / a.mtiles) * a.mtiles;  // whole groups only (148 SMs, 8 query tiles -> 144 CTAs)
+    if (grid > (uint32_t)sm_count) { set_error("tensor scan: more query tiles than SMs"); return CDB_INVALID_PARAMS; }
+    CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 4096, s));
     return stages == 4 ? launch_tensor_scan<4>(mq, mx, a, grid, smem, s) : launch_tensor_scan<3>(mq, mx, a, grid, smem, s);
 }
 
