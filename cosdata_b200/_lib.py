@@ -31,6 +31,20 @@ class IndexDesc(C.Structure):
     ]
 
 
+class GraphDesc(C.Structure):
+    _fields_ = [
+        ("num_levels", C.c_uint32),
+        ("neighbors_count", C.c_uint32),
+        ("level0_neighbors_count", C.c_uint32),
+        ("entry", C.c_uint32),
+        ("root_row", C.c_uint32),
+        ("level_counts", C.c_void_p),
+        ("node_row", C.c_void_p),
+        ("adjacency", C.c_void_p),
+        ("child", C.c_void_p),
+    ]
+
+
 class SearchParams(C.Structure):
     _fields_ = [
         ("k", C.c_uint32),
@@ -60,6 +74,8 @@ PROTOTYPES = {
     "cdb_index_append_codes": (C.c_int32, [C.c_void_p, c_vp, c_f32p, C.c_uint64]),
     "cdb_index_append_synthetic": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "cdb_index_read_codes": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, c_vp, c_f32p]),
+    "cdb_index_set_graph": (C.c_int32, [C.c_void_p, C.POINTER(GraphDesc)]),
+    "cdb_index_hnsw_counters": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "cdb_search_batch": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p]),
     "cdb_search_batch_device": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p, C.c_void_p]),
     "cdb_score_ids": (C.c_int32, [C.c_void_p, c_f32p, c_u32p, C.c_uint32, c_f32p, c_i32p]),

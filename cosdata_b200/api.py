@@ -18,7 +18,7 @@ import enum
 import numpy as np
 
 from . import _lib
-from ._lib import IndexDesc, SearchParams
+from ._lib import GraphDesc, IndexDesc, SearchParams
 
 INVALID_ID = 0xFFFFFFFF
 
@@ -276,3 +276,23 @@ class DenseIndex:
         out = np.zeros(n, dtype=np.uint32)
         _check(self._lib.cdb_index_last_candidate_counts(self._h, n, _ptr(out)))
         return out
+
+    # -- HNSW graph
+    def set_graph(self, num_levels, neighbors_count, level0_neighbors_count, entry, root_row, node_row, adjacency, child):
+        """flat graph arrays per level (lists of uint32 numpy arrays), see include/cosdata_b200.h"""
+        L1 = num_levels + 1
+        nr = [np.ascontiguousarray(a, dtype=np.uint32) for a in node_row]
+        ad = [np.ascontiguousarray(a, dtype=np.uint32) for a in adjacency]
+        ch = [np.ascontiguousarray(a, dtype=np.uint32) for a in child]
+        cnt = np.array([a.size for a in nr], dtype=np.uint32)
+        t_nr = (C.c_void_p * L1)(*[a.ctypes.data for a in nr])
+        t_ad = (C.c_void_p * L1)(*[a.ctypes.data for a in ad])
+        t_ch = (C.c_void_p * L1)(*[a.ctypes.data for a in ch])
+        gd = GraphDesc(num_levels, neighbors_count, level0_neighbors_count, entry, root_row, cnt.ctypes.data,
+                       C.cast(t_nr, C.c_void_p), C.cast(t_ad, C.c_void_p), C.cast(t_ch, C.c_void_p))
+        _check(self._lib.cdb_index_set_graph(self._h, C.byref(gd)))
+
+    def hnsw_counters(self):
+        out = np.zeros(2, dtype=np.uint64)
+        _check(self._lib.cdb_index_hnsw_counters(self._h, _ptr(out)))
+        return int(out[0]), int(out[1])

@@ -108,6 +108,11 @@ struct cdb_index {
     std::mutex mu;
     DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
     DevBuf qh, gthr, cand, cand_cnt, flags, progress;
+    // HNSW graph (cdb_index_set_graph)
+    bool has_graph = false;
+    GraphDev graph{};
+    std::vector<void *> graph_allocs;
+    DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags;
 };
 
 #define CDB_REQUIRE(cond, msg)                              \
@@ -261,9 +266,11 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     if (ix->raw_owned && ix->d_raw) cudaFree(ix->d_raw);
     if (ix->raw_mags_owned && ix->d_raw_mags) cudaFree(ix->d_raw_mags);
     if (ix->d_xh) cudaFree(ix->d_xh);
+    for (void *g : ix->graph_allocs) cudaFree(g);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
-                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress})
+                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters,
+                      &ix->qraw, &ix->qraw_mags})
         b->release();
     for (auto &ev : ix->ev)
         if (ev) cudaEventDestroy(ev);
@@ -400,6 +407,84 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
     return CDB_OK;
 }
 
+// search_internal (hnsw/mod.rs:390-440): quantized ann_search on the uploaded graph, then
+// remove_duplicates_and_filter and the exact f32 re-rank of finalize_ann_results.
+static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+                                     uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+    const cdb_index_desc &d = ix->desc;
+    CDB_REQUIRE(ix->has_graph, "CDB_MODE_HNSW needs cdb_index_set_graph");
+    CDB_REQUIRE(ix->d_raw, "HNSW search re-ranks with raw f32 rows (F32 storage or keep_raw_f32)");
+    CDB_REQUIRE(p->shortlist_size >= 1 && p->shortlist_size <= 64, "shortlist_size must be in 1..64");
+    CDB_REQUIRE(p->ef_search >= 1 && p->ef_search <= 4096, "ef_search must be in 1..4096");
+    cdb_status rc;
+    if ((rc = arm_status(d.metric, d.storage_type)) != CDB_OK) {
+        set_error("metric/storage arm is an Err in the reference (StorageMismatch / unimplemented)");
+        return rc;
+    }
+    const uint32_t out_cap = (ix->graph.num_levels + 1) * 100;
+    const uint32_t k5 = 5 * p->k;
+    const uint32_t rpitch = ix->raw_pitch_elems * 4;
+    if ((rc = ix->q_codes.ensure((size_t)nq * ix->row_pitch)) || (rc = ix->q_mags.ensure((size_t)nq * 4)) ||
+        (rc = ix->qraw.ensure((size_t)nq * rpitch)) || (rc = ix->qraw_mags.ensure((size_t)nq * 4)) ||
+        (rc = ix->hn_rows.ensure((size_t)nq * out_cap * 4)) || (rc = ix->hn_scores.ensure((size_t)nq * out_cap * 4)) ||
+        (rc = ix->hn_n.ensure((size_t)nq * 4)) || (rc = ix->err32.ensure((size_t)nq * 4)) ||
+        (rc = ix->cand.ensure((size_t)nq * k5 * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)))
+        return rc;
+    if (!ix->hn_counters.p) {
+        if ((rc = ix->hn_counters.ensure(16))) return rc;
+        CDB_CUDA_TRY(cudaMemsetAsync(ix->hn_counters.p, 0, 16, s));
+    }
+    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)nq * ix->row_pitch, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(ix->qraw.p, 0, (size_t)nq * rpitch, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
+    // the query is quantized like a stored vector (hnsw/mod.rs:399-403); the re-rank uses the raw query
+    if ((rc = quantize_rows_device(d_queries, nq, d.dim, d.storage_type, d.range_lo, d.range_hi, ix->q_codes.as<uint8_t>(),
+                                   ix->row_pitch, ix->q_mags.as<float>(), nullptr, 0, s)) ||
+        (rc = quantize_rows_device(d_queries, nq, d.dim, CDB_ST_F32, 0.f, 0.f, ix->qraw.as<uint8_t>(), rpitch,
+                                   ix->qraw_mags.as<float>(), nullptr, 0, s)))
+        return rc;
+    HnswArgs a{};
+    a.g = ix->graph;
+    a.rows = ix->d_codes;
+    a.row_pitch = ix->row_pitch;
+    a.mags = ix->d_mags;
+    a.dim = d.dim;
+    a.st = d.storage_type;
+    a.metric = d.metric;
+    a.q = ix->q_codes.as<uint8_t>();
+    a.qmags = ix->q_mags.as<float>();
+    a.nq = nq;
+    a.ef = p->ef_search;
+    a.shortlist = p->shortlist_size;
+    a.out_cap = out_cap;
+    a.out_rows = ix->hn_rows.as<uint32_t>();
+    a.out_scores = ix->hn_scores.as<float>();
+    a.out_n = ix->hn_n.as<uint32_t>();
+    a.err32 = ix->err32.as<uint32_t>();
+    a.counters = ix->hn_counters.as<unsigned long long>();
+    const int slot = (int)(ix->n_search % cdb_index::EV_RING);
+    ix->n_search++;
+    CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
+    CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+    if ((rc = hnsw_search_device(a, s))) return rc;
+    CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+    if ((rc = hnsw_dedup_device(a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, ix->graph.root_row, d.id_base, k5, nq,
+                                ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
+        return rc;
+    if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
+                                ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
+                                ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
+        return rc;
+    if (d_err) {
+        err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
+        CDB_LAUNCH_CHECK();
+    }
+    CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
+    CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
+    ix->ev_valid = true;
+    return CDB_OK;
+}
+
 // rigorous bound on |approximate cosine - reference cosine| of the fp16 tensor-core prefilter
 // (two fp16 roundings, fp32 tensor accumulation, f32 norms)
 static float prefilter_eps(uint32_t dim) { return 1.0e-3f + 8.0e-7f * (float)dim; }
@@ -411,9 +496,10 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
     if (nq == 0) return CDB_OK;
     cdb_status rc;
+    if (p->mode == CDB_MODE_HNSW) return hnsw_search_locked(ix, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
     if (p->mode != CDB_MODE_BRUTE_RAW && p->mode != CDB_MODE_BRUTE_CODES) {
-        set_error("search mode not implemented");
-        return CDB_UNSUPPORTED;
+        set_error("unknown search mode");
+        return CDB_INVALID_PARAMS;
     }
     const bool raw = p->mode == CDB_MODE_BRUTE_RAW;
     if (raw) CDB_REQUIRE(ix->d_raw, "BRUTE_RAW needs raw f32 rows (F32 storage or keep_raw_f32)");
@@ -613,6 +699,67 @@ cdb_status cdb_index_last_kernel_ms(const cdb_index *ix, float *scan_ms, float *
     return CDB_OK;
 }
 
+
+cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
+    CDB_REQUIRE(ix && gd && gd->level_counts && gd->node_row && gd->adjacency && gd->child, "null argument");
+    CDB_REQUIRE(gd->num_levels <= 31, "too many levels");
+    CDB_REQUIRE(gd->neighbors_count >= 1 && gd->neighbors_count <= 64 && gd->level0_neighbors_count >= 1 &&
+                    gd->level0_neighbors_count <= 64, "neighbour counts must be in 1..64");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(gd->level_counts[0] == ix->size, "level 0 must contain every row of the index");
+    CDB_REQUIRE(gd->root_row < ix->size, "root_row out of range");
+    CDB_REQUIRE(gd->entry < gd->level_counts[gd->num_levels], "entry out of range");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    for (void *g : ix->graph_allocs) cudaFree(g);
+    ix->graph_allocs.clear();
+    ix->has_graph = false;
+    const uint32_t L1 = gd->num_levels + 1;
+    std::vector<const uint32_t *> nr(L1), ad(L1), ch(L1);
+    auto upload = [&](const uint32_t *src, size_t n, const uint32_t **dst) -> cdb_status {
+        void *p = nullptr;
+        CDB_CUDA_TRY(cudaMalloc(&p, (n ? n : 1) * 4));
+        ix->graph_allocs.push_back(p);
+        if (n) CDB_CUDA_TRY(cudaMemcpy(p, src, n * 4, cudaMemcpyHostToDevice));
+        *dst = (const uint32_t *)p;
+        return CDB_OK;
+    };
+    cdb_status rc;
+    for (uint32_t L = 0; L < L1; ++L) {
+        const uint32_t cnt = gd->level_counts[L];
+        const uint32_t nb = L == 0 ? gd->level0_neighbors_count : gd->neighbors_count;
+        if ((rc = upload(gd->node_row[L], cnt, &nr[L])) || (rc = upload(gd->adjacency[L], (size_t)cnt * nb, &ad[L]))) return rc;
+        if (L == 0) ch[L] = nullptr;
+        else if ((rc = upload(gd->child[L], cnt, &ch[L]))) return rc;
+    }
+    const uint32_t *tbl[3] = {nullptr, nullptr, nullptr};
+    const std::vector<const uint32_t *> *src[3] = {&nr, &ad, &ch};
+    for (int t = 0; t < 3; ++t) {
+        void *p = nullptr;
+        CDB_CUDA_TRY(cudaMalloc(&p, L1 * sizeof(void *)));
+        ix->graph_allocs.push_back(p);
+        CDB_CUDA_TRY(cudaMemcpy(p, src[t]->data(), L1 * sizeof(void *), cudaMemcpyHostToDevice));
+        tbl[t] = (const uint32_t *)p;
+    }
+    ix->graph.num_levels = gd->num_levels;
+    ix->graph.nbrs = gd->neighbors_count;
+    ix->graph.nbrs0 = gd->level0_neighbors_count;
+    ix->graph.entry = gd->entry;
+    ix->graph.root_row = gd->root_row;
+    ix->graph.node_row = reinterpret_cast<const uint32_t *const *>(tbl[0]);
+    ix->graph.adj = reinterpret_cast<const uint32_t *const *>(tbl[1]);
+    ix->graph.child = reinterpret_cast<const uint32_t *const *>(tbl[2]);
+    ix->has_graph = true;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_hnsw_counters(const cdb_index *ix, uint64_t *out2) {
+    CDB_REQUIRE(ix && out2, "null argument");
+    out2[0] = out2[1] = 0;
+    if (!ix->hn_counters.p) return CDB_OK;
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    CDB_CUDA_TRY(cudaMemcpy(out2, ix->hn_counters.p, 16, cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
 
 cdb_status cdb_index_stats(const cdb_index *ix, uint64_t *out4) {
     CDB_REQUIRE(ix && out4, "null argument");

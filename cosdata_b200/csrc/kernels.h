@@ -58,6 +58,35 @@ cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t
 cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
                             uint32_t k, uint64_t *d_keys, cudaStream_t s);
 
+// ---- hnsw.cu
+struct GraphDev {
+    uint32_t num_levels, nbrs, nbrs0, entry, root_row;
+    const uint32_t *const *node_row;  // device arrays of device pointers, [num_levels+1]
+    const uint32_t *const *adj;
+    const uint32_t *const *child;
+};
+struct HnswArgs {
+    GraphDev g;
+    const uint8_t *rows;
+    uint32_t row_pitch;
+    const float *mags;
+    uint32_t dim;
+    int st, metric;
+    const uint8_t *q;
+    const float *qmags;
+    uint32_t nq, ef, shortlist;
+    uint32_t out_cap;
+    uint32_t *out_rows;
+    float *out_scores;
+    uint32_t *out_n;
+    uint32_t *err32;
+    unsigned long long *counters;
+};
+cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s);
+cdb_status hnsw_dedup_device(const uint32_t *d_rows, const float *d_scores, const uint32_t *d_n, uint32_t in_cap, int metric,
+                             uint32_t root_row, uint32_t id_base, uint32_t k5, uint32_t nq, uint32_t *d_cand, uint32_t *d_cand_cnt,
+                             cudaStream_t s);
+
 // ---- tensor_scan.cu (tcgen05 prefilter)
 cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
                                 void *d_out, uint32_t out_pitch_halfs, uint32_t *d_zero_count, cudaStream_t s);

@@ -156,6 +156,28 @@ cdb_status cdb_index_append_synthetic(cdb_index *index, uint64_t seed, uint64_t 
 /* copy stored state back (tests): codes/mags of rows [first, first+n) */
 cdb_status cdb_index_read_codes(const cdb_index *index, uint64_t first, uint64_t n, void *out_codes, float *out_mags);
 
+/* ------------------------------------------------------------ HNSW graph upload
+ * Flat export of the reference's ProbNode graph (src/models/prob_node.rs:99-109): the vector of node
+ * i at level L is row node_row[L][i] of the index; adjacency[L][i*nbrs(L)+s] is the level-local index
+ * of the neighbour in slot s (CDB_INVALID_ID = empty slot, slot order preserved: the search examines
+ * the first shortlist_size slots); child[L][i] is the level-local index one level down (L >= 1).
+ * Level 0 must contain every row (node_row[0][i] == i).  root_row is the row holding the root vector
+ * (id u32::MAX in the reference, vector_store.rs:57-67); it is never returned.  Arrays are copied. */
+typedef struct {
+    uint32_t num_levels;              /* hnsw_params.num_layers: levels 0..=num_levels */
+    uint32_t neighbors_count;         /* slots per node, levels >= 1 (<= 64) */
+    uint32_t level0_neighbors_count;  /* slots per node, level 0 (<= 64) */
+    uint32_t entry;                   /* root's local index at the top level */
+    uint32_t root_row;
+    const uint32_t *level_counts;     /* [num_levels+1] */
+    const uint32_t *const *node_row;  /* [num_levels+1] host arrays */
+    const uint32_t *const *adjacency;
+    const uint32_t *const *child;     /* child[0] ignored */
+} cdb_graph_desc;
+cdb_status cdb_index_set_graph(cdb_index *index, const cdb_graph_desc *graph);
+/* cumulative {distance evaluations, pops} of CDB_MODE_HNSW searches (roofline accounting) */
+cdb_status cdb_index_hnsw_counters(const cdb_index *index, uint64_t *out2);
+
 /* --------------------------------------------------- S1 IndexOps::batch_search
  * queries: B x dim raw f32 (search_internal quantizes them with the index's
  * storage type, hnsw/mod.rs:399-403).  out_ids/out_scores: B x k, best first;
