@@ -167,8 +167,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    rows_local = args.rows // world + (1 if rank < args.rows % world else 0)
-    row0 = rank * (args.rows // world) + min(rank, args.rows % world)
+    from cosdata_b200.sharding import cuda_merge_fn, gather_and_merge, shard_range
+    row0, rows_local = shard_range(args.rows, world, rank)
     B, D, k = args.batch, args.dim, args.k
 
     ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.FullPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
@@ -185,8 +185,6 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         g_ids = torch.empty((world, B, k), dtype=torch.int32, device=dev)
         g_scores = torch.empty((world, B, k), dtype=torch.float32, device=dev)
-        m_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
-        m_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
     out_ids = torch.empty((B, k), dtype=torch.int32).pin_memory()
     out_scores = torch.empty((B, k), dtype=torch.float32).pin_memory()
 
@@ -196,14 +194,12 @@ def run_ours(args, rank, world, local_rank):
     def step_device():
         ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
                                stream.cuda_stream, exact_only=args.exact_only)
-        if world > 1:
-            dist.all_gather_into_tensor(g_ids.view(-1), d_ids.view(-1))
-            dist.all_gather_into_tensor(g_scores.view(-1), d_scores.view(-1))
-            rc = ix._lib.cdb_merge_topk_device(local_rank, 0, g_ids.data_ptr(), g_scores.data_ptr(), world, B, k,
-                                               m_ids.data_ptr(), m_scores.data_ptr(), stream.cuda_stream)
-            assert rc == 0
-            return m_ids, m_scores
-        return d_ids, d_scores
+        def all_gather(x):
+            out = g_ids if x.dtype == torch.int32 else g_scores
+            dist.all_gather_into_tensor(out.view(-1), x.view(-1))
+            return out
+
+        return gather_and_merge(d_ids, d_scores, world, all_gather, cuda_merge_fn(ix._lib, local_rank, 0, stream.cuda_stream))
 
     def step_e2e():
         # host queries in, host results out, through the public C-ABI call with HOST buffers

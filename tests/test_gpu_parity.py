@@ -236,3 +236,30 @@ def test_rerank_matches_oracle(st):
     assert cnt == 10
     assert np.array_equal(ids, want_ids) and np.array_equal(bits(scores), bits(want_scores))
     ix.close()
+
+
+# ------------------------------------------------------------------ multi-shard merge on one GPU
+
+def test_merge_topk_device_over_three_shards_equals_single_index():
+    import torch
+    from cosdata_b200.sharding import cuda_merge_fn, gather_and_merge, shard_range
+    n, dim, nq, k, world = 30011, 96, 21, 10, 3
+    corpus = orc.synth_matrix(3000, n, dim)
+    q = orc.synth_matrix(3001, nq, dim)
+    per_ids, per_scores = [], []
+    for r in range(world):
+        row0, nloc = shard_range(n, world, r)
+        ix = cdb.DenseIndex(dim=dim, capacity=nloc, id_base=row0)
+        ix.append_synthetic(3000, nloc, first_row=row0)
+        ids, scores, _, _ = ix.batch_search(q, k)
+        per_ids.append(torch.from_numpy(ids.view(np.int32)).cuda())
+        per_scores.append(torch.from_numpy(scores).cuda())
+        ix.close()
+    g_ids, g_scores = torch.stack(per_ids).contiguous(), torch.stack(per_scores).contiguous()
+    import cosdata_b200._lib as L
+    merge = cuda_merge_fn(L.load(), 0, 0, None)
+    m_ids, m_scores = merge(g_ids, g_scores)
+    torch.cuda.synchronize()
+    want_ids, want_scores = orc.brute_topk_f32(corpus, q, k)
+    assert np.array_equal(m_ids.cpu().numpy().view(np.uint32), want_ids)
+    assert np.array_equal(bits(m_scores.cpu().numpy()), bits(want_scores))
