@@ -94,6 +94,8 @@ struct cdb_index {
     float *d_raw = nullptr;       // raw f32 rows (may alias d_codes)
     float *d_raw_mags = nullptr;  // |raw row| (may alias d_mags)
     bool raw_owned = false, raw_mags_owned = false;
+    uint8_t *d_digits = nullptr;   // sub-byte storage unpacked to u8 digits for tcgen05 kind::i8 (tensor_scan_u8.cu)
+    uint32_t digit_pitch = 0;
     void *d_xh = nullptr;          // fp16 L2-normalised rows for the tcgen05 prefilter (tensor_scan.cu)
     uint32_t xh_pitch = 0;         // halfs per shadow row
     uint64_t n_zero_rows = 0;      // rows with |v| == 0 (their exact score is NaN)
@@ -249,6 +251,11 @@ cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
         if ((e = cudaMalloc(&ix->d_xh, (size_t)d->capacity * ix->xh_pitch * 2)) != cudaSuccess) return fail(e, "cudaMalloc(fp16 shadow)");
         if ((e = cudaMemsetAsync(ix->d_xh, 0, (size_t)d->capacity * ix->xh_pitch * 2, ix->stream)) != cudaSuccess) return fail(e, "memset");
     }
+    if (d->tensor_prefilter && d->storage_type >= CDB_ST_SUB1 && d->storage_type <= CDB_ST_SUB3) {
+        ix->digit_pitch = round_up(d->dim, 16);
+        if ((e = cudaMalloc(&ix->d_digits, (size_t)d->capacity * ix->digit_pitch)) != cudaSuccess) return fail(e, "cudaMalloc(digits)");
+        if ((e = cudaMemsetAsync(ix->d_digits, 0, (size_t)d->capacity * ix->digit_pitch, ix->stream)) != cudaSuccess) return fail(e, "memset");
+    }
     if ((e = cudaMallocHost(&ix->h_flags, 16)) != cudaSuccess) return fail(e, "cudaMallocHost");
     if (ix->flags.ensure(16) != CDB_OK) return fail(cudaErrorMemoryAllocation, "flags");
     if ((e = cudaMemsetAsync(ix->flags.p, 0, 16, ix->stream)) != cudaSuccess) return fail(e, "memset");
@@ -266,6 +273,7 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     if (ix->raw_owned && ix->d_raw) cudaFree(ix->d_raw);
     if (ix->raw_mags_owned && ix->d_raw_mags) cudaFree(ix->d_raw_mags);
     if (ix->d_xh) cudaFree(ix->d_xh);
+    if (ix->d_digits) cudaFree(ix->d_digits);
     for (void *g : ix->graph_allocs) cudaFree(g);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
@@ -290,6 +298,10 @@ static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) 
     if (ix->raw_mags_owned &&
         (rc = raw_mags_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, n, ix->desc.dim,
                               ix->d_raw_mags + first, ix->stream)))
+        return rc;
+    if (ix->d_digits &&
+        (rc = unpack_digits_device(ix->d_codes + first * ix->row_pitch, ix->row_pitch, n, ix->desc.dim, ix->desc.storage_type,
+                                   ix->d_digits + first * ix->digit_pitch, ix->digit_pitch, ix->stream)))
         return rc;
     if (ix->d_xh) {
         // flags[1] accumulates the number of zero-norm rows
@@ -338,6 +350,7 @@ cdb_status cdb_index_append_codes(cdb_index *ix, const void *codes, const float 
     cdb_status rc = copy_codes(ix->d_codes + ix->size * ix->row_pitch, codes, ix->desc.storage_type, ix->desc.dim, n, true, ix->stream);
     if (rc) return rc;
     CDB_CUDA_TRY(cudaMemcpyAsync(ix->d_mags + ix->size, mags, n * 4, cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = index_after_append(ix, ix->size, n))) return rc;
     CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
     ix->size += n;
     return CDB_OK;
@@ -490,8 +503,8 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
 static float prefilter_eps(uint32_t dim) { return 1.0e-3f + 8.0e-7f * (float)dim; }
 static const uint32_t PREFILTER_CAP = 4096;
 
-static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
-                                       uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+                                      uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
     const cdb_index_desc &d = ix->desc;
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
     if (nq == 0) return CDB_OK;
@@ -558,6 +571,45 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
         if (!done) ix->stat_fallbacks++;
         else if (d_err) CDB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nq, s));
     }
+    // ---- exact integer scoring on tcgen05 kind::i8: u8 codes in place, sub-byte codes through the digit copy
+    const uint8_t *u8_rows = !raw ? (st == CDB_ST_U8 ? ix->d_codes : ix->d_digits) : nullptr;
+    const bool u8_ok = u8_rows && !p->exact_only && (metric == CDB_METRIC_COSINE || metric == CDB_METRIC_DOT_PRODUCT) &&
+                       ix->size >= 16384 && p->k <= 128 && tensor_u8_smem_bytes(p->k) <= 227 * 1024 &&
+                       (nq + 127) / 128 <= (uint32_t)ix->sm_count;
+    if (u8_ok) {
+        const uint32_t mt = (nq + 127) / 128;
+        const uint32_t upitch = st == CDB_ST_U8 ? ix->row_pitch : ix->digit_pitch;
+        const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 4096u : 2048u));
+        if ((rc = ix->qh.ensure((size_t)mt * 128 * upitch)) || (rc = ix->gthr.ensure((size_t)nq * 4)) ||
+            (rc = ix->cand.ensure((size_t)nq * cap * 8)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) ||
+            (rc = ix->progress.ensure(4096)) || (rc = ix->err32.ensure((size_t)nq * 4)))
+            return rc;
+        uint32_t *flags = ix->flags.as<uint32_t>();
+        CDB_CUDA_TRY(cudaMemsetAsync(flags, 0, 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * upitch, s));
+        if (st == CDB_ST_U8)
+            CDB_CUDA_TRY(cudaMemcpyAsync(ix->qh.p, ix->q_codes.p, (size_t)nq * upitch, cudaMemcpyDeviceToDevice, s));
+        else if ((rc = unpack_digits_device(ix->q_codes.as<uint8_t>(), pitch, nq, d.dim, st, ix->qh.as<uint8_t>(), upitch, s)))
+            return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+        if ((rc = tensor_u8_scan_device(u8_rows, ix->qh.as<uint8_t>(), upitch, ix->size, nq, d.dim, p->k, metric, ix->d_mags,
+                                        ix->q_mags.as<float>(), d.id_base, ix->gthr.as<int>(), ix->cand.as<uint64_t>(),
+                                        ix->cand_cnt.as<uint32_t>(), cap, ix->err32.as<uint32_t>(), ix->progress.as<uint32_t>(),
+                                        d_ids, d_scores, d_counts, ix->sm_count, s)))
+            return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+        if ((rc = overflow_check_device(ix->cand_cnt.as<uint32_t>(), cap, nq, flags, s))) return rc;
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags, flags, 4, cudaMemcpyDeviceToHost, s));
+        CDB_CUDA_TRY(cudaStreamSynchronize(s));
+        ix->stat_tensor_searches++;
+        done = ix->h_flags[0] == 0;
+        if (!done) ix->stat_fallbacks++;
+        else if (d_err) {
+            err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(ix->err32.as<uint32_t>(), d_err, nq);
+            CDB_LAUNCH_CHECK();
+        }
+    }
     if (!done) {
         if (!tensor_ok) CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
         if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s))) return rc;
@@ -566,6 +618,20 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
     ix->ev_valid = true;
+    return CDB_OK;
+}
+
+// Batches are processed in chunks of <= 2048 queries (16 query tiles of 128): 148 SMs then split into 9 whole
+// CTA groups (144 CTAs) for the tensor-core kernels, and per-chunk scratch stays bounded.
+static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+                                       uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+    const uint32_t CH = 2048;
+    for (uint32_t off = 0; off < nq; off += CH) {
+        const uint32_t m = nq - off < CH ? nq - off : CH;
+        cdb_status rc = search_chunk_locked(ix, d_queries + (size_t)off * ix->desc.dim, m, p, d_ids + (size_t)off * p->k,
+                                            d_scores + (size_t)off * p->k, d_counts + off, d_err ? d_err + off : nullptr, s);
+        if (rc) return rc;
+    }
     return CDB_OK;
 }
 

@@ -96,4 +96,13 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
                               uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, int sm_count, cudaStream_t s);
 cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s);
 
+// ---- tensor_scan_u8.cu (exact integer scoring on tcgen05 kind::i8)
+size_t tensor_u8_smem_bytes(uint32_t k);
+cdb_status unpack_digits_device(const uint8_t *d_codes, uint32_t row_pitch, uint64_t n, uint32_t dim, int res, uint8_t *d_out,
+                                uint32_t out_pitch, cudaStream_t s);
+cdb_status tensor_u8_scan_device(const uint8_t *d_x, const uint8_t *d_q, uint32_t pitch, uint64_t n_rows, uint32_t nq, uint32_t dim,
+                                 uint32_t k, int metric, const float *d_mags, const float *d_qmags, uint32_t id_base, int *d_gthr,
+                                 uint64_t *d_cand, uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_err32, uint32_t *d_progress,
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, int sm_count, cudaStream_t s);
+
 }  // namespace cdb
