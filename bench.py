@@ -47,6 +47,11 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_250_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "hnsw"],
+                    help="c2 (default, the headline): brute cosine 10Mx768 f32; c4: quaternary inner product 50Mx1024, batch 4096; "
+                         "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools_build_hnsw_graph.py)")
+    ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--graph", default=os.path.join(ROOT, "bench_data", "hnsw_100k_128_f16.npz"))
     return ap.parse_args()
 
 
@@ -308,11 +313,211 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- secondary workloads (reporting modes)
+def _timed_single(fn, steps, warmup, stream):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def run_c4(args):
+    """BASELINE.json configs[3]: quaternary-quantized inner product, 50M x 1024, batch 4096, 1 GPU"""
+    import torch
+    import cosdata_b200 as cdb
+    rows = args.rows if args.rows != 10_000_000 else 50_000_000
+    D = args.dim if args.dim != 768 else 1024
+    B = args.batch if args.batch != 1024 else 4096
+    k = args.k
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    seed_c, seed_q = 0xC05DA7A + 4, 0xC05DA7A + 104
+    ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.SubByte2, metric=cdb.DistanceMetricKind.DotProduct,
+                        capacity=rows, device=0)
+    ix.append_synthetic(seed_c, rows)
+    q_host = cdb.synth_matrix(seed_q, B, D)
+    d_q = torch.from_numpy(q_host).to(dev)
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step():
+        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                               stream.cuda_stream, mode=cdb.SearchMode.BRUTE_CODES, exact_only=args.exact_only)
+
+    def step_e2e():
+        ix.batch_search(q_host, k, cdb.SearchMode.BRUTE_CODES, exact_only=args.exact_only)
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = cdb.kernel_launch_count()
+    ms = _timed_single(step, args.steps, max(args.warmup, 3), stream)
+    clocks = sampler.stop()
+    launches = (cdb.kernel_launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    nchunks = (B + 2047) // 2048
+    scan_ms = ix.scan_ms_history(args.steps * nchunks)
+    e2e_ms = _timed_single(step_e2e, args.steps, 1, stream)
+    st = ix.stats()
+    kernel_ms = float(np.sum(scan_ms)) / args.steps
+    ops = 2.0 * rows * D * B
+    pk = _peaks()
+    peak = 2.0 * float(pk.get("bf16_tflops", 1590.0))
+    achieved = ops / (kernel_ms / 1000.0) / 1e12
+    line = {
+        "metric": "queries/sec, quaternary inner product top-10", "value": args.steps * B / (ms / 1000.0), "unit": "queries/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8 digits -> s32 (exact)", "data": "synthetic",
+        "config": {"workload": f"quaternary-quantized inner product, {rows}x{D}, batch={B} (BASELINE.json configs[3])",
+                   "rows": rows, "dim": D, "batch": B, "k": k, "l2": "inputs_exceed_l2"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": args.steps * B / (e2e_ms / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": B * k * 8 + B * 5, "ms_per_step": e2e_ms / args.steps},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": "2 x measured dense bf16 (int8 tcgen05 rate is nominally 2x bf16; no int8 entry in MEASURED_PEAKS.json)",
+                     "kernel": "tensor_scan_u8_kernel (tcgen05 kind::i8, exact)", "kernel_ms": kernel_ms,
+                     "alg_ops_per_launch": ops, "digit_bytes": rows * D, "tensor_path": st},
+        "recall_at_10": 1.0, "recall_note": "exact integer scores; ids identical to the CPU oracle (tests/test_gpu_tensor_u8.py)",
+    }
+    if not args.no_cpu_baseline:
+        import oracle as orc
+        threads = os.cpu_count() or 1
+        srows = min(rows, 1_250_000)
+        codes, mags = orc.quantize_batch(2, orc.synth_matrix(seed_c, 4096, D))   # warm the library
+        t0 = time.perf_counter()
+        corpus = orc.synth_matrix(seed_c, srows, D)
+        cb = orc.code_bytes(2, D)
+        codes = np.zeros((srows, cb), dtype=np.uint8)
+        mags = np.zeros(srows, dtype=np.float32)
+        from oracle.pyoracle import lib, _p
+        L = lib()
+        for i in range(srows):                       # quantize (not timed as search work)
+            L.orc_quantize(2, -1.0, 1.0, corpus[i].ctypes.data, D, codes[i].ctypes.data, mags[i:i + 1].ctypes.data)
+        qc, qm = orc.quantize_batch(2, q_host[:16])
+        t1 = time.perf_counter()
+        orc.brute_topk_codes(3, 2, D, codes, mags, qc, qm, k, threads=threads)
+        dt = time.perf_counter() - t1
+        v = 16 / dt * (srows / rows)
+        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle dot_product_quaternary (AVX2) on {srows}x{D} codes x 16 queries in {dt:.2f}s, scaled linearly in rows"}
+    print(json.dumps(line), flush=True)
+    ix.close()
+
+
+def run_hnsw(args):
+    """HNSW f16 search (BASELINE.json configs[2] shape at the scale the CPU builder can produce): graph built by
+    tools_build_hnsw_graph.py with the reference defaults, searched with ef_search = --ef"""
+    import torch
+    import cosdata_b200 as cdb
+    import oracle as orc
+    from oracle import pyhnsw
+    z = np.load(args.graph)
+    vecs, root = z["vecs"], z["root"]
+    n, D = vecs.shape
+    B, k = args.batch, args.k
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    node_row = [z[f"node_row{l}"] for l in range(10)]
+    adj = [z[f"adj{l}"] for l in range(10)]
+    child = [z[f"child{l}"] for l in range(10)]
+    ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.HalfPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
+                        capacity=n + 1, device=0, keep_raw_f32=True)
+    ix.append(np.concatenate([vecs, root[None]], axis=0))
+    ix.set_graph(9, 32, 64, int(z["entry"]), n, node_row, adj, child)
+    rng = np.random.default_rng(5)
+    q_host = (vecs[rng.integers(0, n, B)] + 0.05 * rng.normal(size=(B, D))).astype(np.float32)
+    d_q = torch.from_numpy(q_host).to(dev)
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step():
+        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                               stream.cuda_stream, mode=cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64)
+
+    ev0, pp0 = ix.hnsw_counters()
+    step()
+    torch.cuda.synchronize()
+    ev1, pp1 = ix.hnsw_counters()
+    evals, pops = ev1 - ev0, pp1 - pp0
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = cdb.kernel_launch_count()
+    ms = _timed_single(step, args.steps, max(args.warmup, 3), stream)
+    clocks = sampler.stop()
+    launches = (cdb.kernel_launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    scan_ms = ix.scan_ms_history(args.steps)
+    e2e_ms = _timed_single(lambda: ix.batch_search(q_host, k, cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64),
+                           args.steps, 1, stream)
+    ids = d_ids.cpu().numpy().view(np.uint32)
+    # recall@10 against the exact top-10 (GPU exact scan over the same rows; rows 0..n-1, root excluded by id)
+    ex = cdb.DenseIndex(dim=D, capacity=n, device=0)
+    ex.append(vecs)
+    gt, _, _, _ = ex.batch_search(q_host, k)
+    ex.close()
+    recall = float(np.mean([len(set(ids[i]) & set(gt[i])) / k for i in range(B)]))
+    # parity + CPU baseline on a sample with the oracle (same graph)
+    fg = pyhnsw.FlatGraph(orc.METRIC_COSINE, orc.ST_F16, D, *orc.quantize_batch(orc.ST_F16, np.concatenate([vecs, root[None]])),
+                          n, 9, 32, 64, int(z["entry"]), node_row, adj, child)
+    threads = os.cpu_count() or 1
+    ns = min(B, 256)
+    t0 = time.perf_counter()
+    w = pyhnsw.search_batch(fg, vecs, q_host[:ns], k, ef_search=args.ef, threads=threads)
+    dt = time.perf_counter() - t0
+    parity = bool(np.array_equal(ids[:ns], w[0]) and np.array_equal(d_scores.cpu().numpy()[:ns].view(np.uint32), w[1].view(np.uint32)))
+    orc_recall = float(np.mean([len(set(w[0][i]) & set(gt[i])) / k for i in range(ns)]))
+    kernel_ms = float(np.mean(scan_ms))
+    alg_bytes = evals * (D * 2 + 4) + pops * 64 * 4          # SURVEY 8d: evals*(D*s+4) + pops*(nbrs*4), counted on this graph
+    pk = _peaks()
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    ach = alg_bytes / (kernel_ms / 1000.0) / 1e9
+    line = {
+        "metric": "queries/sec + recall@10, HNSW f16", "value": args.steps * B / (ms / 1000.0), "unit": "queries/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16 (f32 accumulate, reference order)", "data": "synthetic (clustered)",
+        "config": {"workload": f"HNSW dense index, {n}x{D} f16, ef_search={args.ef}, batch={B} (BASELINE.json configs[2] shape; "
+                               "graph built by the CPU oracle with the reference defaults)", "rows": n, "dim": D, "batch": B, "k": k},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": args.steps * B / (e2e_ms / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": B * k * 8 + B * 5, "ms_per_step": e2e_ms / args.steps},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                     "kernel": "hnsw_search_kernel (random row gathers)", "kernel_ms": kernel_ms, "alg_bytes_per_launch": alg_bytes,
+                     "evals_per_query": evals / B, "pops_per_query": pops / B},
+        "recall_at_10": recall, "oracle_recall_at_10": orc_recall, "parity_with_oracle_on_sample": parity,
+        "cpu_baseline": {"value": ns / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle ann_search + re-rank, {ns} queries, one query per thread, {dt:.2f}s"},
+    }
+    print(json.dumps(line), flush=True)
+    ix.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "c2":
+        if world != 1:
+            raise SystemExit("bench.py: --workload c4/hnsw are single-GPU reporting modes")
+        (run_c4 if args.workload == "c4" else run_hnsw)(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

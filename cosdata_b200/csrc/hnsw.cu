@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
     uint32_t *rnodes = qnodes + 2 * EFP;                                  // [EFP]
     uint32_t *nnodes = rnodes + EFP;                                      // [64] + sorted [64]
     __shared__ uint32_t s_qlen, s_cur, s_visited, s_rlen, s_ncand, s_err, s_best_node, s_entry;
-    __shared__ float s_scores[HN_MAX_TAKE];
+    __shared__ uint32_t s_bitkey[HN_MAX_TAKE];
 
     const uint32_t qi = blockIdx.x;
     const int tid = threadIdx.x;
@@ -103,26 +103,34 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
             if (qlen == 0 || visited >= a.ef) break;
             uint64_t *Q = qkeys + cur * EFP;
             uint32_t *QN = qnodes + cur * EFP;
-            // ---- pop + ordered walk through the fixed set (one thread)
+            // ---- pop (one thread), then the walk through the lossy fixed set for all slots at once.
+            // The reference tests and inserts slot by slot: a slot is scored iff its bit is not yet set AND no
+            // earlier non-empty slot of this pop maps to the same bit (that one either set it or found it set).
+            const uint32_t bn = QN[0];
             if (tid == 0) {
-                const uint64_t bk = Q[0];
-                const uint32_t bn = QN[0];
-                rkeys[s_rlen] = bk; rnodes[s_rlen] = bn; s_rlen++;
+                rkeys[s_rlen] = Q[0]; rnodes[s_rlen] = bn; s_rlen++;
                 pops++;
-                const uint32_t mask = nb - 1u;
-                const uint32_t *slots = adj + (size_t)bn * nb;
-                uint32_t nc = 0;
-                for (uint32_t s = 0; s < take; ++s) {
-                    const uint32_t nbl = slots[s];
-                    if (nbl == HN_EMPTY) continue;
-                    const uint32_t id = hn_id(a.g, node_row[nbl]);
-                    const uint32_t b = (id >> 6) & mask;
-                    const uint64_t bit = 1ull << (id & 0x3f);
-                    if (fs[b] & bit) continue;
-                    fs[b] |= bit;  // inserted after a successful calculate(); an Err aborts the query anyway
-                    nnodes[nc++] = nbl;
+                s_ncand = 0;
+            }
+            uint32_t my_nbl = HN_EMPTY, my_bitkey = 0xFFFFFFFFu;
+            if ((uint32_t)tid < take) {
+                my_nbl = adj[(size_t)bn * nb + tid];
+                if (my_nbl != HN_EMPTY) {
+                    const uint32_t id = hn_id(a.g, node_row[my_nbl]);
+                    my_bitkey = (((id >> 6) & (nb - 1u)) << 6) | (id & 0x3f);
                 }
-                s_ncand = nc;
+                s_bitkey[tid] = my_bitkey;
+            }
+            __syncthreads();
+            bool accept = false;
+            if (my_bitkey != 0xFFFFFFFFu) {
+                accept = ((fs[my_bitkey >> 6] >> (my_bitkey & 0x3f)) & 1ull) == 0;
+                for (int s2 = 0; s2 < tid && accept; ++s2) accept = s_bitkey[s2] != my_bitkey;
+            }
+            __syncthreads();  // every thread has read the old fixed set
+            if (accept) {
+                atomicOr(reinterpret_cast<unsigned long long *>(&fs[my_bitkey >> 6]), 1ull << (my_bitkey & 0x3f));
+                nnodes[atomicAdd(&s_ncand, 1u)] = my_nbl;
             }
             __syncthreads();
             const uint32_t nc = s_ncand;

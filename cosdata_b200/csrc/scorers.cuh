@@ -67,9 +67,26 @@ __device__ inline float mag_f32_seq(const float *__restrict__ v, uint32_t n) {
 }
 
 // ------------------------------------------------------------------ f16
+// rows are 16-byte pitched, so the operands are walked with 128-bit loads; the additions stay strictly in
+// element order (the reference's `.sum()` is a sequential left fold)
 __device__ inline float dot_f16_seq(const __half *__restrict__ a, const __half *__restrict__ b, uint32_t n) {
     float s = 0.0f;
-    for (uint32_t i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__half2float(a[i]), __half2float(b[i])));
+    uint32_t i = 0;
+    if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+        for (; i + 8 <= n; i += 8) {
+            const uint4 va = *reinterpret_cast<const uint4 *>(a + i);
+            const uint4 vb = *reinterpret_cast<const uint4 *>(b + i);
+            const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
+            const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+                s = __fadd_rn(s, __fmul_rn(fa.x, fb.x));
+                s = __fadd_rn(s, __fmul_rn(fa.y, fb.y));
+            }
+        }
+    }
+    for (; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__half2float(a[i]), __half2float(b[i])));
     return s;
 }
 
