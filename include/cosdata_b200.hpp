@@ -1,0 +1,125 @@
+// cosdata_b200.hpp -- C++17 host-side mirror of the reference's operator surface for the distance hot
+// path, header-only over the C ABI (cosdata_b200.h).  The reference is Rust; where its toolchain is absent
+// this is the compiled-language host side: same names, argument meaning and error behaviour as
+//   enum Storage / StorageType          src/storage/mod.rs:7-25, src/quantization/mod.rs:19-25
+//   Quantization::quantize              src/quantization/mod.rs:8-17, scalar.rs:10-52
+//   DistanceFunction::calculate         src/distance/mod.rs:8-22, src/models/types.rs:460-496
+//   IndexOps::batch_search              src/indexes/mod.rs:260-272
+//   finalize_ann_results                src/vector_store.rs:404-445
+// Nothing is computed here: every method is one call into libcosdata_b200.so.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "cosdata_b200.h"
+
+namespace cosdata {
+
+enum class StorageType : int32_t { UnsignedByte = 0, SubByte1 = 1, SubByte2 = 2, SubByte3 = 3, HalfPrecisionFP = 4, FullPrecisionFP = 5 };
+enum class DistanceMetricKind : int32_t { Cosine = 0, Euclidean = 1, Hamming = 2, DotProduct = 3 };
+enum class SearchMode : int32_t { BruteRaw = 0, BruteCodes = 1, Hnsw = 2 };
+
+// DistanceError::{StorageMismatch, CalculationError} and the library's own failures
+struct Error : std::runtime_error {
+    cdb_status status;
+    Error(cdb_status s, const std::string &what) : std::runtime_error(what), status(s) {}
+};
+struct DistanceError : Error { using Error::Error; };
+
+inline void check(cdb_status s) {
+    if (s != CDB_OK) throw Error(s, cdb_last_error_string());
+}
+
+// enum Storage: one quantized vector
+struct Storage {
+    StorageType storage_type;
+    float mag;
+    uint32_t dim;
+    std::vector<uint8_t> code;  // tight layout of include/cosdata_b200.h (planes [r][ceil(D/8)] for SubByte)
+};
+
+// impl Quantization for ScalarQuantization
+struct ScalarQuantization {
+    int device = 0;
+    Storage quantize(const std::vector<float> &v, StorageType st, std::pair<float, float> range = {-1.f, 1.f}) const {
+        Storage s{st, 0.f, (uint32_t)v.size(), std::vector<uint8_t>(cdb_code_bytes((int32_t)st, (uint32_t)v.size()))};
+        check(cdb_quantize_batch(device, (int32_t)st, range.first, range.second, v.data(), 1, s.dim, s.code.data(), &s.mag));
+        return s;
+    }
+    void train(const std::vector<std::vector<float>> &) const {}  // scalar.rs:54-57
+};
+
+// enum DistanceMetric + impl DistanceFunction (pairwise)
+struct DistanceMetric {
+    DistanceMetricKind kind;
+    int device = 0;
+    float calculate(const Storage &x, const Storage &y) const {
+        if (x.storage_type != y.storage_type) throw DistanceError(CDB_STORAGE_MISMATCH, "storage variants differ");  // cosine.rs:214
+        float out = 0.f;
+        int32_t st = 0;
+        check(cdb_distance_pairs(device, (int32_t)kind, (int32_t)x.storage_type, x.dim, x.code.data(), &x.mag, y.code.data(), &y.mag, 1, &out, &st));
+        if (st != CDB_OK) throw DistanceError(st, st == CDB_STORAGE_MISMATCH ? "StorageMismatch" : "CalculationError");
+        return out;
+    }
+};
+
+struct SearchResults {
+    uint32_t k = 0;
+    std::vector<uint32_t> ids;     // [B][k], CDB_INVALID_ID padded
+    std::vector<float> scores;     // [B][k]
+    std::vector<uint32_t> counts;  // [B]
+    std::vector<uint8_t> err;      // [B] CDB_ERRFLAG_* (the Err the reference would return for that query)
+};
+
+// one device-resident index shard
+class DenseIndex {
+  public:
+    DenseIndex(uint32_t dim, StorageType st, DistanceMetricKind metric, uint64_t capacity, int device = 0,
+               std::pair<float, float> range = {-1.f, 1.f}, bool keep_raw_f32 = false, uint32_t id_base = 0, bool tensor_prefilter = true) {
+        cdb_index_desc d{dim, (int32_t)st, (int32_t)metric, range.first, range.second, capacity, device, keep_raw_f32 ? 1 : 0, id_base,
+                         tensor_prefilter ? 1u : 0u};
+        check(cdb_index_create(&d, &h_));
+        dim_ = dim;
+    }
+    ~DenseIndex() { if (h_) cdb_index_destroy(h_); }
+    DenseIndex(const DenseIndex &) = delete;
+    DenseIndex &operator=(const DenseIndex &) = delete;
+
+    uint64_t size() const { return cdb_index_size(h_); }
+    void append(const float *vecs, uint64_t n) { check(cdb_index_append_f32(h_, vecs, n)); }
+    void set_graph(const cdb_graph_desc &g) { check(cdb_index_set_graph(h_, &g)); }
+
+    // IndexOps::batch_search
+    SearchResults batch_search(const float *queries, uint32_t b, uint32_t k, SearchMode mode = SearchMode::BruteRaw,
+                               uint32_t ef_search = 256, uint32_t shortlist_size = 64) const {
+        SearchResults r;
+        r.k = k;
+        r.ids.resize((size_t)b * k);
+        r.scores.resize((size_t)b * k);
+        r.counts.resize(b);
+        r.err.resize(b);
+        cdb_search_params p{k, (int32_t)mode, ef_search, shortlist_size, 0, 0, 0, 0};
+        check(cdb_search_batch(h_, queries, b, &p, r.ids.data(), r.scores.data(), r.counts.data(), r.err.data()));
+        return r;
+    }
+    // finalize_ann_results
+    std::vector<std::pair<uint32_t, float>> rerank(const float *query, const std::vector<uint32_t> &cand, uint32_t k) const {
+        std::vector<uint32_t> ids(k);
+        std::vector<float> sc(k);
+        uint32_t n = 0;
+        check(cdb_rerank_f32(h_, query, cand.data(), (uint32_t)cand.size(), k, ids.data(), sc.data(), &n));
+        std::vector<std::pair<uint32_t, float>> out;
+        for (uint32_t i = 0; i < n; ++i) out.emplace_back(ids[i], sc[i]);
+        return out;
+    }
+    cdb_index *handle() const { return h_; }
+
+  private:
+    cdb_index *h_ = nullptr;
+    uint32_t dim_ = 0;
+};
+
+}  // namespace cosdata
