@@ -45,6 +45,18 @@ class GraphDesc(C.Structure):
     ]
 
 
+class BuildParams(C.Structure):
+    _fields_ = [
+        ("num_levels", C.c_uint32),
+        ("neighbors_count", C.c_uint32),
+        ("level0_neighbors_count", C.c_uint32),
+        ("ef_construction", C.c_uint32),
+        ("shortlist_size", C.c_uint32),
+        ("max_batch", C.c_uint32),
+        ("seed", C.c_uint64),
+    ]
+
+
 class SearchParams(C.Structure):
     _fields_ = [
         ("k", C.c_uint32),
@@ -75,6 +87,9 @@ PROTOTYPES = {
     "cdb_index_append_synthetic": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "cdb_index_read_codes": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, c_vp, c_f32p]),
     "cdb_index_set_graph": (C.c_int32, [C.c_void_p, C.POINTER(GraphDesc)]),
+    "cdb_index_build_graph": (C.c_int32, [C.c_void_p, C.POINTER(BuildParams)]),
+    "cdb_index_graph_info": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdb_index_read_graph_level": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdb_index_hnsw_counters": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "cdb_search_batch": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p]),
     "cdb_search_batch_device": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p, C.c_void_p]),

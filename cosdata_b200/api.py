@@ -18,7 +18,7 @@ import enum
 import numpy as np
 
 from . import _lib
-from ._lib import GraphDesc, IndexDesc, SearchParams
+from ._lib import BuildParams, GraphDesc, IndexDesc, SearchParams
 
 INVALID_ID = 0xFFFFFFFF
 
@@ -296,3 +296,25 @@ class DenseIndex:
         out = np.zeros(2, dtype=np.uint64)
         _check(self._lib.cdb_index_hnsw_counters(self._h, _ptr(out)))
         return int(out[0]), int(out[1])
+
+    def build_graph(self, num_levels=9, neighbors_count=32, level0_neighbors_count=64, ef_construction=128,
+                    shortlist_size=64, max_batch=4096, seed=1):
+        """GPU-side index_embeddings: appends the root row and builds the HNSW graph (reference defaults)"""
+        bp = BuildParams(num_levels, neighbors_count, level0_neighbors_count, ef_construction, shortlist_size, max_batch, seed)
+        _check(self._lib.cdb_index_build_graph(self._h, C.byref(bp)))
+
+    def read_graph(self):
+        """-> dict(num_levels, neighbors_count, level0_neighbors_count, entry, root_row, node_row[], adj[], child[])"""
+        info = np.zeros(5, dtype=np.uint32)
+        counts = np.zeros(32, dtype=np.uint32)
+        _check(self._lib.cdb_index_graph_info(self._h, _ptr(info), _ptr(counts)))
+        L1 = int(info[0]) + 1
+        node_row, adj, child = [], [], []
+        for lv in range(L1):
+            c = int(counts[lv])
+            nb = int(info[2]) if lv == 0 else int(info[1])
+            nr, ad, ch = np.zeros(c, np.uint32), np.zeros(c * nb, np.uint32), np.full(c, 0xFFFFFFFF, np.uint32)
+            _check(self._lib.cdb_index_read_graph_level(self._h, lv, _ptr(nr), _ptr(ad), _ptr(ch)))
+            node_row.append(nr); adj.append(ad); child.append(ch)
+        return dict(num_levels=int(info[0]), neighbors_count=int(info[1]), level0_neighbors_count=int(info[2]),
+                    entry=int(info[3]), root_row=int(info[4]), node_row=node_row, adj=adj, child=child)

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "hnsw_traverse.cuh"
 
 namespace cdb {
 
@@ -114,6 +115,8 @@ struct cdb_index {
     bool has_graph = false;
     GraphDev graph{};
     std::vector<void *> graph_allocs;
+    std::vector<uint32_t> g_cnt;
+    std::vector<const uint32_t *> g_nr, g_ad, g_ch;  // host copies of the per-level device pointers
     DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags;
 };
 
@@ -316,9 +319,13 @@ static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) 
     return CDB_OK;
 }
 
+static cdb_status append_f32_locked(cdb_index *ix, const float *vecs, uint64_t n);
 cdb_status cdb_index_append_f32(cdb_index *ix, const float *vecs, uint64_t n) {
     CDB_REQUIRE(ix && (vecs || !n), "null argument");
     std::lock_guard<std::mutex> lock(ix->mu);
+    return append_f32_locked(ix, vecs, n);
+}
+static cdb_status append_f32_locked(cdb_index *ix, const float *vecs, uint64_t n) {
     CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     const uint32_t dim = ix->desc.dim;
@@ -806,6 +813,8 @@ cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
         CDB_CUDA_TRY(cudaMemcpy(p, src[t]->data(), L1 * sizeof(void *), cudaMemcpyHostToDevice));
         tbl[t] = (const uint32_t *)p;
     }
+    ix->g_nr = nr; ix->g_ad = ad; ix->g_ch = ch;
+    ix->g_cnt.assign(gd->level_counts, gd->level_counts + L1);
     ix->graph.num_levels = gd->num_levels;
     ix->graph.nbrs = gd->neighbors_count;
     ix->graph.nbrs0 = gd->level0_neighbors_count;
@@ -815,6 +824,56 @@ cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
     ix->graph.adj = reinterpret_cast<const uint32_t *const *>(tbl[1]);
     ix->graph.child = reinterpret_cast<const uint32_t *const *>(tbl[2]);
     ix->has_graph = true;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_build_graph(cdb_index *ix, const cdb_build_params *bp) {
+    CDB_REQUIRE(ix && bp, "null argument");
+    CDB_REQUIRE(bp->neighbors_count >= 1 && bp->neighbors_count <= 64 && bp->level0_neighbors_count >= 1 &&
+                    bp->level0_neighbors_count <= 64, "neighbour counts must be in 1..64");
+    CDB_REQUIRE(bp->ef_construction >= 1 && bp->ef_construction <= 4096 && bp->shortlist_size >= 1 && bp->shortlist_size <= 64 &&
+                    bp->num_levels <= 15, "bad build parameters");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->size >= 1 && ix->size + 1 <= ix->desc.capacity, "build needs >= 1 row and capacity for the root row");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    cdb_status rc;
+    if ((rc = arm_status(ix->desc.metric, ix->desc.storage_type)) != CDB_OK) {
+        set_error("metric/storage arm is an Err in the reference");
+        return rc;
+    }
+    const uint32_t n = (uint32_t)ix->size;
+    // root vector: uniform in [range_lo, range_hi) (vector_store.rs:57-64)
+    std::vector<float> root(ix->desc.dim);
+    for (uint32_t c = 0; c < ix->desc.dim; ++c)
+        root[c] = ix->desc.range_lo + (synth_value(bp->seed ^ 0x526F6F74ull, c) + 1.0f) * 0.5f * (ix->desc.range_hi - ix->desc.range_lo);
+    if ((rc = append_f32_locked(ix, root.data(), 1))) return rc;
+    for (void *g : ix->graph_allocs) cudaFree(g);
+    ix->graph_allocs.clear();
+    ix->has_graph = false;
+    HnScoreCtx sc{ix->d_codes, ix->row_pitch, ix->d_mags, ix->desc.dim, ix->desc.storage_type, ix->desc.metric, n};
+    rc = hnsw_build_device(sc, n, bp->num_levels, bp->neighbors_count, bp->level0_neighbors_count, bp->ef_construction,
+                           bp->shortlist_size, bp->max_batch, bp->seed, &ix->graph, &ix->graph_allocs, &ix->g_cnt, &ix->g_nr,
+                           &ix->g_ad, &ix->g_ch, ix->stream);
+    if (rc) return rc;
+    ix->has_graph = true;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_graph_info(const cdb_index *ix, uint32_t *info5, uint32_t *level_counts) {
+    CDB_REQUIRE(ix && info5, "null argument");
+    CDB_REQUIRE(ix->has_graph, "no graph");
+    info5[0] = ix->graph.num_levels; info5[1] = ix->graph.nbrs; info5[2] = ix->graph.nbrs0; info5[3] = ix->graph.entry; info5[4] = ix->graph.root_row;
+    if (level_counts) for (size_t i = 0; i < ix->g_cnt.size(); ++i) level_counts[i] = ix->g_cnt[i];
+    return CDB_OK;
+}
+
+cdb_status cdb_index_read_graph_level(const cdb_index *ix, uint32_t level, uint32_t *node_row, uint32_t *adjacency, uint32_t *child) {
+    CDB_REQUIRE(ix && ix->has_graph && level <= ix->graph.num_levels, "no graph / bad level");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    const uint32_t cnt = ix->g_cnt[level], nb = level == 0 ? ix->graph.nbrs0 : ix->graph.nbrs;
+    if (node_row) CDB_CUDA_TRY(cudaMemcpy(node_row, ix->g_nr[level], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    if (adjacency) CDB_CUDA_TRY(cudaMemcpy(adjacency, ix->g_ad[level], (size_t)cnt * nb * 4, cudaMemcpyDeviceToHost));
+    if (child && level > 0) CDB_CUDA_TRY(cudaMemcpy(child, ix->g_ch[level], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
     return CDB_OK;
 }
 

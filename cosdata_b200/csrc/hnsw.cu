@@ -14,197 +14,50 @@
 // below the number of pops still to come can never be popped: the queue is a sorted array of at
 // most `ef` entries and the pop order is identical to the heap's.  Keys are
 // (order_key(score) << 32 | ~id): "better score first, then smaller id" -- the oracle's tie rule.
-#include "kernels.h"
+#include "hnsw_traverse.cuh"
 
 namespace cdb {
 
-constexpr int HN_THREADS = 128;
-constexpr uint32_t HN_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t HN_ROOT_ID = 0xFFFFFFFFu;
-constexpr uint32_t HN_QUERY_ID = 0xFFFFFFFEu;  // hnsw/mod.rs:398
-constexpr uint32_t HN_MAX_TAKE = 64;            // slots examined per pop (<= shortlist_size, config.toml:32)
-constexpr uint32_t HN_FINAL_LEN = 100;          // vector_store.rs:1194
-
-__device__ __forceinline__ uint32_t hn_id(const GraphDev &g, uint32_t row) { return row == g.root_row ? HN_ROOT_ID : row; }
-
-// bitonic sort (descending) of n keys with a payload, padded to P (power of two) with zeros
-__device__ void hn_sort_desc(uint64_t *keys, uint32_t *vals, uint32_t n, uint32_t P) {
-    for (uint32_t i = n + threadIdx.x; i < P; i += blockDim.x) { keys[i] = 0ull; vals[i] = 0; }
-    __syncthreads();
-    for (uint32_t size = 2; size <= P; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
-                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                const bool desc = (lo & size) == 0;
-                const uint64_t x = keys[lo], y = keys[hi];
-                if ((x < y) == desc) {
-                    keys[lo] = y; keys[hi] = x;
-                    const uint32_t v = vals[lo]; vals[lo] = vals[hi]; vals[hi] = v;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
+constexpr uint32_t HN_FINAL_LEN = 100;  // vector_store.rs:1194
 
 __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t EFP = [&] { uint32_t p = 1; while (p < a.ef) p <<= 1; return p < 128 ? 128u : p; }();  // queue / result capacity
-    uint8_t *qs = smem;                                                   // [row_pitch]
-    uint64_t *qkeys = reinterpret_cast<uint64_t *>(qs + round_up(a.row_pitch, 16));  // [2][EFP]
-    uint64_t *rkeys = qkeys + 2 * EFP;                                    // [EFP]
-    uint64_t *nkeys = rkeys + EFP;                                        // [64] new candidates, then sorted copy [64]
-    uint64_t *fs = nkeys + 2 * HN_MAX_TAKE;                               // [64] fixed set buckets
-    uint32_t *qnodes = reinterpret_cast<uint32_t *>(fs + 64);             // [2][EFP]
-    uint32_t *rnodes = qnodes + 2 * EFP;                                  // [EFP]
-    uint32_t *nnodes = rnodes + EFP;                                      // [64] + sorted [64]
-    __shared__ uint32_t s_qlen, s_cur, s_visited, s_rlen, s_ncand, s_err, s_best_node, s_entry;
-    __shared__ uint32_t s_bitkey[HN_MAX_TAKE];
-
+    const HnSmem m = hn_carve(smem, a.row_pitch, a.ef);
+    __shared__ HnShared sh;
     const uint32_t qi = blockIdx.x;
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < a.row_pitch / 4; i += HN_THREADS)
-        reinterpret_cast<uint32_t *>(qs)[i] = reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[i];
+        reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[i];
     const float qmag = a.qmags[qi];
-    const uint32_t pp = plane_pitch(a.dim);
-    if (tid == 0) { s_err = 0; s_entry = a.g.entry; }
-    uint32_t out_total = 0;  // meaningful in thread 0
+    const HnScoreCtx sc{a.rows, a.row_pitch, a.mags, a.dim, a.st, a.metric, a.g.root_row};
+    if (tid == 0) { sh.err = 0; sh.entry = a.g.entry; }
+    uint32_t out_total = 0;
     unsigned long long evals = 0, pops = 0;
     __syncthreads();
 
+    // ann_search (vector_store.rs:256-402): fresh fixed set and ef budget per level, results of all levels
+    // concatenated, child of the best result is the entry of the next level
     for (int level = (int)a.g.num_levels; level >= 0; --level) {
         const uint32_t nb = level == 0 ? a.g.nbrs0 : a.g.nbrs;
         const uint32_t take = min(min(a.shortlist, nb), HN_MAX_TAKE);
         const uint32_t *node_row = a.g.node_row[level];
-        const uint32_t *adj = a.g.adj[level];
-        // fresh fixed set per level, pre-seeded with the query id (vector_store.rs:266-271)
-        if (tid < 64) fs[tid] = 0ull;
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t mask = nb - 1u;
-            fs[(HN_QUERY_ID >> 6) & mask] |= 1ull << (HN_QUERY_ID & 0x3f);
-            const uint32_t entry = s_entry;
-            const uint32_t erow = node_row[entry];
-            float d = 0.f;
-            const int rc = pair_distance(a.metric, a.st, a.dim, qs, qmag, pp, a.rows + (size_t)erow * a.row_pitch, a.mags[erow], pp, &d);
-            evals++;
-            if (rc != CDB_OK) s_err = rc == CDB_CALCULATION_ERROR ? CDB_ERRFLAG_CALCULATION : 2;
-            const uint32_t eid = hn_id(a.g, erow);
-            fs[(eid >> 6) & mask] |= 1ull << (eid & 0x3f);
-            qkeys[0] = make_key64(order_key(a.metric, __float_as_uint(d)), eid);
-            qnodes[0] = entry;
-            s_qlen = 1; s_cur = 0; s_visited = 0; s_rlen = 0;
-        }
-        __syncthreads();
-        if (s_err) break;
-
-        while (true) {
-            const uint32_t qlen = s_qlen, cur = s_cur, visited = s_visited;
-            if (qlen == 0 || visited >= a.ef) break;
-            uint64_t *Q = qkeys + cur * EFP;
-            uint32_t *QN = qnodes + cur * EFP;
-            // ---- pop (one thread), then the walk through the lossy fixed set for all slots at once.
-            // The reference tests and inserts slot by slot: a slot is scored iff its bit is not yet set AND no
-            // earlier non-empty slot of this pop maps to the same bit (that one either set it or found it set).
-            const uint32_t bn = QN[0];
-            if (tid == 0) {
-                rkeys[s_rlen] = Q[0]; rnodes[s_rlen] = bn; s_rlen++;
-                pops++;
-                s_ncand = 0;
-            }
-            uint32_t my_nbl = HN_EMPTY, my_bitkey = 0xFFFFFFFFu;
-            if ((uint32_t)tid < take) {
-                my_nbl = adj[(size_t)bn * nb + tid];
-                if (my_nbl != HN_EMPTY) {
-                    const uint32_t id = hn_id(a.g, node_row[my_nbl]);
-                    my_bitkey = (((id >> 6) & (nb - 1u)) << 6) | (id & 0x3f);
-                }
-                s_bitkey[tid] = my_bitkey;
-            }
-            __syncthreads();
-            bool accept = false;
-            if (my_bitkey != 0xFFFFFFFFu) {
-                accept = ((fs[my_bitkey >> 6] >> (my_bitkey & 0x3f)) & 1ull) == 0;
-                for (int s2 = 0; s2 < tid && accept; ++s2) accept = s_bitkey[s2] != my_bitkey;
-            }
-            __syncthreads();  // every thread has read the old fixed set
-            if (accept) {
-                atomicOr(reinterpret_cast<unsigned long long *>(&fs[my_bitkey >> 6]), 1ull << (my_bitkey & 0x3f));
-                nnodes[atomicAdd(&s_ncand, 1u)] = my_nbl;
-            }
-            __syncthreads();
-            const uint32_t nc = s_ncand;
-            // ---- score the new neighbours, one thread each, reference arithmetic
-            if ((uint32_t)tid < nc) {
-                const uint32_t nbl = nnodes[tid];
-                const uint32_t row = node_row[nbl];
-                float d = 0.f;
-                const int rc = pair_distance(a.metric, a.st, a.dim, qs, qmag, pp, a.rows + (size_t)row * a.row_pitch, a.mags[row], pp, &d);
-                if (rc != CDB_OK) atomicOr(&s_err, rc == CDB_CALCULATION_ERROR ? (uint32_t)CDB_ERRFLAG_CALCULATION : 2u);
-                nkeys[tid] = make_key64(order_key(a.metric, __float_as_uint(d)), hn_id(a.g, row));
-            }
-            if (tid == 0) evals += nc;
-            __syncthreads();
-            if (s_err) break;
-            // ---- sort the new entries (rank sort, nc <= 64) into nkeys[64..], nnodes[64..]
-            if ((uint32_t)tid < nc) {
-                const uint64_t k = nkeys[tid];
-                uint32_t r = 0;
-                for (uint32_t j = 0; j < nc; ++j) r += nkeys[j] > k;
-                nkeys[HN_MAX_TAKE + r] = k;
-                nnodes[HN_MAX_TAKE + r] = nnodes[tid];
-            }
-            __syncthreads();
-            // ---- merge old queue (minus the popped head) with the new entries, keep what can still be popped
-            {
-                const uint64_t *NK = nkeys + HN_MAX_TAKE;
-                const uint32_t *NN = nnodes + HN_MAX_TAKE;
-                const uint32_t oldn = qlen - 1;
-                const uint32_t cap = min(a.ef - (visited + 1), EFP);  // pops still to come
-                uint64_t *D = qkeys + (cur ^ 1) * EFP;
-                uint32_t *DN = qnodes + (cur ^ 1) * EFP;
-                for (uint32_t i = tid; i < oldn; i += HN_THREADS) {
-                    const uint64_t k = Q[1 + i];
-                    uint32_t lo = 0, hi = nc;  // number of new entries better than k
-                    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (NK[m] > k) lo = m + 1; else hi = m; }
-                    const uint32_t pos = i + lo;
-                    if (pos < cap) { D[pos] = k; DN[pos] = QN[1 + i]; }
-                }
-                for (uint32_t j = tid; j < nc; j += HN_THREADS) {
-                    const uint64_t k = NK[j];
-                    uint32_t lo = 0, hi = oldn;  // number of old entries better than k
-                    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (Q[1 + m] > k) lo = m + 1; else hi = m; }
-                    const uint32_t pos = j + lo;
-                    if (pos < cap) { D[pos] = k; DN[pos] = NN[j]; }
-                }
-                __syncthreads();
-                if (tid == 0) { s_qlen = min(oldn + nc, cap); s_cur = cur ^ 1; s_visited = visited + 1; }
-            }
-            __syncthreads();
-        }
-        __syncthreads();
-        if (s_err) break;
-        // ---- results of this level: sort best-first, keep 100, append; child of the best is the next entry
-        const uint32_t rlen = s_rlen;
-        uint32_t P = 1;
-        while (P < rlen) P <<= 1;
-        hn_sort_desc(rkeys, rnodes, rlen, P);
-        const uint32_t keep = min(rlen, HN_FINAL_LEN);
-        const uint32_t base = out_total;
+        hn_traverse_level(node_row, a.g.adj[level], nb, take, sc, m, sh, qmag, HN_QUERY_ID, a.ef, evals, pops);
+        if (sh.err) break;
+        const uint32_t keep = min(sh.rlen, HN_FINAL_LEN);
         for (uint32_t i = tid; i < keep; i += HN_THREADS) {
-            const uint32_t slot = base + i;
+            const uint32_t slot = out_total + i;
             if (slot < a.out_cap) {
-                a.out_rows[(size_t)qi * a.out_cap + slot] = node_row[rnodes[i]];
-                a.out_scores[(size_t)qi * a.out_cap + slot] = __uint_as_float(key_to_bits(a.metric, (uint32_t)(rkeys[i] >> 32)));
+                a.out_rows[(size_t)qi * a.out_cap + slot] = node_row[m.rnodes[i]];
+                a.out_scores[(size_t)qi * a.out_cap + slot] = __uint_as_float(key_to_bits(a.metric, (uint32_t)(m.rkeys[i] >> 32)));
             }
         }
         out_total += keep;
-        if (tid == 0 && level > 0) s_entry = a.g.child[level][rnodes[0]];
+        if (tid == 0 && level > 0) sh.entry = a.g.child[level][m.rnodes[0]];
         __syncthreads();
     }
     if (tid == 0) {
-        a.out_n[qi] = s_err ? 0u : min(out_total, a.out_cap);
-        if (s_err) atomicOr(a.err32 + qi, s_err);
+        a.out_n[qi] = sh.err ? 0u : min(out_total, a.out_cap);
+        if (sh.err) atomicOr(a.err32 + qi, sh.err);
         if (a.counters) { atomicAdd(a.counters, evals); atomicAdd(a.counters + 1, pops); }
     }
 }
@@ -257,12 +110,7 @@ __global__ void __launch_bounds__(256) hnsw_dedup_kernel(const uint32_t *__restr
     if (threadIdx.x == 0) cand_cnt[q] = m;
 }
 
-size_t hnsw_search_smem(uint32_t row_pitch, uint32_t ef) {
-    uint32_t efp = 1;
-    while (efp < ef) efp <<= 1;
-    if (efp < 128) efp = 128;
-    return round_up(row_pitch, 16) + (size_t)(3 * efp + 2 * HN_MAX_TAKE + 64) * 8 + (size_t)(3 * efp + 2 * HN_MAX_TAKE) * 4 + 64;
-}
+size_t hnsw_search_smem(uint32_t row_pitch, uint32_t ef) { return hn_smem_bytes(row_pitch, ef); }
 
 cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s) {
     if (!a.nq) return CDB_OK;

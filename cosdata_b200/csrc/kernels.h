@@ -1,5 +1,7 @@
 // kernels.h -- internal launch wrappers shared between the .cu files.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "scorers.cuh"
 
@@ -86,6 +88,14 @@ cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s);
 cdb_status hnsw_dedup_device(const uint32_t *d_rows, const float *d_scores, const uint32_t *d_n, uint32_t in_cap, int metric,
                              uint32_t root_row, uint32_t id_base, uint32_t k5, uint32_t nq, uint32_t *d_cand, uint32_t *d_cand_cnt,
                              cudaStream_t s);
+
+// ---- hnsw_build.cu
+struct HnScoreCtx;
+cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n, uint32_t num_levels, uint32_t nbrs, uint32_t nbrs0,
+                             uint32_t ef_construction, uint32_t shortlist, uint32_t max_batch, uint64_t seed, GraphDev *out_graph,
+                             std::vector<void *> *out_allocs, std::vector<uint32_t> *out_counts,
+                             std::vector<const uint32_t *> *out_nr, std::vector<const uint32_t *> *out_ad,
+                             std::vector<const uint32_t *> *out_ch, cudaStream_t s);
 
 // ---- tensor_scan.cu (tcgen05 prefilter)
 cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,

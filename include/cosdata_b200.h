@@ -175,6 +175,24 @@ typedef struct {
     const uint32_t *const *child;     /* child[0] ignored */
 } cdb_graph_desc;
 cdb_status cdb_index_set_graph(cdb_index *index, const cdb_graph_desc *graph);
+/* GPU-side index build (index_embeddings, src/vector_store.rs:714-940): appends the root vector (random in
+ * values_range, id u32::MAX; vector_store.rs:57-67) as the last row and builds the HNSW graph over all rows with the
+ * reference's algorithm (traverse with ef_construction per level, create_node_edges / add_neighbor with
+ * lowest-similarity eviction), batches of up to max_batch vectors in flight like the reference's concurrent build.
+ * The index needs capacity for one more row.  The result replaces any uploaded graph and can be read back. */
+typedef struct {
+    uint32_t num_levels;              /* hnsw.default_num_layer = 9 (config.toml:19-25) */
+    uint32_t neighbors_count;         /* 32 */
+    uint32_t level0_neighbors_count;  /* 64 */
+    uint32_t ef_construction;         /* 128 */
+    uint32_t shortlist_size;          /* 64 */
+    uint32_t max_batch;               /* vectors inserted concurrently (0 = 4096) */
+    uint64_t seed;                    /* level assignment + root vector */
+} cdb_build_params;
+cdb_status cdb_index_build_graph(cdb_index *index, const cdb_build_params *params);
+/* read the current graph back: info5 = {num_levels, neighbors_count, level0_neighbors_count, entry, root_row} */
+cdb_status cdb_index_graph_info(const cdb_index *index, uint32_t *info5, uint32_t *level_counts /* [num_levels+1] or NULL */);
+cdb_status cdb_index_read_graph_level(const cdb_index *index, uint32_t level, uint32_t *node_row, uint32_t *adjacency, uint32_t *child);
 /* cumulative {distance evaluations, pops} of CDB_MODE_HNSW searches (roofline accounting) */
 cdb_status cdb_index_hnsw_counters(const cdb_index *index, uint64_t *out2);
 
