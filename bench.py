@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_250_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "hnsw"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "hnsw"],
                     help="c2 (default, the headline): brute cosine 10Mx768 f32; c4: quaternary inner product 50Mx1024, batch 4096; "
                          "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools_build_hnsw_graph.py)")
     ap.add_argument("--ef", type=int, default=128)
@@ -508,6 +508,96 @@ def run_hnsw(args):
     ix.close()
 
 
+def run_c3(args):
+    """BASELINE.json configs[2]: HNSW dense index, 10M x 768 f16 ("bf16" in the JSON; the reference has IEEE f16 only),
+    ef_search=128, batch=1024.  The graph is built ON THE GPU by cdb_index_build_graph with the reference defaults
+    (nbrs 32/64, ef_construction 128, 9 layers); data = clustered synthetic rows generated on device with torch."""
+    import torch
+    import cosdata_b200 as cdb
+    rows, D, B, k = args.rows, args.dim, args.batch, args.k
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    ncent = 4096
+    centres = torch.randn((ncent, D), generator=g, device=dev)
+    scale = 1.0 / (4.5 * 1.06)            # |x| < 1 with overwhelming probability; clamp below keeps the quantizer's domain
+    ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.HalfPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
+                        capacity=rows + 1, device=0, keep_raw_f32=True)
+    chunk = 500_000
+    t0 = time.perf_counter()
+    for off in range(0, rows, chunk):
+        m = min(chunk, rows - off)
+        idx = torch.randint(0, ncent, (m,), generator=g, device=dev)
+        x = ((centres[idx] + 0.35 * torch.randn((m, D), generator=g, device=dev)) * scale).clamp_(-0.999, 0.999).contiguous()
+        torch.cuda.synchronize()
+        ix.append_device(x.data_ptr(), m)
+        del x, idx
+    t_load = time.perf_counter() - t0
+    # queries: perturbed stored rows (generated the same way from a few row indices is not possible without keeping
+    # the rows, so draw fresh points from the same mixture)
+    idx = torch.randint(0, ncent, (B,), generator=g, device=dev)
+    d_q = ((centres[idx] + 0.35 * torch.randn((B, D), generator=g, device=dev)) * scale).clamp_(-0.999, 0.999).contiguous()
+    q_host = d_q.cpu().numpy()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ix.build_graph(9, 32, 64, 128, 64, 4096, 7)
+    t_build = time.perf_counter() - t0
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step():
+        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                               stream.cuda_stream, mode=cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64)
+
+    ev0, pp0 = ix.hnsw_counters()
+    step()
+    torch.cuda.synchronize()
+    ev1, pp1 = ix.hnsw_counters()
+    evals, pops = ev1 - ev0, pp1 - pp0
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = cdb.kernel_launch_count()
+    ms = _timed_single(step, args.steps, max(args.warmup, 3), stream)
+    clocks = sampler.stop()
+    launches = (cdb.kernel_launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    scan_ms = ix.scan_ms_history(args.steps)
+    e2e_ms = _timed_single(lambda: ix.batch_search(q_host, k, cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64),
+                           args.steps, 1, stream)
+    ids = d_ids.cpu().numpy().view(np.uint32)
+    sc = d_scores.cpu().numpy()
+    # recall@10 against the exact top-10: the exact scan over the same raw rows (itself oracle-verified); the root row
+    # (id = rows) is not a data row and is ignored
+    gt, gts, _, _ = ix.batch_search(q_host, k + 1, cdb.SearchMode.BRUTE_RAW)
+    gt = [[i for i in row if i != rows][:k] for row in gt]
+    recall = float(np.mean([len(set(ids[i]) & set(gt[i])) / k for i in range(B)]))
+    kernel_ms = float(np.mean(scan_ms))
+    alg_bytes = evals * (D * 2 + 4) + pops * 64 * 4
+    pk = _peaks()
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    ach = alg_bytes / (kernel_ms / 1000.0) / 1e9
+    line = {
+        "metric": "queries/sec + recall@10, HNSW f16", "value": args.steps * B / (ms / 1000.0), "unit": "queries/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16 (f32 accumulate, reference order)", "data": "synthetic (4096 Gaussian clusters)",
+        "config": {"workload": f"HNSW dense index, {rows}x{D} f16, ef_search={args.ef}, batch={B} (BASELINE.json configs[2]); graph built on the GPU "
+                               "with the reference defaults", "rows": rows, "dim": D, "batch": B, "k": k},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": args.steps * B / (e2e_ms / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
+                "d2h_bytes_per_step": B * k * 8 + B * 5, "ms_per_step": e2e_ms / args.steps},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                     "kernel": "hnsw_search_kernel (random row gathers)", "kernel_ms": kernel_ms, "alg_bytes_per_launch": alg_bytes,
+                     "evals_per_query": evals / B, "pops_per_query": pops / B},
+        "recall_at_10": recall, "build_seconds": t_build, "build_rows_per_s": rows / t_build, "load_seconds": t_load,
+        "mean_top1_score": float(sc[:, 0].mean()),
+    }
+    print(json.dumps(line), flush=True)
+    ix.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -516,7 +606,7 @@ def main():
     if args.workload != "c2":
         if world != 1:
             raise SystemExit("bench.py: --workload c4/hnsw are single-GPU reporting modes")
-        (run_c4 if args.workload == "c4" else run_hnsw)(args)
+        {"c4": run_c4, "hnsw": run_hnsw, "c3": run_c3}[args.workload](args)
         return
     if args.impl == "reference":
         run_reference(args, rank, world)

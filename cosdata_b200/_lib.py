@@ -83,6 +83,7 @@ PROTOTYPES = {
     "cdb_index_destroy": (C.c_int32, [C.c_void_p]),
     "cdb_index_size": (C.c_uint64, [C.c_void_p]),
     "cdb_index_append_f32": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint64]),
+    "cdb_index_append_f32_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "cdb_index_append_codes": (C.c_int32, [C.c_void_p, c_vp, c_f32p, C.c_uint64]),
     "cdb_index_append_synthetic": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "cdb_index_read_codes": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, c_vp, c_f32p]),

@@ -318,3 +318,7 @@ class DenseIndex:
             node_row.append(nr); adj.append(ad); child.append(ch)
         return dict(num_levels=int(info[0]), neighbors_count=int(info[1]), level0_neighbors_count=int(info[2]),
                     entry=int(info[3]), root_row=int(info[4]), node_row=node_row, adj=adj, child=child)
+
+    def append_device(self, d_ptr, n):
+        """rows already on the index's device: d_ptr = address of n*dim contiguous f32"""
+        _check(self._lib.cdb_index_append_f32_device(self._h, d_ptr, n))

@@ -348,6 +348,24 @@ static cdb_status append_f32_locked(cdb_index *ix, const float *vecs, uint64_t n
     return CDB_OK;
 }
 
+cdb_status cdb_index_append_f32_device(cdb_index *ix, const float *d_vecs, uint64_t n) {
+    CDB_REQUIRE(ix && (d_vecs || !n), "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    if (!n) return CDB_OK;
+    const uint64_t first = ix->size;
+    float *raw = ix->raw_owned ? ix->d_raw + first * ix->raw_pitch_elems : nullptr;
+    cdb_status rc = quantize_rows_device(d_vecs, n, ix->desc.dim, ix->desc.storage_type, ix->desc.range_lo, ix->desc.range_hi,
+                                         ix->d_codes + first * ix->row_pitch, ix->row_pitch, ix->d_mags + first, raw,
+                                         ix->raw_pitch_elems, ix->stream);
+    if (rc) return rc;
+    if ((rc = index_after_append(ix, first, n))) return rc;
+    CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->size += n;
+    return CDB_OK;
+}
+
 cdb_status cdb_index_append_codes(cdb_index *ix, const void *codes, const float *mags, uint64_t n) {
     CDB_REQUIRE(ix && ((codes && mags) || !n), "null argument");
     std::lock_guard<std::mutex> lock(ix->mu);

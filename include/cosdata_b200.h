@@ -148,6 +148,8 @@ uint64_t cdb_index_size(const cdb_index *index);
 /* preprocess_embedding (vector_store.rs:629-712): quantize with the index's
  * StorageType/range and append; raw rows kept when keep_raw_f32. */
 cdb_status cdb_index_append_f32(cdb_index *index, const float *vecs, uint64_t n);
+/* same, rows already in DEVICE memory on the index's device (n x dim f32, dense) */
+cdb_status cdb_index_append_f32_device(cdb_index *index, const float *d_vecs, uint64_t n);
 /* append already-quantized rows (prop.data payloads) */
 cdb_status cdb_index_append_codes(cdb_index *index, const void *codes, const float *mags, uint64_t n);
 /* generate rows [first_row, first_row+n) of synthetic stream `seed` ON DEVICE and append

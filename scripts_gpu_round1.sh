@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_hnsw_build.py tests/test_gpu_hnsw.py -m gpu -x -q > gpurun_out/pytest_build.log 2>&1; echo "pytest build rc=$?"; tail -25 gpurun_out/pytest_build.log | cut -c1-400
+timeout 1500 python bench.py --workload c3 --rows 10000000 --steps 5 --warmup 3 > gpurun_out/bench_c3_10m.log 2> gpurun_out/bench_c3_10m.err; echo "c3 10M rc=$?"; cut -c1-2600 gpurun_out/bench_c3_10m.log; tail -5 gpurun_out/bench_c3_10m.err
