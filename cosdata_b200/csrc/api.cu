@@ -560,7 +560,7 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
 
     // ---- tcgen05 prefilter + exact re-rank: identical results, far fewer exact dot products
-    const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 128 &&
+    const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 64 &&
                            ix->size - ix->n_zero_rows >= p->k && tensor_scan_smem_bytes(p->k) <= 227 * 1024 &&
                            (nq + 127) / 128 <= (uint32_t)ix->sm_count;
     bool done = false;
@@ -568,7 +568,7 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
         const uint32_t mt = (nq + 127) / 128;
         // candidate slots per query (power of two; ~32 MB in total): long lists only arise for few queries
         const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 8192u : PREFILTER_CAP));
-        if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)nq * 4)) ||
+        if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)mt * 128 * 64 * 4)) ||
             (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) || (rc = ix->progress.ensure(4096)))
             return rc;
         uint32_t *flags = ix->flags.as<uint32_t>();  // [0] overflowed queries, [2] zero-norm queries

@@ -102,7 +102,7 @@ cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const 
                                 void *d_out, uint32_t out_pitch_halfs, uint32_t *d_zero_count, cudaStream_t s);
 size_t tensor_scan_smem_bytes(uint32_t k);
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
-                              uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_gthr, uint32_t *d_cand,
+                              uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_ggm, uint32_t *d_cand,
                               uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, int sm_count, cudaStream_t s);
 cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s);
 

@@ -45,7 +45,8 @@ struct TensorScanArgs {
     float two_eps;
     uint32_t id_base;
     uint32_t emit;       // 0: seeding pass (only tightens gthr), 1: emit candidates
-    int *gthr;           // [n_queries] shared lower bound of A_k (ordered int), init f2ord(-inf)
+    int *ggm;            // [mtiles][64][128] shared class maxima (ordered int, class-major so a warp's 32 queries are
+                         // contiguous), init f2ord(-inf)
     uint32_t *cand;      // [n_queries][cand_cap] global ids
     uint32_t *cand_cnt;  // [n_queries]
     uint32_t cand_cap;
@@ -53,59 +54,37 @@ struct TensorScanArgs {
     uint32_t window;     // a CTA may run at most `window` tiles ahead of the slowest CTA of its group
 };
 
-constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory)
+constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory), slot 0 = count
+constexpr int TS_GROUPS = 64;       // group maxima per query; the filter supports k <= TS_GROUPS
 
-// per-thread (= per-query) epilogue state
-struct EpiState {
-    float *heap;          // [k] min-heap of the k best approximate scores seen by this CTA
-    uint32_t *stage;      // [TS_LSTAGE] staged candidate ids
-    uint32_t hcnt, scnt;
-    float local_min;      // A_k of this CTA's share once the heap is full
-    float bound, thr;     // current lower bound of the global A_k, thr = bound - 2 eps
-};
-
-__device__ __forceinline__ void epi_flush(const TensorScanArgs &a, EpiState &st, uint32_t qi) {
-    if (!st.scnt) return;
-    const uint32_t pos = atomicAdd(a.cand_cnt + qi, st.scnt);
-    for (uint32_t i = 0; i < st.scnt; ++i)
-        if (pos + i < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos + i] = st.stage[i];
-    st.scnt = 0;
+// rare path: one approximate score passed the threshold -> stage the row id, flush 32 at a time
+__device__ __noinline__ void epi_emit(const TensorScanArgs &a, uint32_t qi, uint32_t *stage, uint32_t id) {
+    uint32_t c = stage[0];
+    stage[1 + c] = id;
+    if (++c == TS_LSTAGE) {
+        const uint32_t pos = atomicAdd(a.cand_cnt + qi, c);
+        for (uint32_t i = 0; i < c; ++i)
+            if (pos + i < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos + i] = stage[1 + i];
+        c = 0;
+    }
+    stage[0] = c;
 }
 
-// slow path: a score passed the threshold test (rare after warm-up)
-__device__ __noinline__ void epi_accept(const TensorScanArgs &a, EpiState &st, uint32_t qi, float v, uint64_t row) {
-    if (row >= a.n_rows) return;  // TMA zero-fill rows past the end
-    if (a.emit) {
-        st.stage[st.scnt++] = a.id_base + (uint32_t)row;
-        if (st.scnt == TS_LSTAGE) epi_flush(a, st, qi);
-    }
-    if (st.hcnt < a.k || v > st.local_min) {
-        float *h = st.heap;
-        if (st.hcnt < a.k) {
-            uint32_t i = st.hcnt++;
-            h[i] = v;
-            while (i > 0) {
-                uint32_t p = (i - 1) >> 1;
-                if (h[p] <= h[i]) break;
-                float t = h[p]; h[p] = h[i]; h[i] = t;
-                i = p;
+// bitonic sort of 64 register values, descending (fully unrolled: all indices are compile-time)
+__device__ __forceinline__ void sort64_desc(float (&v)[TS_GROUPS]) {
+#pragma unroll
+    for (int size = 2; size <= TS_GROUPS; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int t = 0; t < TS_GROUPS / 2; ++t) {
+                const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const float x = v[lo], y = v[hi];
+                const float mx = fmaxf(x, y), mn = fminf(x, y);
+                v[lo] = desc ? mx : mn;
+                v[hi] = desc ? mn : mx;
             }
-        } else {
-            h[0] = v;
-            uint32_t i = 0;
-            for (;;) {
-                uint32_t l = 2 * i + 1, r = l + 1, m = i;
-                if (l < a.k && h[l] < h[m]) m = l;
-                if (r < a.k && h[r] < h[m]) m = r;
-                if (m == i) break;
-                float t = h[m]; h[m] = h[i]; h[i] = t;
-                i = m;
-            }
-        }
-        if (st.hcnt == a.k) {
-            st.local_min = h[0];
-            atomicMax(a.gthr + qi, f2ord(st.local_min));  // result unused -> RED, does not stall
-            if (st.local_min > st.bound) { st.bound = st.local_min; st.thr = st.bound - a.two_eps; }
         }
     }
 }
@@ -117,9 +96,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *tiles = smem;
-    uint32_t *lstage = reinterpret_cast<uint32_t *>(tiles + STAGES * TS_STAGE_BYTES);       // [128][TS_LSTAGE]
-    float *heaps = reinterpret_cast<float *>(lstage + TS_BLOCK_M * TS_LSTAGE);               // [128][k]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(heaps + (size_t)TS_BLOCK_M * a.k);          // 128*k floats: 8B aligned
+    uint32_t *lstage = reinterpret_cast<uint32_t *>(tiles + STAGES * TS_STAGE_BYTES);       // [128][TS_LSTAGE+1]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(lstage + TS_BLOCK_M * (TS_LSTAGE + 2));     // 8-byte aligned
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
@@ -201,26 +179,33 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t ql = lane_base + lane;                  // query within the tile == TMEM lane
         const uint32_t qi = mt * TS_BLOCK_M + ql;
         const bool qvalid = qi < a.n_queries;
-        EpiState st;
-        st.heap = heaps + (size_t)ql * a.k;
-        st.stage = lstage + (size_t)ql * TS_LSTAGE;
-        st.hcnt = 0;
-        st.scnt = 0;
-        st.local_min = -INFINITY;
-        st.bound = -INFINITY;
-        st.thr = -INFINITY;
-        uint32_t as = 0, aphase = 0;
-        for (uint32_t nt = g; nt < a.ntiles; nt += G) {
-            // pick up what the other CTAs have learnt (the load overlaps the wait for the accumulator)
-            int gnow = (int)0x807FFFFF;
-            if (qvalid) gnow = *reinterpret_cast<volatile int *>(a.gthr + qi);
+        // Bound maintenance without a heap and without divergence: the thread keeps the maximum of each of 64
+        // column classes (class = column mod 64).  The classes are disjoint row sets, so "the k-th largest class
+        // maximum" is a valid lower bound of A_k; the maxima are shared between CTAs through atomicMax on
+        // ggm[query][64] (class sets of different CTAs are disjoint too), which makes the bound GLOBAL: about as
+        // tight as the exact running k-th best, at one FMNMX per value.
+        uint32_t *stage = lstage + (size_t)ql * (TS_LSTAGE + 1);
+        stage[0] = 0;
+        float gm[TS_GROUPS];
+#pragma unroll
+        for (int i = 0; i < TS_GROUPS; ++i) gm[i] = -INFINITY;
+        float bound = -INFINITY, thr = -INFINITY;
+        int *ggm_q = a.ggm + (size_t)mt * TS_GROUPS * TS_BLOCK_M + ql;  // + class * 128
+        if (qvalid) {  // what earlier launches (the seeding pass) and other CTAs already know
+            float g2[TS_GROUPS];
+#pragma unroll
+            for (int i = 0; i < TS_GROUPS; ++i) g2[i] = ord2f(*reinterpret_cast<volatile int *>(ggm_q + (size_t)i * TS_BLOCK_M));
+            sort64_desc(g2);
+#pragma unroll
+            for (int i = 0; i < TS_GROUPS; ++i) if ((uint32_t)i == a.k - 1) bound = g2[i];
+            thr = bound - a.two_eps;
+        }
+        uint32_t as = 0, aphase = 0, t = 0;
+        for (uint32_t nt = g; nt < a.ntiles; nt += G, ++t) {
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tcgen05_fence_after();
-            {
-                const float gb = ord2f(gnow);
-                if (gb > st.bound) { st.bound = gb; st.thr = st.bound - a.two_eps; }
-            }
             const uint64_t row0 = (uint64_t)nt * TS_BLOCK_N;
+            const bool full_tile = row0 + TS_BLOCK_N <= a.n_rows;  // only the corpus' last tile can be partial (TMA zero fill)
 #pragma unroll 1
             for (int c = 0; c < TS_BLOCK_N / 64; ++c) {
                 uint32_t r0[32], r1[32];
@@ -228,28 +213,68 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tmem_ld_32x32(taddr, r0);
                 tmem_ld_32x32(taddr + 32, r1);
                 tmem_ld_wait();
-                // fast path: one predicate per value, no memory traffic
                 uint32_t m0 = 0, m1 = 0;
-                const float thr = st.thr;
+                if (full_tile) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    m0 |= (__uint_as_float(r0[j]) >= thr ? 1u : 0u) << j;
-                    m1 |= (__uint_as_float(r1[j]) >= thr ? 1u : 0u) << j;
+                    for (int j = 0; j < 32; ++j) {
+                        const float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r1[j]);
+                        m0 |= (v0 >= thr ? 1u : 0u) << j;
+                        m1 |= (v1 >= thr ? 1u : 0u) << j;
+                        gm[j] = fmaxf(gm[j], v0);
+                        gm[32 + j] = fmaxf(gm[32 + j], v1);
+                    }
+                } else {
+                    const uint64_t left = a.n_rows > row0 + c * 64 ? a.n_rows - (row0 + c * 64) : 0;  // valid columns in this chunk
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r1[j]);
+                        const bool ok0 = (uint64_t)j < left, ok1 = (uint64_t)(32 + j) < left;
+                        m0 |= ((ok0 && v0 >= thr) ? 1u : 0u) << j;
+                        m1 |= ((ok1 && v1 >= thr) ? 1u : 0u) << j;
+                        if (ok0) gm[j] = fmaxf(gm[j], v0);
+                        if (ok1) gm[32 + j] = fmaxf(gm[32 + j], v1);
+                    }
                 }
-                if (qvalid && (m0 | m1)) {
+                if (qvalid && a.emit && (m0 | m1)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if ((m0 >> j) & 1u) { const float v = __uint_as_float(r0[j]); if (v >= st.thr) epi_accept(a, st, qi, v, row0 + c * 64 + j); }
+                        if ((m0 >> j) & 1u) epi_emit(a, qi, stage, a.id_base + (uint32_t)(row0 + c * 64 + j));
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if ((m1 >> j) & 1u) { const float v = __uint_as_float(r1[j]); if (v >= st.thr) epi_accept(a, st, qi, v, row0 + c * 64 + 32 + j); }
+                        if ((m1 >> j) & 1u) epi_emit(a, qi, stage, a.id_base + (uint32_t)(row0 + c * 64 + 32 + j));
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[as]));
+            mbar_arrive(smem_u32(&tempty_bar[as]));  // the accumulator stage is free: the MMA warp can run ahead
             if (++as == 2) { as = 0; aphase ^= 1; }
+            // refresh the shared bound: every tile early on (and in the seeding pass), then every 8th tile
+            if (qvalid && (t < 8 || (t & 7) == 7 || !a.emit)) {
+                float g2[TS_GROUPS];
+#pragma unroll
+                for (int i = 0; i < TS_GROUPS; ++i) {
+                    int *p = ggm_q + (size_t)i * TS_BLOCK_M;
+                    const int mine = f2ord(gm[i]);
+                    const int seen = *reinterpret_cast<volatile int *>(p);
+                    if (mine > seen) atomicMax(p, mine);
+                    g2[i] = ord2f(mine > seen ? mine : seen);
+                }
+                sort64_desc(g2);
+                float nb = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < TS_GROUPS; ++i) if ((uint32_t)i == a.k - 1) nb = g2[i];
+                if (nb > bound) { bound = nb; thr = bound - a.two_eps; }
+            }
         }
-        if (qvalid && a.emit) epi_flush(a, st, qi);
+        if (qvalid) {  // final publish + flush of the staged candidates
+#pragma unroll
+            for (int i = 0; i < TS_GROUPS; ++i) atomicMax(ggm_q + (size_t)i * TS_BLOCK_M, f2ord(gm[i]));
+            const uint32_t c = stage[0];
+            if (a.emit && c) {
+                const uint32_t pos = atomicAdd(a.cand_cnt + qi, c);
+                for (uint32_t i = 0; i < c; ++i)
+                    if (pos + i < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos + i] = stage[1 + i];
+            }
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -325,18 +350,12 @@ static cdb_status make_map_f16(CUtensorMap *map, const void *base, uint64_t rows
 }
 
 static int tensor_scan_stages(uint32_t k) {
-    auto bytes = [&](int stages) {
-        return 1024 + (size_t)stages * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * TS_LSTAGE * 4 + (size_t)TS_BLOCK_M * k * 4 +
-               (2 * stages + 4) * 8 + 16;
-    };
-    if (bytes(4) <= 227 * 1024) return 4;
-    if (bytes(3) <= 227 * 1024) return 3;
-    return 0;
+    if (k > (uint32_t)TS_GROUPS) return 0;  // the class-maximum bound needs k <= 64 disjoint classes
+    return TS_STAGES;
 }
 size_t tensor_scan_smem_bytes(uint32_t k) {
-    int st = tensor_scan_stages(k);
-    if (!st) return (size_t)1 << 30;
-    return 1024 + (size_t)st * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * TS_LSTAGE * 4 + (size_t)TS_BLOCK_M * k * 4 + (2 * st + 4) * 8 + 16;
+    if (!tensor_scan_stages(k)) return (size_t)1 << 30;
+    return 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * TS_STAGES + 4) * 8 + 16;
 }
 
 template <int STAGES>
@@ -352,7 +371,7 @@ static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &m
 // d_xh: fp16 normalised corpus [n_rows][pitch_halfs]; d_qh: fp16 normalised queries, padded with zero
 // rows to a multiple of 128 [mtiles*128][pitch_halfs].
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
-                              uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_gthr, uint32_t *d_cand,
+                              uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_ggm, uint32_t *d_cand,
                               uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, int sm_count, cudaStream_t s) {
     TensorScanArgs a{};
     a.progress = d_progress;
@@ -365,7 +384,7 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     a.ntiles = (uint32_t)((n_rows + TS_BLOCK_N - 1) / TS_BLOCK_N);
     a.two_eps = two_eps;
     a.id_base = id_base;
-    a.gthr = d_gthr;
+    a.ggm = d_ggm;
     a.cand = d_cand;
     a.cand_cnt = d_cand_cnt;
     a.cand_cap = cand_cap;
@@ -376,7 +395,7 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     cdb_status rc;
     if ((rc = make_map_f16(&mq, d_qh, (uint64_t)a.mtiles * TS_BLOCK_M, dim, pitch_halfs, TS_BLOCK_M))) return rc;
     if ((rc = make_map_f16(&mx, d_xh, n_rows, dim, pitch_halfs, TS_BLOCK_N))) return rc;
-    fill_i32_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_gthr, (int)0x807FFFFF /* f2ord(-inf) */, nq);
+    fill_i32_kernel<<<(a.mtiles * TS_BLOCK_M * TS_GROUPS + 255) / 256, 256, 0, s>>>(d_ggm, (int)0x807FFFFF /* f2ord(-inf) */, a.mtiles * TS_BLOCK_M * TS_GROUPS);
     CDB_LAUNCH_CHECK();
     CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
 
@@ -393,7 +412,7 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
         per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 8));
         const uint32_t sgrid = a.mtiles * per_m;
         CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 4096, s));
-        rc = stages == 4 ? launch_tensor_scan<4>(mq, mx, sa, sgrid, smem, s) : launch_tensor_scan<3>(mq, mx, sa, sgrid, smem, s);
+        rc = launch_tensor_scan<TS_STAGES>(mq, mx, sa, sgrid, smem, s);
         if (rc) return rc;
     }
     // 2. main pass.  Every CTA should own several corpus tiles, so tiny corpora are not shredded over all SMs.
@@ -403,7 +422,7 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     grid = std::max<uint32_t>(1, grid / a.mtiles) * a.mtiles;  // whole groups only (148 SMs, 8 query tiles -> 144 CTAs)
     if (grid > (uint32_t)sm_count) { set_error("tensor scan: more query tiles than SMs"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 4096, s));
-    return stages == 4 ? launch_tensor_scan<4>(mq, mx, a, grid, smem, s) : launch_tensor_scan<3>(mq, mx, a, grid, smem, s);
+    return launch_tensor_scan<TS_STAGES>(mq, mx, a, grid, smem, s);
 }
 
 cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s) {

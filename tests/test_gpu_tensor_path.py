@@ -43,7 +43,7 @@ def test_prefilter_equals_exact_on_uniform_data(dim, nq):
     assert cand.max() < 4096 and cand.min() >= 10
 
 
-@pytest.mark.parametrize("k", [1, 10, 64, 128])
+@pytest.mark.parametrize("k", [1, 10, 33, 64])
 def test_prefilter_k_sweep(k):
     corpus = orc.synth_matrix(2200, 30000, 256)
     q = orc.synth_matrix(2201, 33, 256)
