@@ -19,6 +19,8 @@
 //   warp 1      MMA issuer     tcgen05.mma cta_group::1 M128 x N256 x K16, commit -> mbarrier
 //   warps 2..5  epilogue       tcgen05.ld 32x32b.x32 from a double-buffered TMEM accumulator
 // Tile: 128 queries (A, K-major) x 256 corpus rows (B, K-major), K block = 64 halfs (128 B).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -52,10 +54,11 @@ struct TensorScanArgs {
     uint32_t cand_cap;
     uint32_t *progress;  // [groups] tiles completed by the CTAs of a group (bounded-drift window), zeroed per launch
     uint32_t window;     // a CTA may run at most `window` tiles ahead of the slowest CTA of its group
+    uint32_t refresh_mask;  // the shared bound is refreshed when (tile & mask) == mask (and for the first tiles)
 };
 
 constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory), slot 0 = count
-constexpr int TS_GROUPS = 64;       // group maxima per query; the filter supports k <= TS_GROUPS
+constexpr int TS_GROUPS = 64;       // at most 64 class maxima per query; the filter supports k <= TS_GROUPS
 
 // rare path: one approximate score passed the threshold -> stage the row id, flush 32 at a time
 __device__ __noinline__ void epi_emit(const TensorScanArgs &a, uint32_t qi, uint32_t *stage, uint32_t id) {
@@ -70,14 +73,15 @@ __device__ __noinline__ void epi_emit(const TensorScanArgs &a, uint32_t qi, uint
     stage[0] = c;
 }
 
-// bitonic sort of 64 register values, descending (fully unrolled: all indices are compile-time)
-__device__ __forceinline__ void sort64_desc(float (&v)[TS_GROUPS]) {
+// bitonic sort of NG register values, descending (fully unrolled: all indices are compile-time)
+template <int NG>
+__device__ __forceinline__ void sort_desc(float (&v)[NG]) {
 #pragma unroll
-    for (int size = 2; size <= TS_GROUPS; size <<= 1) {
+    for (int size = 2; size <= NG; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
 #pragma unroll
-            for (int t = 0; t < TS_GROUPS / 2; ++t) {
+            for (int t = 0; t < NG / 2; ++t) {
                 const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
                 const bool desc = (lo & size) == 0;
                 const float x = v[lo], y = v[hi];
@@ -89,7 +93,7 @@ __device__ __forceinline__ void sort64_desc(float (&v)[TS_GROUPS]) {
     }
 }
 
-template <int STAGES>
+template <int STAGES, int NG>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TensorScanArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -179,25 +183,25 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t ql = lane_base + lane;                  // query within the tile == TMEM lane
         const uint32_t qi = mt * TS_BLOCK_M + ql;
         const bool qvalid = qi < a.n_queries;
-        // Bound maintenance without a heap and without divergence: the thread keeps the maximum of each of 64
-        // column classes (class = column mod 64).  The classes are disjoint row sets, so "the k-th largest class
+        // Bound maintenance without a heap and without divergence: the thread keeps the maximum of each of NG
+        // row classes (class = row mod NG; NG = 16/32/64 chosen from k).  The classes are disjoint row sets, so "the k-th largest class
         // maximum" is a valid lower bound of A_k; the maxima are shared between CTAs through atomicMax on
         // ggm[query][64] (class sets of different CTAs are disjoint too), which makes the bound GLOBAL: about as
         // tight as the exact running k-th best, at one FMNMX per value.
         uint32_t *stage = lstage + (size_t)ql * (TS_LSTAGE + 1);
         stage[0] = 0;
-        float gm[TS_GROUPS];
+        float gm[NG];
 #pragma unroll
-        for (int i = 0; i < TS_GROUPS; ++i) gm[i] = -INFINITY;
+        for (int i = 0; i < NG; ++i) gm[i] = -INFINITY;
         float bound = -INFINITY, thr = -INFINITY;
-        int *ggm_q = a.ggm + (size_t)mt * TS_GROUPS * TS_BLOCK_M + ql;  // + class * 128
+        int *ggm_q = a.ggm + (size_t)mt * NG * TS_BLOCK_M + ql;  // + class * 128
         if (qvalid) {  // what earlier launches (the seeding pass) and other CTAs already know
-            float g2[TS_GROUPS];
+            float g2[NG];
 #pragma unroll
-            for (int i = 0; i < TS_GROUPS; ++i) g2[i] = ord2f(*reinterpret_cast<volatile int *>(ggm_q + (size_t)i * TS_BLOCK_M));
-            sort64_desc(g2);
+            for (int i = 0; i < NG; ++i) g2[i] = ord2f(*reinterpret_cast<volatile int *>(ggm_q + (size_t)i * TS_BLOCK_M));
+            sort_desc<NG>(g2);
 #pragma unroll
-            for (int i = 0; i < TS_GROUPS; ++i) if ((uint32_t)i == a.k - 1) bound = g2[i];
+            for (int i = 0; i < NG; ++i) if ((uint32_t)i == a.k - 1) bound = g2[i];
             thr = bound - a.two_eps;
         }
         uint32_t as = 0, aphase = 0, t = 0;
@@ -215,13 +219,25 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 tmem_ld_wait();
                 uint32_t m0 = 0, m1 = 0;
                 if (full_tile) {
+                    // common case: fold the 64 values into the class maxima (max trees, FMNMX/FMNMX3) and test only the
+                    // chunk maximum against the threshold; the per-value masks are built on the rare hit
+                    float cm[NG];
+#pragma unroll
+                    for (int i = 0; i < NG; ++i) cm[i] = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r1[j]);
-                        m0 |= (v0 >= thr ? 1u : 0u) << j;
-                        m1 |= (v1 >= thr ? 1u : 0u) << j;
-                        gm[j] = fmaxf(gm[j], v0);
-                        gm[32 + j] = fmaxf(gm[32 + j], v1);
+                        cm[j & (NG - 1)] = fmaxf(cm[j & (NG - 1)], __uint_as_float(r0[j]));
+                        cm[(32 + j) & (NG - 1)] = fmaxf(cm[(32 + j) & (NG - 1)], __uint_as_float(r1[j]));
+                    }
+                    float cmax = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < NG; ++i) { cmax = fmaxf(cmax, cm[i]); gm[i] = fmaxf(gm[i], cm[i]); }
+                    if (cmax >= thr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            m0 |= (__uint_as_float(r0[j]) >= thr ? 1u : 0u) << j;
+                            m1 |= (__uint_as_float(r1[j]) >= thr ? 1u : 0u) << j;
+                        }
                     }
                 } else {
                     const uint64_t left = a.n_rows > row0 + c * 64 ? a.n_rows - (row0 + c * 64) : 0;  // valid columns in this chunk
@@ -231,8 +247,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         const bool ok0 = (uint64_t)j < left, ok1 = (uint64_t)(32 + j) < left;
                         m0 |= ((ok0 && v0 >= thr) ? 1u : 0u) << j;
                         m1 |= ((ok1 && v1 >= thr) ? 1u : 0u) << j;
-                        if (ok0) gm[j] = fmaxf(gm[j], v0);
-                        if (ok1) gm[32 + j] = fmaxf(gm[32 + j], v1);
+                        if (ok0) gm[j & (NG - 1)] = fmaxf(gm[j & (NG - 1)], v0);
+                        if (ok1) gm[(32 + j) & (NG - 1)] = fmaxf(gm[(32 + j) & (NG - 1)], v1);
                     }
                 }
                 if (qvalid && a.emit && (m0 | m1)) {
@@ -248,26 +264,26 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_arrive(smem_u32(&tempty_bar[as]));  // the accumulator stage is free: the MMA warp can run ahead
             if (++as == 2) { as = 0; aphase ^= 1; }
             // refresh the shared bound: every tile early on (and in the seeding pass), then every 8th tile
-            if (qvalid && (t < 8 || (t & 7) == 7 || !a.emit)) {
-                float g2[TS_GROUPS];
+            if (qvalid && (t < 8 || (t & a.refresh_mask) == a.refresh_mask || !a.emit)) {
+                float g2[NG];
 #pragma unroll
-                for (int i = 0; i < TS_GROUPS; ++i) {
+                for (int i = 0; i < NG; ++i) {
                     int *p = ggm_q + (size_t)i * TS_BLOCK_M;
                     const int mine = f2ord(gm[i]);
                     const int seen = *reinterpret_cast<volatile int *>(p);
                     if (mine > seen) atomicMax(p, mine);
                     g2[i] = ord2f(mine > seen ? mine : seen);
                 }
-                sort64_desc(g2);
+                sort_desc<NG>(g2);
                 float nb = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < TS_GROUPS; ++i) if ((uint32_t)i == a.k - 1) nb = g2[i];
+                for (int i = 0; i < NG; ++i) if ((uint32_t)i == a.k - 1) nb = g2[i];
                 if (nb > bound) { bound = nb; thr = bound - a.two_eps; }
             }
         }
         if (qvalid) {  // final publish + flush of the staged candidates
 #pragma unroll
-            for (int i = 0; i < TS_GROUPS; ++i) atomicMax(ggm_q + (size_t)i * TS_BLOCK_M, f2ord(gm[i]));
+            for (int i = 0; i < NG; ++i) atomicMax(ggm_q + (size_t)i * TS_BLOCK_M, f2ord(gm[i]));
             const uint32_t c = stage[0];
             if (a.emit && c) {
                 const uint32_t pos = atomicAdd(a.cand_cnt + qi, c);
@@ -358,14 +374,24 @@ size_t tensor_scan_smem_bytes(uint32_t k) {
     return 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * TS_STAGES + 4) * 8 + 16;
 }
 
-template <int STAGES>
-static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
-                                     size_t smem, cudaStream_t s) {
-    auto kern = tensor_scan_kernel<STAGES>;
+template <int STAGES, int NG>
+static cdb_status launch_tensor_scan_g(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
+                                       size_t smem, cudaStream_t s) {
+    auto kern = tensor_scan_kernel<STAGES, NG>;
     CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
+}
+
+// fewer classes = cheaper bound refresh (the sort network grows as NG log^2 NG); the bound stays within ~1.5x of the
+// exact k-th best as long as k is well below NG
+template <int STAGES>
+static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
+                                     size_t smem, cudaStream_t s) {
+    if (a.k <= 12) return launch_tensor_scan_g<STAGES, 16>(mq, mx, a, grid, smem, s);
+    if (a.k <= 28) return launch_tensor_scan_g<STAGES, 32>(mq, mx, a, grid, smem, s);
+    return launch_tensor_scan_g<STAGES, 64>(mq, mx, a, grid, smem, s);
 }
 
 // d_xh: fp16 normalised corpus [n_rows][pitch_halfs]; d_qh: fp16 normalised queries, padded with zero
@@ -376,6 +402,9 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     TensorScanArgs a{};
     a.progress = d_progress;
     a.window = 3;
+    a.refresh_mask = 15;
+    if (const char *e = getenv("CDB_TS_WINDOW")) a.window = (uint32_t)atoi(e);      // tuning knobs (bench experiments)
+    if (const char *e = getenv("CDB_TS_REFRESH")) a.refresh_mask = (uint32_t)atoi(e);
     a.n_rows = n_rows;
     a.n_queries = nq;
     a.k = k;
