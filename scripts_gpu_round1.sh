@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_tensor_path.py tests/test_gpu_fullsize.py -m gpu -x -q > gpurun_out/pytest_t.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_t.log | cut -c1-300
-run() { timeout 300 python bench.py --rows $2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/b.log 2>gpurun_out/b.err; echo "$1: $(grep -o '"kernel_ms": [0-9.]*' gpurun_out/b.log) $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/b.log | head -1) $(grep -o '"candidates_per_query": {[^}]*}' gpurun_out/b.log)"; }
-CDB_TS_REFRESH=7 run "refresh7" 10000000; run "default" 10000000
-CDB_TS_REFRESH=15 run "refresh15" 10000000
-CDB_TS_REFRESH=31 run "refresh31" 10000000
-CDB_TS_REFRESH=15 run "refresh15 1.25M" 1250000
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest.log | cut -c1-300
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-2400 gpurun_out/bench.log; tail -3 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cut -c1-400 gpurun_out/bench_ref.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tensor_scan_kernel -s 3 -c 1 -o gpurun_out/prof_tensor python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_tensor.log 2>&1; echo "ncu tensor rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "launch list rc=$?"

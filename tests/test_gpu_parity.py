@@ -263,3 +263,26 @@ def test_merge_topk_device_over_three_shards_equals_single_index():
     want_ids, want_scores = orc.brute_topk_f32(corpus, q, k)
     assert np.array_equal(m_ids.cpu().numpy().view(np.uint32), want_ids)
     assert np.array_equal(bits(m_scores.cpu().numpy()), bits(want_scores))
+
+
+# ------------------------------------------------------------------ empty / degenerate inputs
+
+def test_empty_index_empty_batch_and_k_larger_than_n():
+    ix = cdb.DenseIndex(dim=24, capacity=8)
+    q = orc.synth_matrix(5000, 3, 24)
+    ids, scores, counts, err = ix.batch_search(q, 5)                    # empty index: nothing to return
+    assert np.all(ids == cdb.INVALID_ID) and np.all(counts == 0) and np.all(scores == 0)
+    ids, scores, counts, err = ix.batch_search(np.zeros((0, 24), np.float32), 5)   # empty batch
+    assert ids.shape == (0, 5)
+    ix.append(orc.synth_matrix(5001, 2, 24))
+    ids, scores, counts, err = ix.batch_search(q, 5)                    # k > n
+    want_ids, want_scores = orc.brute_topk_f32(orc.synth_matrix(5001, 2, 24), q, 5)
+    assert np.array_equal(ids, want_ids) and np.array_equal(bits(scores), bits(want_scores)) and np.all(counts == 2)
+    with pytest.raises(cdb.CosdataError):
+        ix.append(orc.synth_matrix(5002, 7, 24))                        # exceeds capacity: refused, nothing written
+    assert len(ix) == 2
+    with pytest.raises(cdb.CosdataError):
+        ix.batch_search(q, 0)                                           # k must be >= 1
+    out, st = ix.score_ids(q[0], np.array([0, 1, 7], dtype=np.uint32))  # out-of-range id is reported per id
+    assert st.tolist() == [0, 0, int(cdb.Status.INVALID_PARAMS)]
+    ix.close()
