@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_250_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "hnsw"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "hnsw"],
                     help="c2 (default, the headline): brute cosine 10Mx768 f32; c4: quaternary inner product 50Mx1024, batch 4096; "
                          "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools_build_hnsw_graph.py)")
     ap.add_argument("--ef", type=int, default=128)
@@ -598,11 +598,149 @@ def run_c3(args):
     ix.close()
 
 
+def run_c5(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: sharded HNSW, 100M x 768 fp32, batch 4096, 8 x B200 with an NCCL top-k merge.
+    One independent HNSW per shard (12.5M rows per GPU by default), built on the GPU; every rank searches the same
+    queries on its shard; one all-gather of the per-shard top-k; merge with the common ordering rule."""
+    import torch
+    import torch.distributed as dist
+    import cosdata_b200 as cdb
+    from cosdata_b200.sharding import cuda_merge_fn, gather_and_merge
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rows_local = (args.rows // world) if args.rows != 10_000_000 else 12_500_000
+    rows_total = rows_local * world
+    D, k = args.dim, args.k
+    B = args.batch if args.batch != 1024 else 4096
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    gc = torch.Generator(device=dev)
+    gc.manual_seed(1234)                                  # same centres and queries on every rank
+    ncent = 4096
+    centres = torch.randn((ncent, D), generator=gc, device=dev)
+    scale = 1.0 / (4.5 * 1.06)
+    idx = torch.randint(0, ncent, (B,), generator=gc, device=dev)
+    d_q = ((centres[idx] + 0.35 * torch.randn((B, D), generator=gc, device=dev)) * scale).clamp_(-0.999, 0.999).contiguous()
+    g = torch.Generator(device=dev)
+    g.manual_seed(777 + rank)                             # different rows per shard
+    ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.FullPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
+                        capacity=rows_local + 1, device=local_rank, id_base=rank * (rows_local + 1), tensor_prefilter=False)
+    chunk = 500_000
+    for off in range(0, rows_local, chunk):
+        m = min(chunk, rows_local - off)
+        ii = torch.randint(0, ncent, (m,), generator=g, device=dev)
+        x = ((centres[ii] + 0.35 * torch.randn((m, D), generator=g, device=dev)) * scale).clamp_(-0.999, 0.999).contiguous()
+        torch.cuda.synchronize()
+        ix.append_device(x.data_ptr(), m)
+        del x, ii
+    t0 = time.perf_counter()
+    ix.build_graph(9, 32, 64, 128, 64, 4096, 7 + rank)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    g_ids = torch.empty((world, B, k), dtype=torch.int32, device=dev)
+    g_scores = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+    merge = cuda_merge_fn(ix._lib, local_rank, 0, stream.cuda_stream)
+
+    def all_gather(x):
+        out = g_ids if x.dtype == torch.int32 else g_scores
+        dist.all_gather_into_tensor(out.view(-1), x.view(-1))
+        return out
+
+    def step(mode=cdb.SearchMode.HNSW):
+        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                               stream.cuda_stream, mode=mode, ef_search=args.ef, shortlist_size=64)
+        return gather_and_merge(d_ids, d_scores, world, all_gather, merge)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ev0, pp0 = ix.hnsw_counters()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev1, pp1 = ix.hnsw_counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = cdb.kernel_launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        m_ids, m_scores = step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = cdb.kernel_launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    ann = m_ids.cpu().numpy().view(np.uint32).copy()
+    scan_ms = ix.scan_ms_history(args.steps * ((B + 2047) // 2048))   # before the exact scan below enters the history
+    # exact global top-k for recall: exact scan of every shard (root rows excluded), same merge
+    d_ids2 = torch.empty((B, k + 1), dtype=torch.int32, device=dev)
+    d_sc2 = torch.empty((B, k + 1), dtype=torch.float32, device=dev)
+    d_cn2 = torch.empty((B,), dtype=torch.int32, device=dev)
+    ix.batch_search_device(d_q.data_ptr(), B, k + 1, d_ids2.data_ptr(), d_sc2.data_ptr(), d_cn2.data_ptr(), None,
+                           stream.cuda_stream, mode=cdb.SearchMode.BRUTE_RAW)
+    g2i = torch.empty((world, B, k + 1), dtype=torch.int32, device=dev)
+    g2s = torch.empty((world, B, k + 1), dtype=torch.float32, device=dev)
+    if world > 1:
+        dist.all_gather_into_tensor(g2i.view(-1), d_ids2.view(-1))
+        dist.all_gather_into_tensor(g2s.view(-1), d_sc2.view(-1))
+    else:
+        g2i[0], g2s[0] = d_ids2, d_sc2
+    torch.cuda.synchronize()
+    gi, gs = g2i.cpu().numpy().view(np.uint32), g2s.cpu().numpy()
+    roots = {r * (rows_local + 1) + rows_local for r in range(world)}
+    recall = 0.0
+    for q in range(B):
+        cand = [(float(gs[w, q, j]), int(gi[w, q, j])) for w in range(world) for j in range(k + 1) if int(gi[w, q, j]) not in roots]
+        cand.sort(key=lambda t: (-t[0], t[1]))
+        gt = {i for _, i in cand[:k]}
+        recall += len(gt & set(ann[q].tolist())) / k
+    recall /= B
+    evals, pops = (ev1 - ev0) / max(args.warmup, 3), (pp1 - pp0) / max(args.warmup, 3)
+    kernel_ms = float(np.sum(scan_ms)) / args.steps
+    alg_bytes = evals * (D * 4 + 4) + pops * 64 * 4
+    hbm = float(_peaks().get("hbm_gbs", 6650.0))
+    ach = alg_bytes / (kernel_ms / 1000.0) / 1e9
+    tb = torch.tensor([t_build], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {
+            "metric": "queries/sec + recall@10, sharded HNSW f32", "value": args.steps * B / (ms / 1000.0), "unit": "queries/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (4096 Gaussian clusters)",
+            "config": {"workload": f"sharded HNSW, {rows_total}x{D} fp32 in {world} shards of {rows_local}, ef_search={args.ef}, batch={B}, "
+                                   "NCCL all-gather + top-k merge (BASELINE.json configs[4])", "rows": rows_total, "dim": D, "batch": B, "k": k},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                         "kernel": "hnsw_search_kernel (rank 0)", "kernel_ms": kernel_ms, "alg_bytes_per_launch": alg_bytes,
+                         "evals_per_query": evals / B, "pops_per_query": pops / B},
+            "recall_at_10": recall, "build_seconds_max_over_ranks": float(tb.item()),
+        }
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c5":
+        run_c5(args, rank, world, local_rank)
+        return
     if args.workload != "c2":
         if world != 1:
             raise SystemExit("bench.py: --workload c4/hnsw are single-GPU reporting modes")

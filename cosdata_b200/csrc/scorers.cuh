@@ -18,20 +18,43 @@
 namespace cdb {
 
 // ------------------------------------------------------------------ f32
-// single-thread version: lane j of the AVX register is acc[j].
+// single-thread version: lane j of the AVX register is acc[j].  Rows are 16-byte pitched: when both operands are
+// 16B-aligned the row is fetched 32 floats at a time (8 independent 128-bit loads in flight) before the FMAs, which
+// keep the reference's order (chunk i feeds lane j with element 8i+j).
 __device__ inline float dot_f32_avx_order_1t(const float *__restrict__ a, const float *__restrict__ b, uint32_t n) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    uint32_t chunks = n / 8;
-    for (uint32_t i = 0; i < chunks; ++i) {
+    const uint32_t chunks = n / 8;
+    uint32_t i = 0;
+    if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+        for (; i + 4 <= chunks; i += 4) {
+            float4 vb[8], va[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) vb[t] = *reinterpret_cast<const float4 *>(b + 8 * i + 4 * t);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) va[t] = *reinterpret_cast<const float4 *>(a + 8 * i + 4 * t);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[0] = __fmaf_rn(va[2 * c].x, vb[2 * c].x, acc[0]);
+                acc[1] = __fmaf_rn(va[2 * c].y, vb[2 * c].y, acc[1]);
+                acc[2] = __fmaf_rn(va[2 * c].z, vb[2 * c].z, acc[2]);
+                acc[3] = __fmaf_rn(va[2 * c].w, vb[2 * c].w, acc[3]);
+                acc[4] = __fmaf_rn(va[2 * c + 1].x, vb[2 * c + 1].x, acc[4]);
+                acc[5] = __fmaf_rn(va[2 * c + 1].y, vb[2 * c + 1].y, acc[5]);
+                acc[6] = __fmaf_rn(va[2 * c + 1].z, vb[2 * c + 1].z, acc[6]);
+                acc[7] = __fmaf_rn(va[2 * c + 1].w, vb[2 * c + 1].w, acc[7]);
+            }
+        }
+    }
+    for (; i < chunks; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = __fmaf_rn(a[8 * i + j], b[8 * i + j], acc[j]);
     }
     float lo = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
     float hi = __fadd_rn(__fadd_rn(acc[4], acc[5]), __fadd_rn(acc[6], acc[7]));
     float r = __fadd_rn(lo, hi);
-    for (uint32_t i = chunks * 8; i < n; ++i) r = __fadd_rn(r, __fmul_rn(a[i], b[i]));
+    for (uint32_t t = chunks * 8; t < n; ++t) r = __fadd_rn(r, __fmul_rn(a[t], b[t]));
     return r;
 }
 
@@ -67,12 +90,29 @@ __device__ inline float mag_f32_seq(const float *__restrict__ v, uint32_t n) {
 }
 
 // ------------------------------------------------------------------ f16
-// rows are 16-byte pitched, so the operands are walked with 128-bit loads; the additions stay strictly in
-// element order (the reference's `.sum()` is a sequential left fold)
+// rows are 16-byte pitched, so the operands are walked with 128-bit loads, 64 elements of the stored row in flight
+// at a time; the additions stay strictly in element order (the reference's `.sum()` is a sequential left fold)
 __device__ inline float dot_f16_seq(const __half *__restrict__ a, const __half *__restrict__ b, uint32_t n) {
     float s = 0.0f;
     uint32_t i = 0;
     if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+        for (; i + 64 <= n; i += 64) {
+            uint4 vb[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) vb[t] = *reinterpret_cast<const uint4 *>(b + i + 8 * t);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const uint4 va = *reinterpret_cast<const uint4 *>(a + i + 8 * t);
+                const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
+                const __half2 *hb = reinterpret_cast<const __half2 *>(&vb[t]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+                    s = __fadd_rn(s, __fmul_rn(fa.x, fb.x));
+                    s = __fadd_rn(s, __fmul_rn(fa.y, fb.y));
+                }
+            }
+        }
         for (; i + 8 <= n; i += 8) {
             const uint4 va = *reinterpret_cast<const uint4 *>(a + i);
             const uint4 vb = *reinterpret_cast<const uint4 *>(b + i);
@@ -95,6 +135,23 @@ __device__ inline uint64_t dot_u8_int(const uint8_t *__restrict__ a, const uint8
     uint64_t total = 0;
     uint32_t acc = 0;
     uint32_t i = 0;
+    if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+        for (; i + 64 <= n; i += 64) {  // 16 dp4a per block: flush well before u32 could overflow (16384 dp4a)
+            uint4 vb[4], va[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) vb[t] = *reinterpret_cast<const uint4 *>(b + i + 16 * t);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) va[t] = *reinterpret_cast<const uint4 *>(a + i + 16 * t);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                acc = __dp4a(va[t].x, vb[t].x, acc);
+                acc = __dp4a(va[t].y, vb[t].y, acc);
+                acc = __dp4a(va[t].z, vb[t].z, acc);
+                acc = __dp4a(va[t].w, vb[t].w, acc);
+            }
+            if ((i & 0xFFC0) == 0xFFC0) { total += acc; acc = 0; }
+        }
+    }
     // rows are 16B-pitched so 4-byte reads are aligned
     for (; i + 4 <= n; i += 4) {
         uint32_t x = *reinterpret_cast<const uint32_t *>(a + i), y = *reinterpret_cast<const uint32_t *>(b + i);

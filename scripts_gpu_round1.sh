@@ -1,8 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest.log | cut -c1-300
-timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-2400 gpurun_out/bench.log; tail -3 gpurun_out/bench.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cut -c1-400 gpurun_out/bench_ref.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tensor_scan_kernel -s 3 -c 1 -o gpurun_out/prof_tensor python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_tensor.log 2>&1; echo "ncu tensor rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "launch list rc=$?"
+N=$(nvidia-smi -L | wc -l); echo "gpus=$N"
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711 bench.py --workload c5 --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_c5.log 2> gpurun_out/bench_c5.err; echo "c5 rc=$?"; cut -c1-2200 gpurun_out/bench_c5.log; grep -v "OMP_NUM_THREADS\|^\*\*\*\|^$" gpurun_out/bench_c5.err | tail -5 | cut -c1-300
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29712 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_c2_${N}gpu.log 2> gpurun_out/bench_c2_${N}gpu.err; echo "c2 x$N rc=$?"; grep -o '"value": [0-9.]*' gpurun_out/bench_c2_${N}gpu.log | head -1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_c2_${N}gpu.log | head -1
