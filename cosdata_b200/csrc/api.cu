@@ -75,9 +75,14 @@ static cdb_status copy_codes(void *dst, const void *src, int st, uint32_t dim, u
     return CDB_OK;
 }
 
-__global__ void err32_to_u8_kernel(const uint32_t *e, uint8_t *out, uint32_t n) {
+__global__ void err32_to_u8_kernel(const uint32_t *e, uint8_t *out, uint32_t n, const uint32_t *run_if = nullptr) {
+    if (run_if && (run_if[0] | run_if[2]) == 0) return;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint8_t)e[i];
+}
+// flags = {overflowed queries, zero-norm rows (persistent), zero-norm queries, fallback counter}
+__global__ void count_fallback_kernel(uint32_t *flags) {
+    if (flags[0] | flags[2]) flags[3] += 1;
 }
 
 }  // namespace cdb
@@ -414,7 +419,8 @@ cdb_status cdb_index_read_codes(const cdb_index *ix, uint64_t first, uint64_t n,
 
 // prepared (quantized) queries live in ix->q_codes / ix->q_mags
 static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric, uint32_t pitch, uint32_t nq, uint32_t k,
-                                    uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+                                    uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s,
+                                    const uint32_t *run_if = nullptr) {
     const cdb_index_desc &d = ix->desc;
     cdb_status rc;
     ScanArgs a{};
@@ -435,11 +441,12 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
     if ((rc = ix->partial.ensure((size_t)nq * a.nsplit * k * 8)) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
     a.partial = ix->partial.as<uint64_t>();
     a.err32 = ix->err32.as<uint32_t>();
+    a.run_if = run_if;
     CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));
     if ((rc = scan_topk_device(a, s))) return rc;
-    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s))) return rc;
+    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, run_if))) return rc;
     if (d_err) {
-        err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
+        err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq, run_if);
         CDB_LAUNCH_CHECK();
     }
     return CDB_OK;
@@ -563,7 +570,7 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
     const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 64 &&
                            ix->size - ix->n_zero_rows >= p->k && tensor_scan_smem_bytes(p->k) <= 227 * 1024 &&
                            (nq + 127) / 128 <= (uint32_t)ix->sm_count;
-    bool done = false;
+    const uint32_t *run_if = nullptr;
     if (tensor_ok) {
         const uint32_t mt = (nq + 127) / 128;
         // candidate slots per query (power of two; ~32 MB in total): long lists only arise for few queries
@@ -589,12 +596,11 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
                                     cap, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
             return rc;
         if ((rc = overflow_check_device(ix->cand_cnt.as<uint32_t>(), cap, nq, flags, s))) return rc;
-        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags, flags, 12, cudaMemcpyDeviceToHost, s));
-        CDB_CUDA_TRY(cudaStreamSynchronize(s));  // the fallback decision needs the flags on the host
+        count_fallback_kernel<<<1, 1, 0, s>>>(flags);
+        CDB_LAUNCH_CHECK();
+        if (d_err) CDB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nq, s));
         ix->stat_tensor_searches++;
-        done = ix->h_flags[0] == 0 && ix->h_flags[2] == 0;
-        if (!done) ix->stat_fallbacks++;
-        else if (d_err) CDB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nq, s));
+        run_if = flags;  // the exact scan below only runs (on the device's own decision) if a list overflowed or a query has zero norm
     }
     // ---- exact integer scoring on tcgen05 kind::i8: u8 codes in place, sub-byte codes through the digit copy
     const uint8_t *u8_rows = !raw ? (st == CDB_ST_U8 ? ix->d_codes : ix->d_digits) : nullptr;
@@ -611,6 +617,7 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
             return rc;
         uint32_t *flags = ix->flags.as<uint32_t>();
         CDB_CUDA_TRY(cudaMemsetAsync(flags, 0, 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(flags + 2, 0, 4, s));
         CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
         CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * upitch, s));
         if (st == CDB_ST_U8)
@@ -625,20 +632,22 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = overflow_check_device(ix->cand_cnt.as<uint32_t>(), cap, nq, flags, s))) return rc;
-        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags, flags, 4, cudaMemcpyDeviceToHost, s));
-        CDB_CUDA_TRY(cudaStreamSynchronize(s));
-        ix->stat_tensor_searches++;
-        done = ix->h_flags[0] == 0;
-        if (!done) ix->stat_fallbacks++;
-        else if (d_err) {
+        count_fallback_kernel<<<1, 1, 0, s>>>(flags);
+        CDB_LAUNCH_CHECK();
+        if (d_err) {
             err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(ix->err32.as<uint32_t>(), d_err, nq);
             CDB_LAUNCH_CHECK();
         }
+        ix->stat_tensor_searches++;
+        run_if = flags;
     }
-    if (!done) {
-        if (!tensor_ok) CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-        if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s))) return rc;
-        if (!tensor_ok) CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+    {
+        // exact scan: unconditional when no tensor-core path applies, otherwise a device-side conditional fallback
+        // (its kernels return immediately unless the flags say the prefilter result is unusable) -- no host sync
+        const bool fast = run_if != nullptr;
+        if (!fast) CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+        if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s, run_if))) return rc;
+        if (!fast) CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
     }
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
@@ -906,8 +915,14 @@ cdb_status cdb_index_hnsw_counters(const cdb_index *ix, uint64_t *out2) {
 
 cdb_status cdb_index_stats(const cdb_index *ix, uint64_t *out4) {
     CDB_REQUIRE(ix && out4, "null argument");
+    uint32_t fb = 0;
+    if (ix->flags.p) {
+        CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+        CDB_CUDA_TRY(cudaDeviceSynchronize());
+        CDB_CUDA_TRY(cudaMemcpy(&fb, ix->flags.as<uint32_t>() + 3, 4, cudaMemcpyDeviceToHost));
+    }
     out4[0] = ix->stat_tensor_searches;
-    out4[1] = ix->stat_fallbacks;
+    out4[1] = fb;
     out4[2] = ix->n_zero_rows;
     out4[3] = ix->d_xh ? 1 : 0;
     return CDB_OK;

@@ -49,13 +49,16 @@ struct ScanArgs {
     uint64_t *partial;     // [nq][nsplit][k] selection keys
     uint32_t nsplit;
     uint32_t *err32;       // [nq] error bits (atomicOr) or null
+    const uint32_t *run_if;  // null, or device flags {overflowed queries, -, zero-norm queries}: the kernel is a no-op
+                             // unless one of them is non-zero (device-side fallback decision, no host sync)
 };
 // picks grid/template; returns nsplit chosen through args.nsplit (caller sizes `partial` with scan_max_partials)
 uint32_t scan_plan_nsplit(const ScanArgs &a, int sm_count);
 cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s);
 // partial [nq][nsplit][k] -> ids/scores/counts
 cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
-                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s);
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s,
+                                 const uint32_t *run_if = nullptr);
 // [n_shards][nq][k] ids/scores -> keys [nq][n_shards][k]
 cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
                             uint32_t k, uint64_t *d_keys, cudaStream_t s);

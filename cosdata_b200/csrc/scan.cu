@@ -102,8 +102,11 @@ __device__ inline void topk_finish(const TopK &t, uint32_t qb, uint32_t nqv, uin
 }
 
 // ------------------------------------------------------------------ f32 exact scan
+__device__ __forceinline__ bool scan_skipped(const uint32_t *run_if) { return run_if && (run_if[0] | run_if[2]) == 0; }
+
 template <int QB, int R>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_f32_kernel(ScanArgs a) {
+    if (scan_skipped(a.run_if)) return;  // device-side decision: the prefilter succeeded, nothing to redo
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t qp = a.row_pitch / 4;  // floats per (padded) query row
     float *qs = reinterpret_cast<float *>(smem);
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_f32_kernel(ScanArgs a) {
 // ------------------------------------------------------------------ generic scan
 template <int QB>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_generic_kernel(ScanArgs a) {
+    if (scan_skipped(a.run_if)) return;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *qs = smem;  // [QB][row_pitch]
     float *qmag = reinterpret_cast<float *>(qs + (size_t)QB * a.row_pitch);
@@ -310,7 +314,9 @@ cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s) {
 // ------------------------------------------------------------------ merge
 // one CTA per query: rank-select the best k of nlists*k keys (0 = empty)
 __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ partial, uint32_t nlists, uint32_t k,
-                                      uint32_t *__restrict__ ids, float *__restrict__ scores, uint32_t *__restrict__ counts) {
+                                      uint32_t *__restrict__ ids, float *__restrict__ scores, uint32_t *__restrict__ counts,
+                                      const uint32_t *__restrict__ run_if) {
+    if (scan_skipped(run_if)) return;
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem);
     __shared__ int nvalid;
@@ -340,12 +346,12 @@ __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ p
 }
 
 cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
-                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s) {
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s, const uint32_t *run_if) {
     if (nq == 0) return CDB_OK;
     size_t smem = (size_t)nlists * k * 8;
     if (smem > 200 * 1024) { set_error("merge: too many partial candidates"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_partials_kernel<<<nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts);
+    merge_partials_kernel<<<nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts, run_if);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }
