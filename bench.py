@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "hnsw"],
                     help="c2 (default, the headline): brute cosine 10Mx768 f32; c4: quaternary inner product 50Mx1024, batch 4096; "
-                         "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools_build_hnsw_graph.py)")
+                         "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools/build_hnsw_graph.py)")
     ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--graph", default=os.path.join(ROOT, "bench_data", "hnsw_100k_128_f16.npz"))
     return ap.parse_args()
@@ -421,7 +421,7 @@ def run_c4(args):
 
 def run_hnsw(args):
     """HNSW f16 search (BASELINE.json configs[2] shape at the scale the CPU builder can produce): graph built by
-    tools_build_hnsw_graph.py with the reference defaults, searched with ef_search = --ef"""
+    tools/build_hnsw_graph.py with the reference defaults, searched with ef_search = --ef"""
     import torch
     import cosdata_b200 as cdb
     import oracle as orc

@@ -3,10 +3,14 @@
 nbrs 32/64, ef_construction 128, 9 layers, config.toml:19-25) and stores the flat arrays for the
 HNSW bench / large parity test.  TEST/BENCH INFRASTRUCTURE (uses oracle/).
 
-    python tools_build_hnsw_graph.py --rows 100000 --dim 128 --out bench_data/hnsw_100k_128_f16.npz
+    python tools/build_hnsw_graph.py --rows 100000 --dim 128 --out bench_data/hnsw_100k_128_f16.npz
 """
 import argparse
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
