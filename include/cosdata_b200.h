@@ -107,8 +107,9 @@ typedef struct {
     int32_t mode;            /* CDB_MODE_* */
     uint32_t ef_search;      /* hnsw_params.ef_search   (config.toml:23) */
     uint32_t shortlist_size; /* config.search.shortlist_size (config.toml:32) */
-    int32_t exact_only;      /* 1: never use the tensor-core prefilter (pure FFMA scan) */
-    uint32_t prefilter_k;    /* candidates kept by the prefilter (0 = default) */
+    int32_t exact_only;      /* 1: never take a tensor-core path (pure SIMT scan); results are identical either way */
+    uint32_t prefilter_k;    /* candidate slots per query of the tensor-core paths (power of two, 0 = default);
+                                an overflowing list makes the batch fall back to the exact scan on the device */
     uint32_t reserved0;
     uint32_t reserved1;
 } cdb_search_params;
@@ -202,7 +203,10 @@ cdb_status cdb_index_hnsw_counters(const cdb_index *index, uint64_t *out2);
  * queries: B x dim raw f32 (search_internal quantizes them with the index's
  * storage type, hnsw/mod.rs:399-403).  out_ids/out_scores: B x k, best first;
  * unused slots get CDB_INVALID_ID / 0.  out_counts[q] = valid slots.
- * err_flags may be NULL. */
+ * err_flags may be NULL.  k <= 1024.
+ * Execution paths (same results, chosen by shape): BRUTE_RAW with an fp16 shadow, >= 4 queries, >= 16384 rows and
+ * k <= 64 -> tcgen05 fp16 prefilter + exact re-rank; BRUTE_CODES over u8 / sub-byte codes with cosine or dot product,
+ * >= 16384 rows and k <= 128 -> exact tcgen05 kind::i8 scoring; everything else -> exact SIMT scan. */
 cdb_status cdb_search_batch(cdb_index *index, const float *queries, uint32_t n_queries,
                             const cdb_search_params *params,
                             uint32_t *out_ids, float *out_scores, uint32_t *out_counts,
