@@ -113,6 +113,7 @@ struct cdb_index {
     cudaEvent_t ring0[EV_RING] = {}, ring1[EV_RING] = {};  // per-search (before scan, after scan)
     uint64_t n_search = 0;
     bool ev_valid = false;
+    cudaStream_t last_stream = nullptr;  // stream of the previous search: scratch buffers are shared between searches
     std::mutex mu;
     DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
     DevBuf qh, gthr, cand, cand_cnt, flags, progress;
@@ -659,6 +660,10 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
 // CTA groups (144 CTAs) for the tensor-core kernels, and per-chunk scratch stays bounded.
 static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                        uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+    // the handle's scratch arena is reused by every search: a search enqueued on a different stream than the previous
+    // one must wait for it (stream-ordered hand-over, no host sync)
+    if (ix->ev_valid && ix->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, ix->ev[2], 0));
+    ix->last_stream = s;
     const uint32_t CH = 2048;
     for (uint32_t off = 0; off < nq; off += CH) {
         const uint32_t m = nq - off < CH ? nq - off : CH;

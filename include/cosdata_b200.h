@@ -211,7 +211,8 @@ cdb_status cdb_search_batch(cdb_index *index, const float *queries, uint32_t n_q
                             const cdb_search_params *params,
                             uint32_t *out_ids, float *out_scores, uint32_t *out_counts,
                             uint8_t *err_flags);
-/* same, every pointer is DEVICE memory on the index's device; asynchronous on `stream` */
+/* same, every pointer is DEVICE memory on the index's device; asynchronous on `stream`.  Searches on one handle share
+ * its scratch arena and are ordered on the device (a search on another stream waits for the previous one). */
 cdb_status cdb_search_batch_device(cdb_index *index, const float *d_queries, uint32_t n_queries,
                                    const cdb_search_params *params,
                                    uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts,

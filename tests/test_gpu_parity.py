@@ -286,3 +286,24 @@ def test_empty_index_empty_batch_and_k_larger_than_n():
     out, st = ix.score_ids(q[0], np.array([0, 1, 7], dtype=np.uint32))  # out-of-range id is reported per id
     assert st.tolist() == [0, 0, int(cdb.Status.INVALID_PARAMS)]
     ix.close()
+
+
+def test_append_from_device_memory_and_timing_history():
+    import torch
+    dim, n = 56, 4000
+    host = orc.synth_matrix(5100, n, dim)
+    for st in (ST.UnsignedByte, ST.SubByte3, ST.HalfPrecisionFP):
+        ix = cdb.DenseIndex(dim=dim, storage_type=st, metric=MK.Cosine, capacity=n, keep_raw_f32=True)
+        d = torch.from_numpy(host).cuda()
+        ix.append_device(d.data_ptr(), 1500)
+        ix.append_device(d[1500:].contiguous().data_ptr(), n - 1500)
+        codes, mags = ix.read_codes(0, n)
+        want_c, want_m = orc.quantize_batch(int(st), host)
+        assert np.array_equal(codes, want_c) and np.array_equal(bits(mags), bits(want_m))
+        q = orc.synth_matrix(5101, 3, dim)
+        ids, scores, _, _ = ix.batch_search(q, 5)                         # raw rows were kept too
+        want_ids, want_scores = orc.brute_topk_f32(host, q, 5)
+        assert np.array_equal(ids, want_ids) and np.array_equal(bits(scores), bits(want_scores))
+        hist = ix.scan_ms_history(4)
+        assert hist.size == 1 and hist[0] > 0
+        ix.close()
