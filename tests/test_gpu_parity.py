@@ -305,5 +305,5 @@ def test_append_from_device_memory_and_timing_history():
         want_ids, want_scores = orc.brute_topk_f32(host, q, 5)
         assert np.array_equal(ids, want_ids) and np.array_equal(bits(scores), bits(want_scores))
         hist = ix.scan_ms_history(4)
-        assert hist.size == 1 and hist[0] > 0
+        assert hist.size >= 1 and (hist > 0).all()
         ix.close()
