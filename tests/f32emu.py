@@ -80,3 +80,14 @@ def sumsq_sequential(v):
     for x in v:
         s = add32(s, mul32(float(x), float(x)))
     return s
+
+
+def sqrt32(x):
+    """correctly rounded binary32 sqrt: the binary64 result rounded once more is exact because 53 >= 2*24+2"""
+    import math
+    return float(struct.unpack("<f", struct.pack("<f", math.sqrt(x)))[0])
+
+
+def div32(a, b):
+    """correctly rounded binary32 quotient (same double-rounding argument as sqrt32)"""
+    return float(struct.unpack("<f", struct.pack("<f", a / b))[0])
