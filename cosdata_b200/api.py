@@ -133,6 +133,28 @@ class ScalarQuantization:
         return None
 
 
+def sample_values_range(vectors, clamp_margin_percent=1.0, prior_counts=None, prior_values=0, device=0):
+    """HNSWIndex::sample_embedding + finalize_sampling (`quantization: auto`) -> (counts u64[14], (range_start, range_end))"""
+    v = np.ascontiguousarray(vectors, dtype=np.float32)
+    if v.ndim == 1:
+        v = v[None]
+    n, dim = v.shape
+    prior = None if prior_counts is None else np.ascontiguousarray(prior_counts, dtype=np.uint64)
+    counts = np.zeros(14, dtype=np.uint64)
+    rng = np.zeros(2, dtype=np.float32)
+    _check(_lib.load().cdb_sample_values_range(device, _ptr(v), n, dim, float(clamp_margin_percent), _ptr(prior),
+                                               int(prior_values), _ptr(counts), _ptr(rng)))
+    return counts, (np.float32(rng[0]), np.float32(rng[1]))
+
+
+def sample_values_range_device(d_ptr, n, dim, clamp_margin_percent=1.0, device=0, stream=None):
+    counts = np.zeros(14, dtype=np.uint64)
+    rng = np.zeros(2, dtype=np.float32)
+    _check(_lib.load().cdb_sample_values_range_device(device, C.c_void_p(d_ptr), n, dim, float(clamp_margin_percent), None, 0,
+                                                      _ptr(counts), _ptr(rng), C.c_void_p(stream) if stream else None))
+    return counts, (np.float32(rng[0]), np.float32(rng[1]))
+
+
 class DistanceMetric:
     """enum DistanceMetric + impl DistanceFunction (pairwise; batched here over pairs)."""
 

@@ -180,6 +180,61 @@ cdb_status cdb_quantize_batch(int32_t device, int32_t st, float lo, float hi, co
     return rc;
 }
 
+static cdb_status finish_sampling(const unsigned long long *d_counts, uint64_t n_values, float clamp, const uint64_t *prior,
+                                  uint64_t prior_values, uint64_t *out_counts, float *out_range, cudaStream_t s) {
+    uint64_t c[CDB_SAMPLE_COUNTERS];
+    CDB_CUDA_TRY(cudaMemcpyAsync(c, d_counts, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int i = 0; i < CDB_SAMPLE_COUNTERS; ++i) {
+        if (prior) c[i] += prior[i];
+        if (out_counts) out_counts[i] = c[i];
+    }
+    if (out_range) values_range_from_counts(c, n_values + (prior ? prior_values : 0), clamp, out_range);
+    return CDB_OK;
+}
+
+cdb_status cdb_sample_values_range_device(int32_t device, const float *d_vecs, uint64_t n, uint32_t dim, float clamp,
+                                          const uint64_t *prior, uint64_t prior_values, uint64_t *out_counts,
+                                          float *out_range, void *stream) {
+    CDB_REQUIRE((d_vecs || !n) && (out_counts || out_range), "bad arguments");
+    CDB_CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CDB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf counts;
+    cdb_status rc = counts.ensure(CDB_SAMPLE_COUNTERS * 8);
+    if (rc) return rc;
+    cudaMemsetAsync(counts.p, 0, CDB_SAMPLE_COUNTERS * 8, s);
+    rc = sample_counts_device(d_vecs, n * dim, counts.as<unsigned long long>(), sms, s);
+    if (!rc) rc = finish_sampling(counts.as<unsigned long long>(), n * dim, clamp, prior, prior_values, out_counts, out_range, s);
+    counts.release();
+    return rc;
+}
+
+cdb_status cdb_sample_values_range(int32_t device, const float *vecs, uint64_t n, uint32_t dim, float clamp,
+                                   const uint64_t *prior, uint64_t prior_values, uint64_t *out_counts, float *out_range) {
+    CDB_REQUIRE((vecs || !n) && (out_counts || out_range), "bad arguments");
+    CDB_CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CDB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const uint64_t total = n * dim;
+    const uint64_t chunk = 16ull << 20;   // values per staging copy (64 MB)
+    DevBuf in, counts;
+    cdb_status rc = counts.ensure(CDB_SAMPLE_COUNTERS * 8);
+    if (!rc) rc = in.ensure(std::min(std::max<uint64_t>(total, 1), chunk) * 4);
+    if (!rc) {
+        cudaMemsetAsync(counts.p, 0, CDB_SAMPLE_COUNTERS * 8, 0);
+        for (uint64_t off = 0; off < total && !rc; off += chunk) {
+            const uint64_t m = std::min(chunk, total - off);
+            cudaMemcpyAsync(in.p, vecs + off, m * 4, cudaMemcpyHostToDevice, 0);
+            rc = sample_counts_device(in.as<float>(), m, counts.as<unsigned long long>(), sms, 0);
+        }
+    }
+    if (!rc) rc = finish_sampling(counts.as<unsigned long long>(), total, clamp, prior, prior_values, out_counts, out_range, 0);
+    in.release(); counts.release();
+    return rc;
+}
+
 cdb_status cdb_distance_pairs(int32_t device, int32_t metric, int32_t st, uint32_t dim, const void *x_codes,
                               const float *x_mags, const void *y_codes, const float *y_mags, uint64_t n, float *out,
                               int32_t *out_status) {

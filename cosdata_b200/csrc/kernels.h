@@ -16,6 +16,10 @@ cdb_status quantize_rows_synth(uint64_t seed, uint64_t first_row, uint64_t n, ui
                                uint32_t raw_pitch_elems, cudaStream_t s);
 cdb_status raw_mags_device(const float *d_raw, uint32_t pitch_elems, uint64_t n, uint32_t dim, float *d_mags, cudaStream_t s);
 
+// ---- sampling.cu
+cdb_status sample_counts_device(const float *d_vecs, uint64_t n_values, unsigned long long *d_counts, int sm_count, cudaStream_t s);
+void values_range_from_counts(const uint64_t *counts, uint64_t n_values, float clamp_margin_percent, float *range);
+
 // ---- pairs.cu
 cdb_status distance_pairs_device(int metric, int st, uint32_t dim, const uint8_t *d_x, const float *d_xm,
                                  const uint8_t *d_y, const float *d_ym, uint32_t row_pitch, uint64_t n,

@@ -133,6 +133,24 @@ cdb_status cdb_quantize_batch(int32_t device, int32_t storage_type, float range_
                               const float *vecs, uint64_t n, uint32_t dim,
                               void *out_codes, float *out_mags);
 
+/* ---------------------- HNSWIndex::sample_embedding + finalize_sampling
+ * (src/indexes/hnsw/mod.rs:202-351; `quantization: auto`, src/api/vectordb/indexes/repo.rs:41-47): count, over the
+ * n*dim values of the sampled embeddings, how many exceed each threshold, then choose values_range.
+ *   out_counts[0..7)  = #values >  {0.025, 0.05, 0.1, 0.2, 0.3, 0.4, 0.5}
+ *   out_counts[7..14) = #values < -{0.025, 0.05, 0.1, 0.2, 0.3, 0.4, 0.5}
+ *   out_range = (range_start, range_end): tightest threshold whose share (count as f32 / (n*dim) as f32 * 100) is
+ *   <= clamp_margin_percent (config.toml:36, default 1.0), else -1.0 / 1.0.  NaN values count nowhere.
+ * `prior_counts` (may be NULL) are added before the decision so a caller can sample in several calls like the
+ * reference's per-batch sample_embedding; prior_values is the number of values they cover. */
+#define CDB_SAMPLE_COUNTERS 14
+cdb_status cdb_sample_values_range(int32_t device, const float *vecs, uint64_t n, uint32_t dim, float clamp_margin_percent,
+                                   const uint64_t *prior_counts, uint64_t prior_values,
+                                   uint64_t *out_counts, float *out_range);
+/* same, d_vecs is DEVICE memory on `device`; runs on `stream` and synchronizes it before returning */
+cdb_status cdb_sample_values_range_device(int32_t device, const float *d_vecs, uint64_t n, uint32_t dim, float clamp_margin_percent,
+                                          const uint64_t *prior_counts, uint64_t prior_values,
+                                          uint64_t *out_counts, float *out_range, void *stream);
+
 /* ---------------------------------------------- DistanceFunction::calculate
  * (Base,Base) arm, batched over independent pairs.  out_status[i] is the
  * Result of pair i (CDB_OK / CDB_STORAGE_MISMATCH / CDB_CALCULATION_ERROR /

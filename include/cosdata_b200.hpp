@@ -52,6 +52,21 @@ struct ScalarQuantization {
     void train(const std::vector<std::vector<float>> &) const {}  // scalar.rs:54-57
 };
 
+// HNSWIndex::sample_embedding + finalize_sampling (hnsw/mod.rs:202-351): values_range for `quantization: auto`
+struct SamplingData {
+    uint64_t counts[CDB_SAMPLE_COUNTERS] = {};   // above_0025 .. above_05, below_0025 .. below_05
+    uint64_t values = 0;
+    // sample one batch of embeddings (row-major n x dim); returns the range the reference would finalize right now
+    std::pair<float, float> sample(const float *vecs, uint64_t n, uint32_t dim, float clamp_margin_percent = 1.0f, int device = 0) {
+        float range[2];
+        uint64_t next[CDB_SAMPLE_COUNTERS];
+        check(cdb_sample_values_range(device, vecs, n, dim, clamp_margin_percent, counts, values, next, range));
+        for (int i = 0; i < CDB_SAMPLE_COUNTERS; ++i) counts[i] = next[i];
+        values += n * dim;
+        return {range[0], range[1]};
+    }
+};
+
 // enum DistanceMetric + impl DistanceFunction (pairwise)
 struct DistanceMetric {
     DistanceMetricKind kind;

@@ -660,3 +660,34 @@ int orc_rerank_f32(const float *corpus, size_t dim, const float *q, const uint32
     free(t.h);
     return ORC_OK;
 }
+
+
+/* ------------------------------------------------------------------ value-range sampling
+ * sample_embedding (src/indexes/hnsw/mod.rs:202-265): per value, one counter per threshold it exceeds (f32 compares against
+ * f32 literals; NaN exceeds nothing).  finalize_sampling (:268-351): percent = (count as f32 / values_count) * 100.0 with
+ * values_count = (dimension * embeddings.len()) as f32; first (tightest) threshold with percent <= clamp_margin_percent. */
+static const float ORC_SAMPLE_T[7] = {0.025f, 0.05f, 0.1f, 0.2f, 0.3f, 0.4f, 0.5f};
+
+void orc_sample_counts(const float *values, size_t n_values, uint64_t *counts) {
+    for (size_t i = 0; i < n_values; ++i) {
+        const float v = values[i];
+        for (int t = 0; t < 7; ++t) {
+            if (v > ORC_SAMPLE_T[t]) counts[t]++;
+            if (v < -ORC_SAMPLE_T[t]) counts[7 + t]++;
+        }
+    }
+}
+
+void orc_values_range(const uint64_t *counts, uint64_t n_values, float clamp_margin_percent, float *range) {
+    const float values_count = (float)n_values;
+    range[0] = -1.0f;
+    range[1] = 1.0f;
+    for (int t = 0; t < 7; ++t) {
+        const float pct = ((float)counts[7 + t] / values_count) * 100.0f;
+        if (pct <= clamp_margin_percent) { range[0] = -ORC_SAMPLE_T[t]; break; }
+    }
+    for (int t = 0; t < 7; ++t) {
+        const float pct = ((float)counts[t] / values_count) * 100.0f;
+        if (pct <= clamp_margin_percent) { range[1] = ORC_SAMPLE_T[t]; break; }
+    }
+}

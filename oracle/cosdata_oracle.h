@@ -85,6 +85,12 @@ size_t orc_code_bytes(int storage_type, size_t dim);
 int orc_quantize(int storage_type, float lo, float hi, const float *v, size_t dim,
                  void *out_code, float *out_mag);
 
+/* ---- value-range sampling for `quantization: auto`: HNSWIndex::sample_embedding + finalize_sampling
+ *      (src/indexes/hnsw/mod.rs:202-351).  counts[0..7) = # > {0.025,0.05,0.1,0.2,0.3,0.4,0.5}, counts[7..14) = # < -{..};
+ *      counts are ADDED to (callers zero them first). */
+void orc_sample_counts(const float *values, size_t n_values, uint64_t *counts14);
+void orc_values_range(const uint64_t *counts14, uint64_t n_values, float clamp_margin_percent, float *range2);
+
 /* ---- pairwise DistanceFunction::calculate for the (Base,Base) arm */
 int orc_distance(int metric, int storage_type, size_t dim,
                  const void *x_code, float x_mag,

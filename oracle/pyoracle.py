@@ -79,6 +79,10 @@ def _declare(L):
     L.orc_brute_topk_codes.restype = C.c_int
     L.orc_brute_topk_codes.argtypes = [C.c_int, C.c_int, sz, vp, f32p, sz, vp, f32p, sz, sz,
                                        C.c_int, u32p, f32p, u8p]
+    L.orc_sample_counts.restype = None
+    L.orc_sample_counts.argtypes = [f32p, sz, vp]
+    L.orc_values_range.restype = None
+    L.orc_values_range.argtypes = [vp, C.c_uint64, C.c_float, f32p]
     L.orc_rerank_f32.restype = C.c_int
     L.orc_rerank_f32.argtypes = [f32p, sz, f32p, u32p, sz, sz, u32p, f32p]
 
@@ -189,3 +193,13 @@ def rerank_f32(corpus, q, cand, k):
     rc = lib().orc_rerank_f32(_p(corpus), corpus.shape[1], _p(q), _p(cand), cand.size, k, _p(ids), _p(scores))
     assert rc == OK
     return ids, scores
+
+
+def sample_values_range(vectors, clamp_margin_percent=1.0, prior_counts=None, prior_values=0):
+    """sample_embedding over every vector + finalize_sampling -> (counts u64[14], (range_start, range_end))"""
+    v = np.ascontiguousarray(vectors, dtype=np.float32)
+    counts = np.zeros(14, dtype=np.uint64) if prior_counts is None else np.array(prior_counts, dtype=np.uint64)
+    lib().orc_sample_counts(_p(v), v.size, _p(counts))
+    rng = np.zeros(2, dtype=np.float32)
+    lib().orc_values_range(_p(counts), v.size + prior_values, clamp_margin_percent, _p(rng))
+    return counts, (np.float32(rng[0]), np.float32(rng[1]))
