@@ -14,6 +14,7 @@ Python:
 """
 import ctypes as C
 import enum
+import os
 
 import numpy as np
 
@@ -155,6 +156,29 @@ def sample_values_range_device(d_ptr, n, dim, clamp_margin_percent=1.0, device=0
     return counts, (np.float32(rng[0]), np.float32(rng[1]))
 
 
+def prop_file_scan(path):
+    """prop.data (file_persist.rs:58-108) -> (records, StorageType or None, elems per vector, code bytes per record)"""
+    n, st, el, cb = C.c_uint64(0), C.c_int32(-1), C.c_uint32(0), C.c_uint64(0)
+    _check(_lib.load().cdb_prop_file_scan(os.fsencode(path), C.byref(n), C.byref(st), C.byref(el), C.byref(cb)))
+    return n.value, (StorageType(st.value) if st.value >= 0 else None), el.value, cb.value
+
+
+def prop_file_load(path, first_record=0, max_records=None):
+    """-> dict(ids u32[n], codes u8[n, code_bytes], mags f32[n], offsets u64[n], lengths u32[n], storage_type)"""
+    total, st, _, cb = prop_file_scan(path)
+    n = max(0, total - first_record) if max_records is None else min(max_records, max(0, total - first_record))
+    ids = np.zeros(n, dtype=np.uint32)
+    codes = np.zeros((n, cb), dtype=np.uint8)
+    mags = np.zeros(n, dtype=np.float32)
+    offsets = np.zeros(n, dtype=np.uint64)
+    lengths = np.zeros(n, dtype=np.uint32)
+    got = C.c_uint64(0)
+    _check(_lib.load().cdb_prop_file_load(os.fsencode(path), first_record, n, _ptr(ids), _ptr(codes), _ptr(mags),
+                                          _ptr(offsets), _ptr(lengths), C.byref(got)))
+    assert got.value == n
+    return {"ids": ids, "codes": codes, "mags": mags, "offsets": offsets, "lengths": lengths, "storage_type": st}
+
+
 class DistanceMetric:
     """enum DistanceMetric + impl DistanceFunction (pairwise; batched here over pairs)."""
 
@@ -222,6 +246,13 @@ class DenseIndex:
         c = np.ascontiguousarray(codes, dtype=np.uint8)
         m = np.ascontiguousarray(mags, dtype=np.float32)
         _check(self._lib.cdb_index_append_codes(self._h, _ptr(c), _ptr(m), m.size))
+
+    def append_prop_file(self, path, max_ids=0):
+        """append every Storage record of a reference prop.data file (row = record number) -> (n, ids u32[min(n, max_ids)])"""
+        ids = np.zeros(max_ids, dtype=np.uint32)
+        n = C.c_uint64(0)
+        _check(self._lib.cdb_index_append_prop_file(self._h, os.fsencode(path), _ptr(ids) if max_ids else None, max_ids, C.byref(n)))
+        return n.value, ids[: min(n.value, max_ids)]
 
     def append_synthetic(self, seed, n, first_row=None):
         """rows [first_row, first_row+n) of synthetic stream `seed` (default: continue at len(self))"""

@@ -355,6 +355,12 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     return CDB_OK;
 }
 
+cdb_status cdb_index_describe(const cdb_index *ix, cdb_index_desc *out) {
+    CDB_REQUIRE(ix && out, "null argument");
+    *out = ix->desc;
+    return CDB_OK;
+}
+
 uint64_t cdb_index_size(const cdb_index *ix) { return ix ? ix->size : 0; }
 
 static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) {

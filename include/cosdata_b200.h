@@ -164,6 +164,7 @@ cdb_status cdb_distance_pairs(int32_t device, int32_t metric, int32_t storage_ty
 cdb_status cdb_index_create(const cdb_index_desc *desc, cdb_index **out);
 cdb_status cdb_index_destroy(cdb_index *index);
 uint64_t cdb_index_size(const cdb_index *index);
+cdb_status cdb_index_describe(const cdb_index *index, cdb_index_desc *out);   /* the descriptor it was created with */
 /* preprocess_embedding (vector_store.rs:629-712): quantize with the index's
  * StorageType/range and append; raw rows kept when keep_raw_f32. */
 cdb_status cdb_index_append_f32(cdb_index *index, const float *vecs, uint64_t n);
@@ -171,6 +172,20 @@ cdb_status cdb_index_append_f32(cdb_index *index, const float *vecs, uint64_t n)
 cdb_status cdb_index_append_f32_device(cdb_index *index, const float *d_vecs, uint64_t n);
 /* append already-quantized rows (prop.data payloads) */
 cdb_status cdb_index_append_codes(cdb_index *index, const void *codes, const float *mags, uint64_t n);
+/* ---- prop.data: the reference's node property file (src/models/file_persist.rs:58-108), a concatenation of serde_cbor
+ * records { id: InternalId, value: Storage }; ProbNode stores each record's (FileOffset, BytesToRead)
+ * (src/models/serializer/hnsw/node.rs:51-54).  Host-side readers, no GPU work:
+ *   scan  -> number of records, their StorageType, elements per vector (bytes per plane for SubByte) and bytes per code in
+ *            the tight layout of cdb_code_bytes(); CDB_STORAGE_MISMATCH if records differ in variant or length.
+ *   load  -> records [first_record, first_record+max_records): ids, codes (tight layout), mags, and each record's byte
+ *            offset/length in the file (= the node's prop_value.location).  Any out pointer may be NULL.
+ *   cdb_index_append_prop_file -> append every record to the index in file order (row = record number); records must match
+ *            the index's StorageType and dim (else CDB_STORAGE_MISMATCH, like the reference's calculate()). */
+cdb_status cdb_prop_file_scan(const char *path, uint64_t *out_records, int32_t *out_storage_type, uint32_t *out_elems,
+                              uint64_t *out_code_bytes);
+cdb_status cdb_prop_file_load(const char *path, uint64_t first_record, uint64_t max_records, uint32_t *out_ids, void *out_codes,
+                              float *out_mags, uint64_t *out_offsets, uint32_t *out_lengths, uint64_t *out_read);
+cdb_status cdb_index_append_prop_file(cdb_index *index, const char *path, uint32_t *out_ids, uint64_t max_ids, uint64_t *out_appended);
 /* generate rows [first_row, first_row+n) of synthetic stream `seed` ON DEVICE and append
  * them (exactly what cdb_index_append_f32 would store for the same values) */
 cdb_status cdb_index_append_synthetic(cdb_index *index, uint64_t seed, uint64_t first_row, uint64_t n);
