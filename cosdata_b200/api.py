@@ -179,6 +179,33 @@ def prop_file_load(path, first_record=0, max_records=None):
     return {"ids": ids, "codes": codes, "mags": mags, "offsets": offsets, "lengths": lengths, "storage_type": st}
 
 
+def itoe_scan(collection_dir):
+    """itoe.dim / itoe.<version>.data (collection.rs:149-164) -> (live dense embeddings, dim, max internal id)"""
+    n, dim, mx = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
+    _check(_lib.load().cdb_itoe_scan(os.fsencode(collection_dir), C.byref(n), C.byref(dim), C.byref(mx)))
+    return n.value, dim.value, mx.value
+
+
+def itoe_load(collection_dir, first_entry=0, max_entries=None):
+    """-> (internal ids u32[n] ascending, vectors f32[n, dim])"""
+    total, dim, _ = itoe_scan(collection_dir)
+    n = max(0, total - first_entry) if max_entries is None else min(max_entries, max(0, total - first_entry))
+    ids = np.zeros(n, dtype=np.uint32)
+    vecs = np.zeros((n, dim), dtype=np.float32)
+    got = C.c_uint64(0)
+    _check(_lib.load().cdb_itoe_load(os.fsencode(collection_dir), first_entry, n, _ptr(ids), _ptr(vecs), C.byref(got)))
+    assert got.value == n
+    return ids, vecs
+
+
+def itoe_get(collection_dir, internal_id, capacity=65536):
+    """Collection::get_raw_emb_by_internal_id -> f32[dim] or None"""
+    out = np.zeros(capacity, dtype=np.float32)
+    n = C.c_uint32(0)
+    _check(_lib.load().cdb_itoe_get(os.fsencode(collection_dir), int(internal_id), _ptr(out), capacity, C.byref(n)))
+    return out[: n.value].copy() if n.value else None
+
+
 class DistanceMetric:
     """enum DistanceMetric + impl DistanceFunction (pairwise; batched here over pairs)."""
 
@@ -252,6 +279,13 @@ class DenseIndex:
         ids = np.zeros(max_ids, dtype=np.uint32)
         n = C.c_uint64(0)
         _check(self._lib.cdb_index_append_prop_file(self._h, os.fsencode(path), _ptr(ids) if max_ids else None, max_ids, C.byref(n)))
+        return n.value, ids[: min(n.value, max_ids)]
+
+    def append_itoe(self, collection_dir, max_ids=0):
+        """append every live raw embedding of a reference collection directory, ascending internal id -> (n, internal ids)"""
+        ids = np.zeros(max_ids, dtype=np.uint32)
+        n = C.c_uint64(0)
+        _check(self._lib.cdb_index_append_itoe(self._h, os.fsencode(collection_dir), _ptr(ids) if max_ids else None, max_ids, C.byref(n)))
         return n.value, ids[: min(n.value, max_ids)]
 
     def append_synthetic(self, seed, n, first_row=None):

@@ -186,6 +186,20 @@ cdb_status cdb_prop_file_scan(const char *path, uint64_t *out_records, int32_t *
 cdb_status cdb_prop_file_load(const char *path, uint64_t first_record, uint64_t max_records, uint32_t *out_ids, void *out_codes,
                               float *out_mags, uint64_t *out_offsets, uint32_t *out_lengths, uint64_t *out_read);
 cdb_status cdb_index_append_prop_file(cdb_index *index, const char *path, uint32_t *out_ids, uint64_t max_ids, uint64_t *out_appended);
+/* ---- itoe.dim + itoe.<version>.data: the reference's raw-embedding store, TreeMap<InternalId, RawVectorEmbedding>
+ * (src/models/collection.rs:110, 149-164; formats in src/models/serializer/tree_map/*.rs and raw_vector_embedding.rs),
+ * which finalize_ann_results reads for the exact re-rank (collection.rs:368-384).  Host-side readers, no GPU work.  Only the
+ * newest state of every key counts (tree_map.rs:262-268); deleted keys and embeddings without dense values are skipped.
+ *   scan -> number of live dense embeddings, their dimension, the largest internal id
+ *   load -> entries [first_entry, ..) in ascending internal-id order: ids and row-major f32 vectors
+ *   get  -> TreeMap::get_latest for one internal id (*out_len = 0 when absent/deleted)
+ *   cdb_index_append_itoe -> cdb_index_append_f32 of every live embedding in ascending internal-id order */
+cdb_status cdb_itoe_scan(const char *collection_dir, uint64_t *out_entries, uint32_t *out_dim, uint64_t *out_max_internal_id);
+cdb_status cdb_itoe_load(const char *collection_dir, uint64_t first_entry, uint64_t max_entries, uint32_t *out_internal_ids,
+                         float *out_vectors, uint64_t *out_read);
+cdb_status cdb_itoe_get(const char *collection_dir, uint32_t internal_id, float *out_vector, uint32_t capacity, uint32_t *out_len);
+cdb_status cdb_index_append_itoe(cdb_index *index, const char *collection_dir, uint32_t *out_internal_ids, uint64_t max_ids,
+                                 uint64_t *out_appended);
 /* generate rows [first_row, first_row+n) of synthetic stream `seed` ON DEVICE and append
  * them (exactly what cdb_index_append_f32 would store for the same values) */
 cdb_status cdb_index_append_synthetic(cdb_index *index, uint64_t seed, uint64_t first_row, uint64_t n);
