@@ -45,6 +45,30 @@ class GraphDesc(C.Structure):
     ]
 
 
+class GraphMetadata(C.Structure):
+    _fields_ = [
+        ("md_dims", C.c_uint32),
+        ("n_md", C.c_uint32),
+        ("md_bits", C.c_void_p),
+        ("md_mags", C.c_void_p),
+        ("node_id", C.c_void_p),
+        ("node_md", C.c_void_p),
+        ("pseudo_entry", C.c_uint32),
+    ]
+
+
+class VectorDataBatch(C.Structure):
+    _fields_ = [
+        ("codes", C.c_void_p),
+        ("mags", C.c_void_p),
+        ("ids", C.c_void_p),
+        ("has_id", C.c_void_p),
+        ("md_bits", C.c_void_p),
+        ("md_mags", C.c_void_p),
+        ("has_md", C.c_void_p),
+    ]
+
+
 class BuildParams(C.Structure):
     _fields_ = [
         ("num_levels", C.c_uint32),
@@ -87,6 +111,9 @@ PROTOTYPES = {
     "cdb_itoe_load": (C.c_int32, [C.c_char_p, C.c_uint64, C.c_uint64, c_vp, c_f32p, c_vp]),
     "cdb_itoe_get": (C.c_int32, [C.c_char_p, C.c_uint32, c_f32p, C.c_uint32, c_vp]),
     "cdb_index_append_itoe": (C.c_int32, [c_vp, C.c_char_p, c_vp, C.c_uint64, c_vp]),
+    "cdb_distance_pairs_md": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32, c_vp, c_vp, C.c_uint64, c_f32p, c_vp]),
+    "cdb_index_set_graph_metadata": (C.c_int32, [c_vp, c_vp]),
+    "cdb_search_batch_filtered": (C.c_int32, [c_vp, c_f32p, C.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32p, c_vp, c_vp]),
     "cdb_quantize_batch": (C.c_int32, [C.c_int32, C.c_int32, C.c_float, C.c_float, c_f32p, C.c_uint64, C.c_uint32, c_vp, c_f32p]),
     "cdb_distance_pairs": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, c_vp, c_f32p, c_vp, c_f32p, C.c_uint64, c_f32p, c_i32p]),
     "cdb_index_create": (C.c_int32, [C.POINTER(IndexDesc), C.POINTER(C.c_void_p)]),

@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 from . import _lib
-from ._lib import BuildParams, GraphDesc, IndexDesc, SearchParams
+from ._lib import BuildParams, GraphDesc, GraphMetadata, IndexDesc, SearchParams, VectorDataBatch
 
 INVALID_ID = 0xFFFFFFFF
 
@@ -226,6 +226,30 @@ class DistanceMetric:
                                               _ptr(y), _ptr(ym), n, _ptr(out), _ptr(st)))
         return out, st
 
+    def calculate_pairs_md(self, storage_type, dim, md_dims, x, y):
+        """DistanceFunction::calculate over pairs of VectorData { id, quantized_vec, metadata } (cosine.rs:34-102).
+        x / y: dict(codes, mags, ids=None, has_id=None, md_bits=None, md_mags=None, has_md=None); x is the query side.
+        -> (values f32[n], status int32[n])"""
+        keep = []
+
+        def side(v):
+            def arr(key, dt):
+                a = v.get(key)
+                if a is None:
+                    return None
+                a = np.ascontiguousarray(a, dtype=dt)
+                keep.append(a)
+                return a.ctypes.data
+            return VectorDataBatch(arr("codes", np.uint8), arr("mags", np.float32), arr("ids", np.uint32), arr("has_id", np.uint8),
+                                   arr("md_bits", np.int32), arr("md_mags", np.float32), arr("has_md", np.uint8))
+        bx, by = side(x), side(y)
+        n = np.asarray(x["mags"]).size
+        out = np.zeros(n, dtype=np.float32)
+        st = np.zeros(n, dtype=np.int32)
+        _check(_lib.load().cdb_distance_pairs_md(self.device, int(self.kind), int(storage_type), dim, md_dims, C.byref(bx), C.byref(by),
+                                                 n, _ptr(out), _ptr(st)))
+        return out, st
+
     def calculate(self, x: Storage, y: Storage):
         """DistanceFunction::calculate(x, y) -> f32 or raises DistanceError."""
         if x.storage_type != y.storage_type:
@@ -378,6 +402,44 @@ class DenseIndex:
         gd = GraphDesc(num_levels, neighbors_count, level0_neighbors_count, entry, root_row, cnt.ctypes.data,
                        C.cast(t_nr, C.c_void_p), C.cast(t_ad, C.c_void_p), C.cast(t_ch, C.c_void_p))
         _check(self._lib.cdb_index_set_graph(self._h, C.byref(gd)))
+
+    def set_graph_metadata(self, md_bits, md_mags, node_id, node_md, pseudo_entry):
+        """replica ids / metadata rows per graph node + the metadata table + the pseudo root (include/cosdata_b200.h)"""
+        bits = np.ascontiguousarray(md_bits, dtype=np.int32)
+        mags = np.ascontiguousarray(md_mags, dtype=np.float32)
+        ni = [np.ascontiguousarray(a, dtype=np.uint32) for a in node_id]
+        nm = [np.ascontiguousarray(a, dtype=np.uint32) for a in node_md]
+        t_ni = (C.c_void_p * len(ni))(*[a.ctypes.data for a in ni])
+        t_nm = (C.c_void_p * len(nm))(*[a.ctypes.data for a in nm])
+        md = GraphMetadata(bits.shape[1], bits.shape[0], bits.ctypes.data, mags.ctypes.data, C.cast(t_ni, C.c_void_p),
+                           C.cast(t_nm, C.c_void_p), int(pseudo_entry))
+        _check(self._lib.cdb_index_set_graph_metadata(self._h, C.byref(md)))
+        self.md_dims = bits.shape[1]
+
+    def batch_search_filtered(self, queries, filters, k, **kw):
+        """search_internal with per-query metadata filters: filters[q] is None or a list of int8[md_dims] (QueryFilterDimensions)
+        -> (replica ids u32[B,k], scores f32[B,k], counts u32[B], err u8[B])"""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None]
+        b = q.shape[0]
+        offs, rows, has = [0], [], []
+        for f in filters:
+            has.append(0 if f is None else 1)
+            for dims in (f or []):
+                rows.append(np.asarray(dims, dtype=np.int8).reshape(self.md_dims))
+            offs.append(len(rows))
+        offs = np.array(offs, dtype=np.uint32)
+        has = np.array(has, dtype=np.uint8)
+        dims = np.ascontiguousarray(np.stack(rows)) if rows else np.zeros((1, self.md_dims), dtype=np.int8)
+        ids = np.zeros((b, k), dtype=np.uint32)
+        scores = np.zeros((b, k), dtype=np.float32)
+        counts = np.zeros(b, dtype=np.uint32)
+        err = np.zeros(b, dtype=np.uint8)
+        p = self.params(k, SearchMode.HNSW, **kw)
+        _check(self._lib.cdb_search_batch_filtered(self._h, _ptr(q), b, C.byref(p), _ptr(offs), _ptr(dims), _ptr(has), _ptr(ids),
+                                                   _ptr(scores), _ptr(counts), _ptr(err)))
+        return ids, scores, counts, err
 
     def hnsw_counters(self):
         out = np.zeros(2, dtype=np.uint64)

@@ -121,6 +121,14 @@ struct cdb_index {
     bool has_graph = false;
     GraphDev graph{};
     std::vector<void *> graph_allocs;
+    // replica ids / metadata of the graph nodes (cdb_index_set_graph_metadata)
+    bool has_md = false;
+    std::vector<void *> md_allocs;
+    const uint32_t *const *md_node_id = nullptr, *const *md_node_md = nullptr;
+    const int32_t *md_bits = nullptr;
+    const float *md_mags = nullptr;
+    uint32_t md_dims = 0, md_pseudo_entry = 0;
+    DevBuf hn_ids, hn_labels, flt_off, flt_dims, flt_has;
     std::vector<uint32_t> g_cnt;
     std::vector<const uint32_t *> g_nr, g_ad, g_ch;  // host copies of the per-level device pointers
     DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags;
@@ -267,6 +275,55 @@ done:
     return rc;
 }
 
+cdb_status cdb_distance_pairs_md(int32_t device, int32_t metric, int32_t st, uint32_t dim, uint32_t M, const cdb_vector_data_batch *x,
+                                 const cdb_vector_data_batch *y, uint64_t n, float *out, int32_t *out_status) {
+    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_F32 && metric >= 0 && metric <= 3 && dim > 0, "bad metric/storage/dim");
+    CDB_REQUIRE(x && y, "null argument");
+    if (!n) return CDB_OK;
+    CDB_REQUIRE(x->codes && y->codes && x->mags && y->mags && out && out_status, "null buffer");
+    CDB_REQUIRE((!x->md_bits || (x->md_mags && M)) && (!y->md_bits || (y->md_mags && M)), "metadata needs md_mags and md_dims");
+    CDB_CUDA_TRY(cudaSetDevice(device));
+    const uint32_t pitch = row_pitch_bytes(st, dim);
+    std::vector<DevBuf> bufs(16);
+    size_t nb = 0;
+    cdb_status rc = CDB_OK;
+    auto up = [&](const void *src, size_t bytes) -> const void * {
+        if (!src || rc) return nullptr;
+        DevBuf &b = bufs[nb++];
+        if ((rc = b.ensure(bytes))) return nullptr;
+        cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, 0);
+        return b.p;
+    };
+    auto side = [&](const cdb_vector_data_batch *v) -> MdBatchDev {
+        MdBatchDev d{};
+        DevBuf &c = bufs[nb++];
+        if (!rc && !(rc = c.ensure(n * pitch))) {
+            cudaMemsetAsync(c.p, 0, n * pitch, 0);
+            rc = copy_codes(c.p, v->codes, st, dim, n, true, 0);
+        }
+        d.codes = c.as<uint8_t>();
+        d.mags = (const float *)up(v->mags, n * 4);
+        d.ids = (const uint32_t *)up(v->ids, n * 4);
+        d.has_id = (const uint8_t *)up(v->ids ? v->has_id : nullptr, n);
+        d.md_bits = (const int32_t *)up(v->md_bits, n * (size_t)M * 4);
+        d.md_mags = (const float *)up(v->md_bits ? v->md_mags : nullptr, n * 4);
+        d.has_md = (const uint8_t *)up(v->md_bits ? v->has_md : nullptr, n);
+        return d;
+    };
+    const MdBatchDev dx = side(x), dy = side(y);
+    DevBuf &o = bufs[nb++], &os = bufs[nb++];
+    if (!rc && !(rc = o.ensure(n * 4)) && !(rc = os.ensure(n * 4)))
+        rc = distance_pairs_md_device(metric, st, dim, M, dx, dy, pitch, n, o.as<float>(), os.as<int32_t>(), 0);
+    if (!rc) {
+        cudaMemcpyAsync(out, o.p, n * 4, cudaMemcpyDeviceToHost, 0);
+        cudaMemcpyAsync(out_status, os.p, n * 4, cudaMemcpyDeviceToHost, 0);
+        cudaError_t e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = CDB_CUDA_ERROR; }
+    }
+    for (DevBuf &b : bufs) b.release();
+    return rc;
+}
+
 // ------------------------------------------------------------------ index lifecycle
 
 cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
@@ -339,10 +396,11 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     if (ix->d_xh) cudaFree(ix->d_xh);
     if (ix->d_digits) cudaFree(ix->d_digits);
     for (void *g : ix->graph_allocs) cudaFree(g);
+    for (void *g : ix->md_allocs) cudaFree(g);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
                       &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters,
-                      &ix->qraw, &ix->qraw_mags})
+                      &ix->qraw, &ix->qraw_mags, &ix->hn_ids, &ix->hn_labels, &ix->flt_off, &ix->flt_dims, &ix->flt_has})
         b->release();
     for (auto &ev : ix->ev)
         if (ev) cudaEventDestroy(ev);
@@ -517,9 +575,11 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
 // search_internal (hnsw/mod.rs:390-440): quantized ann_search on the uploaded graph, then
 // remove_duplicates_and_filter and the exact f32 re-rank of finalize_ann_results.
 static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
-                                     uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
+                                     uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s,
+                                     const uint32_t *d_foff = nullptr, const int8_t *d_fdims = nullptr, const uint8_t *d_fhas = nullptr) {
     const cdb_index_desc &d = ix->desc;
     CDB_REQUIRE(ix->has_graph, "CDB_MODE_HNSW needs cdb_index_set_graph");
+    CDB_REQUIRE(ix->has_md || !d_fhas, "metadata filters need cdb_index_set_graph_metadata");
     CDB_REQUIRE(ix->d_raw, "HNSW search re-ranks with raw f32 rows (F32 storage or keep_raw_f32)");
     CDB_REQUIRE(p->shortlist_size >= 1 && p->shortlist_size <= 64, "shortlist_size must be in 1..64");
     CDB_REQUIRE(p->ef_search >= 1 && p->ef_search <= 4096, "ef_search must be in 1..4096");
@@ -537,6 +597,7 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
         (rc = ix->hn_n.ensure((size_t)nq * 4)) || (rc = ix->err32.ensure((size_t)nq * 4)) ||
         (rc = ix->cand.ensure((size_t)nq * k5 * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)))
         return rc;
+    if (ix->has_md && ((rc = ix->hn_ids.ensure((size_t)nq * out_cap * 4)) || (rc = ix->hn_labels.ensure((size_t)nq * k5 * 4)))) return rc;
     if (!ix->hn_counters.p) {
         if ((rc = ix->hn_counters.ensure(16))) return rc;
         CDB_CUDA_TRY(cudaMemsetAsync(ix->hn_counters.p, 0, 16, s));
@@ -573,15 +634,42 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
     ix->n_search++;
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
     CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-    if ((rc = hnsw_search_device(a, s))) return rc;
-    CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
-    if ((rc = hnsw_dedup_device(a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, ix->graph.root_row, d.id_base, k5, nq,
-                                ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
-        return rc;
-    if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
-                                ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
-                                ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
-        return rc;
+    if (ix->has_md) {
+        // graph with replica nodes: metadata-aware traversal (hnsw_md.cu); results carry replica ids, the re-rank scores
+        // the base vector of each replica (collection.rs:368-384)
+        HnswMdArgs ma{};
+        ma.a = a;
+        ma.node_id = ix->md_node_id;
+        ma.node_md = ix->md_node_md;
+        ma.md_bits = ix->md_bits;
+        ma.md_mags = ix->md_mags;
+        ma.M = ix->md_dims;
+        ma.pseudo_entry = ix->md_pseudo_entry;
+        ma.filter_offsets = d_foff;
+        ma.filter_dims = d_fdims;
+        ma.has_filter = d_fhas;
+        ma.out_ids = ix->hn_ids.as<uint32_t>();
+        if ((rc = hnsw_search_md_device(ma, s))) return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+        if ((rc = hnsw_dedup_md_device(ma.out_ids, a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, d.id_base, k5, nq,
+                                       ix->cand.as<uint32_t>(), ix->hn_labels.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
+            return rc;
+        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
+                                    ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
+                                    ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s,
+                                    ix->hn_labels.as<uint32_t>())))
+            return rc;
+    } else {
+        if ((rc = hnsw_search_device(a, s))) return rc;
+        CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
+        if ((rc = hnsw_dedup_device(a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, ix->graph.root_row, d.id_base, k5, nq,
+                                    ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
+            return rc;
+        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
+                                    ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
+                                    ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
+            return rc;
+    }
     if (d_err) {
         err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
         CDB_LAUNCH_CHECK();
@@ -774,6 +862,61 @@ cdb_status cdb_search_batch(cdb_index *ix, const float *queries, uint32_t nq, co
     return CDB_OK;
 }
 
+cdb_status cdb_search_batch_filtered(cdb_index *ix, const float *queries, uint32_t nq, const cdb_search_params *p,
+                                     const uint32_t *filter_offsets, const int8_t *filter_dims, const uint8_t *has_filter,
+                                     uint32_t *out_ids, float *out_scores, uint32_t *out_counts, uint8_t *err_flags) {
+    CDB_REQUIRE(ix && p && (queries || !nq) && (out_ids || !nq) && (out_scores || !nq), "null argument");
+    CDB_REQUIRE(p->mode == CDB_MODE_HNSW, "metadata filters apply to CDB_MODE_HNSW");
+    CDB_REQUIRE(!has_filter || filter_offsets, "has_filter needs filter_offsets");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    if (!nq) return CDB_OK;
+    CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
+    CDB_REQUIRE(ix->has_md, "metadata filters need cdb_index_set_graph_metadata");
+    cudaStream_t s = ix->stream;
+    const size_t nk = (size_t)nq * p->k;
+    cdb_status rc;
+    if ((rc = ix->io_q.ensure((size_t)nq * ix->desc.dim * 4)) || (rc = ix->io_ids.ensure(nk * 4)) ||
+        (rc = ix->io_scores.ensure(nk * 4)) || (rc = ix->io_counts.ensure((size_t)nq * 4)) || (rc = ix->io_err.ensure(nq)))
+        return rc;
+    const uint32_t *d_off = nullptr;
+    const int8_t *d_dims = nullptr;
+    const uint8_t *d_has = nullptr;
+    if (has_filter) {
+        uint32_t total = 0;
+        for (uint32_t q = 0; q < nq; ++q) {
+            CDB_REQUIRE(filter_offsets[q] <= filter_offsets[q + 1], "filter_offsets must be non-decreasing");
+            CDB_REQUIRE(!has_filter[q] || filter_offsets[q + 1] - filter_offsets[q] <= 4096, "too many filters for one query");
+        }
+        total = filter_offsets[nq];
+        CDB_REQUIRE(filter_dims || !total, "null filter_dims");
+        if ((rc = ix->flt_off.ensure((size_t)(nq + 1) * 4)) || (rc = ix->flt_has.ensure(nq)) ||
+            (rc = ix->flt_dims.ensure((size_t)total * ix->md_dims + 1)))
+            return rc;
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->flt_off.p, filter_offsets, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->flt_has.p, has_filter, nq, cudaMemcpyHostToDevice, s));
+        if (total) CDB_CUDA_TRY(cudaMemcpyAsync(ix->flt_dims.p, filter_dims, (size_t)total * ix->md_dims, cudaMemcpyHostToDevice, s));
+        d_off = ix->flt_off.as<uint32_t>(); d_dims = ix->flt_dims.as<int8_t>(); d_has = ix->flt_has.as<uint8_t>();
+    }
+    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, queries, (size_t)nq * ix->desc.dim * 4, cudaMemcpyHostToDevice, s));
+    if (ix->ev_valid && ix->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, ix->ev[2], 0));
+    ix->last_stream = s;
+    const uint32_t CH = 2048;
+    for (uint32_t q0 = 0; q0 < nq; q0 += CH) {
+        const uint32_t m = std::min(CH, nq - q0);
+        rc = hnsw_search_locked(ix, ix->io_q.as<float>() + (size_t)q0 * ix->desc.dim, m, p, ix->io_ids.as<uint32_t>() + (size_t)q0 * p->k,
+                                ix->io_scores.as<float>() + (size_t)q0 * p->k, ix->io_counts.as<uint32_t>() + q0,
+                                ix->io_err.as<uint8_t>() + q0, s, d_off ? d_off + q0 : nullptr, d_dims, d_has ? d_has + q0 : nullptr);
+        if (rc) return rc;
+    }
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, ix->io_scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    if (out_counts) CDB_CUDA_TRY(cudaMemcpyAsync(out_counts, ix->io_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    if (err_flags) CDB_CUDA_TRY(cudaMemcpyAsync(err_flags, ix->io_err.p, nq, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaStreamSynchronize(s));
+    return CDB_OK;
+}
+
 // ------------------------------------------------------------------ S2 / S3
 
 cdb_status cdb_score_ids(cdb_index *ix, const float *query, const uint32_t *ids, uint32_t n, float *out, int32_t *out_status) {
@@ -872,12 +1015,25 @@ cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
     CDB_REQUIRE(gd->neighbors_count >= 1 && gd->neighbors_count <= 64 && gd->level0_neighbors_count >= 1 &&
                     gd->level0_neighbors_count <= 64, "neighbour counts must be in 1..64");
     std::lock_guard<std::mutex> lock(ix->mu);
-    CDB_REQUIRE(gd->level_counts[0] == ix->size, "level 0 must contain every row of the index");
+    CDB_REQUIRE(gd->level_counts[0] >= 1, "level 0 is empty");
     CDB_REQUIRE(gd->root_row < ix->size, "root_row out of range");
     CDB_REQUIRE(gd->entry < gd->level_counts[gd->num_levels], "entry out of range");
+    for (uint32_t L = 0; L <= gd->num_levels; ++L) {   // every index the kernels will follow
+        const uint32_t cnt = gd->level_counts[L], nb = L == 0 ? gd->level0_neighbors_count : gd->neighbors_count;
+        CDB_REQUIRE(gd->node_row[L] && gd->adjacency[L] && (L == 0 || gd->child[L]), "null level array");
+        for (uint32_t i = 0; i < cnt; ++i) {
+            CDB_REQUIRE(gd->node_row[L][i] < ix->size, "node_row entry out of range");
+            if (L > 0) CDB_REQUIRE(gd->child[L][i] < gd->level_counts[L - 1], "child entry out of range");
+        }
+        for (size_t t = 0; t < (size_t)cnt * nb; ++t)
+            CDB_REQUIRE(gd->adjacency[L][t] == CDB_INVALID_ID || gd->adjacency[L][t] < cnt, "adjacency entry out of range");
+    }
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     for (void *g : ix->graph_allocs) cudaFree(g);
     ix->graph_allocs.clear();
+    for (void *g : ix->md_allocs) cudaFree(g);
+    ix->md_allocs.clear();
+    ix->has_md = false;
     ix->has_graph = false;
     const uint32_t L1 = gd->num_levels + 1;
     std::vector<const uint32_t *> nr(L1), ad(L1), ch(L1);
@@ -920,6 +1076,50 @@ cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
     return CDB_OK;
 }
 
+cdb_status cdb_index_set_graph_metadata(cdb_index *ix, const cdb_graph_metadata *md) {
+    CDB_REQUIRE(ix && md && md->node_id && md->node_md, "null argument");
+    CDB_REQUIRE(md->md_dims >= 1 && md->md_dims <= 4096, "md_dims must be in 1..4096");
+    CDB_REQUIRE((md->md_bits && md->md_mags) || !md->n_md, "null metadata table");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_REQUIRE(ix->has_graph, "cdb_index_set_graph_metadata needs cdb_index_set_graph first");
+    const uint32_t L1 = ix->graph.num_levels + 1;
+    CDB_REQUIRE(md->pseudo_entry < ix->g_cnt[L1 - 1], "pseudo_entry out of range");
+    for (uint32_t L = 0; L < L1; ++L) {
+        CDB_REQUIRE(md->node_id[L] && md->node_md[L], "null level array");
+        for (uint32_t i = 0; i < ix->g_cnt[L]; ++i)
+            CDB_REQUIRE(md->node_md[L][i] == CDB_INVALID_ID || md->node_md[L][i] < md->n_md, "node_md entry out of range");
+    }
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    for (void *g : ix->md_allocs) cudaFree(g);
+    ix->md_allocs.clear();
+    ix->has_md = false;
+    auto upload = [&](const void *src, size_t bytes, const void **dst) -> cdb_status {
+        void *p = nullptr;
+        CDB_CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 4));
+        ix->md_allocs.push_back(p);
+        if (bytes) CDB_CUDA_TRY(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        *dst = p;
+        return CDB_OK;
+    };
+    cdb_status rc;
+    std::vector<const void *> ids(L1), mds(L1);
+    for (uint32_t L = 0; L < L1; ++L)
+        if ((rc = upload(md->node_id[L], (size_t)ix->g_cnt[L] * 4, &ids[L])) || (rc = upload(md->node_md[L], (size_t)ix->g_cnt[L] * 4, &mds[L])))
+            return rc;
+    const void *t_id = nullptr, *t_md = nullptr, *bits = nullptr, *mags = nullptr;
+    if ((rc = upload(ids.data(), L1 * sizeof(void *), &t_id)) || (rc = upload(mds.data(), L1 * sizeof(void *), &t_md)) ||
+        (rc = upload(md->md_bits, (size_t)md->n_md * md->md_dims * 4, &bits)) || (rc = upload(md->md_mags, (size_t)md->n_md * 4, &mags)))
+        return rc;
+    ix->md_node_id = reinterpret_cast<const uint32_t *const *>(t_id);
+    ix->md_node_md = reinterpret_cast<const uint32_t *const *>(t_md);
+    ix->md_bits = reinterpret_cast<const int32_t *>(bits);
+    ix->md_mags = reinterpret_cast<const float *>(mags);
+    ix->md_dims = md->md_dims;
+    ix->md_pseudo_entry = md->pseudo_entry;
+    ix->has_md = true;
+    return CDB_OK;
+}
+
 cdb_status cdb_index_build_graph(cdb_index *ix, const cdb_build_params *bp) {
     CDB_REQUIRE(ix && bp, "null argument");
     CDB_REQUIRE(bp->neighbors_count >= 1 && bp->neighbors_count <= 64 && bp->level0_neighbors_count >= 1 &&
@@ -940,6 +1140,9 @@ cdb_status cdb_index_build_graph(cdb_index *ix, const cdb_build_params *bp) {
     for (uint32_t c = 0; c < ix->desc.dim; ++c)
         root[c] = ix->desc.range_lo + (synth_value(bp->seed ^ 0x526F6F74ull, c) + 1.0f) * 0.5f * (ix->desc.range_hi - ix->desc.range_lo);
     if ((rc = append_f32_locked(ix, root.data(), 1))) return rc;
+    for (void *g : ix->md_allocs) cudaFree(g);
+    ix->md_allocs.clear();
+    ix->has_md = false;
     for (void *g : ix->graph_allocs) cudaFree(g);
     ix->graph_allocs.clear();
     ix->has_graph = false;

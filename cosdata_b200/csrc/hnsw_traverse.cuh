@@ -7,6 +7,7 @@
 // smaller id (the oracle's tie rule where the reference's (MetricResult, pointer) order is unspecified).
 #pragma once
 #include "kernels.h"
+#include "metadata.cuh"
 
 namespace cdb {
 
@@ -27,7 +28,20 @@ struct HnSmem {
 };
 struct HnShared {
     uint32_t qlen, cur, visited, rlen, ncand, err, entry;
+    uint32_t accmask[2];   // accepted slots of the current pop (slot order is kept: the reference scores them in that order)
+    uint32_t err_first;    // (position << 8 | flag) of the first failing evaluation of the current pop
     uint32_t bitkey[HN_MAX_TAKE];
+};
+// metadata-filtered search (cosine.rs:34-102): per-node replica ids / metadata rows of the level and the query-side metadata
+struct HnMdCtx {
+    const uint32_t *node_id;   // [cnt] ProbNode::get_id()
+    const uint32_t *node_md;   // [cnt] row of the metadata table, HN_EMPTY = prop_metadata None
+    const int32_t *md_bits;    // [n_md][M]
+    const float *md_mags;      // [n_md]
+    uint32_t M;
+    const int32_t *q_bits;     // query-side Metadata.mbits (shared memory), nullptr = None
+    float q_mag;
+    bool keep_fs;              // keep the fixed set of the previous traversal of this level (vector_store.rs:266-291)
 };
 struct HnScoreCtx {
     const uint8_t *rows;
@@ -85,24 +99,42 @@ __device__ inline void hn_sort_desc(uint64_t *keys, uint32_t *vals, uint32_t n, 
 // One level.  On return (sh.err == 0) rkeys/rnodes[0..sh.rlen) hold every popped entry sorted best first
 // (the caller truncates to 100 / 64).  All threads of the CTA must call it.  `self_id` is pre-inserted into the
 // fixed set (the query id while searching, the new node's id while indexing: vector_store.rs:271, 807).
+// score node `local` of the level against the query (reference arithmetic); *id = the id the fixed set / keys use
+__device__ __forceinline__ int hn_score_node(const uint32_t *__restrict__ node_row, uint32_t local, const HnScoreCtx &sc, const HnSmem &m,
+                                             float qmag, uint32_t pp, const HnMdCtx *md, float *d, uint32_t *id) {
+    const uint32_t row = node_row[local];
+    const uint8_t *code = sc.rows + (size_t)row * sc.row_pitch;
+    if (!md) {
+        *id = hn_id(sc.root_row, row);
+        return pair_distance(sc.metric, sc.st, sc.dim, m.qs, qmag, pp, code, sc.mags[row], pp, d);
+    }
+    *id = md->node_id[local];
+    const uint32_t mrow = md->node_md[local];
+    const MdSide x{m.qs, qmag, pp, false, 0u, md->q_bits, md->q_mag};
+    const MdSide y{code, sc.mags[row], pp, true, *id, mrow == HN_EMPTY ? nullptr : md->md_bits + (size_t)mrow * md->M,
+                   mrow == HN_EMPTY ? 0.0f : md->md_mags[mrow]};
+    return md_pair_distance(sc.metric, sc.st, sc.dim, md->M, x, y, d);
+}
+
 __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, const uint32_t *__restrict__ adj, uint32_t nb,
                                          uint32_t take, const HnScoreCtx &sc, const HnSmem &m, HnShared &sh, float qmag,
-                                         uint32_t self_id, uint32_t ef, unsigned long long &evals, unsigned long long &pops) {
+                                         uint32_t self_id, uint32_t ef, unsigned long long &evals, unsigned long long &pops,
+                                         const HnMdCtx *md = nullptr) {
     const int tid = threadIdx.x;
     const uint32_t pp = plane_pitch(sc.dim);
     const uint32_t EFP = m.EFP;
-    if (tid < 64) m.fs[tid] = 0ull;
+    const bool keep_fs = md && md->keep_fs;
+    if (tid < 64 && !keep_fs) m.fs[tid] = 0ull;
     __syncthreads();
     if (tid == 0) {
         const uint32_t mask = nb - 1u;
         m.fs[(self_id >> 6) & mask] |= 1ull << (self_id & 0x3f);
         const uint32_t entry = sh.entry;
-        const uint32_t erow = node_row[entry];
         float d = 0.f;
-        const int rc = pair_distance(sc.metric, sc.st, sc.dim, m.qs, qmag, pp, sc.rows + (size_t)erow * sc.row_pitch, sc.mags[erow], pp, &d);
+        uint32_t eid;
+        const int rc = hn_score_node(node_row, entry, sc, m, qmag, pp, md, &d, &eid);
         evals++;
-        if (rc != CDB_OK) sh.err = rc == CDB_CALCULATION_ERROR ? CDB_ERRFLAG_CALCULATION : 2;
-        const uint32_t eid = hn_id(sc.root_row, erow);
+        if (rc != CDB_OK) sh.err = md_err_flag(rc);
         m.fs[(eid >> 6) & mask] |= 1ull << (eid & 0x3f);
         m.qkeys[0] = make_key64(order_key(sc.metric, __float_as_uint(d)), eid);
         m.qnodes[0] = entry;
@@ -126,10 +158,11 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
             sh.ncand = 0;
         }
         uint32_t my_nbl = HN_EMPTY, my_bitkey = 0xFFFFFFFFu;
+        if (tid == 0) sh.err_first = 0xFFFFFFFFu;
         if ((uint32_t)tid < take) {
             my_nbl = adj[(size_t)bn * nb + tid];
             if (my_nbl != HN_EMPTY) {
-                const uint32_t id = hn_id(sc.root_row, node_row[my_nbl]);
+                const uint32_t id = md ? md->node_id[my_nbl] : hn_id(sc.root_row, node_row[my_nbl]);
                 my_bitkey = (((id >> 6) & (nb - 1u)) << 6) | (id & 0x3f);
             }
             sh.bitkey[tid] = my_bitkey;
@@ -140,25 +173,33 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
             accept = ((m.fs[my_bitkey >> 6] >> (my_bitkey & 0x3f)) & 1ull) == 0;
             for (int s2 = 0; s2 < tid && accept; ++s2) accept = sh.bitkey[s2] != my_bitkey;
         }
+        const uint32_t ball = __ballot_sync(0xFFFFFFFFu, accept);   // HN_MAX_TAKE = 64: warps 0 and 1 hold every slot
+        if ((tid & 31) == 0 && tid < 64) sh.accmask[tid >> 5] = ball;
         __syncthreads();  // every thread has read the old fixed set
         if (accept) {
             atomicOr(reinterpret_cast<unsigned long long *>(&m.fs[my_bitkey >> 6]), 1ull << (my_bitkey & 0x3f));
-            m.nnodes[atomicAdd(&sh.ncand, 1u)] = my_nbl;
+            const uint32_t rank = (tid < 32 ? 0u : (uint32_t)__popc(sh.accmask[0])) + (uint32_t)__popc(ball & ((1u << (tid & 31)) - 1u));
+            m.nnodes[rank] = my_nbl;   // compacted in slot order
         }
+        if (tid == 0) sh.ncand = (uint32_t)(__popc(sh.accmask[0]) + __popc(sh.accmask[1]));
         __syncthreads();
         const uint32_t nc = sh.ncand;
         // ---- score the new neighbours, one thread each, reference arithmetic
         if ((uint32_t)tid < nc) {
             const uint32_t nbl = m.nnodes[tid];
-            const uint32_t row = node_row[nbl];
             float d = 0.f;
-            const int rc = pair_distance(sc.metric, sc.st, sc.dim, m.qs, qmag, pp, sc.rows + (size_t)row * sc.row_pitch, sc.mags[row], pp, &d);
-            if (rc != CDB_OK) atomicOr(&sh.err, rc == CDB_CALCULATION_ERROR ? (uint32_t)CDB_ERRFLAG_CALCULATION : 2u);
-            m.nkeys[tid] = make_key64(order_key(sc.metric, __float_as_uint(d)), hn_id(sc.root_row, row));
+            uint32_t nid;
+            const int rc = hn_score_node(node_row, nbl, sc, m, qmag, pp, md, &d, &nid);
+            if (rc != CDB_OK) atomicMin(&sh.err_first, ((uint32_t)tid << 8) | md_err_flag(rc));   // the reference stops at the first Err
+            m.nkeys[tid] = make_key64(order_key(sc.metric, __float_as_uint(d)), nid);
         }
         if (tid == 0) evals += nc;
         __syncthreads();
-        if (sh.err) return;
+        if (sh.err_first != 0xFFFFFFFFu) {
+            if (tid == 0) sh.err = sh.err_first & 0xFFu;
+            __syncthreads();
+            return;
+        }
         // ---- sort the new entries (rank sort, nc <= 64) into nkeys[64..], nnodes[64..]
         if ((uint32_t)tid < nc) {
             const uint64_t k = m.nkeys[tid];

@@ -24,6 +24,18 @@ void values_range_from_counts(const uint64_t *counts, uint64_t n_values, float c
 cdb_status distance_pairs_device(int metric, int st, uint32_t dim, const uint8_t *d_x, const float *d_xm,
                                  const uint8_t *d_y, const float *d_ym, uint32_t row_pitch, uint64_t n,
                                  float *d_out, int32_t *d_status, cudaStream_t s);
+// one side of a batch of VectorData (device pointers; nullptr = None for every element)
+struct MdBatchDev {
+    const uint8_t *codes;
+    const float *mags;
+    const uint32_t *ids;
+    const uint8_t *has_id;
+    const int32_t *md_bits;
+    const float *md_mags;
+    const uint8_t *has_md;
+};
+cdb_status distance_pairs_md_device(int metric, int st, uint32_t dim, uint32_t M, const MdBatchDev &x, const MdBatchDev &y,
+                                    uint32_t row_pitch, uint64_t n, float *d_out, int32_t *d_status, cudaStream_t s);
 // gather-score: one query against rows ids[0..n) of a stored matrix
 cdb_status score_ids_device(int metric, int st, uint32_t dim, const uint8_t *d_q, float qmag,
                             const uint8_t *d_rows, const float *d_mags, uint32_t row_pitch, uint64_t n_rows,
@@ -33,7 +45,8 @@ cdb_status score_ids_device(int metric, int st, uint32_t dim, const uint8_t *d_q
 cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
                              uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
                              const uint32_t *d_cand, const uint32_t *d_cand_counts, uint32_t ncand, uint32_t k, uint32_t id_base,
-                             uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s);
+                             uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s,
+                             const uint32_t *d_labels = nullptr);   // labels: ids reported instead of the candidate ids (replica ids)
 
 // ---- scan.cu
 struct ScanArgs {
@@ -95,6 +108,25 @@ cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s);
 cdb_status hnsw_dedup_device(const uint32_t *d_rows, const float *d_scores, const uint32_t *d_n, uint32_t in_cap, int metric,
                              uint32_t root_row, uint32_t id_base, uint32_t k5, uint32_t nq, uint32_t *d_cand, uint32_t *d_cand_cnt,
                              cudaStream_t s);
+
+// ---- hnsw_md.cu (metadata-filtered search on graphs with replica nodes)
+struct HnswMdArgs {
+    HnswArgs a;                       // out_rows = vector row of each result (CDB_INVALID_ID for pseudo nodes)
+    const uint32_t *const *node_id;   // device table [num_levels+1] of device arrays
+    const uint32_t *const *node_md;
+    const int32_t *md_bits;           // [n_md][M]
+    const float *md_mags;
+    uint32_t M;
+    uint32_t pseudo_entry;
+    const uint32_t *filter_offsets;   // [nq+1] rows of filter_dims per query
+    const int8_t *filter_dims;        // [total][M]
+    const uint8_t *has_filter;        // [nq] (nullptr = no query has a filter)
+    uint32_t *out_ids;                // [nq][out_cap] replica ids
+};
+cdb_status hnsw_search_md_device(const HnswMdArgs &a, cudaStream_t s);
+cdb_status hnsw_dedup_md_device(const uint32_t *d_ids, const uint32_t *d_rows, const float *d_scores, const uint32_t *d_n,
+                                uint32_t in_cap, int metric, uint32_t id_base, uint32_t k5, uint32_t nq, uint32_t *d_cand,
+                                uint32_t *d_labels, uint32_t *d_cand_cnt, cudaStream_t s);
 
 // ---- hnsw_build.cu
 struct HnScoreCtx;

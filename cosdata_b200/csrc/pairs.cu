@@ -2,6 +2,7 @@
 // gather-score for neighbour expansion (S2, src/vector_store.rs:1161-1191) and the
 // exact f32 re-rank of finalize_ann_results (S3, src/vector_store.rs:404-445).
 #include "kernels.h"
+#include "metadata.cuh"
 
 namespace cdb {
 
@@ -23,6 +24,31 @@ cdb_status distance_pairs_device(int metric, int st, uint32_t dim, const uint8_t
                                  float *d_out, int32_t *d_status, cudaStream_t s) {
     if (!n) return CDB_OK;
     distance_pairs_kernel<<<(uint32_t)((n + 63) / 64), 64, 0, s>>>(metric, st, dim, d_x, d_xm, d_y, d_ym, row_pitch, n, d_out, d_status);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+// DistanceMetric::calculate with metadata (replica-kind arms, cosine.rs:34-102); one thread per pair
+__global__ void distance_pairs_md_kernel(int metric, int st, uint32_t dim, uint32_t M, MdBatchDev x, MdBatchDev y, uint32_t pitch,
+                                         uint64_t n, float *__restrict__ out, int32_t *__restrict__ status) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pp = plane_pitch(dim);
+    auto side = [&](const MdBatchDev &b) {
+        const bool has_md = b.md_bits && (!b.has_md || b.has_md[i]);
+        return MdSide{b.codes + i * pitch, b.mags[i], pp, b.ids && (!b.has_id || b.has_id[i]), b.ids ? b.ids[i] : 0u,
+                      has_md ? b.md_bits + i * M : nullptr, has_md ? b.md_mags[i] : 0.0f};
+    };
+    float v = 0.0f;
+    const int rc = md_pair_distance(metric, st, dim, M, side(x), side(y), &v);
+    out[i] = rc == CDB_OK ? v : 0.0f;
+    status[i] = rc;
+}
+
+cdb_status distance_pairs_md_device(int metric, int st, uint32_t dim, uint32_t M, const MdBatchDev &x, const MdBatchDev &y,
+                                    uint32_t row_pitch, uint64_t n, float *d_out, int32_t *d_status, cudaStream_t s) {
+    if (!n) return CDB_OK;
+    distance_pairs_md_kernel<<<(uint32_t)((n + 63) / 64), 64, 0, s>>>(metric, st, dim, M, x, y, row_pitch, n, d_out, d_status);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }
@@ -63,7 +89,8 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
     const float *__restrict__ raw, uint32_t pitch_elems, const float *__restrict__ raw_mags, uint64_t n_rows,
     uint32_t dim, const float *__restrict__ q, uint32_t q_pitch_elems, const float *__restrict__ qmags,
     const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_counts, uint32_t cand_stride, uint32_t k, uint32_t id_base,
-    uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, uint32_t *__restrict__ out_counts) {
+    uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, uint32_t *__restrict__ out_counts,
+    const uint32_t *__restrict__ labels) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *qs = reinterpret_cast<float *>(smem);
     uint64_t *keys = reinterpret_cast<uint64_t *>(qs + round_up(dim, 4));
@@ -87,7 +114,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
             uint64_t key = 0;
             if (ok) {
                 float cs = canon_nan(__fdiv_rn(dp, __fmul_rn(mag_q, raw_mags[rowi])));
-                key = make_key64(order_key(CDB_METRIC_COSINE, __float_as_uint(cs)), id);
+                key = make_key64(order_key(CDB_METRIC_COSINE, __float_as_uint(cs)), labels ? labels[(size_t)b * cand_stride + ci] : id);
             }
             keys[ci] = key;
             if (ok) atomicAdd(&nvalid, 1);
@@ -122,7 +149,8 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
 cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const float *d_raw_mags, uint64_t n_rows,
                              uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
                              const uint32_t *d_cand, const uint32_t *d_cand_counts, uint32_t ncand, uint32_t k, uint32_t id_base,
-                             uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s) {
+                             uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s,
+                             const uint32_t *d_labels) {
     if (!nq) return CDB_OK;
     if (k == 0) { set_error("rerank: k must be > 0"); return CDB_INVALID_PARAMS; }
     uint32_t pcap = 1;
@@ -131,7 +159,7 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
     if (smem > 200 * 1024) { set_error("rerank: too many candidates per query"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(rerank_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_f32_kernel<<<nq, RERANK_THREADS, smem, s>>>(d_raw, pitch_elems, d_raw_mags, n_rows, dim, d_q, q_pitch_elems,
-                                                        d_qmags, d_cand, d_cand_counts, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts);
+                                                        d_qmags, d_cand, d_cand_counts, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts, d_labels);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

@@ -46,7 +46,8 @@ enum {
     CDB_INVALID_PARAMS = 3,
     CDB_CUDA_ERROR = 4,
     CDB_NCCL_ERROR = 5,
-    CDB_UNSUPPORTED = 6        /* reference hits unimplemented!() / metadata replica arms */
+    CDB_UNSUPPORTED = 6,       /* reference hits unimplemented!() */
+    CDB_UNREACHABLE_ARM = 7    /* replica-kind pair the reference marks unreachable!() (cosine.rs:56-58, 68-70, 91-98): it would panic */
 };
 
 /* StorageType (src/quantization/mod.rs:19-25); SubByte(r) is CDB_ST_SUB1..3. */
@@ -79,8 +80,10 @@ enum {
 
 /* per-query error flag bits (u8 err_flags[B]) */
 enum {
-    CDB_ERRFLAG_CALCULATION = 1 /* some scored pair had a zero denominator (cosine.rs:230-231);
-                                   the reference `?`-propagates this and fails the query */
+    CDB_ERRFLAG_CALCULATION = 1, /* some scored pair had a zero denominator (cosine.rs:230-231);
+                                    the reference `?`-propagates this and fails the query */
+    CDB_ERRFLAG_OTHER = 2,       /* another Err of DistanceFunction::calculate */
+    CDB_ERRFLAG_UNREACHABLE = 4  /* a replica-kind pair the reference marks unreachable!() was scored (the reference panics) */
 };
 
 #define CDB_INVALID_ID 0xFFFFFFFFu
@@ -206,12 +209,34 @@ cdb_status cdb_index_append_synthetic(cdb_index *index, uint64_t seed, uint64_t 
 /* copy stored state back (tests): codes/mags of rows [first, first+n) */
 cdb_status cdb_index_read_codes(const cdb_index *index, uint64_t first, uint64_t n, void *out_codes, float *out_mags);
 
+/* ---- DistanceFunction::calculate with metadata: the replica-kind arms of CosineSimilarity (src/distance/cosine.rs:34-102).
+ * One side of a batch of VectorData { id: Option<&InternalId>, quantized_vec, metadata: Option<&Metadata> }
+ * (src/models/types.rs:203-212): ids == NULL -> id None for all, has_id (optional) marks per-element Some/None;
+ * md_bits == NULL -> metadata None for all, has_md (optional) per element; md_bits is [n x md_dims] i32 (Metadata.mbits),
+ * md_mags[n] = Metadata.mag.  x is the query side (fvec_data), y the node side: kinds Pseudo/Base/Metadata follow
+ * VectorData::replica_node_kind (types.rs:223-243).  out_status: CDB_OK, CDB_CALCULATION_ERROR (zero metadata or vector
+ * norm product), CDB_UNREACHABLE_ARM (pairs the reference marks unreachable!()), or the storage arms' errors.  Metrics
+ * other than cosine ignore the metadata, as in the reference. */
+typedef struct {
+    const void *codes;       /* tight layout of cdb_code_bytes() */
+    const float *mags;
+    const uint32_t *ids;
+    const uint8_t *has_id;
+    const int32_t *md_bits;
+    const float *md_mags;
+    const uint8_t *has_md;
+} cdb_vector_data_batch;
+cdb_status cdb_distance_pairs_md(int32_t device, int32_t metric, int32_t storage_type, uint32_t dim, uint32_t md_dims,
+                                 const cdb_vector_data_batch *x, const cdb_vector_data_batch *y, uint64_t n_pairs,
+                                 float *out, int32_t *out_status);
+
 /* ------------------------------------------------------------ HNSW graph upload
  * Flat export of the reference's ProbNode graph (src/models/prob_node.rs:99-109): the vector of node
  * i at level L is row node_row[L][i] of the index; adjacency[L][i*nbrs(L)+s] is the level-local index
  * of the neighbour in slot s (CDB_INVALID_ID = empty slot, slot order preserved: the search examines
  * the first shortlist_size slots); child[L][i] is the level-local index one level down (L >= 1).
- * Level 0 must contain every row (node_row[0][i] == i).  root_row is the row holding the root vector
+ * Every index must be in range (checked).  Without graph metadata level 0 holds one node per row and result ids are rows;
+ * with cdb_index_set_graph_metadata several nodes may share a row.  root_row is the row holding the root vector
  * (id u32::MAX in the reference, vector_store.rs:57-67); it is never returned.  Arrays are copied. */
 typedef struct {
     uint32_t num_levels;              /* hnsw_params.num_layers: levels 0..=num_levels */
@@ -225,6 +250,25 @@ typedef struct {
     const uint32_t *const *child;     /* child[0] ignored */
 } cdb_graph_desc;
 cdb_status cdb_index_set_graph(cdb_index *index, const cdb_graph_desc *graph);
+
+/* Replica nodes and metadata of a graph uploaded with cdb_index_set_graph (collections with a metadata schema:
+ * src/vector_store.rs:57-250, 485-712).  One embedding may own several graph nodes (its base replica and one per
+ * metadata dimension set, src/models/types.rs:163-176) that share the embedding's vector row; pseudo nodes share the
+ * pseudo root's row.  node_id[L][i] = ProbNode::get_id() (replica id, or prop_value.id without metadata);
+ * node_md[L][i] = row of the metadata table (md_bits [n_md x md_dims] = Metadata.mbits, md_mags[n_md] = Metadata.mag) or
+ * CDB_INVALID_ID when the node has no metadata; pseudo_entry = top-level index of the pseudo root
+ * (HNSWIndex::get_pseudo_root_vec), the entry of every query that carries a filter (src/indexes/hnsw/mod.rs:416-420).
+ * With metadata attached, results carry replica ids (as the reference's InternalSearchResult does) and
+ * CDB_MODE_HNSW searches must go through cdb_search_batch_filtered. */
+typedef struct {
+    uint32_t md_dims, n_md;
+    const int32_t *md_bits;
+    const float *md_mags;
+    const uint32_t *const *node_id;   /* [num_levels+1][level_counts[L]] */
+    const uint32_t *const *node_md;
+    uint32_t pseudo_entry;
+} cdb_graph_metadata;
+cdb_status cdb_index_set_graph_metadata(cdb_index *index, const cdb_graph_metadata *md);
 /* GPU-side index build (index_embeddings, src/vector_store.rs:714-940): appends the root vector (random in
  * values_range, id u32::MAX; vector_store.rs:57-67) as the last row and builds the HNSW graph over all rows with the
  * reference's algorithm (traverse with ef_construction per level, create_node_edges / add_neighbor with
@@ -258,6 +302,15 @@ cdb_status cdb_search_batch(cdb_index *index, const float *queries, uint32_t n_q
                             const cdb_search_params *params,
                             uint32_t *out_ids, float *out_scores, uint32_t *out_counts,
                             uint8_t *err_flags);
+/* search_internal with metadata filters (src/indexes/hnsw/mod.rs:390-440, ann_search filter branch src/vector_store.rs:273-313):
+ * CDB_MODE_HNSW on a graph with cdb_index_set_graph_metadata.  Query q has the filter Some(filter_dims rows
+ * [filter_offsets[q], filter_offsets[q+1])) when has_filter[q] != 0 -- each row is one QueryFilterDimensions (i8 values
+ * -1/0/1, md_dims wide, src/metadata/query_filtering.rs:27) -- else None (search from the main root).  has_filter == NULL
+ * means no query has a filter.  err_flags: CDB_ERRFLAG_CALCULATION / CDB_ERRFLAG_UNREACHABLE (the reference would panic,
+ * e.g. Some(empty list) or an unfiltered query reaching a metadata node).  out_ids are replica ids. */
+cdb_status cdb_search_batch_filtered(cdb_index *index, const float *queries, uint32_t n_queries, const cdb_search_params *params,
+                                     const uint32_t *filter_offsets, const int8_t *filter_dims, const uint8_t *has_filter,
+                                     uint32_t *out_ids, float *out_scores, uint32_t *out_counts, uint8_t *err_flags);
 /* same, every pointer is DEVICE memory on the index's device; asynchronous on `stream`.  Searches on one handle share
  * its scratch arena and are ordered on the device (a search on another stream waits for the previous one). */
 cdb_status cdb_search_batch_device(cdb_index *index, const float *d_queries, uint32_t n_queries,

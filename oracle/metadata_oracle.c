@@ -1,0 +1,307 @@
+/*
+ * metadata_oracle.c -- see metadata_oracle.h.  TEST INFRASTRUCTURE ONLY.
+ */
+#include "metadata_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* Metadata::from(MetadataDimensions), src/models/types.rs:111-125: sequential sum of (d as f32)^2, clamped, sqrt */
+float orc_metadata_mag(const int32_t *dims, size_t m) {
+    float total = 0.0f;
+    for (size_t i = 0; i < m; ++i) { float x = (float)dims[i]; total += x * x; }
+    if (total > FLT_MAX || total != total) total = FLT_MAX; /* total.min(f32::MAX): inf (and NaN) -> MAX */
+    return sqrtf(total);
+}
+/* Metadata::from(&QueryFilterDimensions), src/models/types.rs:127-146 */
+float orc_query_filter_mag(const int8_t *dims, size_t m) {
+    float total = 0.0f;
+    for (size_t i = 0; i < m; ++i) { float x = (float)dims[i]; total += x * x; }
+    return sqrtf(total);
+}
+
+/* VectorData::replica_node_kind, src/models/types.rs:223-243 */
+int orc_replica_kind(const orc_vector_data *v) {
+    if (!v->md_bits) return ORC_KIND_BASE;
+    if (v->md_mag == 0.0f) return ORC_KIND_BASE;
+    if (v->has_id && v->id >= 0xFFFFFFFFu - 257u && v->id <= 0xFFFFFFFFu - 2u) return ORC_KIND_PSEUDO;
+    return ORC_KIND_METADATA;
+}
+
+/* cosine_similarity_mdims, src/distance/cosine.rs:243-259: dot_product_f32 over the i32 -> f32 dims */
+static int mdims_cosine(size_t m, const orc_vector_data *x, const orc_vector_data *y, float *out) {
+    float *a = (float *)malloc(sizeof(float) * (m ? m : 1)), *b = (float *)malloc(sizeof(float) * (m ? m : 1));
+    for (size_t i = 0; i < m; ++i) { a[i] = (float)x->md_bits[i]; b[i] = (float)y->md_bits[i]; }
+    const float dp = orc_dot_f32_simd(a, b, m);
+    free(a);
+    free(b);
+    const float den = x->md_mag * y->md_mag; /* cosine_similarity_from_dot_product, cosine.rs:223-235 */
+    if (den == 0.0f) return ORC_CALCULATION_ERROR;
+    *out = dp / den;
+    return ORC_OK;
+}
+
+int orc_distance_md(int metric, int st, size_t dim, size_t m, const orc_vector_data *x, const orc_vector_data *y, float *out) {
+    if (metric != ORC_METRIC_COSINE) return orc_distance(metric, st, dim, x->code, x->mag, y->code, y->mag, out);
+    const int xk = orc_replica_kind(x), yk = orc_replica_kind(y);
+    /* match (y_kind, x_kind), cosine.rs:45-100 */
+    if (yk == ORC_KIND_PSEUDO && xk == ORC_KIND_PSEUDO) return mdims_cosine(m, x, y, out);
+    if (yk == ORC_KIND_PSEUDO && xk == ORC_KIND_METADATA) {
+        *out = memcmp(x->md_bits, y->md_bits, sizeof(int32_t) * m) == 0 ? 1.0f : -1.0f;
+        return ORC_OK;
+    }
+    if (yk == ORC_KIND_BASE && xk == ORC_KIND_BASE) return orc_distance(metric, st, dim, x->code, x->mag, y->code, y->mag, out);
+    if (yk == ORC_KIND_METADATA && xk == ORC_KIND_METADATA) {
+        float mc;
+        int rc = mdims_cosine(m, x, y, &mc);
+        if (rc != ORC_OK) return rc;
+        if (mc > 0.99f) return orc_distance(metric, st, dim, x->code, x->mag, y->code, y->mag, out);
+        *out = -1.0f;
+        return ORC_OK;
+    }
+    if (yk == ORC_KIND_BASE && xk == ORC_KIND_METADATA) { *out = 0.0f; return ORC_OK; }
+    return ORC_UNREACHABLE; /* (Pseudo,Base) (Base,Pseudo) (Metadata,Pseudo) (Metadata,Base) */
+}
+
+/* ------------------------------------------------------------------ traversal with metadata */
+static inline uint32_t mg_nbrs(const orc_md_graph *mg, uint32_t level) {
+    return level == 0 ? mg->g.level0_neighbors_count : mg->g.neighbors_count;
+}
+static inline uint64_t mkey(const orc_md_graph *mg, float score, uint32_t id) {
+    return ((uint64_t)orc_order_key(mg->g.metric, score) << 32) | (uint64_t)(~id);
+}
+static inline void fs_insert(uint64_t *b, uint32_t len, uint32_t v) { b[(v >> 6) & (len - 1u)] |= 1ull << (v & 0x3f); }
+static inline int fs_member(const uint64_t *b, uint32_t len, uint32_t v) { return (b[(v >> 6) & (len - 1u)] >> (v & 0x3f)) & 1ull; }
+
+static void node_data(const orc_md_graph *mg, uint32_t level, uint32_t node, orc_vector_data *v) {
+    const uint32_t row = mg->g.node_row[level][node];
+    const uint32_t md = mg->node_md[level][node];
+    v->code = (const uint8_t *)mg->g.codes + (size_t)row * orc_code_bytes(mg->g.storage_type, mg->g.dim);
+    v->mag = mg->g.mags[row];
+    v->has_id = 1;
+    v->id = mg->node_id[level][node];
+    v->md_bits = md == ORC_EMPTY ? NULL : mg->md_bits + (size_t)md * mg->md_dims;
+    v->md_mag = md == ORC_EMPTY ? 0.0f : mg->md_mags[md];
+}
+
+typedef struct { uint64_t key; uint32_t node; float score; } mitem;
+static int cmp_desc(const void *a, const void *b) {
+    uint64_t x = ((const mitem *)a)->key, y = ((const mitem *)b)->key;
+    return (x < y) - (x > y);
+}
+static void push(mitem *h, size_t *n, mitem it) {
+    size_t i = (*n)++;
+    h[i] = it;
+    while (i > 0) { size_t p = (i - 1) / 2; if (h[p].key >= h[i].key) break; mitem t = h[p]; h[p] = h[i]; h[i] = t; i = p; }
+}
+static mitem pop(mitem *h, size_t *n) {
+    mitem top = h[0];
+    h[0] = h[--(*n)];
+    for (size_t i = 0;;) {
+        size_t l = 2 * i + 1, r = l + 1, m = i;
+        if (l < *n && h[l].key > h[m].key) m = l;
+        if (r < *n && h[r].key > h[m].key) m = r;
+        if (m == i) break;
+        mitem t = h[m]; h[m] = h[i]; h[i] = t; i = m;
+    }
+    return top;
+}
+
+/* traverse_find_nearest (vector_store.rs:1112-1204) with fvec metadata `x`; the fixed set is the caller's (shared between
+ * the traversals of one level, vector_store.rs:266-271, 277-291) */
+static int traverse_md(const orc_md_graph *mg, uint32_t level, uint32_t entry, const orc_vector_data *x, uint32_t ef,
+                       uint32_t shortlist, uint64_t *fs, mitem *out, uint32_t *out_n, uint64_t *evals, uint64_t *pops) {
+    const uint32_t nb = mg_nbrs(mg, level);
+    const uint32_t *adj = mg->g.adj[level];
+    const uint32_t take = shortlist < nb ? shortlist : nb;
+    size_t hn = 0, rn = 0;
+    mitem *heap = (mitem *)malloc(sizeof(mitem) * ((size_t)ef * take + 2));
+    mitem *res = (mitem *)malloc(sizeof(mitem) * ((size_t)ef + 1));
+    orc_vector_data y;
+    float d;
+    node_data(mg, level, entry, &y);
+    int rc = orc_distance_md(mg->g.metric, mg->g.storage_type, mg->g.dim, mg->md_dims, x, &y, &d);
+    if (evals) (*evals)++;
+    if (rc != ORC_OK) goto done;
+    fs_insert(fs, nb, y.id);
+    push(heap, &hn, (mitem){mkey(mg, d, y.id), entry, d});
+    uint32_t visited = 0;
+    while (hn > 0) {
+        mitem cur = pop(heap, &hn);
+        if (visited >= ef) break;
+        visited++;
+        if (pops) (*pops)++;
+        res[rn++] = cur;
+        for (uint32_t s = 0; s < take; ++s) {
+            const uint32_t nbl = adj[(size_t)cur.node * nb + s];
+            if (nbl == ORC_EMPTY) continue;
+            node_data(mg, level, nbl, &y);
+            if (fs_member(fs, nb, y.id)) continue;
+            rc = orc_distance_md(mg->g.metric, mg->g.storage_type, mg->g.dim, mg->md_dims, x, &y, &d);
+            if (evals) (*evals)++;
+            if (rc != ORC_OK) goto done;
+            fs_insert(fs, nb, y.id);
+            push(heap, &hn, (mitem){mkey(mg, d, y.id), nbl, d});
+        }
+    }
+    qsort(res, rn, sizeof(mitem), cmp_desc);
+    if (rn > 100) rn = 100;
+    memcpy(out, res, sizeof(mitem) * rn);
+    *out_n = (uint32_t)rn;
+done:
+    free(heap);
+    free(res);
+    return rc;
+}
+
+int orc_ann_search_md(const orc_md_graph *mg, const void *qcode, float qmag, const int8_t *filters, size_t n_filters,
+                      int has_filter, uint32_t ef_search, uint32_t shortlist_size, uint32_t *out_ids, uint32_t *out_rows,
+                      float *out_scores, size_t cap, size_t *out_n, uint64_t *evals, uint64_t *pops) {
+    const size_t M = mg->md_dims;
+    uint32_t entry = has_filter ? mg->pseudo_entry : mg->g.entry; /* hnsw/mod.rs:416-420 */
+    uint32_t maxnb = mg->g.level0_neighbors_count > mg->g.neighbors_count ? mg->g.level0_neighbors_count : mg->g.neighbors_count;
+    uint64_t *fs = (uint64_t *)malloc(sizeof(uint64_t) * maxnb);
+    int32_t *fbits = (int32_t *)malloc(sizeof(int32_t) * (M ? M : 1));
+    mitem *z = (mitem *)malloc(sizeof(mitem) * (100 * (n_filters ? n_filters : 1) + 1));
+    mitem tmp[100];
+    size_t total = 0;
+    int rc = ORC_OK;
+    orc_vector_data x = {qcode, qmag, 0, 0, NULL, 0.0f};
+    for (int level = (int)mg->g.num_levels; level >= 0 && rc == ORC_OK; --level) {
+        const uint32_t nb = mg_nbrs(mg, (uint32_t)level);
+        size_t zn = 0;
+        memset(fs, 0, sizeof(uint64_t) * nb);
+        fs_insert(fs, nb, ORC_QUERY_ID);
+        if (has_filter) {
+            for (size_t f = 0; f < n_filters && rc == ORC_OK; ++f) {
+                for (size_t i = 0; i < M; ++i) fbits[i] = filters[f * M + i];
+                x.md_bits = fbits;
+                x.md_mag = orc_query_filter_mag(filters + f * M, M);
+                uint32_t tn = 0;
+                rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_search, shortlist_size, fs, tmp, &tn, evals, pops);
+                if (rc != ORC_OK) break;
+                for (uint32_t i = 0; i < tn; ++i) {
+                    if (mg->g.metric == ORC_METRIC_COSINE && tmp[i].score == -1.0f) continue; /* vector_store.rs:294-303 */
+                    z[zn++] = tmp[i];
+                }
+            }
+            if (rc != ORC_OK) break;
+            qsort(z, zn, sizeof(mitem), cmp_desc);
+            if (zn > 100) zn = 100;
+        } else {
+            x.md_bits = NULL;
+            uint32_t tn = 0;
+            rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_search, shortlist_size, fs, z, &tn, evals, pops);
+            if (rc != ORC_OK) break;
+            zn = tn;
+        }
+        if (zn == 0) { /* vector_store.rs:329-380 */
+            orc_vector_data y;
+            node_data(mg, (uint32_t)level, entry, &y);
+            float best = 0.0f;
+            if (has_filter) {
+                int have = 0;
+                for (size_t f = 0; f < n_filters && rc == ORC_OK; ++f) {
+                    for (size_t i = 0; i < M; ++i) fbits[i] = filters[f * M + i];
+                    x.md_bits = fbits;
+                    x.md_mag = orc_query_filter_mag(filters + f * M, M);
+                    float d;
+                    rc = orc_distance_md(mg->g.metric, mg->g.storage_type, mg->g.dim, M, &x, &y, &d);
+                    if (rc != ORC_OK) break;
+                    if (!have || orc_order_key(mg->g.metric, d) > orc_order_key(mg->g.metric, best)) { best = d; have = 1; }
+                }
+                if (rc == ORC_OK && !have) rc = ORC_UNREACHABLE; /* dists.into_iter().max().unwrap() on an empty vec panics */
+            } else {
+                x.md_bits = NULL;
+                rc = orc_distance_md(mg->g.metric, mg->g.storage_type, mg->g.dim, M, &x, &y, &best);
+            }
+            if (rc != ORC_OK) break;
+            z[0] = (mitem){mkey(mg, best, y.id), entry, best};
+            zn = 1;
+        }
+        for (size_t i = 0; i < zn && total < cap; ++i) {
+            orc_vector_data y;
+            node_data(mg, (uint32_t)level, z[i].node, &y);
+            out_ids[total] = y.id;
+            out_rows[total] = orc_replica_kind(&y) == ORC_KIND_PSEUDO ? ORC_EMPTY : mg->g.node_row[level][z[i].node];
+            out_scores[total] = z[i].score;
+            total++;
+        }
+        if (level > 0) entry = mg->g.child[level][z[0].node];
+    }
+    free(fs);
+    free(fbits);
+    free(z);
+    *out_n = total;
+    return rc;
+}
+
+int orc_hnsw_search_batch_md(const orc_md_graph *mg, const float *raw, const float *queries, size_t nq, float lo, float hi,
+                             const uint32_t *filter_offsets, const int8_t *filter_dims, const uint8_t *has_filter,
+                             uint32_t ef_search, uint32_t shortlist_size, size_t k, int threads, uint32_t *out_ids,
+                             float *out_scores, uint32_t *out_counts, uint8_t *err, uint64_t *evals, uint64_t *pops) {
+    if (threads < 1) threads = 1;
+    const size_t dim = mg->g.dim, cb = orc_code_bytes(mg->g.storage_type, dim);
+    const size_t cap = ((size_t)mg->g.num_levels + 1) * 100;
+    uint64_t ev_total = 0, pop_total = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1) reduction(+ : ev_total, pop_total)
+    for (long long qi = 0; qi < (long long)nq; ++qi) {
+        const float *q = queries + (size_t)qi * dim;
+        uint8_t *qcode = (uint8_t *)malloc(cb ? cb : 1);
+        float qmag;
+        orc_quantize(mg->g.storage_type, lo, hi, q, dim, qcode, &qmag);
+        uint32_t *ids = (uint32_t *)malloc(sizeof(uint32_t) * cap), *rows = (uint32_t *)malloc(sizeof(uint32_t) * cap);
+        float *sc = (float *)malloc(sizeof(float) * cap);
+        size_t n = 0;
+        uint64_t ev = 0, pp = 0;
+        const int hf = has_filter ? has_filter[qi] : 0;
+        const uint32_t f0 = filter_offsets ? filter_offsets[qi] : 0, f1 = filter_offsets ? filter_offsets[qi + 1] : 0;
+        int rc = orc_ann_search_md(mg, qcode, qmag, filter_dims ? filter_dims + (size_t)f0 * mg->md_dims : NULL, f1 - f0, hf,
+                                   ef_search, shortlist_size, ids, rows, sc, cap, &n, &ev, &pp);
+        ev_total += ev;
+        pop_total += pp;
+        for (size_t j = 0; j < k; ++j) { out_ids[(size_t)qi * k + j] = 0xFFFFFFFFu; out_scores[(size_t)qi * k + j] = 0.0f; }
+        if (out_counts) out_counts[qi] = 0;
+        if (rc != ORC_OK) {
+            if (err) err[qi] = (uint8_t)(rc == ORC_CALCULATION_ERROR ? 1 : rc == ORC_UNREACHABLE ? 4 : 2);
+        } else {
+            if (err) err[qi] = 0;
+            /* remove_duplicates_and_filter (common.rs:381-412): first occurrence per replica id, no root, no pseudo nodes,
+             * sort by the traversal similarity, keep 5k */
+            mitem *c = (mitem *)malloc(sizeof(mitem) * (n ? n : 1));
+            size_t m = 0;
+            for (size_t i = 0; i < n; ++i) {
+                int seen = 0;
+                for (size_t j = 0; j < i; ++j)
+                    if (ids[j] == ids[i]) { seen = 1; break; }
+                if (seen || ids[i] == 0xFFFFFFFFu || rows[i] == ORC_EMPTY) continue;
+                c[m++] = (mitem){mkey(mg, sc[i], ids[i]), (uint32_t)i, sc[i]};
+            }
+            qsort(c, m, sizeof(mitem), cmp_desc);
+            if (m > 5 * k) m = 5 * k;
+            /* finalize_ann_results (vector_store.rs:404-445): exact cosine on the base vector of each replica */
+            const float mag_q = orc_mag_f32(q, dim);
+            for (size_t i = 0; i < m; ++i) {
+                const size_t src = c[i].node;
+                const float cs = orc_rerank_cosine(q, mag_q, raw + (size_t)rows[src] * dim, dim);
+                c[i].key = ((uint64_t)orc_order_key(ORC_METRIC_COSINE, cs) << 32) | (uint64_t)(~ids[src]);
+                c[i].score = cs;
+                c[i].node = ids[src];
+            }
+            qsort(c, m, sizeof(mitem), cmp_desc);
+            const size_t mk = m < k ? m : k;
+            for (size_t i = 0; i < mk; ++i) { out_ids[(size_t)qi * k + i] = c[i].node; out_scores[(size_t)qi * k + i] = c[i].score; }
+            if (out_counts) out_counts[qi] = (uint32_t)mk;
+            free(c);
+        }
+        free(qcode);
+        free(ids);
+        free(rows);
+        free(sc);
+    }
+    if (evals) *evals = ev_total;
+    if (pops) *pops = pop_total;
+    return ORC_OK;
+}

@@ -1,0 +1,221 @@
+"""Pins oracle/metadata_oracle.c (metadata-filter arms, filtered ann_search) against a pure-Python restatement of
+src/distance/cosine.rs:34-102, 243-259, src/models/types.rs:111-147, 223-243 and src/vector_store.rs:256-402."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from oracle import pymeta
+from tests import f32emu, mdgraph
+
+EMPTY = 0xFFFFFFFF
+
+
+def bits(x):
+    return np.float32(x).view(np.uint32)
+
+
+def py_kind(vid, md_bits, md_mag):
+    if md_bits is None or md_mag == 0.0:
+        return "base"
+    if vid is not None and 0xFFFFFFFF - 257 <= vid <= 0xFFFFFFFF - 2:
+        return "pseudo"
+    return "metadata"
+
+
+def py_mdims_cos(xb, xm, yb, ym):
+    dot = f32emu.dot_f32_simd_order([float(v) for v in xb], [float(v) for v in yb])
+    den = f32emu.mul32(float(xm), float(ym))
+    return None if den == 0.0 else np.float32(f32emu.div32(dot, den))
+
+
+def py_distance(metric, st, dim, x, y):
+    """x, y = (code, mag, id or None, md_bits or None, md_mag) -> (rc, value)"""
+    if metric != 0:
+        return orc.distance(metric, st, dim, x[0], x[1], y[0], y[1])
+    xk, yk = py_kind(x[2], x[3], x[4]), py_kind(y[2], y[3], y[4])
+    if (yk, xk) == ("pseudo", "pseudo"):
+        c = py_mdims_cos(x[3], x[4], y[3], y[4])
+        return (2, np.float32(0)) if c is None else (0, c)
+    if (yk, xk) == ("pseudo", "metadata"):
+        return 0, np.float32(1.0 if list(x[3]) == list(y[3]) else -1.0)
+    if (yk, xk) == ("base", "base"):
+        return orc.distance(metric, st, dim, x[0], x[1], y[0], y[1])
+    if (yk, xk) == ("metadata", "metadata"):
+        c = py_mdims_cos(x[3], x[4], y[3], y[4])
+        if c is None:
+            return 2, np.float32(0)
+        return orc.distance(metric, st, dim, x[0], x[1], y[0], y[1]) if c > np.float32(0.99) else (0, np.float32(-1.0))
+    if (yk, xk) == ("base", "metadata"):
+        return 0, np.float32(0.0)
+    return 7, np.float32(0)
+
+
+def test_metadata_magnitudes():
+    assert pymeta.metadata_mag([1, 1, 0, 1]) == np.float32(np.sqrt(np.float32(3)))
+    assert pymeta.metadata_mag([0, 0, 0]) == 0.0
+    assert pymeta.metadata_mag([2 ** 31 - 1] * 64) == np.float32(2.0 ** 34)       # (i32::MAX as f32) = 2^31; 64 * 2^62 = 2^68, far below f32::MAX
+    assert pymeta.query_filter_mag([1, -1, 0, 1]) == np.float32(np.sqrt(np.float32(3)))
+    big = np.arange(1, 40, dtype=np.int32) * 1000
+    assert pymeta.metadata_mag(big) == np.float32(f32emu.sqrt32(f32emu.sumsq_sequential([float(v) for v in big])))
+
+
+def test_replica_kinds_and_every_arm():
+    dim, st, M = 16, 4, 5
+    v = orc.synth_matrix(1, 3, dim)
+    codes, mags = orc.quantize_batch(st, v)
+    pat_a, pat_b = np.array([1, 0, 1, 1, 0], np.int32), np.array([0, 1, 1, 0, 0], np.int32)
+    zeros = np.zeros(M, np.int32)
+    sides = {
+        "none": (None, None, 0.0), "noid_md": (None, pat_a, pymeta.metadata_mag(pat_a)), "zero_md": (5, zeros, 0.0),
+        "meta_a": (8, pat_a, pymeta.metadata_mag(pat_a)), "meta_b": (9, pat_b, pymeta.metadata_mag(pat_b)),
+        "pseudo_lo": (0xFFFFFFFF - 257, pat_a, pymeta.metadata_mag(pat_a)), "pseudo_hi": (0xFFFFFFFF - 2, pat_b, pymeta.metadata_mag(pat_b)),
+        "just_below": (0xFFFFFFFF - 258, pat_a, pymeta.metadata_mag(pat_a)), "query_id": (0xFFFFFFFF - 1, pat_a, pymeta.metadata_mag(pat_a)),
+        "root_id_md": (0xFFFFFFFF, pat_a, pymeta.metadata_mag(pat_a)),
+    }
+    want_kind = {"none": 1, "noid_md": 2, "zero_md": 1, "meta_a": 2, "meta_b": 2, "pseudo_lo": 0, "pseudo_hi": 0, "just_below": 2,
+                 "query_id": 2, "root_id_md": 2}
+    for name, (vid, mb, mm) in sides.items():
+        assert pymeta.replica_kind(pymeta.VectorData(codes[0], mags[0], vid, mb, mm)) == want_kind[name], name
+    seen = set()
+    for xn, (xid, xb, xm) in sides.items():
+        for yn, (yid, yb, ym) in sides.items():
+            for metric in (0, 3):
+                x = pymeta.VectorData(codes[0], mags[0], xid, xb, xm)
+                y = pymeta.VectorData(codes[1], mags[1], yid, yb, ym)
+                rc, val = pymeta.distance_md(metric, st, dim, M, x, y)
+                wrc, wval = py_distance(metric, st, dim, (codes[0], mags[0], xid, xb, xm), (codes[1], mags[1], yid, yb, ym))
+                assert rc == wrc and (rc != 0 or bits(val) == bits(wval)), (xn, yn, metric)
+                if metric == 0:
+                    seen.add((want_kind[yn], want_kind[xn], rc))
+    assert {(0, 0, 0), (0, 2, 0), (1, 1, 0), (2, 2, 0), (1, 2, 0), (0, 1, 7), (1, 0, 7), (2, 0, 7), (2, 1, 7)} <= seen
+
+
+# ------------------------------------------------------------------ filtered ann_search, pure Python
+
+def py_search(mg, vecs, q, filt, k, ef, shortlist):
+    fg = mg.fg
+    st, metric, dim, M = fg.storage_type, fg.metric, fg.dim, mg.md_dims
+    qc, qm = orc.quantize(st, q)
+
+    def node(level, i):
+        row = int(fg.node_row[level][i])
+        md = int(mg.node_md[level][i])
+        return (fg.codes[row], fg.mags[row], int(mg.node_id[level][i]), None if md == EMPTY else mg.md_bits[md],
+                0.0 if md == EMPTY else mg.md_mags[md])
+
+    def key(score, vid):
+        return (orc.order_key(metric, score) << 32) | (~vid & 0xFFFFFFFF)
+
+    def traverse(level, entry, x, fs, nb):
+        adj = fg.adj[level].reshape(-1, nb)
+        take = min(shortlist, nb)
+        y = node(level, entry)
+        rc, d = py_distance(metric, st, dim, x, y)
+        if rc:
+            return rc, []
+        fs.add(((y[2] >> 6) & (nb - 1), y[2] & 63))
+        heap, res, visited = [(key(d, y[2]), entry, d)], [], 0
+        while heap:
+            heap.sort(reverse=True)
+            cur = heap.pop(0)
+            if visited >= ef:
+                break
+            visited += 1
+            res.append(cur)
+            for s in range(take):
+                nbl = int(adj[cur[1]][s])
+                if nbl == EMPTY:
+                    continue
+                y = node(level, nbl)
+                bit = ((y[2] >> 6) & (nb - 1), y[2] & 63)
+                if bit in fs:
+                    continue
+                rc, d = py_distance(metric, st, dim, x, y)
+                if rc:
+                    return rc, []
+                fs.add(bit)
+                heap.append((key(d, y[2]), nbl, d))
+        res.sort(reverse=True)
+        return 0, res[:100]
+
+    entry = mg.pseudo_entry if filt is not None else fg.entry
+    out = []
+    for level in range(fg.num_levels, -1, -1):
+        nb = fg.nbrs(level)
+        qid = 0xFFFFFFFE
+        fs = {((qid >> 6) & (nb - 1), qid & 63)}
+        if filt is not None:
+            z = []
+            for f in filt:
+                x = (qc, qm, None, np.asarray(f, np.int32), pymeta.query_filter_mag(f))
+                rc, r = traverse(level, entry, x, fs, nb)
+                if rc:
+                    return rc, [], []
+                z += [t for t in r if not (metric == 0 and t[2] == np.float32(-1.0))]
+            z.sort(reverse=True)
+            z = z[:100]
+        else:
+            rc, z = traverse(level, entry, (qc, qm, None, None, 0.0), fs, nb)
+            if rc:
+                return rc, [], []
+        if not z:
+            y = node(level, entry)
+            if filt is not None:
+                ds = []
+                for f in filt:
+                    rc, d = py_distance(metric, st, dim, (qc, qm, None, np.asarray(f, np.int32), pymeta.query_filter_mag(f)), y)
+                    if rc:
+                        return rc, [], []
+                    ds.append(d)
+                if not ds:
+                    return 7, [], []
+                d = max(ds, key=lambda v: orc.order_key(metric, v))
+            else:
+                rc, d = py_distance(metric, st, dim, (qc, qm, None, None, 0.0), y)
+                if rc:
+                    return rc, [], []
+            z = [(key(d, y[2]), entry, d)]
+        for _, i, d in z:
+            y = node(level, i)
+            out.append((y[2], EMPTY if py_kind(y[2], y[3], y[4]) == "pseudo" else int(fg.node_row[level][i]), d))
+        if level > 0:
+            entry = int(fg.child[level][z[0][1]])
+    seen, cand = set(), []
+    for vid, row, d in out:
+        if vid in seen:
+            continue
+        seen.add(vid)
+        if vid == 0xFFFFFFFF or row == EMPTY:
+            continue
+        cand.append((key(d, vid), vid, row))
+    cand.sort(reverse=True)
+    cand = cand[: 5 * k]
+    mag_q = orc.mag_f32(q)
+    final = []
+    for _, vid, row in cand:
+        cs = orc.dot_f32_simd(q, vecs[row]) / (mag_q * orc.mag_f32(vecs[row]))
+        final.append((((orc.order_key(0, cs) << 32) | (~vid & 0xFFFFFFFF)), vid, np.float32(cs)))
+    final.sort(reverse=True)
+    return 0, [f[1] for f in final[:k]], [f[2] for f in final[:k]]
+
+
+@pytest.mark.parametrize("st,metric", [(4, 0), (0, 0), (2, 3)])
+def test_filtered_search_matches_python_restatement(st, metric):
+    vecs, mg = mdgraph.build(n=150, dim=16, storage_type=st, metric=metric, seed=3 + st)
+    q, filters = mdgraph.make_queries(vecs, mg, 24, seed=5)
+    filters[5] = []                                                     # Some(empty vec): max().unwrap() panics in the reference
+    k, ef = 5, 12
+    ids, scores, counts, err, _, _ = pymeta.search_batch_md(mg, vecs, q, filters, k, ef_search=ef, shortlist_size=64)
+    outcomes = set()
+    for i in range(q.shape[0]):
+        rc, wids, wsc = py_search(mg, vecs, q[i], filters[i], k, ef, 64)
+        outcomes.add(rc)
+        if rc:
+            assert err[i] == {2: 1, 7: 4}.get(rc, 2) and counts[i] == 0, i
+            continue
+        assert err[i] == 0 and counts[i] == len(wids), i
+        assert ids[i, : len(wids)].tolist() == wids, i
+        assert [bits(s) for s in scores[i, : len(wids)]] == [bits(s) for s in wsc], i
+    assert 0 in outcomes
+    if metric == 0:
+        assert 7 in outcomes                                            # the Some(empty) query
