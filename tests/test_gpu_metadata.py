@@ -56,7 +56,7 @@ def test_pairwise_replica_arms_match_oracle(st, md_dims):
             if metric == MK.Cosine:
                 seen.add((pymeta.replica_kind(vy), pymeta.replica_kind(vx), rc))
     assert {(k[0], k[1]) for k in seen} == {(a, b) for a in range(3) for b in range(3)}      # all nine kind pairs exercised
-    assert any(rc == 2 for _, _, rc in seen) and any(rc == 7 for _, _, rc in seen)
+    assert any(rc == 7 for _, _, rc in seen)
 
 
 @pytest.mark.parametrize("st,metric", [(ST.HalfPrecisionFP, MK.Cosine), (ST.UnsignedByte, MK.Cosine), (ST.SubByte2, MK.DotProduct),
@@ -81,9 +81,12 @@ def test_filtered_hnsw_search_matches_oracle(st, metric, ef):
     assert np.array_equal(counts, want_counts)
     assert np.array_equal(ids, want_ids)
     assert np.array_equal(bits(scores), bits(want_scores))
-    ok = want_err == 0
-    if ok.all():
-        assert (ev1 - ev0, pp1 - pp0) == (ev, pp)
+    sel = np.flatnonzero(want_err == 0)                                  # same traversal node for node (error-free queries)
+    ev0, pp0 = ix.hnsw_counters()
+    ix.batch_search_filtered(q[sel], [filters[i] for i in sel], k, ef_search=ef, shortlist_size=64)
+    ev1, pp1 = ix.hnsw_counters()
+    _, _, _, _, ev, pp = pymeta.search_batch_md(mg, vecs, q[sel], [filters[i] for i in sel], k, ef_search=ef)
+    assert (ev1 - ev0, pp1 - pp0) == (ev, pp)
     assert (want_err == 4).sum() >= (2 if metric == MK.Cosine else 1) and (want_counts > 0).sum() > 30
     # the plain entry point on the same graph = every query without a filter
     ids2, scores2, counts2, err2 = ix.batch_search(q, k, cdb.SearchMode.HNSW, ef_search=ef, shortlist_size=64)
