@@ -25,12 +25,15 @@ struct HnSmem {
     uint64_t *fs;       // [64] PerformantFixedSet buckets
     uint32_t *qnodes, *rnodes, *nnodes;
     uint32_t EFP;
+    uint8_t *stage;     // [stage_rows][stage_pitch] neighbour rows of the current pop, staged by the whole CTA
+    uint32_t stage_pitch, stage_rows;
 };
 struct HnShared {
     uint32_t qlen, cur, visited, rlen, ncand, err, entry;
     uint32_t accmask[2];   // accepted slots of the current pop (slot order is kept: the reference scores them in that order)
     uint32_t err_first;    // (position << 8 | flag) of the first failing evaluation of the current pop
     uint32_t bitkey[HN_MAX_TAKE];
+    uint32_t nrow[HN_MAX_TAKE];   // vector rows of the accepted neighbours
 };
 // metadata-filtered search (cosine.rs:34-102): per-node replica ids / metadata rows of the level and the query-side metadata
 struct HnMdCtx {
@@ -57,10 +60,28 @@ __host__ __device__ inline uint32_t hn_efp(uint32_t ef) {
     while (p < ef) p <<= 1;
     return p < 128 ? 128u : p;
 }
-__host__ __device__ inline size_t hn_smem_bytes(uint32_t row_pitch, uint32_t ef) {
+// Staging buffer: per pop only a handful of neighbours are scored, each by ONE thread (the reference arithmetic is a
+// sequential chain per pair), so per-thread row reads would expose one memory round trip per 128 bytes.  Instead all
+// threads of the CTA copy the rows of a group of neighbours into shared memory with 16-byte cp.async (one round trip for the
+// whole group) and the scoring threads read shared memory.  Row pitch + 16 bytes keeps the threads on different banks.
+constexpr uint32_t HN_STAGE_BYTES = 18 * 1024;
+__host__ __device__ inline uint32_t hn_stage_pitch(uint32_t row_pitch) { return round_up(row_pitch, 16) + 16; }
+__host__ __device__ inline uint32_t hn_stage_rows(uint32_t row_pitch) {
+    const uint32_t r = HN_STAGE_BYTES / hn_stage_pitch(row_pitch);
+    return r > HN_MAX_TAKE ? HN_MAX_TAKE : (r ? r : 1u);
+}
+__host__ __device__ inline size_t hn_base_bytes(uint32_t row_pitch, uint32_t ef) {
     const uint32_t efp = hn_efp(ef);
     return round_up(row_pitch, 16) + (size_t)(3 * efp + 2 * HN_MAX_TAKE + 64) * 8 + (size_t)(3 * efp + 2 * HN_MAX_TAKE) * 4 + 64;
 }
+__host__ __device__ inline size_t hn_smem_bytes(uint32_t row_pitch, uint32_t ef) {
+    return (hn_base_bytes(row_pitch, ef) + 15) / 16 * 16 + (size_t)hn_stage_rows(row_pitch) * hn_stage_pitch(row_pitch);
+}
+__device__ __forceinline__ void hn_cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(__cvta_generic_to_global(gsrc)) : "memory");
+}
+__device__ __forceinline__ void hn_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ inline HnSmem hn_carve(uint8_t *smem, uint32_t row_pitch, uint32_t ef) {
     HnSmem m;
     m.EFP = hn_efp(ef);
@@ -72,6 +93,9 @@ __device__ inline HnSmem hn_carve(uint8_t *smem, uint32_t row_pitch, uint32_t ef
     m.qnodes = reinterpret_cast<uint32_t *>(m.fs + 64);
     m.rnodes = m.qnodes + 2 * m.EFP;
     m.nnodes = m.rnodes + m.EFP;
+    m.stage = smem + (hn_base_bytes(row_pitch, ef) + 15) / 16 * 16;
+    m.stage_pitch = hn_stage_pitch(row_pitch);
+    m.stage_rows = hn_stage_rows(row_pitch);
     return m;
 }
 __device__ __forceinline__ uint32_t hn_id(uint32_t root_row, uint32_t row) { return row == root_row ? HN_ROOT_ID : row; }
@@ -101,9 +125,10 @@ __device__ inline void hn_sort_desc(uint64_t *keys, uint32_t *vals, uint32_t n, 
 // fixed set (the query id while searching, the new node's id while indexing: vector_store.rs:271, 807).
 // score node `local` of the level against the query (reference arithmetic); *id = the id the fixed set / keys use
 __device__ __forceinline__ int hn_score_node(const uint32_t *__restrict__ node_row, uint32_t local, const HnScoreCtx &sc, const HnSmem &m,
-                                             float qmag, uint32_t pp, const HnMdCtx *md, float *d, uint32_t *id) {
+                                             float qmag, uint32_t pp, const HnMdCtx *md, float *d, uint32_t *id,
+                                             const uint8_t *staged = nullptr) {
     const uint32_t row = node_row[local];
-    const uint8_t *code = sc.rows + (size_t)row * sc.row_pitch;
+    const uint8_t *code = staged ? staged : sc.rows + (size_t)row * sc.row_pitch;
     if (!md) {
         *id = hn_id(sc.root_row, row);
         return pair_distance(sc.metric, sc.st, sc.dim, m.qs, qmag, pp, code, sc.mags[row], pp, d);
@@ -184,17 +209,32 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
         if (tid == 0) sh.ncand = (uint32_t)(__popc(sh.accmask[0]) + __popc(sh.accmask[1]));
         __syncthreads();
         const uint32_t nc = sh.ncand;
-        // ---- score the new neighbours, one thread each, reference arithmetic
-        if ((uint32_t)tid < nc) {
-            const uint32_t nbl = m.nnodes[tid];
-            float d = 0.f;
-            uint32_t nid;
-            const int rc = hn_score_node(node_row, nbl, sc, m, qmag, pp, md, &d, &nid);
-            if (rc != CDB_OK) atomicMin(&sh.err_first, ((uint32_t)tid << 8) | md_err_flag(rc));   // the reference stops at the first Err
-            m.nkeys[tid] = make_key64(order_key(sc.metric, __float_as_uint(d)), nid);
+        // ---- score the new neighbours, one thread each, reference arithmetic, rows staged through shared memory
+        if ((uint32_t)tid < nc) sh.nrow[tid] = node_row[m.nnodes[tid]];
+        __syncthreads();
+        {
+            const uint32_t cpr = sc.row_pitch >> 4;   // 16-byte chunks per stored row
+            for (uint32_t g0 = 0; g0 < nc; g0 += m.stage_rows) {
+                const uint32_t gn = min(m.stage_rows, nc - g0);
+                for (uint32_t c = tid; c < gn * cpr; c += HN_THREADS) {
+                    const uint32_t r = c / cpr, o = c - r * cpr;
+                    hn_cp_async16(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 16,
+                                  sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
+                }
+                hn_cp_async_wait_all();
+                __syncthreads();
+                if ((uint32_t)tid < gn) {
+                    const uint32_t pos = g0 + tid;
+                    float d = 0.f;
+                    uint32_t nid;
+                    const int rc = hn_score_node(node_row, m.nnodes[pos], sc, m, qmag, pp, md, &d, &nid, m.stage + (size_t)tid * m.stage_pitch);
+                    if (rc != CDB_OK) atomicMin(&sh.err_first, (pos << 8) | md_err_flag(rc));   // the reference stops at the first Err
+                    m.nkeys[pos] = make_key64(order_key(sc.metric, __float_as_uint(d)), nid);
+                }
+                __syncthreads();   // the stage is reused by the next group
+            }
         }
         if (tid == 0) evals += nc;
-        __syncthreads();
         if (sh.err_first != 0xFFFFFFFFu) {
             if (tid == 0) sh.err = sh.err_first & 0xFFu;
             __syncthreads();
