@@ -68,13 +68,12 @@ __host__ __device__ inline uint32_t hn_efp(uint32_t ef) {
 //
 // f16 storage (config C3): dot_product_f16 is `sum += f32(a) * f32(b)` in element order.  The product of two halfs is exact in
 // f32 (11 x 11 significand bits), so fmaf(a, b, sum) rounds exactly like the reference's separate multiply and add.  Rows are
-// the query is converted to f32 once per kernel and the chain is one conversion (row element) + one FFMA per element instead
-// of two conversions, a multiply and an add -- the chain warps of all resident CTAs share few issue slots, so instructions
-// per element matter.  (Staging the rows already converted to f32 halves the rows per group and measured slower.)
+// therefore staged ALREADY CONVERTED to f32 (the conversion is spread over all threads of the CTA) and the query is converted
+// once, which leaves one FFMA per element on the sequential chain instead of two conversions, a multiply and an add --
+// the chain warps of all resident CTAs share few issue slots, so instructions per element is what bounds the search.
 constexpr uint32_t HN_STAGE_BYTES = 18 * 1024;
 __host__ __device__ inline uint32_t hn_stage_pitch(uint32_t row_pitch, int st) {
-    (void)st;
-    return round_up(row_pitch, 16) + 16;
+    return (st == CDB_ST_F16 ? 2 : 1) * round_up(row_pitch, 16) + 16;
 }
 __host__ __device__ inline uint32_t hn_stage_rows(uint32_t row_pitch, int st) {
     const uint32_t r = HN_STAGE_BYTES / hn_stage_pitch(row_pitch, st);
@@ -239,12 +238,38 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
             const uint32_t rt = ((uint32_t)tid + HN_THREADS - 32u * ((blockIdx.x / 148u + blockIdx.x) & 3u)) & (HN_THREADS - 1);
             for (uint32_t g0 = 0; g0 < nc; g0 += m.stage_rows) {
                 const uint32_t gn = min(m.stage_rows, nc - g0), total = gn * cpr;
-                for (uint32_t c = tid; c < total; c += HN_THREADS) {
-                    const uint32_t r = c / cpr, o = c - r * cpr;
-                    hn_cp_async16(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 16,
-                                  sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
+                if (fast16) {
+                    for (uint32_t c0 = tid; c0 < total; c0 += 4 * HN_THREADS) {   // loads first, then convert + store
+                        uint4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t c = c0 + u * HN_THREADS;
+                            if (c < total) {
+                                const uint32_t r = c / cpr, o = c - r * cpr;
+                                v[u] = *reinterpret_cast<const uint4 *>(sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint32_t c = c0 + u * HN_THREADS;
+                            if (c < total) {
+                                const uint32_t r = c / cpr, o = c - r * cpr;
+                                const __half2 *h = reinterpret_cast<const __half2 *>(&v[u]);
+                                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                                float4 *dst = reinterpret_cast<float4 *>(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 32);
+                                dst[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+                                dst[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+                            }
+                        }
+                    }
+                } else {
+                    for (uint32_t c = tid; c < total; c += HN_THREADS) {
+                        const uint32_t r = c / cpr, o = c - r * cpr;
+                        hn_cp_async16(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 16,
+                                      sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
+                    }
+                    hn_cp_async_wait_all();
                 }
-                hn_cp_async_wait_all();
                 __syncthreads();
                 if (rt < gn) {
                     const uint32_t pos = g0 + rt;
@@ -253,20 +278,15 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
                     int rc;
                     if (fast16) {
                         const float4 *q4 = reinterpret_cast<const float4 *>(m.qf32);
-                        const uint4 *r8 = reinterpret_cast<const uint4 *>(m.stage + (size_t)rt * m.stage_pitch);
+                        const float4 *r4 = reinterpret_cast<const float4 *>(m.stage + (size_t)rt * m.stage_pitch);
                         float s = 0.0f;
-                        const uint32_t n8 = sc.dim >> 3;
-#pragma unroll 2
-                        for (uint32_t i = 0; i < n8; ++i) {
-                            const uint4 rv = r8[i];
-                            const float4 a0 = q4[2 * i], a1 = q4[2 * i + 1];
-                            const __half2 *h = reinterpret_cast<const __half2 *>(&rv);
-                            const float2 b0 = __half22float2(h[0]), b1 = __half22float2(h[1]), b2 = __half22float2(h[2]), b3 = __half22float2(h[3]);
-                            s = __fmaf_rn(a0.x, b0.x, s); s = __fmaf_rn(a0.y, b0.y, s); s = __fmaf_rn(a0.z, b1.x, s); s = __fmaf_rn(a0.w, b1.y, s);
-                            s = __fmaf_rn(a1.x, b2.x, s); s = __fmaf_rn(a1.y, b2.y, s); s = __fmaf_rn(a1.z, b3.x, s); s = __fmaf_rn(a1.w, b3.y, s);
+                        const uint32_t n4 = sc.dim >> 2;
+#pragma unroll 4
+                        for (uint32_t i = 0; i < n4; ++i) {
+                            const float4 a = q4[i], b = r4[i];
+                            s = __fmaf_rn(a.x, b.x, s); s = __fmaf_rn(a.y, b.y, s); s = __fmaf_rn(a.z, b.z, s); s = __fmaf_rn(a.w, b.w, s);
                         }
-                        for (uint32_t i = n8 * 8; i < sc.dim; ++i)
-                            s = __fmaf_rn(m.qf32[i], __half2float(reinterpret_cast<const __half *>(r8)[i]), s);
+                        for (uint32_t i = n4 * 4; i < sc.dim; ++i) s = __fmaf_rn(m.qf32[i], reinterpret_cast<const float *>(r4)[i], s);
                         const uint32_t row = sh.nrow[pos];
                         nid = hn_id(sc.root_row, row);
                         rc = CDB_OK;
