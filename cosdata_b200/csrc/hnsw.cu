@@ -22,7 +22,7 @@ constexpr uint32_t HN_FINAL_LEN = 100;  // vector_store.rs:1194
 
 __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const HnSmem m = hn_carve(smem, a.row_pitch, a.ef, a.st);
+    const HnSmem m = hn_carve(smem, a.row_pitch, a.ef);
     __shared__ HnShared sh;
     const uint32_t qi = blockIdx.x;
     const int tid = threadIdx.x;
@@ -34,7 +34,6 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
     uint32_t out_total = 0;
     unsigned long long evals = 0, pops = 0;
     __syncthreads();
-    hn_prepare_query(m, sc);   // ordered before its first use by the barriers inside hn_traverse_level
 
     // ann_search (vector_store.rs:256-402): fresh fixed set and ef budget per level, results of all levels
     // concatenated, child of the best result is the entry of the next level
@@ -111,12 +110,12 @@ __global__ void __launch_bounds__(256) hnsw_dedup_kernel(const uint32_t *__restr
     if (threadIdx.x == 0) cand_cnt[q] = m;
 }
 
-size_t hnsw_search_smem(uint32_t row_pitch, uint32_t ef, int st) { return hn_smem_bytes(row_pitch, ef, st); }
+size_t hnsw_search_smem(uint32_t row_pitch, uint32_t ef) { return hn_smem_bytes(row_pitch, ef); }
 
 cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s) {
     if (!a.nq) return CDB_OK;
     if (a.ef == 0 || a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
-    const size_t smem = hnsw_search_smem(a.row_pitch, a.ef, a.st);
+    const size_t smem = hnsw_search_smem(a.row_pitch, a.ef);
     if (smem > 200 * 1024) { set_error("hnsw: ef_search too large for shared memory"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hnsw_search_kernel<<<a.nq, HN_THREADS, smem, s>>>(a);

@@ -61,7 +61,7 @@ __device__ inline uint32_t build_local(const BuildLevel &l, uint32_t level, uint
 
 __global__ void __launch_bounds__(HN_THREADS) hnsw_build_search_kernel(BuildArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const HnSmem m = hn_carve(smem, a.sc.row_pitch, a.ef, a.sc.st);
+    const HnSmem m = hn_carve(smem, a.sc.row_pitch, a.ef);
     __shared__ HnShared sh;
     const uint32_t b = blockIdx.x, r = a.first + b;
     const int tid = threadIdx.x;
@@ -73,7 +73,6 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_build_search_kernel(BuildArgs
     if (tid == 0) { sh.err = 0; sh.entry = a.g.entry; }
     unsigned long long evals = 0, pops = 0;
     __syncthreads();
-    hn_prepare_query(m, a.sc);
     for (int level = (int)a.g.num_levels; level >= 0; --level) {
         const BuildLevel &l = a.g.lv[level];
         const uint32_t take = min(min(a.shortlist, l.nb), HN_MAX_TAKE);
@@ -266,7 +265,7 @@ cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n /* data rows; root
     CDB_CUDA_TRY(cudaMalloc(&z_keys, (size_t)max_batch * L1 * 64 * 4));
     CDB_CUDA_TRY(cudaMalloc(&z_n, (size_t)max_batch * L1 * 4));
     CDB_CUDA_TRY(cudaMalloc(&failed, max_batch));
-    const size_t smem = hn_smem_bytes(sc.row_pitch, ef_construction, sc.st);
+    const size_t smem = hn_smem_bytes(sc.row_pitch, ef_construction);
     CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_build_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BuildArgs a{};
     a.g = bg.g;

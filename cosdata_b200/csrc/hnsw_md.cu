@@ -23,8 +23,8 @@ __device__ __forceinline__ bool hnm_is_pseudo(const HnswMdArgs &a, int level, ui
 
 __global__ void __launch_bounds__(HN_THREADS) hnsw_search_md_kernel(HnswMdArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const HnSmem m = hn_carve(smem, a.a.row_pitch, a.a.ef, a.a.st);
-    uint64_t *zkeys = reinterpret_cast<uint64_t *>(smem + round_up((uint32_t)hn_smem_bytes(a.a.row_pitch, a.a.ef, a.a.st), 16));
+    const HnSmem m = hn_carve(smem, a.a.row_pitch, a.a.ef);
+    uint64_t *zkeys = reinterpret_cast<uint64_t *>(smem + round_up((uint32_t)hn_smem_bytes(a.a.row_pitch, a.a.ef), 16));
     uint32_t *znodes = reinterpret_cast<uint32_t *>(zkeys + HNM_Z);
     int32_t *qbits = reinterpret_cast<int32_t *>(znodes + HNM_Z);
     __shared__ HnShared sh;
@@ -42,7 +42,6 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_md_kernel(HnswMdArgs a
     uint32_t out_total = 0;
     unsigned long long evals = 0, pops = 0;
     __syncthreads();
-    hn_prepare_query(m, sc);
 
     // Metadata::from(&QueryFilterDimensions) (types.rs:127-146): mbits = dims as i32, mag = sqrt(sequential sum of squares)
     auto load_filter = [&](uint32_t f) {
@@ -198,7 +197,7 @@ __global__ void __launch_bounds__(256) hnsw_dedup_md_kernel(const uint32_t *__re
 cdb_status hnsw_search_md_device(const HnswMdArgs &a, cudaStream_t s) {
     if (!a.a.nq) return CDB_OK;
     if (a.a.ef == 0 || a.a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
-    const size_t smem = round_up((uint32_t)hn_smem_bytes(a.a.row_pitch, a.a.ef, a.a.st), 16) + (size_t)HNM_Z * 12 + (size_t)a.M * 4 + 16;
+    const size_t smem = round_up((uint32_t)hn_smem_bytes(a.a.row_pitch, a.a.ef), 16) + (size_t)HNM_Z * 12 + (size_t)a.M * 4 + 16;
     if (smem > 200 * 1024) { set_error("hnsw: ef_search / metadata dims too large for shared memory"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_md_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hnsw_search_md_kernel<<<a.a.nq, HN_THREADS, smem, s>>>(a);

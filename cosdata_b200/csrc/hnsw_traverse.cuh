@@ -27,7 +27,6 @@ struct HnSmem {
     uint32_t EFP;
     uint8_t *stage;     // [stage_rows][stage_pitch] neighbour rows of the current pop, staged by the whole CTA
     uint32_t stage_pitch, stage_rows;
-    float *qf32;        // f16 storage only: the query converted to f32 once (hn_prepare_query)
 };
 struct HnShared {
     uint32_t qlen, cur, visited, rlen, ncand, err, entry;
@@ -65,34 +64,25 @@ __host__ __device__ inline uint32_t hn_efp(uint32_t ef) {
 // sequential chain per pair), so per-thread row reads would expose one memory round trip per 128 bytes.  Instead all
 // threads of the CTA copy the rows of a group of neighbours into shared memory with 16-byte cp.async (one round trip for the
 // whole group) and the scoring threads read shared memory.  Row pitch + 16 bytes keeps the threads on different banks.
-//
-// f16 storage (config C3): dot_product_f16 is `sum += f32(a) * f32(b)` in element order.  The product of two halfs is exact in
-// f32 (11 x 11 significand bits), so fmaf(a, b, sum) rounds exactly like the reference's separate multiply and add.  Rows are
-// therefore staged ALREADY CONVERTED to f32 (the conversion is spread over all threads of the CTA) and the query is converted
-// once, which leaves one FFMA per element on the sequential chain instead of two conversions, a multiply and an add --
-// the chain warps of all resident CTAs share few issue slots, so instructions per element is what bounds the search.
 constexpr uint32_t HN_STAGE_BYTES = 18 * 1024;
-__host__ __device__ inline uint32_t hn_stage_pitch(uint32_t row_pitch, int st) {
-    return (st == CDB_ST_F16 ? 2 : 1) * round_up(row_pitch, 16) + 16;
-}
-__host__ __device__ inline uint32_t hn_stage_rows(uint32_t row_pitch, int st) {
-    const uint32_t r = HN_STAGE_BYTES / hn_stage_pitch(row_pitch, st);
+__host__ __device__ inline uint32_t hn_stage_pitch(uint32_t row_pitch) { return round_up(row_pitch, 16) + 16; }
+__host__ __device__ inline uint32_t hn_stage_rows(uint32_t row_pitch) {
+    const uint32_t r = HN_STAGE_BYTES / hn_stage_pitch(row_pitch);
     return r > HN_MAX_TAKE ? HN_MAX_TAKE : (r ? r : 1u);
 }
 __host__ __device__ inline size_t hn_base_bytes(uint32_t row_pitch, uint32_t ef) {
     const uint32_t efp = hn_efp(ef);
     return round_up(row_pitch, 16) + (size_t)(3 * efp + 2 * HN_MAX_TAKE + 64) * 8 + (size_t)(3 * efp + 2 * HN_MAX_TAKE) * 4 + 64;
 }
-__host__ __device__ inline size_t hn_smem_bytes(uint32_t row_pitch, uint32_t ef, int st) {
-    return (hn_base_bytes(row_pitch, ef) + 15) / 16 * 16 + (size_t)hn_stage_rows(row_pitch, st) * hn_stage_pitch(row_pitch, st) +
-           (st == CDB_ST_F16 ? 2 * (size_t)round_up(row_pitch, 16) : 0);
+__host__ __device__ inline size_t hn_smem_bytes(uint32_t row_pitch, uint32_t ef) {
+    return (hn_base_bytes(row_pitch, ef) + 15) / 16 * 16 + (size_t)hn_stage_rows(row_pitch) * hn_stage_pitch(row_pitch);
 }
 __device__ __forceinline__ void hn_cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(__cvta_generic_to_global(gsrc)) : "memory");
 }
 __device__ __forceinline__ void hn_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ inline HnSmem hn_carve(uint8_t *smem, uint32_t row_pitch, uint32_t ef, int st) {
+__device__ inline HnSmem hn_carve(uint8_t *smem, uint32_t row_pitch, uint32_t ef) {
     HnSmem m;
     m.EFP = hn_efp(ef);
     m.qs = smem;
@@ -104,9 +94,8 @@ __device__ inline HnSmem hn_carve(uint8_t *smem, uint32_t row_pitch, uint32_t ef
     m.rnodes = m.qnodes + 2 * m.EFP;
     m.nnodes = m.rnodes + m.EFP;
     m.stage = smem + (hn_base_bytes(row_pitch, ef) + 15) / 16 * 16;
-    m.stage_pitch = hn_stage_pitch(row_pitch, st);
-    m.stage_rows = hn_stage_rows(row_pitch, st);
-    m.qf32 = st == CDB_ST_F16 ? reinterpret_cast<float *>(m.stage + (size_t)m.stage_rows * m.stage_pitch) : nullptr;
+    m.stage_pitch = hn_stage_pitch(row_pitch);
+    m.stage_rows = hn_stage_rows(row_pitch);
     return m;
 }
 __device__ __forceinline__ uint32_t hn_id(uint32_t root_row, uint32_t row) { return row == root_row ? HN_ROOT_ID : row; }
@@ -134,13 +123,6 @@ __device__ inline void hn_sort_desc(uint64_t *keys, uint32_t *vals, uint32_t n, 
 // One level.  On return (sh.err == 0) rkeys/rnodes[0..sh.rlen) hold every popped entry sorted best first
 // (the caller truncates to 100 / 64).  All threads of the CTA must call it.  `self_id` is pre-inserted into the
 // fixed set (the query id while searching, the new node's id while indexing: vector_store.rs:271, 807).
-// after m.qs is loaded (all threads, followed by a __syncthreads() of the caller): f32 copy of an f16 query
-__device__ inline void hn_prepare_query(const HnSmem &m, const HnScoreCtx &sc) {
-    if (sc.st != CDB_ST_F16) return;
-    const __half *h = reinterpret_cast<const __half *>(m.qs);
-    for (uint32_t i = threadIdx.x; i < sc.dim; i += blockDim.x) m.qf32[i] = __half2float(h[i]);
-}
-
 // score node `local` of the level against the query (reference arithmetic); *id = the id the fixed set / keys use
 __device__ __forceinline__ int hn_score_node(const uint32_t *__restrict__ node_row, uint32_t local, const HnScoreCtx &sc, const HnSmem &m,
                                              float qmag, uint32_t pp, const HnMdCtx *md, float *d, uint32_t *id,
@@ -232,72 +214,20 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
         __syncthreads();
         {
             const uint32_t cpr = sc.row_pitch >> 4;   // 16-byte chunks per stored row
-            const bool fast16 = sc.st == CDB_ST_F16 && !md && (sc.metric == CDB_METRIC_COSINE || sc.metric == CDB_METRIC_DOT_PRODUCT);
-            // The scoring threads of one CTA sit in one warp (a warp costs the same issue slots for 1 or 32 active lanes);
-            // which warp is rotated per CTA so that the CTAs resident on an SM do not all load the same scheduler.
-            const uint32_t rt = ((uint32_t)tid + HN_THREADS - 32u * ((blockIdx.x / 148u + blockIdx.x) & 3u)) & (HN_THREADS - 1);
             for (uint32_t g0 = 0; g0 < nc; g0 += m.stage_rows) {
-                const uint32_t gn = min(m.stage_rows, nc - g0), total = gn * cpr;
-                if (fast16) {
-                    for (uint32_t c0 = tid; c0 < total; c0 += 4 * HN_THREADS) {   // loads first, then convert + store
-                        uint4 v[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const uint32_t c = c0 + u * HN_THREADS;
-                            if (c < total) {
-                                const uint32_t r = c / cpr, o = c - r * cpr;
-                                v[u] = *reinterpret_cast<const uint4 *>(sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const uint32_t c = c0 + u * HN_THREADS;
-                            if (c < total) {
-                                const uint32_t r = c / cpr, o = c - r * cpr;
-                                const __half2 *h = reinterpret_cast<const __half2 *>(&v[u]);
-                                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-                                float4 *dst = reinterpret_cast<float4 *>(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 32);
-                                dst[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
-                                dst[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
-                            }
-                        }
-                    }
-                } else {
-                    for (uint32_t c = tid; c < total; c += HN_THREADS) {
-                        const uint32_t r = c / cpr, o = c - r * cpr;
-                        hn_cp_async16(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 16,
-                                      sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
-                    }
-                    hn_cp_async_wait_all();
+                const uint32_t gn = min(m.stage_rows, nc - g0);
+                for (uint32_t c = tid; c < gn * cpr; c += HN_THREADS) {
+                    const uint32_t r = c / cpr, o = c - r * cpr;
+                    hn_cp_async16(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 16,
+                                  sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
                 }
+                hn_cp_async_wait_all();
                 __syncthreads();
-                if (rt < gn) {
-                    const uint32_t pos = g0 + rt;
+                if ((uint32_t)tid < gn) {
+                    const uint32_t pos = g0 + tid;
                     float d = 0.f;
                     uint32_t nid;
-                    int rc;
-                    if (fast16) {
-                        const float4 *q4 = reinterpret_cast<const float4 *>(m.qf32);
-                        const float4 *r4 = reinterpret_cast<const float4 *>(m.stage + (size_t)rt * m.stage_pitch);
-                        float s = 0.0f;
-                        const uint32_t n4 = sc.dim >> 2;
-#pragma unroll 4
-                        for (uint32_t i = 0; i < n4; ++i) {
-                            const float4 a = q4[i], b = r4[i];
-                            s = __fmaf_rn(a.x, b.x, s); s = __fmaf_rn(a.y, b.y, s); s = __fmaf_rn(a.z, b.z, s); s = __fmaf_rn(a.w, b.w, s);
-                        }
-                        for (uint32_t i = n4 * 4; i < sc.dim; ++i) s = __fmaf_rn(m.qf32[i], reinterpret_cast<const float *>(r4)[i], s);
-                        const uint32_t row = sh.nrow[pos];
-                        nid = hn_id(sc.root_row, row);
-                        rc = CDB_OK;
-                        if (sc.metric == CDB_METRIC_COSINE) {
-                            const float denom = __fmul_rn(qmag, sc.mags[row]);
-                            if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
-                            else d = canon_nan(__fdiv_rn(s, denom));
-                        } else d = s;
-                    } else {
-                        rc = hn_score_node(node_row, m.nnodes[pos], sc, m, qmag, pp, md, &d, &nid, m.stage + (size_t)rt * m.stage_pitch);
-                    }
+                    const int rc = hn_score_node(node_row, m.nnodes[pos], sc, m, qmag, pp, md, &d, &nid, m.stage + (size_t)tid * m.stage_pitch);
                     if (rc != CDB_OK) atomicMin(&sh.err_first, (pos << 8) | md_err_flag(rc));   // the reference stops at the first Err
                     m.nkeys[pos] = make_key64(order_key(sc.metric, __float_as_uint(d)), nid);
                 }
