@@ -106,7 +106,7 @@ struct cdb_index {
     uint32_t xh_pitch = 0;         // halfs per shadow row
     uint64_t n_zero_rows = 0;      // rows with |v| == 0 (their exact score is NaN)
     uint32_t *h_flags = nullptr;   // pinned host copy of d_flags
-    uint64_t stat_tensor_searches = 0, stat_fallbacks = 0, stat_candidates = 0;
+    uint64_t stat_tensor_searches = 0;
     cudaStream_t stream = nullptr;
     static constexpr int EV_RING = 64;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
