@@ -190,7 +190,7 @@ cdb_status cdb_prop_file_load(const char *path, uint64_t first_record, uint64_t 
                               float *out_mags, uint64_t *out_offsets, uint32_t *out_lengths, uint64_t *out_read);
 cdb_status cdb_index_append_prop_file(cdb_index *index, const char *path, uint32_t *out_ids, uint64_t max_ids, uint64_t *out_appended);
 /* ---- itoe.dim + itoe.<version>.data: the reference's raw-embedding store, TreeMap<InternalId, RawVectorEmbedding>
- * (src/models/collection.rs:110, 149-164; formats in src/models/serializer/tree_map/*.rs and raw_vector_embedding.rs),
+ * (src/models/collection.rs:110, 149-164; formats in src/models/serializer/tree_map/ and raw_vector_embedding.rs),
  * which finalize_ann_results reads for the exact re-rank (collection.rs:368-384).  Host-side readers, no GPU work.  Only the
  * newest state of every key counts (tree_map.rs:262-268); deleted keys and embeddings without dense values are skipped.
  *   scan -> number of live dense embeddings, their dimension, the largest internal id

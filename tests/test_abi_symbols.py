@@ -53,3 +53,14 @@ def test_invalid_params_are_rejected_before_touching_the_device():
     assert lib.cdb_quantize_batch(0, 9, -1.0, 1.0, None, 0, 8, None, None) == cdb.Status.INVALID_PARAMS
     assert lib.cdb_index_create(None, None) == cdb.Status.INVALID_PARAMS
     assert b"" != lib.cdb_last_error_string()
+
+
+def test_header_is_plain_c11(tmp_path):
+    """the boundary is a C ABI: the header must compile as C (no C++-isms, no CUDA/torch types)"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "cosdata_b200.h"\nint main(void) { cdb_index_desc d; cdb_graph_metadata m; (void)d; (void)m; return 0; }\n')
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
