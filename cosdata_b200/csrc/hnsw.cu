@@ -14,22 +14,19 @@
 // below the number of pops still to come can never be popped: the queue is a sorted array of at
 // most `ef` entries and the pop order is identical to the heap's.  Keys are
 // (order_key(score) << 32 | ~id): "better score first, then smaller id" -- the oracle's tie rule.
-#include <cstdlib>
-
 #include "hnsw_traverse.cuh"
 
 namespace cdb {
 
 constexpr uint32_t HN_FINAL_LEN = 100;  // vector_store.rs:1194
 
-template <int THREADS, bool PIPE16>
-__global__ void __launch_bounds__(THREADS, PIPE16 ? 8 : 0) hnsw_search_kernel(HnswArgs a) {
+__global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const HnSmem m = hn_carve(smem, a.row_pitch, a.ef);
     __shared__ HnShared sh;
     const uint32_t qi = blockIdx.x;
     const int tid = threadIdx.x;
-    for (uint32_t i = tid; i < a.row_pitch / 4; i += THREADS)
+    for (uint32_t i = tid; i < a.row_pitch / 4; i += HN_THREADS)
         reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[i];
     const float qmag = a.qmags[qi];
     const HnScoreCtx sc{a.rows, a.row_pitch, a.mags, a.dim, a.st, a.metric, a.g.root_row};
@@ -44,10 +41,10 @@ __global__ void __launch_bounds__(THREADS, PIPE16 ? 8 : 0) hnsw_search_kernel(Hn
         const uint32_t nb = level == 0 ? a.g.nbrs0 : a.g.nbrs;
         const uint32_t take = min(min(a.shortlist, nb), HN_MAX_TAKE);
         const uint32_t *node_row = a.g.node_row[level];
-        hn_traverse_level<THREADS, PIPE16>(node_row, a.g.adj[level], nb, take, sc, m, sh, qmag, HN_QUERY_ID, a.ef, evals, pops);
+        hn_traverse_level(node_row, a.g.adj[level], nb, take, sc, m, sh, qmag, HN_QUERY_ID, a.ef, evals, pops);
         if (sh.err) break;
         const uint32_t keep = min(sh.rlen, HN_FINAL_LEN);
-        for (uint32_t i = tid; i < keep; i += THREADS) {
+        for (uint32_t i = tid; i < keep; i += HN_THREADS) {
             const uint32_t slot = out_total + i;
             if (slot < a.out_cap) {
                 a.out_rows[(size_t)qi * a.out_cap + slot] = node_row[m.rnodes[i]];
@@ -120,15 +117,8 @@ cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s) {
     if (a.ef == 0 || a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
     const size_t smem = hnsw_search_smem(a.row_pitch, a.ef);
     if (smem > 200 * 1024) { set_error("hnsw: ef_search too large for shared memory"); return CDB_INVALID_PARAMS; }
-    // CDB_HNSW_V2=1 selects the experimental variant (64 threads per query, software-pipelined f16 chain); default = validated path
-    static const bool v2 = [] { const char *e = getenv("CDB_HNSW_V2"); return e && e[0] == '1'; }();
-    if (v2) {
-        CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hnsw_search_kernel<64, true><<<a.nq, 64, smem, s>>>(a);
-    } else {
-        CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_kernel<HN_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hnsw_search_kernel<HN_THREADS, false><<<a.nq, HN_THREADS, smem, s>>>(a);
-    }
+    CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hnsw_search_kernel<<<a.nq, HN_THREADS, smem, s>>>(a);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

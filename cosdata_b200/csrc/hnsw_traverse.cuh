@@ -141,54 +141,6 @@ __device__ __forceinline__ int hn_score_node(const uint32_t *__restrict__ node_r
     return md_pair_distance(sc.metric, sc.st, sc.dim, md->M, x, y, d);
 }
 
-// sequential f32 sum of the (exact) products of two f16 rows that sit in SHARED memory, element order (dot_product_f16,
-// dot_product.rs:13-19).  Software pipelined over 16-element blocks: while the 16 dependent FADDs of block b retire (4 cycles
-// each) the operands of block b+1 are loaded, converted and multiplied, so the chain, not its feeding, sets the pace.
-__device__ __forceinline__ void hn_lds128(uint32_t addr, uint4 &v) {
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-}
-__device__ __forceinline__ void hn_mul16(const uint4 (&a)[2], const uint4 (&b)[2], float (&p)[16]) {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const __half2 *ha = reinterpret_cast<const __half2 *>(&a[t]);
-        const __half2 *hb = reinterpret_cast<const __half2 *>(&b[t]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
-            p[8 * t + 2 * e] = __fmul_rn(fa.x, fb.x);
-            p[8 * t + 2 * e + 1] = __fmul_rn(fa.y, fb.y);
-        }
-    }
-}
-__device__ __forceinline__ float hn_dot_f16_seq_smem(const uint8_t *a_sm, const uint8_t *b_sm, uint32_t n) {
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(a_sm), b = (uint32_t)__cvta_generic_to_shared(b_sm);
-    float s = 0.0f;
-    const uint32_t nblk = n >> 4;
-    if (nblk) {
-        uint4 ra[2], rb[2];
-        float p[16];
-        hn_lds128(a, ra[0]); hn_lds128(a + 16, ra[1]); hn_lds128(b, rb[0]); hn_lds128(b + 16, rb[1]);
-        hn_mul16(ra, rb, p);
-        for (uint32_t blk = 1; blk < nblk; ++blk) {
-            float q[16];
-            hn_lds128(a + 32 * blk, ra[0]); hn_lds128(a + 32 * blk + 16, ra[1]);
-            hn_lds128(b + 32 * blk, rb[0]); hn_lds128(b + 32 * blk + 16, rb[1]);
-            hn_mul16(ra, rb, q);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) s = __fadd_rn(s, p[i]);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) p[i] = q[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s = __fadd_rn(s, p[i]);
-    }
-    const __half *ha = reinterpret_cast<const __half *>(a_sm), *hb = reinterpret_cast<const __half *>(b_sm);
-    for (uint32_t i = nblk << 4; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__half2float(ha[i]), __half2float(hb[i])));
-    return s;
-}
-
-// THREADS = threads per CTA (>= 64: warps 0 and 1 hold the 64 slots); PIPE16 = pipelined shared-memory chain for f16 rows
-template <int THREADS = HN_THREADS, bool PIPE16 = false>
 __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, const uint32_t *__restrict__ adj, uint32_t nb,
                                          uint32_t take, const HnScoreCtx &sc, const HnSmem &m, HnShared &sh, float qmag,
                                          uint32_t self_id, uint32_t ef, unsigned long long &evals, unsigned long long &pops,
@@ -264,7 +216,7 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
             const uint32_t cpr = sc.row_pitch >> 4;   // 16-byte chunks per stored row
             for (uint32_t g0 = 0; g0 < nc; g0 += m.stage_rows) {
                 const uint32_t gn = min(m.stage_rows, nc - g0);
-                for (uint32_t c = tid; c < gn * cpr; c += THREADS) {
+                for (uint32_t c = tid; c < gn * cpr; c += HN_THREADS) {
                     const uint32_t r = c / cpr, o = c - r * cpr;
                     hn_cp_async16(m.stage + (size_t)r * m.stage_pitch + (size_t)o * 16,
                                   sc.rows + (size_t)sh.nrow[g0 + r] * sc.row_pitch + (size_t)o * 16);
@@ -275,19 +227,7 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
                     const uint32_t pos = g0 + tid;
                     float d = 0.f;
                     uint32_t nid;
-                    int rc;
-                    if (PIPE16 && !md && sc.st == CDB_ST_F16 && (sc.metric == CDB_METRIC_COSINE || sc.metric == CDB_METRIC_DOT_PRODUCT)) {
-                        const float dot = hn_dot_f16_seq_smem(m.qs, m.stage + (size_t)tid * m.stage_pitch, sc.dim);
-                        const uint32_t row = sh.nrow[pos];
-                        nid = hn_id(sc.root_row, row);
-                        rc = CDB_OK;
-                        if (sc.metric == CDB_METRIC_COSINE) {
-                            const float denom = __fmul_rn(qmag, sc.mags[row]);
-                            if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
-                            else d = canon_nan(__fdiv_rn(dot, denom));
-                        } else d = dot;
-                    } else
-                    rc = hn_score_node(node_row, m.nnodes[pos], sc, m, qmag, pp, md, &d, &nid, m.stage + (size_t)tid * m.stage_pitch);
+                    const int rc = hn_score_node(node_row, m.nnodes[pos], sc, m, qmag, pp, md, &d, &nid, m.stage + (size_t)tid * m.stage_pitch);
                     if (rc != CDB_OK) atomicMin(&sh.err_first, (pos << 8) | md_err_flag(rc));   // the reference stops at the first Err
                     m.nkeys[pos] = make_key64(order_key(sc.metric, __float_as_uint(d)), nid);
                 }
@@ -317,14 +257,14 @@ __device__ inline void hn_traverse_level(const uint32_t *__restrict__ node_row, 
             const uint32_t cap = min(ef - (visited + 1), EFP);  // pops still to come
             uint64_t *D = m.qkeys + (cur ^ 1) * EFP;
             uint32_t *DN = m.qnodes + (cur ^ 1) * EFP;
-            for (uint32_t i = tid; i < oldn; i += THREADS) {
+            for (uint32_t i = tid; i < oldn; i += HN_THREADS) {
                 const uint64_t k = Q[1 + i];
                 uint32_t lo = 0, hi = nc;  // number of new entries better than k
                 while (lo < hi) { const uint32_t md = (lo + hi) >> 1; if (NK[md] > k) lo = md + 1; else hi = md; }
                 const uint32_t pos = i + lo;
                 if (pos < cap) { D[pos] = k; DN[pos] = QN[1 + i]; }
             }
-            for (uint32_t j = tid; j < nc; j += THREADS) {
+            for (uint32_t j = tid; j < nc; j += HN_THREADS) {
                 const uint64_t k = NK[j];
                 uint32_t lo = 0, hi = oldn;  // number of old entries better than k
                 while (lo < hi) { const uint32_t md = (lo + hi) >> 1; if (Q[1 + md] > k) lo = md + 1; else hi = md; }
