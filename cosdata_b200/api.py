@@ -179,6 +179,23 @@ def prop_file_load(path, first_record=0, max_records=None):
     return {"ids": ids, "codes": codes, "mags": mags, "offsets": offsets, "lengths": lengths, "storage_type": st}
 
 
+def prop_file_load_metadata(path):
+    """replica Metadata records of a prop.data file -> dict(replica_ids, mags, mbits i32[n, md_dims], offsets, lengths)"""
+    n, dims = C.c_uint64(0), C.c_uint32(0)
+    _check(_lib.load().cdb_prop_file_scan_metadata(os.fsencode(path), C.byref(n), C.byref(dims)))
+    n, dims = n.value, dims.value
+    ids = np.zeros(n, dtype=np.uint32)
+    mags = np.zeros(n, dtype=np.float32)
+    mbits = np.zeros((n, dims), dtype=np.int32)
+    offsets = np.zeros(n, dtype=np.uint64)
+    lengths = np.zeros(n, dtype=np.uint32)
+    got = C.c_uint64(0)
+    _check(_lib.load().cdb_prop_file_load_metadata(os.fsencode(path), n, dims, _ptr(ids), _ptr(mags), _ptr(mbits), _ptr(offsets),
+                                                   _ptr(lengths), C.byref(got)))
+    assert got.value == n
+    return {"replica_ids": ids, "mags": mags, "mbits": mbits, "offsets": offsets, "lengths": lengths}
+
+
 def itoe_scan(collection_dir):
     """itoe.dim / itoe.<version>.data (collection.rs:149-164) -> (live dense embeddings, dim, max internal id)"""
     n, dim, mx = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)

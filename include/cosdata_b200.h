@@ -189,6 +189,14 @@ cdb_status cdb_prop_file_scan(const char *path, uint64_t *out_records, int32_t *
 cdb_status cdb_prop_file_load(const char *path, uint64_t first_record, uint64_t max_records, uint32_t *out_ids, void *out_codes,
                               float *out_mags, uint64_t *out_offsets, uint32_t *out_lengths, uint64_t *out_read);
 cdb_status cdb_index_append_prop_file(cdb_index *index, const char *path, uint32_t *out_ids, uint64_t max_ids, uint64_t *out_appended);
+/* Collections with a metadata schema interleave replica Metadata records { replica_id, vec: { mag, mbits } }
+ * (write_prop_metadata_to_file, file_persist.rs:110-139) with the Storage records in the same file; the three functions above
+ * skip them (rows = Storage records only).  These two read them: count + dimension, then ids, mags, mbits [n x md_dims] and
+ * each record's byte offset / length (= NodePropMetadata.location, what a ProbNode stores). */
+cdb_status cdb_prop_file_scan_metadata(const char *path, uint64_t *out_records, uint32_t *out_md_dims);
+cdb_status cdb_prop_file_load_metadata(const char *path, uint64_t max_records, uint32_t md_dims, uint32_t *out_replica_ids,
+                                       float *out_mags, int32_t *out_mbits, uint64_t *out_offsets, uint32_t *out_lengths,
+                                       uint64_t *out_read);
 /* ---- itoe.dim + itoe.<version>.data: the reference's raw-embedding store, TreeMap<InternalId, RawVectorEmbedding>
  * (src/models/collection.rs:110, 149-164; formats in src/models/serializer/tree_map/ and raw_vector_embedding.rs),
  * which finalize_ann_results reads for the exact re-rank (collection.rs:368-384).  Host-side readers, no GPU work.  Only the

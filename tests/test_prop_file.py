@@ -182,3 +182,49 @@ def test_index_fed_from_prop_file_searches_like_index_fed_from_vectors(tmp_path,
         wrong.append_prop_file(path)
     assert e.value.status == cdb.Status.STORAGE_MISMATCH
     ix.close(); wrong.close()
+
+
+def enc_int(v):
+    return head(0, int(v)) if v >= 0 else head(1, -1 - int(v))
+
+
+def enc_metadata_record(replica_id, mag, mbits):
+    """write_prop_metadata_to_file (file_persist.rs:110-139): { replica_id, vec: Metadata { mag, mbits } }"""
+    return enc_map([("replica_id", enc_uint(replica_id)), ("vec", enc_map([("mag", enc_f32(mag)), ("mbits", enc_array([enc_int(b) for b in mbits]))]))])
+
+
+def test_prop_file_with_interleaved_metadata_records(tmp_path):
+    """collections with a metadata schema write the replicas' Metadata into the same file (vector_store.rs:560-585)"""
+    from oracle import pymeta
+    dim, n, M = 24, 40, 6
+    vecs = orc.synth_matrix(77, n, dim)
+    codes, mags = orc.quantize_batch(0, vecs)
+    rng = np.random.default_rng(5)
+    path = str(tmp_path / "prop.data")
+    value_locs, md_want = [], []
+    with open(path, "wb") as f:
+        for i in range(n):
+            rec = enc_record(i * 4, ST.UnsignedByte, mags[i], codes[i], dim)
+            value_locs.append((f.tell(), len(rec)))
+            f.write(rec)
+            for j in range(int(rng.integers(0, 3))):                        # 0-2 replicas with metadata after the vector
+                mb = rng.integers(-3, 1025, M).astype(np.int32)
+                mg = pymeta.metadata_mag(mb)
+                rec = enc_metadata_record(i * 4 + j, mg, mb)
+                md_want.append((i * 4 + j, mg, mb, f.tell(), len(rec)))
+                f.write(rec)
+    total, st, elems, cb = cdb.prop_file_scan(path)
+    assert (total, st, cb) == (n, ST.UnsignedByte, dim)
+    rec = cdb.prop_file_load(path)
+    assert rec["ids"].tolist() == [i * 4 for i in range(n)] and np.array_equal(rec["codes"], codes)
+    assert [(int(o), int(l)) for o, l in zip(rec["offsets"], rec["lengths"])] == value_locs
+    part = cdb.prop_file_load(path, first_record=30, max_records=5)            # ordinals count Storage records only
+    assert part["ids"].tolist() == [i * 4 for i in range(30, 35)]
+    md = cdb.prop_file_load_metadata(path)
+    assert md["replica_ids"].tolist() == [w[0] for w in md_want]
+    assert np.array_equal(bits(md["mags"]), bits(np.array([w[1] for w in md_want], dtype=np.float32)))
+    assert np.array_equal(md["mbits"], np.stack([w[2] for w in md_want]))
+    assert [(int(o), int(l)) for o, l in zip(md["offsets"], md["lengths"])] == [(w[3], w[4]) for w in md_want]
+    open(path, "ab").write(enc_map([("replica_id", enc_uint(1)), ("value", enc_uint(3))]))      # neither kind of record
+    with pytest.raises(cdb.CosdataError):
+        cdb.prop_file_load_metadata(path)
