@@ -196,6 +196,44 @@ def prop_file_load_metadata(path):
     return {"replica_ids": ids, "mags": mags, "mbits": mbits, "offsets": offsets, "lengths": lengths}
 
 
+class HnswFiles:
+    """the reference's on-disk HNSW index (prop.data, nodes.ptr, <id>.index) flattened to the set_graph arrays"""
+
+    def __init__(self, index_dir, root_link_offset, pseudo_root_link_offset=INVALID_ID):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _check(self._lib.cdb_hnsw_files_open(os.fsencode(index_dir), int(root_link_offset), int(pseudo_root_link_offset), C.byref(self._h)))
+        info = np.zeros(8, dtype=np.uint32)
+        counts = np.zeros(33, dtype=np.uint32)
+        _check(self._lib.cdb_hnsw_files_info(self._h, _ptr(info), _ptr(counts)))
+        (self.num_levels, self.neighbors_count, self.level0_neighbors_count, self.entry, self.pseudo_entry, self.root_row,
+         self.md_dims, self.n_md) = (int(x) for x in info)
+        self.level_counts = counts[: self.num_levels + 1].copy()
+        self.node_row, self.node_id, self.node_md, self.adj, self.child = [], [], [], [], []
+        for lv in range(self.num_levels + 1):
+            c = int(self.level_counts[lv])
+            nb = self.level0_neighbors_count if lv == 0 else self.neighbors_count
+            arrs = [np.zeros(c, np.uint32), np.zeros(c, np.uint32), np.zeros(c, np.uint32), np.zeros(c * nb, np.uint32), np.zeros(c, np.uint32)]
+            _check(self._lib.cdb_hnsw_files_level(self._h, lv, *[_ptr(a) for a in arrs]))
+            for dst, a in zip((self.node_row, self.node_id, self.node_md, self.adj, self.child), arrs):
+                dst.append(a)
+        self.md_bits = np.zeros((self.n_md, max(self.md_dims, 1)), dtype=np.int32)
+        self.md_mags = np.zeros(self.n_md, dtype=np.float32)
+        _check(self._lib.cdb_hnsw_files_metadata(self._h, _ptr(self.md_bits), _ptr(self.md_mags)))
+
+    def apply(self, index):
+        """cdb_index_set_graph_from_files"""
+        _check(self._lib.cdb_index_set_graph_from_files(index._h, self._h))
+        index.md_dims = max(self.md_dims, 1)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.cdb_hnsw_files_close(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+
 def itoe_scan(collection_dir):
     """itoe.dim / itoe.<version>.data (collection.rs:149-164) -> (live dense embeddings, dim, max internal id)"""
     n, dim, mx = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)

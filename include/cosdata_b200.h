@@ -259,6 +259,23 @@ typedef struct {
 } cdb_graph_desc;
 cdb_status cdb_index_set_graph(cdb_index *index, const cdb_graph_desc *graph);
 
+/* ---- the reference's on-disk HNSW index (prop.data + nodes.ptr + <id>.index in one index directory; formats in
+ * src/models/serializer/hnsw/{node,neighbors,latest_node}.rs) flattened into the arrays above.  The two entry links
+ * (root_vec_ptr_offset, pseudo_root_vec_ptr_offset; CDB_INVALID_ID when the collection has no metadata schema) are kept by the
+ * reference in LMDB next to the index parameters (src/models/types.rs:899-945) and are passed in.  Host-side, no GPU work.
+ *   info8 = {num_levels, neighbors_count, level0_neighbors_count, entry, pseudo_entry, root_row, md_dims, n_md}
+ *   level -> node_row (ordinal of the node's Storage record in prop.data = the row cdb_index_append_prop_file gives it),
+ *            node_id (ProbNode::get_id()), node_md (metadata table row or CDB_INVALID_ID), adjacency, child
+ *   cdb_index_set_graph_from_files = cdb_index_set_graph + cdb_index_set_graph_metadata (node ids are always attached so that
+ *            the fixed set and the reported ids are the reference's InternalIds; searches go through the metadata-aware kernel). */
+typedef struct cdb_hnsw_files cdb_hnsw_files;
+cdb_status cdb_hnsw_files_open(const char *index_dir, uint32_t root_link_offset, uint32_t pseudo_root_link_offset, cdb_hnsw_files **out);
+cdb_status cdb_hnsw_files_close(cdb_hnsw_files *files);
+cdb_status cdb_hnsw_files_info(const cdb_hnsw_files *files, uint32_t *info8, uint32_t *level_counts);
+cdb_status cdb_hnsw_files_level(const cdb_hnsw_files *files, uint32_t level, uint32_t *node_row, uint32_t *node_id, uint32_t *node_md,
+                                uint32_t *adjacency, uint32_t *child);
+cdb_status cdb_hnsw_files_metadata(const cdb_hnsw_files *files, int32_t *md_bits, float *md_mags);
+
 /* Replica nodes and metadata of a graph uploaded with cdb_index_set_graph (collections with a metadata schema:
  * src/vector_store.rs:57-250, 485-712).  One embedding may own several graph nodes (its base replica and one per
  * metadata dimension set, src/models/types.rs:163-176) that share the embedding's vector row; pseudo nodes share the
@@ -277,6 +294,7 @@ typedef struct {
     uint32_t pseudo_entry;
 } cdb_graph_metadata;
 cdb_status cdb_index_set_graph_metadata(cdb_index *index, const cdb_graph_metadata *md);
+cdb_status cdb_index_set_graph_from_files(cdb_index *index, const cdb_hnsw_files *files);
 /* GPU-side index build (index_embeddings, src/vector_store.rs:714-940): appends the root vector (random in
  * values_range, id u32::MAX; vector_store.rs:57-67) as the last row and builds the HNSW graph over all rows with the
  * reference's algorithm (traverse with ef_construction per level, create_node_edges / add_neighbor with
