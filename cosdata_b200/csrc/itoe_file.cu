@@ -121,8 +121,9 @@ struct ItoeStore {
         if (off == UINT32_MAX) return true;
         if (!dim.has(off, 8)) return fail("QuotientsMap outside itoe.dim");
         const uint64_t len = dim.u64(off);
-        uint64_t o = (uint64_t)off + 8;
+        uint64_t o = (uint64_t)off + 8, chunks = 0;
         for (uint64_t i = 0; i < len;) {
+            if (++chunks > dim.len / 68 + 1) return fail("QuotientsMap chunk chain does not end");   // a damaged next pointer
             if (!dim.has(o, 4 * 16 + 4)) return fail("QuotientsMap chunk outside itoe.dim");
             for (int s = 0; s < 4 && i < len; ++s, ++i) {
                 const uint64_t key = dim.u64(o + s * 16);
@@ -140,9 +141,12 @@ struct ItoeStore {
         return true;
     }
 
+    std::vector<uint32_t> seen_nodes;
     bool walk(uint32_t node_off, std::vector<Entry> &out, int depth) {
         if (depth > 64) return fail("TreeMapNode nesting too deep");   // a path has at most 3 hops per power of 4: 24
         if (!dim.has(node_off, 38)) return fail("TreeMapNode outside itoe.dim");
+        if (seen_nodes.size() > dim.len / 38 + 1) return fail("TreeMapNode links form a cycle");   // more visits than nodes fit in the file
+        seen_nodes.push_back(node_off);
         if (!quotients(dim.u32((uint64_t)node_off + 34), &out, nullptr, nullptr, nullptr)) return false;
         for (int c = 0; c < 8; ++c) {
             const uint32_t child = dim.u32((uint64_t)node_off + 2 + c * 4);

@@ -238,3 +238,26 @@ def test_index_fed_from_itoe_store_reranks_like_the_oracle(tmp_path):
         wrong.append_itoe(d)
     assert e.value.status == cdb.Status.STORAGE_MISMATCH
     ix.close(); wrong.close()
+
+
+def test_itoe_cyclic_links_are_rejected(tmp_path):
+    d = str(tmp_path / "coll")
+    sample_store(d, dim=8, n=120)
+    blob = bytearray(open(os.path.join(d, "itoe.dim"), "rb").read())
+    root = struct.unpack("<I", blob[0:4])[0]
+    first_child = next(c for c in struct.unpack("<8I", blob[root + 2:root + 34]) if c != NONE32)
+    cyc = bytearray(blob)
+    slot = next(i for i in range(8) if struct.unpack("<I", cyc[first_child + 2 + 4 * i:first_child + 6 + 4 * i])[0] != NONE32
+                or True)
+    cyc[first_child + 2 + 4 * slot:first_child + 6 + 4 * slot] = struct.pack("<I", root)     # a child pointing back at the root
+    open(os.path.join(d, "itoe.dim"), "wb").write(bytes(cyc))
+    with pytest.raises(cdb.CosdataError):
+        cdb.itoe_scan(d)
+    cyc = bytearray(blob)
+    q = struct.unpack("<I", cyc[root + 34:root + 38])[0]                                      # root's quotient map: chunk -> itself
+    assert q != NONE32
+    cyc[q:q + 8] = struct.pack("<Q", 1 << 40)
+    cyc[q + 8 + 64:q + 8 + 68] = struct.pack("<I", q + 8)
+    open(os.path.join(d, "itoe.dim"), "wb").write(bytes(cyc))
+    with pytest.raises(cdb.CosdataError):
+        cdb.itoe_scan(d)
