@@ -67,6 +67,27 @@ struct SamplingData {
     }
 };
 
+// prop.data: the Storage payloads of an index directory (file_persist.rs:58-108), row = record number
+struct PropFile {
+    uint64_t records = 0, code_bytes = 0;
+    StorageType storage_type = StorageType::UnsignedByte;
+    uint32_t elems = 0;
+    std::vector<uint32_t> ids;
+    std::vector<uint8_t> codes;
+    std::vector<float> mags;
+    std::vector<uint64_t> offsets;   // == ProbNode prop_value.location.0
+    std::vector<uint32_t> lengths;
+    explicit PropFile(const std::string &path) {
+        int32_t st = -1;
+        check(cdb_prop_file_scan(path.c_str(), &records, &st, &elems, &code_bytes));
+        if (!records) return;
+        storage_type = (StorageType)st;
+        ids.resize(records); codes.resize(records * code_bytes); mags.resize(records); offsets.resize(records); lengths.resize(records);
+        uint64_t got = 0;
+        check(cdb_prop_file_load(path.c_str(), 0, records, ids.data(), codes.data(), mags.data(), offsets.data(), lengths.data(), &got));
+    }
+};
+
 // enum DistanceMetric + impl DistanceFunction (pairwise)
 struct DistanceMetric {
     DistanceMetricKind kind;
