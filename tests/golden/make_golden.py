@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 import oracle as orc  # noqa: E402
-from oracle import pyhnsw  # noqa: E402
+from oracle import pyhnsw, pymeta  # noqa: E402
 
 DIMS = (8, 31, 32, 33, 128, 768, 1024)
 STORAGES = (0, 1, 2, 3, 4, 5)       # UnsignedByte, SubByte1..3, HalfPrecisionFP, FullPrecisionFP
@@ -92,6 +92,32 @@ def generate():
         codes, mags = orc.quantize_batch(0, m, -0.5, 0.75)
         out[f"d{dim}/st0_range/codes"] = codes
         out[f"d{dim}/st0_range/mag_bits"] = bits(mags)
+
+    # ---- quantization:auto value-range sampling (hnsw/mod.rs:202-351)
+    base = orc.synth_matrix(0x5A4D, 64, 48)
+    for tag, arr, clamp in (("uniform", base, 1.0), ("x019", (base * np.float32(0.19)).astype(np.float32), 1.0),
+                            ("pos004", (np.abs(base) * np.float32(0.04)).astype(np.float32), 1.0),
+                            ("x03_tight", (base * np.float32(0.3)).astype(np.float32), 0.05)):
+        counts, rng_ = orc.sample_values_range(arr, clamp)
+        out[f"sampling/{tag}/values"] = arr
+        out[f"sampling/{tag}/clamp_counts"] = np.concatenate([np.array([clamp], dtype=np.float64), counts.astype(np.float64)])
+        out[f"sampling/{tag}/range_bits"] = bits(np.array(rng_, dtype=np.float32))
+
+    # ---- metadata replica-kind arms of the cosine metric (cosine.rs:34-102), f16 storage, D = 16, 5 metadata dims
+    mv = orc.synth_matrix(0x3D7A, 2, 16)
+    mcodes, mmags = orc.quantize_batch(4, mv)
+    pat_a, pat_b, zeros = np.array([1, 0, 1, 1, 0], np.int32), np.array([0, 1, 1, 0, 0], np.int32), np.zeros(5, np.int32)
+    sides = [(None, None), (None, pat_a), (5, zeros), (8, pat_a), (9, pat_b), (0xFFFFFFFF - 257, pat_a), (0xFFFFFFFF - 2, pat_b),
+             (0xFFFFFFFF - 258, pat_a), (0xFFFFFFFF, pat_a)]
+    table = np.zeros((len(sides), len(sides), 2), dtype=np.uint32)          # [x][y] = (status, value bits)
+    for xi, (xid, xb) in enumerate(sides):
+        for yi, (yid, yb) in enumerate(sides):
+            x = pymeta.VectorData(mcodes[0], mmags[0], xid, xb, 0.0 if xb is None else pymeta.metadata_mag(xb))
+            y = pymeta.VectorData(mcodes[1], mmags[1], yid, yb, 0.0 if yb is None else pymeta.metadata_mag(yb))
+            rc, val = pymeta.distance_md(0, 4, 16, 5, x, y)
+            table[xi, yi] = (rc, bits(np.array([val if rc == 0 else 0.0], dtype=np.float32))[0])
+    out["metadata/vectors"] = mv
+    out["metadata/arm_table"] = table
 
     # ---- HNSW: oracle builder (deterministic restatement of index_embedding) + ann_search + re-rank
     n, dim, seed = 400, 24, 7
