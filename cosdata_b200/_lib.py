@@ -145,6 +145,7 @@ PROTOTYPES = {
     "cdb_kernel_launch_count": (C.c_uint64, []),
     "cdb_index_last_kernel_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cdb_index_stats": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "cdb_index_stats_ex": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "cdb_index_last_candidate_counts": (C.c_int32, [C.c_void_p, C.c_uint32, c_u32p]),
     "cdb_index_scan_ms_history": (C.c_int32, [C.c_void_p, C.c_uint32, c_f32p, C.POINTER(C.c_uint32)]),
 }

@@ -32,6 +32,7 @@ class Status(enum.IntEnum):
     CUDA_ERROR = 4
     NCCL_ERROR = 5
     UNSUPPORTED = 6
+    UNREACHABLE_ARM = 7
 
 
 class StorageType(enum.IntEnum):
@@ -59,8 +60,13 @@ class SearchMode(enum.IntEnum):
 
 class CosdataError(RuntimeError):
     def __init__(self, status, msg=""):
-        self.status = Status(status)
-        super().__init__(f"{self.status.name}: {msg}")
+        try:
+            self.status = Status(status)
+            name = self.status.name
+        except ValueError:          # a status this mirror does not know yet: keep the number
+            self.status = int(status)
+            name = f"status {int(status)}"
+        super().__init__(f"{name}: {msg}")
 
 
 class DistanceError(CosdataError):
@@ -434,9 +440,10 @@ class DenseIndex:
         return out[: m.value].copy()
 
     def stats(self):
-        out = np.zeros(4, dtype=np.uint64)
-        _check(self._lib.cdb_index_stats(self._h, _ptr(out)))
-        return {"tensor_searches": int(out[0]), "fallbacks": int(out[1]), "zero_rows": int(out[2]), "has_shadow": bool(out[3])}
+        out = np.zeros(6, dtype=np.uint64)
+        _check(self._lib.cdb_index_stats_ex(self._h, _ptr(out), 6))
+        return {"tensor_searches": int(out[0]), "fallbacks": int(out[1]), "zero_rows": int(out[2]), "odd_rows": int(out[3]),
+                "has_shadow": bool(out[4]), "fallback_queries": int(out[5])}
 
     def last_candidate_counts(self, n):
         out = np.zeros(n, dtype=np.uint32)

@@ -75,14 +75,11 @@ static cdb_status copy_codes(void *dst, const void *src, int st, uint32_t dim, u
     return CDB_OK;
 }
 
-__global__ void err32_to_u8_kernel(const uint32_t *e, uint8_t *out, uint32_t n, const uint32_t *run_if = nullptr) {
-    if (run_if && (run_if[0] | run_if[2]) == 0) return;
+// qsel != null: only after a fallback scan ran (n_sel > 0), otherwise the tensor-core path's flags stand
+__global__ void err32_to_u8_kernel(const uint32_t *e, uint8_t *out, uint32_t n, const uint32_t *qsel = nullptr) {
+    if (qsel && qsel[0] == 0) return;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint8_t)e[i];
-}
-// flags = {overflowed queries, zero-norm rows (persistent), zero-norm queries, fallback counter}
-__global__ void count_fallback_kernel(uint32_t *flags) {
-    if (flags[0] | flags[2]) flags[3] += 1;
 }
 
 }  // namespace cdb
@@ -104,8 +101,9 @@ struct cdb_index {
     uint32_t digit_pitch = 0;
     void *d_xh = nullptr;          // fp16 L2-normalised rows for the tcgen05 prefilter (tensor_scan.cu)
     uint32_t xh_pitch = 0;         // halfs per shadow row
-    uint64_t n_zero_rows = 0;      // rows with |v| == 0 (their exact score is NaN)
-    uint32_t *h_flags = nullptr;   // pinned host copy of d_flags
+    uint64_t n_allzero_rows = 0;   // degenerate rows (tensor_scan.cu): all-zero rows score NaN against every query = last
+    uint64_t n_odd_rows = 0;       // other degenerate rows (norm 0/inf/NaN/out of range): ride on every candidate list
+    uint32_t *h_flags = nullptr;   // pinned host staging (16 words)
     uint64_t stat_tensor_searches = 0;
     cudaStream_t stream = nullptr;
     static constexpr int EV_RING = 64;
@@ -116,7 +114,7 @@ struct cdb_index {
     cudaStream_t last_stream = nullptr;  // stream of the previous search: scratch buffers are shared between searches
     std::mutex mu;
     DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
-    DevBuf qh, gthr, cand, cand_cnt, flags, progress;
+    DevBuf qh, gthr, cand, cand_cnt, flags, progress, deg, qsel;
     // HNSW graph (cdb_index_set_graph)
     bool has_graph = false;
     GraphDev graph{};
@@ -332,11 +330,11 @@ cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
     CDB_REQUIRE(d->metric >= CDB_METRIC_COSINE && d->metric <= CDB_METRIC_DOT_PRODUCT, "bad metric");
     CDB_REQUIRE(d->capacity > 0 && d->capacity < 0xFFFFFFFFull, "capacity must be in 1..2^32-2");
     CDB_CUDA_TRY(cudaSetDevice(d->device));
+    int sms = 0;
+    CDB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d->device));
     cdb_index *ix = new cdb_index();
     ix->desc = *d;
-    cudaDeviceProp prop;
-    CDB_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
-    ix->sm_count = prop.multiProcessorCount;
+    ix->sm_count = sms;
     ix->row_pitch = row_pitch_bytes(d->storage_type, d->dim);
     ix->raw_pitch_elems = round_up(d->dim * 4, 16) / 4;
     auto fail = [&](cudaError_t e, const char *what) {
@@ -377,9 +375,11 @@ cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
         if ((e = cudaMalloc(&ix->d_digits, (size_t)d->capacity * ix->digit_pitch)) != cudaSuccess) return fail(e, "cudaMalloc(digits)");
         if ((e = cudaMemsetAsync(ix->d_digits, 0, (size_t)d->capacity * ix->digit_pitch, ix->stream)) != cudaSuccess) return fail(e, "memset");
     }
-    if ((e = cudaMallocHost(&ix->h_flags, 16)) != cudaSuccess) return fail(e, "cudaMallocHost");
+    if ((e = cudaMallocHost(&ix->h_flags, 64)) != cudaSuccess) return fail(e, "cudaMallocHost");
     if (ix->flags.ensure(16) != CDB_OK) return fail(cudaErrorMemoryAllocation, "flags");
     if ((e = cudaMemsetAsync(ix->flags.p, 0, 16, ix->stream)) != cudaSuccess) return fail(e, "memset");
+    if (ix->deg.ensure(TS_DEG_WORDS * 4) != CDB_OK) return fail(cudaErrorMemoryAllocation, "deg");
+    if ((e = cudaMemsetAsync(ix->deg.p, 0, TS_DEG_WORDS * 4, ix->stream)) != cudaSuccess) return fail(e, "memset");
     if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return fail(e, "sync");
     *out = ix;
     return CDB_OK;
@@ -399,7 +399,7 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     for (void *g : ix->md_allocs) cudaFree(g);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
-                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters,
+                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->deg, &ix->qsel, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters,
                       &ix->qraw, &ix->qraw_mags, &ix->hn_ids, &ix->hn_labels, &ix->flt_off, &ix->flt_dims, &ix->flt_has})
         b->release();
     for (auto &ev : ix->ev)
@@ -432,14 +432,17 @@ static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) 
                                    ix->d_digits + first * ix->digit_pitch, ix->digit_pitch, ix->stream)))
         return rc;
     if (ix->d_xh) {
-        // flags[1] accumulates the number of zero-norm rows
         if ((rc = normalize_f16_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, ix->d_raw_mags + first, n,
-                                       ix->desc.dim, (uint8_t *)ix->d_xh + first * ix->xh_pitch * 2, ix->xh_pitch,
-                                       ix->flags.as<uint32_t>() + 1, ix->stream)))
+                                       ix->desc.dim, (uint8_t *)ix->d_xh + first * ix->xh_pitch * 2, ix->xh_pitch, ix->stream)))
             return rc;
-        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags + 1, ix->flags.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, ix->stream));
+        // deg[0], deg[1] accumulate the all-zero / other degenerate rows, deg[2..] lists the first of the latter
+        if ((rc = classify_rows_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, ix->d_raw_mags + first, n,
+                                       ix->desc.dim, (uint32_t)first, ix->deg.as<uint32_t>(), ix->stream)))
+            return rc;
+        CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags + 4, ix->deg.p, 8, cudaMemcpyDeviceToHost, ix->stream));
         CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
-        ix->n_zero_rows = ix->h_flags[1];
+        ix->n_allzero_rows = ix->h_flags[4];
+        ix->n_odd_rows = ix->h_flags[5];
     }
     return CDB_OK;
 }
@@ -537,10 +540,12 @@ cdb_status cdb_index_read_codes(const cdb_index *ix, uint64_t first, uint64_t n,
 
 // ------------------------------------------------------------------ S1 search
 
-// prepared (quantized) queries live in ix->q_codes / ix->q_mags
+// prepared (quantized) queries live in ix->q_codes / ix->q_mags.
+// qsel == null: unconditional scan of the whole batch.  Otherwise the device decides (ScanArgs): a selective scan of the
+// <= SCAN_SEL_CAP queries the tensor-core path could not answer, or -- if there are more -- the whole batch again.
 static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric, uint32_t pitch, uint32_t nq, uint32_t k,
                                     uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s,
-                                    const uint32_t *run_if = nullptr) {
+                                    const uint32_t *qsel = nullptr) {
     const cdb_index_desc &d = ix->desc;
     cdb_status rc;
     ScanArgs a{};
@@ -558,15 +563,26 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
     a.k = k;
     a.id_base = d.id_base;
     a.nsplit = scan_plan_nsplit(a, ix->sm_count);
-    if ((rc = ix->partial.ensure((size_t)nq * a.nsplit * k * 8)) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
+    a.qsel = qsel;
+    a.sel_cap = SCAN_SEL_CAP;
+    a.sel_grid = scan_sel_grid(ix->sm_count, k);
+    const size_t part_full = (size_t)nq * a.nsplit * k * 8, part_sel = qsel ? (size_t)SCAN_SEL_CAP * a.sel_grid * k * 8 : 0;
+    if ((rc = ix->partial.ensure(std::max(part_full, part_sel))) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
     a.partial = ix->partial.as<uint64_t>();
     a.err32 = ix->err32.as<uint32_t>();
-    a.run_if = run_if;
-    CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));
+    if (!qsel) CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));   // the tensor-core path prepared it otherwise
+    if (qsel) {
+        a.sel_mode = 1;
+        if ((rc = scan_topk_device(a, s))) return rc;
+        if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 1,
+                                        a.sel_grid, scan_sel_qb(a))))
+            return rc;
+        a.sel_mode = 0;
+    }
     if ((rc = scan_topk_device(a, s))) return rc;
-    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, run_if))) return rc;
+    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 0))) return rc;
     if (d_err) {
-        err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq, run_if);
+        err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq, qsel);
         CDB_LAUNCH_CHECK();
     }
     return CDB_OK;
@@ -683,7 +699,6 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
 // rigorous bound on |approximate cosine - reference cosine| of the fp16 tensor-core prefilter
 // (two fp16 roundings, fp32 tensor accumulation, f32 norms)
 static float prefilter_eps(uint32_t dim) { return 1.0e-3f + 8.0e-7f * (float)dim; }
-static const uint32_t PREFILTER_CAP = 4096;
 
 static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                       uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
@@ -716,41 +731,45 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
     ix->n_search++;
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
 
-    // ---- tcgen05 prefilter + exact re-rank: identical results, far fewer exact dot products
+    // ---- tcgen05 prefilter + exact re-rank: identical results, far fewer exact dot products.
+    // Needs k proper (non-degenerate) rows for the bound to exist, and few enough odd degenerate rows to carry them on
+    // every candidate list (tensor_scan.cu).
     const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 64 &&
-                           ix->size - ix->n_zero_rows >= p->k && tensor_scan_smem_bytes(p->k) <= 227 * 1024 &&
-                           (nq + 127) / 128 <= (uint32_t)ix->sm_count;
-    const uint32_t *run_if = nullptr;
+                           ix->n_odd_rows <= TS_MAX_ODD && ix->size - ix->n_allzero_rows - ix->n_odd_rows >= p->k &&
+                           tensor_scan_smem_bytes(p->k) <= 227 * 1024 && (nq + 127) / 128 <= (uint32_t)ix->sm_count;
+    const uint32_t *qsel = nullptr;
     if (tensor_ok) {
         const uint32_t mt = (nq + 127) / 128;
-        // candidate slots per query (power of two; ~32 MB in total): long lists only arise for few queries
-        const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 8192u : PREFILTER_CAP));
+        // candidate slots per query (<= 64 MB in total): long lists only arise for few queries, and a query whose list
+        // overflows is re-done alone by the selective exact scan
+        const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 32768u : (nq <= 1024 ? 16384u : 8192u));
         if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)mt * 128 * 64 * 4)) ||
-            (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) || (rc = ix->progress.ensure(4096)))
+            (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) ||
+            (rc = ix->progress.ensure(4096)) || (rc = ix->qsel.ensure((size_t)(nq + 1) * 4)))
             return rc;
-        uint32_t *flags = ix->flags.as<uint32_t>();  // [0] overflowed queries, [2] zero-norm queries
-        CDB_CUDA_TRY(cudaMemsetAsync(flags, 0, 4, s));
-        CDB_CUDA_TRY(cudaMemsetAsync(flags + 2, 0, 4, s));
+        uint32_t *flags = ix->flags.as<uint32_t>();  // [0] queries of the last search that needed the exact scan, [3] searches with a fallback
         CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * ix->xh_pitch * 2, s));
         if ((rc = normalize_f16_device(ix->q_codes.as<float>(), pitch / 4, ix->q_mags.as<float>(), nq, d.dim, ix->qh.p,
-                                       ix->xh_pitch, flags + 2, s)))
+                                       ix->xh_pitch, s)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
+        const bool has_deg = ix->n_allzero_rows + ix->n_odd_rows > 0;
         if ((rc = tensor_scan_device(ix->d_xh, ix->qh.p, ix->xh_pitch, ix->size, nq, d.dim, p->k, 2.0f * prefilter_eps(d.dim),
                                      d.id_base, ix->gthr.as<int>(), ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), cap,
-                                     ix->progress.as<uint32_t>(), ix->sm_count, s)))
+                                     ix->progress.as<uint32_t>(), ix->deg.as<uint32_t>(), has_deg, ix->sm_count, s)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(),
                                     pitch / 4, ix->q_mags.as<float>(), nq, ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(),
                                     cap, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
             return rc;
-        if ((rc = overflow_check_device(ix->cand_cnt.as<uint32_t>(), cap, nq, flags, s))) return rc;
-        count_fallback_kernel<<<1, 1, 0, s>>>(flags);
-        CDB_LAUNCH_CHECK();
+        if ((rc = select_fallback_device(ix->cand_cnt.as<uint32_t>(), cap, ix->q_mags.as<float>(), nq, ix->qsel.as<uint32_t>(), flags, s)))
+            return rc;
+        if ((rc = ix->err32.ensure((size_t)nq * 4))) return rc;
+        CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
         if (d_err) CDB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nq, s));
         ix->stat_tensor_searches++;
-        run_if = flags;  // the exact scan below only runs (on the device's own decision) if a list overflowed or a query has zero norm
+        qsel = ix->qsel.as<uint32_t>();  // the exact scan below only runs (on the device's own decision) for the queries listed there
     }
     // ---- exact integer scoring on tcgen05 kind::i8: u8 codes in place, sub-byte codes through the digit copy
     const uint8_t *u8_rows = !raw ? (st == CDB_ST_U8 ? ix->d_codes : ix->d_digits) : nullptr;
@@ -765,9 +784,8 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
             (rc = ix->cand.ensure((size_t)nq * cap * 8)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) ||
             (rc = ix->progress.ensure(4096)) || (rc = ix->err32.ensure((size_t)nq * 4)))
             return rc;
+        if ((rc = ix->qsel.ensure((size_t)(nq + 1) * 4))) return rc;
         uint32_t *flags = ix->flags.as<uint32_t>();
-        CDB_CUDA_TRY(cudaMemsetAsync(flags, 0, 4, s));
-        CDB_CUDA_TRY(cudaMemsetAsync(flags + 2, 0, 4, s));
         CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
         CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * upitch, s));
         if (st == CDB_ST_U8)
@@ -781,22 +799,20 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
                                         d_ids, d_scores, d_counts, ix->sm_count, s)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
-        if ((rc = overflow_check_device(ix->cand_cnt.as<uint32_t>(), cap, nq, flags, s))) return rc;
-        count_fallback_kernel<<<1, 1, 0, s>>>(flags);
-        CDB_LAUNCH_CHECK();
+        if ((rc = select_fallback_device(ix->cand_cnt.as<uint32_t>(), cap, nullptr, nq, ix->qsel.as<uint32_t>(), flags, s))) return rc;
         if (d_err) {
             err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(ix->err32.as<uint32_t>(), d_err, nq);
             CDB_LAUNCH_CHECK();
         }
         ix->stat_tensor_searches++;
-        run_if = flags;
+        qsel = ix->qsel.as<uint32_t>();
     }
     {
         // exact scan: unconditional when no tensor-core path applies, otherwise a device-side conditional fallback
-        // (its kernels return immediately unless the flags say the prefilter result is unusable) -- no host sync
-        const bool fast = run_if != nullptr;
+        // (its kernels return immediately unless qsel lists queries the tensor-core path could not answer) -- no host sync
+        const bool fast = qsel != nullptr;
         if (!fast) CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-        if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s, run_if))) return rc;
+        if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s, qsel))) return rc;
         if (!fast) CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
     }
     CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
@@ -1192,8 +1208,22 @@ cdb_status cdb_index_stats(const cdb_index *ix, uint64_t *out4) {
     }
     out4[0] = ix->stat_tensor_searches;
     out4[1] = fb;
-    out4[2] = ix->n_zero_rows;
+    out4[2] = ix->n_allzero_rows + ix->n_odd_rows;
     out4[3] = ix->d_xh ? 1 : 0;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_stats_ex(const cdb_index *ix, uint64_t *out, uint32_t n) {
+    CDB_REQUIRE(ix && (out || !n), "null argument");
+    uint32_t fl[4] = {0, 0, 0, 0};
+    if (ix->flags.p) {
+        CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+        CDB_CUDA_TRY(cudaDeviceSynchronize());
+        CDB_CUDA_TRY(cudaMemcpy(fl, ix->flags.p, 16, cudaMemcpyDeviceToHost));
+    }
+    const uint64_t v[CDB_STATS_FIELDS] = {ix->stat_tensor_searches, fl[3], ix->n_allzero_rows, ix->n_odd_rows,
+                                          ix->d_xh ? 1ull : 0ull, fl[0]};
+    for (uint32_t i = 0; i < n && i < CDB_STATS_FIELDS; ++i) out[i] = v[i];
     return CDB_OK;
 }
 

@@ -66,16 +66,27 @@ struct ScanArgs {
     uint64_t *partial;     // [nq][nsplit][k] selection keys
     uint32_t nsplit;
     uint32_t *err32;       // [nq] error bits (atomicOr) or null
-    const uint32_t *run_if;  // null, or device flags {overflowed queries, -, zero-norm queries}: the kernel is a no-op
-                             // unless one of them is non-zero (device-side fallback decision, no host sync)
+    // Device-side fallback decision of the tensor-core paths (no host sync).  qsel = {n_sel, query indices...} is written by
+    // select_fallback_kernel.  Two launches share it:
+    //   selective (sel_mode = 1): 1-D grid; runs only if 0 < n_sel <= sel_cap, over the selected queries only -- the CTAs
+    //       split themselves over ceil(n_sel/QB) query groups, so a single bad query gets the whole GPU;
+    //   full      (sel_mode = 0): the whole batch, runs only if qsel == null (no tensor path) or n_sel > sel_cap.
+    const uint32_t *qsel;
+    uint32_t sel_cap;
+    int sel_mode;
+    uint32_t sel_grid;   // CTAs of the selective launch (scan_sel_grid)
 };
+constexpr uint32_t SCAN_SEL_CAP = 64;
 // picks grid/template; returns nsplit chosen through args.nsplit (caller sizes `partial` with scan_max_partials)
 uint32_t scan_plan_nsplit(const ScanArgs &a, int sm_count);
 cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s);
 // partial [nq][nsplit][k] -> ids/scores/counts
 cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
                                  uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s,
-                                 const uint32_t *run_if = nullptr);
+                                 const uint32_t *qsel = nullptr, uint32_t sel_cap = 0, int sel_mode = 0, uint32_t sel_grid = 0, uint32_t sel_qb = 0);
+// grid of the selective scan (CTAs) and its query block; the partial buffer needs SCAN_SEL_CAP * grid * k keys
+uint32_t scan_sel_grid(int sm_count, uint32_t k);
+uint32_t scan_sel_qb(const ScanArgs &a);
 // [n_shards][nq][k] ids/scores -> keys [nq][n_shards][k]
 cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_scores, uint32_t n_shards, uint32_t nq,
                             uint32_t k, uint64_t *d_keys, cudaStream_t s);
@@ -137,13 +148,20 @@ cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n, uint32_t num_leve
                              std::vector<const uint32_t *> *out_ch, cudaStream_t s);
 
 // ---- tensor_scan.cu (tcgen05 prefilter)
+constexpr uint32_t TS_MAX_ODD = 64;   // degenerate rows that are not all-zero ride on every candidate list; more -> no prefilter
+constexpr uint32_t TS_DEG_WORDS = 2 + TS_MAX_ODD;
 cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
-                                void *d_out, uint32_t out_pitch_halfs, uint32_t *d_zero_count, cudaStream_t s);
+                                void *d_out, uint32_t out_pitch_halfs, cudaStream_t s);
+cdb_status classify_rows_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
+                                uint32_t first_row, uint32_t *d_deg, cudaStream_t s);
 size_t tensor_scan_smem_bytes(uint32_t k);
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
                               uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_ggm, uint32_t *d_cand,
-                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, int sm_count, cudaStream_t s);
-cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s);
+                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, const uint32_t *d_deg, bool has_deg,
+                              int sm_count, cudaStream_t s);
+// queries whose candidate list overflowed (or whose norm is degenerate, d_qmags may be null) -> d_qsel = {n, indices...}
+cdb_status select_fallback_device(const uint32_t *d_cnt, uint32_t cap, const float *d_qmags, uint32_t n, uint32_t *d_qsel,
+                                  uint32_t *d_flags, cudaStream_t s);
 
 // ---- tensor_scan_u8.cu (exact integer scoring on tcgen05 kind::i8)
 size_t tensor_u8_smem_bytes(uint32_t k);

@@ -88,25 +88,55 @@ __device__ inline void topk_end_pass(const TopK &t, uint32_t qb) {
         __syncthreads();
     }
 }
-__device__ inline void topk_finish(const TopK &t, uint32_t qb, uint32_t nqv, uint32_t q0, uint32_t split,
-                                   uint32_t nsplit, uint64_t *partial, uint32_t *err32) {
+// qslot0 = first slot of this CTA's queries in the partial buffer; err goes to the real query index (qidx, may be null)
+__device__ inline void topk_finish(const TopK &t, uint32_t qb, uint32_t nqv, uint32_t qslot0, uint32_t split,
+                                   uint32_t nsplit, uint64_t *partial, uint32_t *err32, const uint32_t *qidx) {
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t b = warp; b < qb; b += SCAN_THREADS / 32) topk_compact_warp(t, b, lane);
     __syncthreads();
     for (uint32_t idx = threadIdx.x; idx < nqv * t.k; idx += blockDim.x) {
         uint32_t b = idx / t.k, j = idx % t.k;
-        partial[((size_t)(q0 + b) * nsplit + split) * t.k + j] = (int)j < t.cnt[b] ? t.buf[(size_t)b * t.cap + j] : 0ull;
+        partial[((size_t)(qslot0 + b) * nsplit + split) * t.k + j] = (int)j < t.cnt[b] ? t.buf[(size_t)b * t.cap + j] : 0ull;
     }
-    if (err32 && threadIdx.x < nqv && t.err[threadIdx.x]) atomicOr(err32 + q0 + threadIdx.x, (uint32_t)t.err[threadIdx.x]);
+    if (err32 && threadIdx.x < nqv && t.err[threadIdx.x])
+        atomicOr(err32 + (qidx ? qidx[qslot0 + threadIdx.x] : qslot0 + threadIdx.x), (uint32_t)t.err[threadIdx.x]);
+}
+
+// Work assignment of one CTA (see ScanArgs).  Returns false when the CTA has nothing to do.
+struct ScanWork {
+    uint32_t q0, nqv, split, nsplit;
+    const uint32_t *qidx;   // null: query index = slot
+};
+template <int QB>
+__device__ __forceinline__ bool scan_work(const ScanArgs &a, ScanWork &w) {
+    if (a.sel_mode) {
+        const uint32_t n_sel = a.qsel[0];
+        if (n_sel == 0 || n_sel > a.sel_cap) return false;
+        const uint32_t groups = (n_sel + QB - 1) / QB;
+        const uint32_t grp = blockIdx.x % groups;
+        w.split = blockIdx.x / groups;
+        w.nsplit = gridDim.x / groups;
+        if (w.split >= w.nsplit) return false;
+        w.q0 = grp * QB;
+        w.nqv = min((uint32_t)QB, n_sel - w.q0);
+        w.qidx = a.qsel + 1;
+        return true;
+    }
+    if (a.qsel && a.qsel[0] <= a.sel_cap) return false;   // the prefilter result stands (or the selective scan handles it)
+    w.q0 = blockIdx.x * QB;
+    w.nqv = min((uint32_t)QB, a.nq - w.q0);
+    w.split = blockIdx.y;
+    w.nsplit = gridDim.y;
+    w.qidx = nullptr;
+    return true;
 }
 
 // ------------------------------------------------------------------ f32 exact scan
-__device__ __forceinline__ bool scan_skipped(const uint32_t *run_if) { return run_if && (run_if[0] | run_if[2]) == 0; }
-
 template <int QB, int R>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_f32_kernel(ScanArgs a) {
-    if (scan_skipped(a.run_if)) return;  // device-side decision: the prefilter succeeded, nothing to redo
+    ScanWork w;
+    if (!scan_work<QB>(a, w)) return;  // device-side decision: the prefilter succeeded, nothing to redo
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t qp = a.row_pitch / 4;  // floats per (padded) query row
     float *qs = reinterpret_cast<float *>(smem);
@@ -114,19 +144,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_f32_kernel(ScanArgs a) {
     TopK tk = topk_carve(reinterpret_cast<uint8_t *>(qmag + ((QB + 3) & ~3)), QB, a.k);
 
     const int tid = threadIdx.x, t = tid & 1, pi = tid >> 1;
-    const uint32_t q0 = blockIdx.x * QB;
-    const uint32_t nqv = min((uint32_t)QB, a.nq - q0);
+    const uint32_t nqv = w.nqv;
     for (uint32_t i = tid; i < QB * qp; i += SCAN_THREADS) {
         uint32_t b = i / qp, c = i % qp;
-        qs[i] = (b < nqv && c < a.dim) ? reinterpret_cast<const float *>(a.q + (size_t)(q0 + b) * a.row_pitch)[c] : 0.0f;
+        const uint32_t qi = b < nqv ? (w.qidx ? w.qidx[w.q0 + b] : w.q0 + b) : 0;
+        qs[i] = (b < nqv && c < a.dim) ? reinterpret_cast<const float *>(a.q + (size_t)qi * a.row_pitch)[c] : 0.0f;
     }
-    if (tid < QB) qmag[tid] = tid < (int)nqv ? a.qmags[q0 + tid] : 0.0f;
+    if (tid < QB) qmag[tid] = tid < (int)nqv ? a.qmags[w.qidx ? w.qidx[w.q0 + tid] : w.q0 + tid] : 0.0f;
     topk_init(tk, QB);
     __syncthreads();
 
     const uint32_t chunks = a.dim / 8;
     const uint64_t npass = (a.n + RPP - 1) / RPP;
-    for (uint64_t pass = blockIdx.y; pass < npass; pass += gridDim.y) {
+    for (uint64_t pass = w.split; pass < npass; pass += w.nsplit) {
         uint64_t row[R];
         const float *xp[R];
 #pragma unroll
@@ -207,30 +237,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_f32_kernel(ScanArgs a) {
         }
         topk_end_pass(tk, QB);
     }
-    topk_finish(tk, QB, nqv, q0, blockIdx.y, a.nsplit, a.partial, a.err32);
+    topk_finish(tk, QB, nqv, w.q0, w.split, a.sel_mode ? gridDim.x : a.nsplit, a.partial, a.err32, w.qidx);
 }
 
 // ------------------------------------------------------------------ generic scan
 template <int QB>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_generic_kernel(ScanArgs a) {
-    if (scan_skipped(a.run_if)) return;
+    ScanWork w;
+    if (!scan_work<QB>(a, w)) return;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *qs = smem;  // [QB][row_pitch]
     float *qmag = reinterpret_cast<float *>(qs + (size_t)QB * a.row_pitch);
     TopK tk = topk_carve(reinterpret_cast<uint8_t *>(qmag + ((QB + 3) & ~3)), QB, a.k);
     const int tid = threadIdx.x;
-    const uint32_t q0 = blockIdx.x * QB;
-    const uint32_t nqv = min((uint32_t)QB, a.nq - q0);
+    const uint32_t nqv = w.nqv;
     for (uint32_t i = tid; i < QB * (a.row_pitch / 4); i += SCAN_THREADS) {
         uint32_t b = i / (a.row_pitch / 4), c = i % (a.row_pitch / 4);
-        reinterpret_cast<uint32_t *>(qs)[i] = b < nqv ? reinterpret_cast<const uint32_t *>(a.q + (size_t)(q0 + b) * a.row_pitch)[c] : 0u;
+        const uint32_t qi = b < nqv ? (w.qidx ? w.qidx[w.q0 + b] : w.q0 + b) : 0;
+        reinterpret_cast<uint32_t *>(qs)[i] = b < nqv ? reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[c] : 0u;
     }
-    if (tid < QB) qmag[tid] = tid < (int)nqv ? a.qmags[q0 + tid] : 0.0f;
+    if (tid < QB) qmag[tid] = tid < (int)nqv ? a.qmags[w.qidx ? w.qidx[w.q0 + tid] : w.q0 + tid] : 0.0f;
     topk_init(tk, QB);
     __syncthreads();
     const uint32_t pp = plane_pitch(a.dim);
     const uint64_t npass = (a.n + RPP - 1) / RPP;
-    for (uint64_t pass = blockIdx.y; pass < npass; pass += gridDim.y) {
+    for (uint64_t pass = w.split; pass < npass; pass += w.nsplit) {
         const uint64_t row = pass * RPP + tid;
         if (row < a.n) {
             const uint8_t *xr = a.rows + row * a.row_pitch;
@@ -246,7 +277,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_generic_kernel(ScanArgs 
         }
         topk_end_pass(tk, QB);
     }
-    topk_finish(tk, QB, nqv, q0, blockIdx.y, a.nsplit, a.partial, a.err32);
+    topk_finish(tk, QB, nqv, w.q0, w.split, a.sel_mode ? gridDim.x : a.nsplit, a.partial, a.err32, w.qidx);
 }
 
 // ------------------------------------------------------------------ planning / launch
@@ -282,9 +313,13 @@ uint32_t scan_plan_nsplit(const ScanArgs &a, int sm_count) {
 }
 
 template <int QB>
-static cdb_status launch_scan(const ScanArgs &a, cudaStream_t s) {
+static cdb_status launch_scan(const ScanArgs &a, uint32_t sel_grid, cudaStream_t s) {
     const uint32_t ngroups = (a.nq + QB - 1) / QB;
     dim3 grid(ngroups, a.nsplit);
+    if (a.sel_mode) {
+        if (!sel_grid) { set_error("scan: selective mode needs sel_grid"); return CDB_INVALID_PARAMS; }
+        grid = dim3(sel_grid, 1);
+    }
     size_t smem = scan_smem(QB, a.row_pitch, a.k);
     const bool f32path = (a.st == CDB_ST_F32 && a.metric == CDB_METRIC_COSINE);
     if (f32path) {
@@ -300,33 +335,55 @@ static cdb_status launch_scan(const ScanArgs &a, cudaStream_t s) {
     return CDB_OK;
 }
 
+uint32_t scan_sel_grid(int sm_count, uint32_t k) {   // the merge holds grid*k keys in shared memory
+    const uint32_t lim = 20480u / (k ? k : 1u);
+    const uint32_t g = 2u * (uint32_t)sm_count;
+    return g < lim ? g : (lim ? lim : 1u);
+}
+uint32_t scan_sel_qb(const ScanArgs &a) { return (uint32_t)pick_qb(SCAN_SEL_CAP, a.row_pitch, a.k); }
+
 cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s) {
     if (a.k == 0 || a.k > 1024) { set_error("scan: k must be in 1..1024"); return CDB_INVALID_PARAMS; }
     if (a.nq == 0) return CDB_OK;
-    switch (pick_qb(a.nq, a.row_pitch, a.k)) {
-    case 8: return launch_scan<8>(a, s);
-    case 4: return launch_scan<4>(a, s);
-    case 2: return launch_scan<2>(a, s);
-    default: return launch_scan<1>(a, s);
+    // the selective scan is planned for SCAN_SEL_CAP queries whatever the batch size
+    const uint32_t sel_grid = a.sel_grid;
+    switch (pick_qb(a.sel_mode ? SCAN_SEL_CAP : a.nq, a.row_pitch, a.k)) {
+    case 8: return launch_scan<8>(a, sel_grid, s);
+    case 4: return launch_scan<4>(a, sel_grid, s);
+    case 2: return launch_scan<2>(a, sel_grid, s);
+    default: return launch_scan<1>(a, sel_grid, s);
     }
 }
 
 // ------------------------------------------------------------------ merge
-// one CTA per query: rank-select the best k of nlists*k keys (0 = empty)
+// one CTA per query: rank-select the best k of nlists*k keys (0 = empty).
+// Fallback forms (see ScanArgs): sel_mode 1 -> CTA i handles selected query qsel[1+i], whose lists are the first
+// (sel_grid / groups) of a stride of sel_grid; sel_mode 0 with qsel -> runs only if n_sel > sel_cap.
 __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ partial, uint32_t nlists, uint32_t k,
                                       uint32_t *__restrict__ ids, float *__restrict__ scores, uint32_t *__restrict__ counts,
-                                      const uint32_t *__restrict__ run_if) {
-    if (scan_skipped(run_if)) return;
+                                      const uint32_t *__restrict__ qsel, uint32_t sel_cap, int sel_mode, uint32_t sel_grid,
+                                      uint32_t sel_qb) {
+    uint32_t q = blockIdx.x, stride = nlists;
+    if (sel_mode) {
+        const uint32_t n_sel = qsel[0];
+        if (n_sel == 0 || n_sel > sel_cap || blockIdx.x >= n_sel) return;
+        q = qsel[1 + blockIdx.x];
+        stride = sel_grid;
+        nlists = sel_grid / ((n_sel + sel_qb - 1) / sel_qb);
+    } else if (qsel && qsel[0] <= sel_cap) {
+        return;
+    }
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem);
     __shared__ int nvalid;
-    const uint32_t q = blockIdx.x, M = nlists * k;
+    const uint32_t M = nlists * k;
+    const uint64_t *src = partial + (size_t)blockIdx.x * stride * k;
     if (threadIdx.x == 0) nvalid = 0;
     for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { ids[(size_t)q * k + j] = CDB_INVALID_ID; scores[(size_t)q * k + j] = 0.0f; }
     __syncthreads();
     int local = 0;
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
-        uint64_t v = partial[(size_t)q * M + i];
+        uint64_t v = src[i];
         keys[i] = v;
         local += v != 0;
     }
@@ -346,12 +403,14 @@ __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ p
 }
 
 cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
-                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s, const uint32_t *run_if) {
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s, const uint32_t *qsel,
+                                 uint32_t sel_cap, int sel_mode, uint32_t sel_grid, uint32_t sel_qb) {
     if (nq == 0) return CDB_OK;
-    size_t smem = (size_t)nlists * k * 8;
+    size_t smem = (size_t)(sel_mode ? sel_grid : nlists) * k * 8;
     if (smem > 200 * 1024) { set_error("merge: too many partial candidates"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_partials_kernel<<<nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts, run_if);
+    merge_partials_kernel<<<sel_mode ? sel_cap : nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts, qsel,
+                                                                      sel_cap, sel_mode, sel_grid, sel_qb);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

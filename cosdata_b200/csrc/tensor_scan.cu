@@ -55,6 +55,7 @@ struct TensorScanArgs {
     uint32_t *progress;  // [groups] tiles completed by the CTAs of a group (bounded-drift window), zeroed per launch
     uint32_t window;     // a CTA may run at most `window` tiles ahead of the slowest CTA of its group
     uint32_t refresh_mask;  // the shared bound is refreshed when (tile & mask) == mask (and for the first tiles)
+    uint32_t has_deg;       // the corpus holds degenerate rows: kernel variant that keeps zero accumulators out of the bound
 };
 
 constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory), slot 0 = count
@@ -93,7 +94,12 @@ __device__ __forceinline__ void sort_desc(float (&v)[NG]) {
     }
 }
 
-template <int STAGES, int NG>
+// HAS_DEG: the corpus holds degenerate rows (zero / non-finite / out-of-range norm).  Their shadow rows are all zero, so
+// they score a == 0.0f exactly, but their exact score is NaN (worst) or +-inf -- the error bound does not cover them.
+// They must not tighten the bound: accumulators that are exactly 0.0f are left out of the class maxima (dropping values
+// from a maximum only loosens a lower bound, so a proper row that happens to score 0.0f is harmless).  Degenerate rows
+// that are not all-zero are put on every candidate list by the host side (api.cu), all-zero rows are provably worst.
+template <int STAGES, int NG, bool HAS_DEG>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TensorScanArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -225,11 +231,18 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int i = 0; i < NG; ++i) cm[i] = -INFINITY;
 #pragma unroll
+                    float zmax = -INFINITY;   // HAS_DEG: 0.0f if some accumulator of the chunk is exactly zero
                     for (int j = 0; j < 32; ++j) {
-                        cm[j & (NG - 1)] = fmaxf(cm[j & (NG - 1)], __uint_as_float(r0[j]));
-                        cm[(32 + j) & (NG - 1)] = fmaxf(cm[(32 + j) & (NG - 1)], __uint_as_float(r1[j]));
+                        float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r1[j]);
+                        if (HAS_DEG) {
+                            zmax = (v0 == 0.0f || v1 == 0.0f) ? 0.0f : zmax;
+                            v0 = v0 == 0.0f ? -INFINITY : v0;
+                            v1 = v1 == 0.0f ? -INFINITY : v1;
+                        }
+                        cm[j & (NG - 1)] = fmaxf(cm[j & (NG - 1)], v0);
+                        cm[(32 + j) & (NG - 1)] = fmaxf(cm[(32 + j) & (NG - 1)], v1);
                     }
-                    float cmax = -INFINITY;
+                    float cmax = zmax;   // the emission test sees every value, the bound only the non-zero ones
 #pragma unroll
                     for (int i = 0; i < NG; ++i) { cmax = fmaxf(cmax, cm[i]); gm[i] = fmaxf(gm[i], cm[i]); }
                     if (cmax >= thr) {
@@ -247,8 +260,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                         const bool ok0 = (uint64_t)j < left, ok1 = (uint64_t)(32 + j) < left;
                         m0 |= ((ok0 && v0 >= thr) ? 1u : 0u) << j;
                         m1 |= ((ok1 && v1 >= thr) ? 1u : 0u) << j;
-                        if (ok0) gm[j & (NG - 1)] = fmaxf(gm[j & (NG - 1)], v0);
-                        if (ok1) gm[(32 + j) & (NG - 1)] = fmaxf(gm[(32 + j) & (NG - 1)], v1);
+                        if (ok0 && !(HAS_DEG && v0 == 0.0f)) gm[j & (NG - 1)] = fmaxf(gm[j & (NG - 1)], v0);
+                        if (ok1 && !(HAS_DEG && v1 == 0.0f)) gm[(32 + j) & (NG - 1)] = fmaxf(gm[(32 + j) & (NG - 1)], v1);
                     }
                 }
                 if (qvalid && a.emit && (m0 | m1)) {
@@ -301,40 +314,90 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 // ------------------------------------------------------------------ fp16 normalised copies
-// x_hat = x / |x| (IEEE), rounded to fp16; zero-norm rows become zero rows.
+// x_hat = x / |x| (IEEE), rounded to fp16.  Rows whose norm is outside [1e-15, 1e15] (zero, underflowed, overflowed,
+// inf/NaN) are DEGENERATE: the error bound of the prefilter does not cover them, their shadow row is all zero.
+__host__ __device__ inline bool norm_is_proper(float m) { return m >= 1.0e-15f && m <= 1.0e15f; }
+
 __global__ void normalize_f16_kernel(const float *__restrict__ raw, uint32_t pitch_elems, const float *__restrict__ mags,
-                                     uint64_t n, uint32_t dim, __half *__restrict__ out, uint32_t out_pitch, uint32_t *zero_flag) {
+                                     uint64_t n, uint32_t dim, __half *__restrict__ out, uint32_t out_pitch) {
     const uint32_t groups = (dim + 7) / 8;
     uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n * groups) return;
     uint64_t row = gid / groups;
     uint32_t c0 = (uint32_t)(gid % groups) * 8;
     const float m = mags[row];
-    if (m == 0.0f && zero_flag && c0 == 0) atomicAdd(zero_flag, 1u);
+    const bool ok = norm_is_proper(m);
     for (uint32_t e = 0; e < 8 && c0 + e < dim; ++e) {
         float v = raw[row * pitch_elems + c0 + e];
-        out[row * out_pitch + c0 + e] = __float2half_rn(m == 0.0f ? 0.0f : __fdiv_rn(v, m));
+        out[row * out_pitch + c0 + e] = __float2half_rn(ok ? __fdiv_rn(v, m) : 0.0f);
     }
 }
 
 cdb_status normalize_f16_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
-                                void *d_out, uint32_t out_pitch_halfs, uint32_t *d_zero_count, cudaStream_t s) {
+                                void *d_out, uint32_t out_pitch_halfs, cudaStream_t s) {
     if (!n) return CDB_OK;
     uint64_t total = n * ((dim + 7) / 8);
     normalize_f16_kernel<<<(uint32_t)((total + 255) / 256), 256, 0, s>>>(d_raw, pitch_elems, d_mags, n, dim,
-                                                                          reinterpret_cast<__half *>(d_out), out_pitch_halfs, d_zero_count);
+                                                                          reinterpret_cast<__half *>(d_out), out_pitch_halfs);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
+}
+
+// Degenerate rows of an appended range.  deg = {all-zero rows, other degenerate rows, ids of the first TS_MAX_ODD of those}.
+// An all-zero row scores 0/0 = NaN against every finite query: provably last.  Any other degenerate row (norm underflowed
+// to 0 with non-zero elements -> +-inf, overflowed norm -> 0 or NaN, inf/NaN elements) can land anywhere in the exact
+// ranking, so those rows are put on every query's candidate list and re-scored exactly.
+__global__ void classify_rows_kernel(const float *__restrict__ raw, uint32_t pitch_elems, const float *__restrict__ mags,
+                                     uint64_t n, uint32_t dim, uint32_t first_row, uint32_t *deg) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    if (norm_is_proper(mags[row])) return;
+    bool allzero = true;
+    for (uint32_t c = 0; c < dim && allzero; ++c) allzero = raw[row * pitch_elems + c] == 0.0f;
+    if (allzero) { atomicAdd(deg, 1u); return; }
+    const uint32_t pos = atomicAdd(deg + 1, 1u);
+    if (pos < TS_MAX_ODD) deg[2 + pos] = first_row + (uint32_t)row;
+}
+cdb_status classify_rows_device(const float *d_raw, uint32_t pitch_elems, const float *d_mags, uint64_t n, uint32_t dim,
+                                uint32_t first_row, uint32_t *d_deg, cudaStream_t s) {
+    if (!n) return CDB_OK;
+    classify_rows_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(d_raw, pitch_elems, d_mags, n, dim, first_row, d_deg);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+// candidate lists start with the odd degenerate rows (global ids); cand_cnt[q] = n_odd
+__global__ void seed_candidates_kernel(const uint32_t *__restrict__ deg, uint32_t id_base, uint32_t nq, uint32_t *cand,
+                                       uint32_t cand_cap, uint32_t *cand_cnt) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t n_odd = min(min(deg[1], (uint32_t)TS_MAX_ODD), cand_cap);
+    for (uint32_t i = 0; i < n_odd; ++i) cand[(size_t)q * cand_cap + i] = id_base + deg[2 + i];
+    cand_cnt[q] = n_odd;
 }
 
 __global__ void fill_i32_kernel(int *p, int v, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// counts queries whose candidate list overflowed (or whose norm is zero) -> flag[0]
-__global__ void overflow_check_kernel(const uint32_t *cnt, uint32_t cap, uint32_t n, uint32_t *flag) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && cnt[i] > cap) atomicAdd(flag, 1u);
+// Fallback selection: a query whose candidate list overflowed, or whose own norm is degenerate, is re-done by the exact
+// scan.  qsel[0] = number of selected queries, qsel[1..] their indices.  flags[0] = that number (stats), flags[3] counts
+// searches that needed any fallback.
+__global__ void select_fallback_kernel(const uint32_t *__restrict__ cnt, uint32_t cap, const float *__restrict__ qmags,
+                                       uint32_t n, uint32_t *qsel, uint32_t *flags) {
+    __shared__ uint32_t total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool bad = cnt[i] > cap || (qmags && !norm_is_proper(qmags[i]));
+        if (bad) qsel[1 + atomicAdd(&total, 1u)] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        qsel[0] = total;
+        flags[0] = total;
+        if (total) flags[3] += 1;
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -374,14 +437,21 @@ size_t tensor_scan_smem_bytes(uint32_t k) {
     return 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * TS_STAGES + 4) * 8 + 16;
 }
 
-template <int STAGES, int NG>
-static cdb_status launch_tensor_scan_g(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
-                                       size_t smem, cudaStream_t s) {
-    auto kern = tensor_scan_kernel<STAGES, NG>;
+template <int STAGES, int NG, bool HAS_DEG>
+static cdb_status launch_tensor_scan_gd(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
+                                        size_t smem, cudaStream_t s) {
+    auto kern = tensor_scan_kernel<STAGES, NG, HAS_DEG>;
     CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
+}
+
+template <int STAGES, int NG>
+static cdb_status launch_tensor_scan_g(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
+                                       size_t smem, cudaStream_t s) {
+    return a.has_deg ? launch_tensor_scan_gd<STAGES, NG, true>(mq, mx, a, grid, smem, s)
+                     : launch_tensor_scan_gd<STAGES, NG, false>(mq, mx, a, grid, smem, s);
 }
 
 // fewer classes = cheaper bound refresh (the sort network grows as NG log^2 NG); the bound stays within ~1.5x of the
@@ -398,8 +468,10 @@ static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &m
 // rows to a multiple of 128 [mtiles*128][pitch_halfs].
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
                               uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_ggm, uint32_t *d_cand,
-                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, int sm_count, cudaStream_t s) {
+                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, const uint32_t *d_deg, bool has_deg,
+                              int sm_count, cudaStream_t s) {
     TensorScanArgs a{};
+    a.has_deg = has_deg ? 1u : 0u;
     a.progress = d_progress;
     a.window = 3;
     a.refresh_mask = 15;
@@ -426,7 +498,12 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     if ((rc = make_map_f16(&mx, d_xh, n_rows, dim, pitch_halfs, TS_BLOCK_N))) return rc;
     fill_i32_kernel<<<(a.mtiles * TS_BLOCK_M * TS_GROUPS + 255) / 256, 256, 0, s>>>(d_ggm, (int)0x807FFFFF /* f2ord(-inf) */, a.mtiles * TS_BLOCK_M * TS_GROUPS);
     CDB_LAUNCH_CHECK();
-    CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
+    if (has_deg) {
+        seed_candidates_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_deg, id_base, nq, d_cand, cand_cap, d_cand_cnt);
+        CDB_LAUNCH_CHECK();
+    } else {
+        CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
+    }
 
     // 1. seeding pass over a prefix of the corpus: a few CTAs per query tile, no emission, only gthr.
     //    Afterwards every CTA of the main pass starts from the k-th best of ~16K rows instead of from
@@ -454,8 +531,9 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     return launch_tensor_scan<TS_STAGES>(mq, mx, a, grid, smem, s);
 }
 
-cdb_status overflow_check_device(const uint32_t *d_cnt, uint32_t cap, uint32_t n, uint32_t *d_flag, cudaStream_t s) {
-    overflow_check_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cnt, cap, n, d_flag);
+cdb_status select_fallback_device(const uint32_t *d_cnt, uint32_t cap, const float *d_qmags, uint32_t n, uint32_t *d_qsel,
+                                  uint32_t *d_flags, cudaStream_t s) {
+    select_fallback_kernel<<<1, 1024, 0, s>>>(d_cnt, cap, d_qmags, n, d_qsel, d_flags);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

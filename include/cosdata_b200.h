@@ -111,8 +111,8 @@ typedef struct {
     uint32_t ef_search;      /* hnsw_params.ef_search   (config.toml:23) */
     uint32_t shortlist_size; /* config.search.shortlist_size (config.toml:32) */
     int32_t exact_only;      /* 1: never take a tensor-core path (pure SIMT scan); results are identical either way */
-    uint32_t prefilter_k;    /* candidate slots per query of the tensor-core paths (power of two, 0 = default);
-                                an overflowing list makes the batch fall back to the exact scan on the device */
+    uint32_t prefilter_k;    /* candidate slots per query of the tensor-core paths (0 = default); a query whose list
+                                overflows is re-done by the exact scan on the device (alone if <= 64 queries overflow) */
     uint32_t reserved0;
     uint32_t reserved1;
 } cdb_search_params;
@@ -373,9 +373,14 @@ cdb_status cdb_index_last_kernel_ms(const cdb_index *index, float *scan_ms, floa
 /* durations (ms) of the dominant (scan) kernel of the last min(n, 64) searches, oldest
  * first, from CUDA events recorded on the launching stream around each launch */
 cdb_status cdb_index_scan_ms_history(const cdb_index *index, uint32_t n, float *out, uint32_t *out_n);
-/* out4 = {searches that took the tcgen05 prefilter path, of those how many fell back to the exact
- * scan (candidate overflow / zero-norm query), zero-norm rows, 1 if an fp16 shadow exists} */
+/* out4 = {searches that took a tensor-core path, of those how many needed the exact scan for some query
+ * (candidate overflow / degenerate query norm), degenerate rows, 1 if an fp16 shadow exists} */
 cdb_status cdb_index_stats(const cdb_index *index, uint64_t *out4);
+/* the first n of: {tensor-core searches, searches where some query needed the exact scan, all-zero rows, other degenerate rows
+ * (norm outside [1e-15, 1e15]: they ride on every prefilter candidate list), fp16 shadow present, queries of the LAST
+ * tensor-core search that were re-done by the exact scan (candidate overflow or degenerate query norm)} */
+#define CDB_STATS_FIELDS 6
+cdb_status cdb_index_stats_ex(const cdb_index *index, uint64_t *out, uint32_t n);
 /* candidates the prefilter emitted for each of the first n queries of the last prefilter search */
 cdb_status cdb_index_last_candidate_counts(const cdb_index *index, uint32_t n, uint32_t *out);
 

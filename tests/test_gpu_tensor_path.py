@@ -79,6 +79,90 @@ def test_zero_norm_rows_and_queries():
     run_case(corpus, q, 10, expect_fallback=True)
 
 
+def _search_checked(corpus, queries, k, **kw):
+    n, dim = corpus.shape
+    ix = cdb.DenseIndex(dim=dim, capacity=n)
+    ix.append(corpus)
+    ids, scores, counts, err = ix.batch_search(queries, k, **kw)
+    st = ix.stats()
+    want_ids, want_scores = orc.brute_topk_f32(corpus, queries, k)
+    assert np.array_equal(ids, want_ids)
+    assert np.array_equal(bits(scores), bits(want_scores))
+    ids2, scores2, _, _ = ix.batch_search(queries, k, exact_only=True)
+    assert np.array_equal(ids2, ids) and np.array_equal(bits(scores2), bits(scores))
+    cand = ix.last_candidate_counts(len(queries)) if st["tensor_searches"] else None
+    ix.close()
+    return st, cand, ids, scores
+
+
+@pytest.mark.parametrize("n_zero_per_class", [1, 3])
+def test_zero_rows_in_every_class_with_all_negative_cosines(n_zero_per_class):
+    # zero-norm rows score 0.0 in the fp16 shadow; if they entered the class maxima the bound would be
+    # ~0 while every real cosine is ~ -0.87, and every real row would be filtered out.
+    n, dim, nq, k = 40000, 128, 32, 10
+    corpus = (np.abs(orc.synth_matrix(2600, n, dim)) * 0.9 + 0.1).astype(np.float32)          # all positive
+    zr = np.concatenate([np.arange(64) + 64 * (7 + 11 * j) for j in range(n_zero_per_class)])   # every residue mod 64 (and 16, 32)
+    corpus[zr] = 0.0
+    q = (-(np.abs(orc.synth_matrix(2601, nq, dim)) * 0.9 + 0.1)).astype(np.float32)            # all negative
+    st, cand, ids, scores = _search_checked(corpus, q, k)
+    assert st["tensor_searches"] == 1 and st["fallbacks"] == 0 and st["zero_rows"] == len(zr)
+    assert scores.max() < -0.5 and not np.isin(ids, zr).any()
+    assert cand.max() < 4096
+
+
+def test_degenerate_rows_that_can_rank_anywhere():
+    # norm underflows to 0 with non-zero elements -> dp/0 = +-inf (first or last); overflowing norm -> 0 or NaN; inf elements
+    # -> NaN.  The error bound does not cover these rows: they ride on every candidate list and are re-scored exactly.
+    n, dim, nq, k = 30000, 96, 20, 10
+    corpus = orc.synth_matrix(2700, n, dim).copy()
+    corpus[5] = 1e-25                  # |v| = 0, dp > 0 for mostly-positive queries -> +inf
+    corpus[64 + 5] = -1e-25            # -inf
+    corpus[900] = 1e20                 # |v| = inf, dp finite -> +-0
+    corpus[901, 3] = np.inf            # NaN (inf/inf)
+    corpus[902, :] = 0.0               # all-zero: NaN, last
+    corpus[903] = 3e-24
+    q = orc.synth_matrix(2701, nq, dim).copy()
+    q[0] = np.abs(q[0]) + 0.1          # dp with the 1e-25 row certainly positive
+    st, cand, ids, scores = _search_checked(corpus, q, k)
+    assert st["tensor_searches"] == 1 and st["fallbacks"] == 0
+    assert st["odd_rows"] == 5 and st["zero_rows"] == 1
+    assert ids[0, 0] in (5, 903) and np.isposinf(scores[0, 0])
+
+
+def test_too_many_odd_rows_disable_the_prefilter():
+    n, dim = 20000, 64
+    corpus = orc.synth_matrix(2800, n, dim).copy()
+    corpus[100:200] = 1e-25
+    q = orc.synth_matrix(2801, 8, dim)
+    st, _, _, _ = _search_checked(corpus, q, 10)
+    assert st["tensor_searches"] == 0 and st["odd_rows"] == 100
+
+
+def test_per_query_fallback_on_clusters_larger_than_the_candidate_cap():
+    # 1M rows: 8 tight clusters of 2000 near-identical rows (spread far below the prefilter's error bound) inside uniform
+    # noise.  Queries aimed at a cluster overflow their 512-slot candidate list and are re-done ALONE by the selective exact
+    # scan; the other queries keep the prefilter result.
+    rng = np.random.default_rng(11)
+    n, dim, k = 1_000_000, 64, 10
+    corpus = orc.synth_matrix(2900, n, dim).copy()
+    centres = rng.normal(size=(8, dim)).astype(np.float32)
+    for c in range(8):
+        rows = rng.choice(n, 2000, replace=False)
+        corpus[rows] = centres[c] + 1e-4 * rng.normal(size=(2000, dim)).astype(np.float32)
+    q = orc.synth_matrix(2901, 40, dim).copy()
+    q[:6] = centres[:6] + 1e-4 * rng.normal(size=(6, dim)).astype(np.float32)
+    st, cand, _, _ = _search_checked(corpus, q, k, prefilter_k=512)
+    assert st["tensor_searches"] == 1 and st["fallbacks"] == 1
+    assert st["fallback_queries"] == 6 and (cand[:6] > 512).all() and (cand[6:] <= 512).all()
+
+
+def test_full_batch_fallback_when_many_queries_overflow():
+    corpus = orc.synth_matrix(3000, 30000, 64)
+    q = orc.synth_matrix(3001, 100, 64)
+    st, cand, _, _ = _search_checked(corpus, q, 10, prefilter_k=4)     # every list overflows: 100 > 64 -> whole batch again
+    assert st["fallbacks"] == 1 and st["fallback_queries"] == 100
+
+
 def test_sharded_id_base_and_device_api_agree():
     import torch
     dim, n, nq, k = 384, 50000, 48, 10
