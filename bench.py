@@ -51,6 +51,9 @@ def parse_args():
                     help="c2 (default, the headline): brute cosine 10Mx768 f32; c4: quaternary inner product 50Mx1024, batch 4096; "
                          "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools/build_hnsw_graph.py)")
     ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--hnsw-prof", action="store_true", help="c3: add the per-phase clock64 breakdown of one search (instrumented kernel variant)")
+    ap.add_argument("--hnsw-variants", action="store_true", help="c3: time every kernel variant (cdb_debug_set_hnsw_flags) on the same graph")
+    ap.add_argument("--dump-ids", default=None, help="c3: write the result ids/scores of the batch to this .npz (A/B runs)")
     ap.add_argument("--graph", default=os.path.join(ROOT, "bench_data", "hnsw_100k_128_f16.npz"))
     return ap.parse_args()
 
@@ -579,10 +582,53 @@ def run_c3(args):
     pk = _peaks()
     hbm = float(pk.get("hbm_gbs", 6650.0))
     ach = alg_bytes / (kernel_ms / 1000.0) / 1e9
+    prof = None
+    if args.hnsw_prof:
+        ix.hnsw_profile(enable=True, read=False)
+        step()
+        torch.cuda.synchronize()
+        pr = ix.hnsw_profile(enable=False, read=True)
+        pp_ = max(pr["pops"], 1)
+        prof = {"cycles_per_pop": {k_: v / pp_ for k_, v in pr.items() if k_ != "pops"}, "pops": pr["pops"],
+                "kernel": "cta-per-query (round 1)" if os.environ.get("CDB_HNSW_CTA", "0") not in ("", "0") else "warp-per-query",
+                "note": "clock64 sums of lane/thread 0 over all queries of one batch / pops"}
+    if args.dump_ids:
+        np.savez(args.dump_ids, ids=ids, scores=sc)
+    variants = None
+    if args.hnsw_variants:
+        # same graph, same queries: kernel time (CUDA events around the search kernel) and phase profile of every variant
+        variants = []
+        ref_ids = ids.copy()
+        for name, fl, nb_ in [("default(preload+atomfs)", 6, B), ("preload only", 2, B),
+                              ("atomfs only", 4, B), ("plain", 0, B), ("cta-per-query (round 1)", 8, B),
+                              ("default, half batch", 6, B // 2), ("default, quarter batch", 6, B // 4)]:
+            cdb.debug_set_hnsw_flags(fl)
+
+            def vstep():
+                ix.batch_search_device(d_q.data_ptr(), nb_, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                                       stream.cuda_stream, mode=cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64)
+            for _ in range(2):
+                vstep()
+            torch.cuda.synchronize()
+            for _ in range(5):
+                vstep()
+            torch.cuda.synchronize()
+            kms = float(np.mean(ix.scan_ms_history(5)))
+            same = bool(np.array_equal(d_ids.cpu().numpy().view(np.uint32)[:nb_], ref_ids[:nb_]))
+            ix.hnsw_profile(enable=True, read=False)
+            vstep()
+            torch.cuda.synchronize()
+            pr = ix.hnsw_profile(enable=False, read=True)
+            pp_ = max(pr["pops"], 1)
+            variants.append({"variant": name, "flags": fl, "batch": nb_, "kernel_ms": kms, "kernel_qps": nb_ / (kms / 1000.0),
+                             "ids_equal_default": same, "cycles_per_pop": {k_: round(v / pp_) for k_, v in pr.items() if k_ != "pops"}})
+        cdb.debug_set_hnsw_flags()
     line = {
+        "hnsw_variants": variants,
         "metric": "queries/sec + recall@10, HNSW f16", "value": args.steps * B / (ms / 1000.0), "unit": "queries/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16 (f32 accumulate, reference order)", "data": "synthetic (4096 Gaussian clusters)",
+        "hnsw_phase_profile": prof,
         "config": {"workload": f"HNSW dense index, {rows}x{D} f16, ef_search={args.ef}, batch={B} (BASELINE.json configs[2]); graph built on the GPU "
                                "with the reference defaults", "rows": rows, "dim": D, "batch": B, "k": k},
         "clocks": clocks, "gpu_launches": int(launches),

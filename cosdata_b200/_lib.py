@@ -117,6 +117,7 @@ PROTOTYPES = {
     "cdb_prop_file_scan_metadata": (C.c_int32, [C.c_char_p, c_vp, c_vp]),
     "cdb_prop_file_load_metadata": (C.c_int32, [C.c_char_p, C.c_uint64, C.c_uint32, c_vp, c_f32p, c_vp, c_vp, c_vp, c_vp]),
     "cdb_hnsw_files_open": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, c_vp]),
+    "cdb_hnsw_files_open_versioned": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, c_vp]),
     "cdb_hnsw_files_close": (C.c_int32, [c_vp]),
     "cdb_hnsw_files_info": (C.c_int32, [c_vp, c_vp, c_vp]),
     "cdb_hnsw_files_level": (C.c_int32, [c_vp, C.c_uint32, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -144,6 +145,8 @@ PROTOTYPES = {
     "cdb_merge_topk_device": (C.c_int32, [C.c_int32, C.c_int32, c_u32p, c_f32p, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_f32p, C.c_void_p]),
     "cdb_kernel_launch_count": (C.c_uint64, []),
     "cdb_index_last_kernel_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "cdb_index_hnsw_profile": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "cdb_debug_set_hnsw_flags": (C.c_int32, [C.c_uint32]),
     "cdb_index_stats": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "cdb_index_stats_ex": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "cdb_index_last_candidate_counts": (C.c_int32, [C.c_void_p, C.c_uint32, c_u32p]),

@@ -89,6 +89,11 @@ def device_count():
     return n.value if rc == 0 else 0
 
 
+def debug_set_hnsw_flags(flags=0xFFFFFFFF):
+    """kernel-variant switch of CDB_MODE_HNSW searches (measurement only; results are identical); default restores"""
+    _check(_lib.load().cdb_debug_set_hnsw_flags(flags & 0xFFFFFFFF))
+
+
 def kernel_launch_count():
     return int(_lib.load().cdb_kernel_launch_count())
 
@@ -205,10 +210,15 @@ def prop_file_load_metadata(path):
 class HnswFiles:
     """the reference's on-disk HNSW index (prop.data, nodes.ptr, <id>.index) flattened to the set_graph arrays"""
 
-    def __init__(self, index_dir, root_link_offset, pseudo_root_link_offset=INVALID_ID):
+    def __init__(self, index_dir, root_link_offset, pseudo_root_link_offset=INVALID_ID, latest_version=None):
+        """latest_version: bound for the "<region>-<version>.ptr" layout of enable_context_history (None = newest)"""
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        _check(self._lib.cdb_hnsw_files_open(os.fsencode(index_dir), int(root_link_offset), int(pseudo_root_link_offset), C.byref(self._h)))
+        if latest_version is None:
+            _check(self._lib.cdb_hnsw_files_open(os.fsencode(index_dir), int(root_link_offset), int(pseudo_root_link_offset), C.byref(self._h)))
+        else:
+            _check(self._lib.cdb_hnsw_files_open_versioned(os.fsencode(index_dir), int(root_link_offset), int(pseudo_root_link_offset),
+                                                           int(latest_version), C.byref(self._h)))
         info = np.zeros(8, dtype=np.uint32)
         counts = np.zeros(33, dtype=np.uint32)
         _check(self._lib.cdb_hnsw_files_info(self._h, _ptr(info), _ptr(counts)))
@@ -438,6 +448,15 @@ class DenseIndex:
         m = C.c_uint32(0)
         _check(self._lib.cdb_index_scan_ms_history(self._h, n, _ptr(out), C.byref(m)))
         return out[: m.value].copy()
+
+    def hnsw_profile(self, enable=True, read=True):
+        """per-phase clock64 sums of the HNSW search kernel (see cdb_index_hnsw_profile); returns a dict or None"""
+        out = np.zeros(16, dtype=np.uint64) if read else None
+        _check(self._lib.cdb_index_hnsw_profile(self._h, 1 if enable else 0, _ptr(out)))
+        if out is None:
+            return None
+        names = ["adjacency", "fixed_set", "stage_issue", "stage_wait", "chains", "merge", "level_sort", "levels_total", "pops"]
+        return {n: int(v) for n, v in zip(names, out)}
 
     def stats(self):
         out = np.zeros(6, dtype=np.uint64)

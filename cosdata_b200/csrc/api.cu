@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" boundary declared in include/cosdata_b200.h.
 // Host-side orchestration only: device buffers, streams, launch order.  No torch,
 // no CPU compute path -- without a CUDA device every entry point fails.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -13,6 +14,7 @@ namespace cdb {
 static thread_local std::string t_last_error;
 void set_error(const std::string &msg) { t_last_error = msg; }
 std::atomic<uint64_t> g_launch_count{0};
+std::atomic<uint32_t> g_hnsw_flags{CDB_HNSW_F_DEFAULT};
 
 struct DevBuf {
     void *p = nullptr;
@@ -129,7 +131,8 @@ struct cdb_index {
     DevBuf hn_ids, hn_labels, flt_off, flt_dims, flt_has;
     std::vector<uint32_t> g_cnt;
     std::vector<const uint32_t *> g_nr, g_ad, g_ch;  // host copies of the per-level device pointers
-    DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags;
+    DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags, hn_prof;
+    bool hn_prof_on = false;
 };
 
 #define CDB_REQUIRE(cond, msg)                              \
@@ -399,7 +402,7 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     for (void *g : ix->md_allocs) cudaFree(g);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
     for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
-                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->deg, &ix->qsel, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters,
+                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->deg, &ix->qsel, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters, &ix->hn_prof,
                       &ix->qraw, &ix->qraw_mags, &ix->hn_ids, &ix->hn_labels, &ix->flt_off, &ix->flt_dims, &ix->flt_has})
         b->release();
     for (auto &ev : ix->ev)
@@ -676,7 +679,10 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
                                     ix->hn_labels.as<uint32_t>())))
             return rc;
     } else {
-        if ((rc = hnsw_search_device(a, s))) return rc;
+        // one warp per query (hnsw_warp.cu); CDB_HNSW_F_CTA selects the round-1 CTA-per-query kernel for A/B measurements
+        a.flags = g_hnsw_flags.load();
+        a.prof = ix->hn_prof_on ? ix->hn_prof.as<unsigned long long>() : nullptr;
+        if ((rc = (a.flags & CDB_HNSW_F_CTA) ? hnsw_search_device(a, s) : hnsw_search_warp_device(a, s))) return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = hnsw_dedup_device(a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, ix->graph.root_row, d.id_base, k5, nq,
                                     ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
@@ -1085,6 +1091,12 @@ cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
     ix->graph.nbrs0 = gd->level0_neighbors_count;
     ix->graph.entry = gd->entry;
     ix->graph.root_row = gd->root_row;
+    ix->graph.identity_mask = 0;
+    for (uint32_t L = 0; L < L1; ++L) {   // levels whose node i is row i: the kernels skip the node_row lookup
+        bool ident = true;
+        for (uint32_t i = 0; i < gd->level_counts[L] && ident; ++i) ident = gd->node_row[L][i] == i;
+        if (ident) ix->graph.identity_mask |= 1u << L;
+    }
     ix->graph.node_row = reinterpret_cast<const uint32_t *const *>(tbl[0]);
     ix->graph.adj = reinterpret_cast<const uint32_t *const *>(tbl[1]);
     ix->graph.child = reinterpret_cast<const uint32_t *const *>(tbl[2]);
@@ -1195,6 +1207,29 @@ cdb_status cdb_index_hnsw_counters(const cdb_index *ix, uint64_t *out2) {
     if (!ix->hn_counters.p) return CDB_OK;
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     CDB_CUDA_TRY(cudaMemcpy(out2, ix->hn_counters.p, 16, cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
+
+cdb_status cdb_debug_set_hnsw_flags(uint32_t flags) {
+    g_hnsw_flags.store(flags == 0xFFFFFFFFu ? CDB_HNSW_F_DEFAULT : flags);
+    return CDB_OK;
+}
+
+cdb_status cdb_index_hnsw_profile(cdb_index *ix, int32_t enable, uint64_t *out) {
+    CDB_REQUIRE(ix, "null index");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    CDB_CUDA_TRY(cudaDeviceSynchronize());
+    if (out) {
+        for (int i = 0; i < CDB_HNSW_PROF_SLOTS; ++i) out[i] = 0;
+        if (ix->hn_prof.p) CDB_CUDA_TRY(cudaMemcpy(out, ix->hn_prof.p, CDB_HNSW_PROF_SLOTS * 8, cudaMemcpyDeviceToHost));
+    }
+    if (enable) {
+        cdb_status rc = ix->hn_prof.ensure(CDB_HNSW_PROF_SLOTS * 8);
+        if (rc) return rc;
+        CDB_CUDA_TRY(cudaMemset(ix->hn_prof.p, 0, CDB_HNSW_PROF_SLOTS * 8));
+    }
+    ix->hn_prof_on = enable != 0;
     return CDB_OK;
 }
 

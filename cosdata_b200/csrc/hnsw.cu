@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
     if (tid == 0) { sh.err = 0; sh.entry = a.g.entry; }
     uint32_t out_total = 0;
     unsigned long long evals = 0, pops = 0;
+    long long prof[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     __syncthreads();
 
     // ann_search (vector_store.rs:256-402): fresh fixed set and ef budget per level, results of all levels
@@ -41,7 +42,8 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
         const uint32_t nb = level == 0 ? a.g.nbrs0 : a.g.nbrs;
         const uint32_t take = min(min(a.shortlist, nb), HN_MAX_TAKE);
         const uint32_t *node_row = a.g.node_row[level];
-        hn_traverse_level(node_row, a.g.adj[level], nb, take, sc, m, sh, qmag, HN_QUERY_ID, a.ef, evals, pops);
+        hn_traverse_level(node_row, a.g.adj[level], nb, take, sc, m, sh, qmag, HN_QUERY_ID, a.ef, evals, pops, nullptr,
+                          a.prof ? prof : nullptr);
         if (sh.err) break;
         const uint32_t keep = min(sh.rlen, HN_FINAL_LEN);
         for (uint32_t i = tid; i < keep; i += HN_THREADS) {
@@ -59,6 +61,10 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(HnswArgs a) {
         a.out_n[qi] = sh.err ? 0u : min(out_total, a.out_cap);
         if (sh.err) atomicOr(a.err32 + qi, sh.err);
         if (a.counters) { atomicAdd(a.counters, evals); atomicAdd(a.counters + 1, pops); }
+        if (a.prof) {
+            prof[8] = (long long)pops;
+            for (int i = 0; i < 9; ++i) atomicAdd(a.prof + i, (unsigned long long)prof[i]);
+        }
     }
 }
 

@@ -308,6 +308,7 @@ cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n /* data rows; root
     out_graph->nbrs0 = nbrs0;
     out_graph->entry = bg.g.entry;
     out_graph->root_row = n;
+    out_graph->identity_mask = 1u;   // level 0: node i is row i (lv_local), the search skips the node_row lookup there
     out_graph->node_row = reinterpret_cast<const uint32_t *const *>(tbl[0]);
     out_graph->adj = reinterpret_cast<const uint32_t *const *>(tbl[1]);
     out_graph->child = reinterpret_cast<const uint32_t *const *>(tbl[2]);

@@ -1,0 +1,594 @@
+// hnsw_warp.cu -- batched HNSW search, ONE WARP PER QUERY (S1, CDB_MODE_HNSW on graphs without metadata):
+//   ann_search              src/vector_store.rs:256-402
+//   traverse_find_nearest   src/vector_store.rs:1112-1204
+//   PerformantFixedSet      src/models/fixedset.rs:2-29
+//
+// Why a warp.  A traversal is a chain of dependent pops; per pop only ~6 neighbours survive the fixed set, and each of
+// them is scored by ONE thread because the reference arithmetic is a sequential chain per pair (dot_product_f16 is a
+// left fold: 768 dependent adds).  The round-1 kernel gave every query a 128-thread CTA: three of its four warps waited
+// at 9 block barriers per pop while one warp ran the chains (ncu: 63 % of warp samples parked at the barrier, 0.27 IPC on
+// the scoring warp).  Here the 32 lanes of one warp ARE the neighbour slots (two slots per lane cover the <= 64 slots a
+// pop examines), every hand-over is a __syncwarp / ballot / match, and the SM's four schedulers each see ~2 independent
+// queries whose chains interleave.  Queue, results, fixed set and the staged neighbour rows live in the warp's slice of
+// shared memory (~24 KB at ef = 128, f16 x 768), so 7-9 queries are resident per SM -- all 1024 queries of a batch at once.
+//
+// Parity.  Pop order, fixed-set walk (slot order, aliasing ids included), first-Err rule, the (score, id) key and the
+// per-level bookkeeping are those of hn_traverse_level (hnsw_traverse.cuh), which the builder and the metadata search keep
+// using; tests/test_gpu_hnsw.py checks ids, scores, counts, error flags AND the evaluation / pop counts against the oracle.
+//
+// f16 chain.  dot_product_f16 = sum_i f32(x_i) * f32(y_i), sequential, no FMA in the reference.  The product of two
+// halfs is exact in f32 (11 + 11 significand bits, exponent range far inside f32), so fma(x, y, s) rounds exactly once
+// at the same place as s + (x * y): one FFMA per element instead of FMUL + FADD, bit-identical.  The query is converted
+// to f32 once per warp; the chain then costs 1 conversion + 1 FFMA per element (+ 3 LDS.128 per 8 elements).
+#include <cstdlib>
+
+#include "hnsw_traverse.cuh"
+
+namespace cdb {
+
+constexpr uint32_t HW_FINAL_LEN = 100;          // vector_store.rs:1194
+constexpr uint32_t HW_STAGE_BYTES = 12800;      // staged neighbour rows per group: 8 rows of f16 x 768, 4 of f32 x 768
+// clock64 sums per query (lane 0): [0] pop + adjacency (+ node_row) loads, [1] fixed-set walk + compaction + prefetches,
+// [2] issue of the row copies, [3] wait for the rows, [4] distance chains, [5] queue merge, [6] end-of-level result sort,
+// [7] whole levels, [8] pops
+constexpr int HW_PROF_SLOTS = 9;
+
+struct HwCarve {
+    uint32_t EFP, stage_pitch, stage_rows;
+    uint32_t off_q32, off_qkeys, off_rkeys, off_nkeys, off_fs, off_qnodes, off_rnodes, off_nnodes, off_nrow, off_bar, off_stage, total;
+};
+
+__host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, uint32_t ef, bool f16fast) {
+    HwCarve c;
+    c.EFP = hn_efp(ef);
+    c.stage_pitch = round_up(row_pitch, 16) + 16;   // + 16 bytes: the lanes' rows start on different banks
+    uint32_t r = HW_STAGE_BYTES / c.stage_pitch;
+    c.stage_rows = r > 32 ? 32 : (r ? r : 1u);      // one lane scores one staged row
+    uint32_t o = round_up(row_pitch, 16);
+    c.off_q32 = o;            o += f16fast ? round_up(dim * 4, 16) : 0;
+    c.off_qkeys = o;          o += 2 * c.EFP * 8;
+    c.off_rkeys = o;          o += c.EFP * 8;
+    c.off_nkeys = o;          o += HN_MAX_TAKE * 8;
+    c.off_bar = o;            o += 8;
+    c.off_fs = o;             o += 128 * 4;
+    c.off_qnodes = o;         o += 2 * c.EFP * 4;
+    c.off_rnodes = o;         o += c.EFP * 4;
+    c.off_nnodes = o;         o += HN_MAX_TAKE * 4;
+    c.off_nrow = o;           o += HN_MAX_TAKE * 4;
+    c.off_stage = round_up(o, 16);
+    c.total = c.off_stage + c.stage_rows * c.stage_pitch;
+    return c;
+}
+
+struct HwSmem {
+    uint8_t *qs;
+    float *q32;
+    uint64_t *qkeys, *rkeys, *nkeys;
+    uint32_t *fs;            // PerformantFixedSet as 128 x 32-bit words: bucket b = words 2b, 2b+1 (native 32-bit shared atomics)
+    uint32_t *qnodes, *rnodes, *nnodes, *nrow;
+    uint8_t *stage;
+    uint32_t bar;            // shared-space address of the warp's mbarrier (row copies complete on it)
+    uint32_t EFP, stage_pitch, stage_rows;
+};
+
+__device__ __forceinline__ void hw_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t hw_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// TMA bulk copy (UBLKCP): `bytes` contiguous bytes global -> shared, completion counted on the mbarrier.  One instruction
+// per row, issued by one lane: no per-lane address arithmetic, no LSU slots (the round-1 kernel issued 96 cp.async per row).
+__device__ __forceinline__ void hw_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void hw_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void hw_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hw_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// sum_i f32(q_i) * f32(row_i), sequential; q is the f32 copy of the (f16-quantized) query, row the staged f16 row.
+// The chain is latency bound (one dependent FFMA per element), so the shared-memory operands of the NEXT 16 elements
+// are loaded before the current 16 FFMAs issue (explicit double buffering: ptxas does not pipeline this loop itself).
+struct HwBlk16 { uint4 r0, r1; float4 q0, q1, q2, q3; };
+__device__ __forceinline__ HwBlk16 hw_ld16(const float *__restrict__ q, const uint8_t *__restrict__ row, uint32_t i) {
+    HwBlk16 b;
+    b.r0 = *reinterpret_cast<const uint4 *>(row + 2 * i);
+    b.r1 = *reinterpret_cast<const uint4 *>(row + 2 * i + 16);
+    b.q0 = *reinterpret_cast<const float4 *>(q + i);
+    b.q1 = *reinterpret_cast<const float4 *>(q + i + 4);
+    b.q2 = *reinterpret_cast<const float4 *>(q + i + 8);
+    b.q3 = *reinterpret_cast<const float4 *>(q + i + 12);
+    return b;
+}
+__device__ __forceinline__ float hw_chain8(float s, const uint4 &vb, const float4 &qa, const float4 &qb) {
+    const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
+    const float2 f0 = __half22float2(hb[0]), f1 = __half22float2(hb[1]), f2 = __half22float2(hb[2]), f3 = __half22float2(hb[3]);
+    s = __fmaf_rn(qa.x, f0.x, s);
+    s = __fmaf_rn(qa.y, f0.y, s);
+    s = __fmaf_rn(qa.z, f1.x, s);
+    s = __fmaf_rn(qa.w, f1.y, s);
+    s = __fmaf_rn(qb.x, f2.x, s);
+    s = __fmaf_rn(qb.y, f2.y, s);
+    s = __fmaf_rn(qb.z, f3.x, s);
+    s = __fmaf_rn(qb.w, f3.y, s);
+    return s;
+}
+__device__ __forceinline__ float hw_dot_f16_q32(const float *__restrict__ q, const uint8_t *__restrict__ row, uint32_t n) {
+    float s = 0.0f;
+    const uint32_t n16 = n & ~15u;
+    uint32_t i = 0;
+    if (n16) {
+        HwBlk16 cur = hw_ld16(q, row, 0);
+        for (; i + 16 < n16; i += 16) {
+            const HwBlk16 nxt = hw_ld16(q, row, i + 16);
+            s = hw_chain8(s, cur.r0, cur.q0, cur.q1);
+            s = hw_chain8(s, cur.r1, cur.q2, cur.q3);
+            cur = nxt;
+        }
+        s = hw_chain8(s, cur.r0, cur.q0, cur.q1);
+        s = hw_chain8(s, cur.r1, cur.q2, cur.q3);
+        i = n16;
+    }
+    if (i + 8 <= n) {
+        s = hw_chain8(s, *reinterpret_cast<const uint4 *>(row + 2 * i), *reinterpret_cast<const float4 *>(q + i),
+                      *reinterpret_cast<const float4 *>(q + i + 4));
+        i += 8;
+    }
+    for (; i < n; ++i) s = __fmaf_rn(q[i], __half2float(reinterpret_cast<const __half *>(row)[i]), s);
+    return s;
+}
+
+// warp bitonic sort, descending, n keys padded to P (power of two) with zeros
+__device__ inline void hw_sort_desc(uint64_t *keys, uint32_t *vals, uint32_t n, uint32_t P, int lane) {
+    for (uint32_t i = n + lane; i < P; i += 32) { keys[i] = 0ull; vals[i] = 0; }
+    __syncwarp();
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = lane; t < P / 2; t += 32) {
+                const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t x = keys[lo], y = keys[hi];
+                if ((x < y) == desc) {
+                    keys[lo] = y; keys[hi] = x;
+                    const uint32_t v = vals[lo]; vals[lo] = vals[hi]; vals[hi] = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct HwState {
+    uint32_t err, rlen, bar_phase;
+    unsigned long long evals, pops;
+    long long prof[HW_PROF_SLOTS];
+};
+
+// Score the compacted neighbours nnodes/nrow[first .. first+n) into nkeys (slot order kept).  Rows are staged through
+// shared memory (one TMA bulk copy per row, all in flight together: one memory round trip per group), then one lane per
+// row runs the reference chain.  Returns the (position << 8 | flag) of the first failing evaluation, 0xFFFFFFFF if none.
+template <bool F16FAST, bool PROF>
+__device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const HwSmem &m, float qmag, uint32_t pp, uint32_t first,
+                                                   uint32_t n, int lane, HwState &st, bool pre_issued) {
+    uint32_t err_first = 0xFFFFFFFFu;
+    for (uint32_t g0 = 0; g0 < n; g0 += m.stage_rows) {
+        const uint32_t gn = min(m.stage_rows, n - g0);
+        long long ts = 0, ti = 0, tw = 0;
+        if (PROF) ts = clock64();
+        uint32_t row = 0;
+        float rmag = 0.0f;
+        if (!(pre_issued && g0 == 0)) {   // the traversal issues the first group's copies itself, straight from the fixed-set walk
+            if (lane == 0) hw_mbar_expect(m.bar, gn * sc.row_pitch);
+            __syncwarp();
+        }
+        if ((uint32_t)lane < gn) {
+            row = m.nrow[first + g0 + lane];
+            if (!(pre_issued && g0 == 0))
+                hw_bulk_g2s(hw_smem_u32(m.stage + (size_t)lane * m.stage_pitch), sc.rows + (size_t)row * sc.row_pitch, sc.row_pitch, m.bar);
+            rmag = sc.mags[row];   // in flight together with the rows
+        }
+        if (PROF) ti = clock64();
+        hw_mbar_wait(m.bar, st.bar_phase);
+        st.bar_phase ^= 1u;
+        if (PROF) tw = clock64();
+        int rc = CDB_OK;
+        if ((uint32_t)lane < gn) {
+            const uint32_t pos = first + g0 + lane;
+            const uint8_t *code = m.stage + (size_t)lane * m.stage_pitch;
+            float d = 0.0f;
+            if (F16FAST) {
+                const float dot = hw_dot_f16_q32(m.q32, code, sc.dim);
+                if (sc.metric == CDB_METRIC_COSINE) {
+                    const float denom = __fmul_rn(qmag, rmag);
+                    if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
+                    else d = canon_nan(__fdiv_rn(dot, denom));
+                } else {
+                    d = dot;
+                }
+            } else {
+                rc = pair_distance(sc.metric, sc.st, sc.dim, m.qs, qmag, pp, code, rmag, pp, &d);
+            }
+            m.nkeys[pos] = make_key64(order_key(sc.metric, __float_as_uint(d)), hn_id(sc.root_row, row));
+        }
+        const uint32_t bad = __ballot_sync(0xFFFFFFFFu, rc != CDB_OK);
+        if (bad && err_first == 0xFFFFFFFFu) {   // the reference stops at the first Err (slot order)
+            const int src_lane = __ffs(bad) - 1;
+            const int flag = __shfl_sync(0xFFFFFFFFu, (int)md_err_flag(rc), src_lane);
+            err_first = ((first + g0 + (uint32_t)src_lane) << 8) | (uint32_t)flag;
+        }
+        __syncwarp();   // nkeys written; the stage is reused by the next group
+        if (PROF) { const long long te = clock64(); st.prof[2] += ti - ts; st.prof[3] += tw - ti; st.prof[4] += te - tw; }
+    }
+    return err_first;
+}
+
+// One level (traverse_find_nearest).  All 32 lanes call it with warp-uniform arguments.  On return (st.err == 0)
+// rkeys/rnodes[0..st.rlen) hold every popped entry sorted best first.
+template <bool F16FAST, bool PROF>
+__device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null: identity */, const uint32_t *__restrict__ adj,
+                                  uint32_t nb, uint32_t take, const HnScoreCtx &sc, const HwSmem &m, float qmag, uint32_t self_id,
+                                  uint32_t ef, uint32_t entry, HwState &st, int lane, uint32_t flags) {
+    const uint32_t pp = plane_pitch(sc.dim);
+    const bool f_preload = (flags & CDB_HNSW_F_PRELOAD) != 0, f_atomfs = (flags & CDB_HNSW_F_ATOMFS) != 0;
+    const uint32_t EFP = m.EFP;
+    const uint32_t bmask = nb - 1u;
+    const uint32_t lt = (1u << lane) - 1u;
+    long long t0 = 0;
+    if (PROF) t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m.fs[lane + 32 * i] = 0u;
+    if (lane == 0) { m.nnodes[0] = entry; m.nrow[0] = node_row ? node_row[entry] : entry; }
+    __syncwarp();
+    {
+        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, 1, lane, st, false);
+        st.evals += 1;
+        if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; return; }
+        if (lane == 0) {
+            const uint32_t eid = hn_id(sc.root_row, m.nrow[0]);
+            const uint32_t b0 = (((self_id >> 6) & bmask) << 6) | (self_id & 0x3f), b1 = (((eid >> 6) & bmask) << 6) | (eid & 0x3f);
+            m.fs[b0 >> 5] |= 1u << (b0 & 31);
+            m.fs[b1 >> 5] |= 1u << (b1 & 31);
+            m.qkeys[0] = m.nkeys[0];
+            m.qnodes[0] = entry;
+        }
+        __syncwarp();
+    }
+    uint32_t qlen = 1, cur = 0, visited = 0, rlen = 0;
+    // adjacency slots of the head, loaded one pop ahead (while the previous pop's queue merge runs)
+    uint32_t pre_node = HN_EMPTY, pre_nbl[2] = {HN_EMPTY, HN_EMPTY};
+    while (qlen > 0 && visited < ef) {
+        uint64_t *Q = m.qkeys + cur * EFP;
+        uint32_t *QN = m.qnodes + cur * EFP;
+        long long t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        if (PROF) t1 = clock64();
+        // ---- pop
+        const uint32_t bn = QN[0];
+        if (lane == 0) { m.rkeys[rlen] = Q[0]; m.rnodes[rlen] = bn; }
+        ++rlen;
+        st.pops += 1;
+        // ---- adjacency: slots lane and lane + 32; ids and fixed-set bit positions
+        uint32_t nbl[2], row[2], bk[2];
+        if (pre_node == bn) {
+            nbl[0] = pre_nbl[0]; nbl[1] = pre_nbl[1];
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t slot = (uint32_t)lane + 32u * h;
+                nbl[h] = slot < take ? __ldg(adj + (size_t)bn * nb + slot) : HN_EMPTY;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            row[h] = 0;
+            bk[h] = 0x80000000u | ((uint32_t)lane + 32u * h);   // unique per slot: never matches another slot
+            if (nbl[h] != HN_EMPTY) {
+                row[h] = node_row ? __ldg(node_row + nbl[h]) : nbl[h];
+                const uint32_t id = hn_id(sc.root_row, row[h]);
+                bk[h] = (((id >> 6) & bmask) << 6) | (id & 0x3f);
+            }
+        }
+        // speculative: the runner-up is the next head unless a new neighbour beats it; its adjacency slots travel while this
+        // pop's rows are fetched and scored
+        uint32_t spec_node = HN_EMPTY, spec_nbl[2] = {HN_EMPTY, HN_EMPTY};
+        if (f_preload && qlen > 1) {
+            spec_node = QN[1];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t slot = (uint32_t)lane + 32u * h;
+                spec_nbl[h] = slot < take ? __ldg(adj + (size_t)spec_node * nb + slot) : HN_EMPTY;
+            }
+        }
+        if (PROF) t2 = clock64();
+        // ---- the walk through the lossy fixed set, slot order: a slot is scored iff its bit is not yet set AND no
+        // earlier non-empty slot of this pop maps to the same bit (that one either set it or found it set).
+        // Candidates = valid slots whose bit is clear (typically ~6).  They all set their bit with an atomicOr; if every
+        // candidate finds it clear no two of them alias (the common case) and all are accepted.  Otherwise (two
+        // candidate slots of one pop on the same bit, ~0.4 % of the pops) the slot-order rule is applied explicitly.
+        bool accept[2];
+        uint32_t nc = 0;
+        {
+            bool clear[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                clear[h] = nbl[h] != HN_EMPTY && ((m.fs[bk[h] >> 5] >> (bk[h] & 31)) & 1u) == 0;
+            const uint32_t cand0 = __ballot_sync(0xFFFFFFFFu, clear[0]), cand1 = __ballot_sync(0xFFFFFFFFu, clear[1]);
+            accept[0] = clear[0]; accept[1] = clear[1];
+            bool resolve = true;   // apply the slot-order rule explicitly
+            if (f_atomfs) {
+                bool won[2] = {false, false};
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (clear[h]) {
+                        const uint32_t bit = 1u << (bk[h] & 31);
+                        won[h] = (atomicOr(&m.fs[bk[h] >> 5], bit) & bit) == 0;
+                    }
+                const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, won[0]), w1 = __ballot_sync(0xFFFFFFFFu, won[1]);
+                resolve = __popc(w0) + __popc(w1) != __popc(cand0) + __popc(cand1);
+            }
+            if (resolve) {
+                for (uint32_t rest = cand0; rest; rest &= rest - 1) {   // ascending slot order
+                    const int c = __ffs(rest) - 1;
+                    const uint32_t cb = __shfl_sync(0xFFFFFFFFu, bk[0], c);
+                    if (lane > c && cb == bk[0]) accept[0] = false;     // an earlier slot of this pop owns the bit
+                    if (cb == bk[1]) accept[1] = false;
+                }
+                for (uint32_t rest = cand1; rest; rest &= rest - 1) {
+                    const int c = __ffs(rest) - 1;
+                    const uint32_t cb = __shfl_sync(0xFFFFFFFFu, bk[1], c);
+                    if (lane > c && cb == bk[1]) accept[1] = false;
+                }
+                if (!f_atomfs) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (accept[h]) atomicOr(&m.fs[bk[h] >> 5], 1u << (bk[h] & 31));
+                }
+            }
+            const uint32_t ball0 = __ballot_sync(0xFFFFFFFFu, accept[0]), ball1 = __ballot_sync(0xFFFFFFFFu, accept[1]);
+            const uint32_t n0 = (uint32_t)__popc(ball0);
+            nc = n0 + (uint32_t)__popc(ball1);
+            if (nc && lane == 0) hw_mbar_expect(m.bar, min(nc, m.stage_rows) * sc.row_pitch);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (accept[h]) {
+                    const uint32_t pos = (h ? n0 : 0u) + (uint32_t)__popc((h ? ball1 : ball0) & lt);   // compacted in slot order
+                    m.nnodes[pos] = nbl[h];
+                    m.nrow[pos] = row[h];
+                    if (pos < m.stage_rows)   // first group: the row copy starts here, no round trip through shared memory
+                        hw_bulk_g2s(hw_smem_u32(m.stage + (size_t)pos * m.stage_pitch), sc.rows + (size_t)row[h] * sc.row_pitch, sc.row_pitch, m.bar);
+                    // the next head is often one of these: pull their adjacency rows towards L2 while the chains run
+                    const uint8_t *ap = reinterpret_cast<const uint8_t *>(adj + (size_t)nbl[h] * nb);
+                    hw_prefetch_l2(ap);
+                    if (nb > 32) hw_prefetch_l2(ap + 128);
+                }
+            __syncwarp();   // compaction visible to the scoring
+        }
+        if (PROF) t3 = clock64();
+        // ---- score the new neighbours
+        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st, true);
+        st.evals += nc;
+        if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; st.rlen = rlen; return; }
+        if (PROF) t4 = clock64();
+        // ---- merge the old queue (minus the popped head) with the new entries, keep what can still be popped.
+        // Final position of an entry = number of entries of the union that are better; no sort of the new entries needed.
+        {
+            const uint32_t oldn = qlen - 1;
+            const uint32_t cap = min(ef - (visited + 1), EFP);
+            uint64_t *D = m.qkeys + (cur ^ 1) * EFP;
+            uint32_t *DN = m.qnodes + (cur ^ 1) * EFP;
+            const uint64_t mynk0 = (uint32_t)lane < nc ? m.nkeys[lane] : 0ull;
+            const uint64_t mynk1 = (uint32_t)lane + 32u < nc ? m.nkeys[lane + 32] : 0ull;
+            // the next head is the better of the runner-up and the best new entry: start loading its adjacency slots now,
+            // the loads complete while the merge below runs
+            pre_node = HN_EMPTY;
+            if (f_preload && cap > 0 && oldn + nc > 0) {
+                const uint64_t best = oldn ? Q[1] : 0ull;
+                pre_node = spec_node; pre_nbl[0] = spec_nbl[0]; pre_nbl[1] = spec_nbl[1];   // (HN_EMPTY when the queue had no runner-up)
+                if (nc) {
+                    // max of the (unique) 64-bit keys: two 32-bit warp reductions (REDUX) instead of a shuffle tree
+                    const uint64_t loc = mynk0 > mynk1 ? mynk0 : mynk1;
+                    const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(loc >> 32));
+                    const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(loc >> 32) == hi ? (uint32_t)loc : 0u);
+                    const uint64_t mx = ((uint64_t)hi << 32) | lo;
+                    if (mx > best) {   // a new neighbour becomes the head: its adjacency loads overlap the merge below
+                        const uint32_t who0 = __ballot_sync(0xFFFFFFFFu, mynk0 == mx), who1 = __ballot_sync(0xFFFFFFFFu, mynk1 == mx);
+                        const uint32_t next = m.nnodes[who0 ? (uint32_t)__ffs(who0) - 1u : 32u + (uint32_t)__ffs(who1) - 1u];
+                        pre_node = next;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t slot = (uint32_t)lane + 32u * h;
+                            pre_nbl[h] = slot < take ? __ldg(adj + (size_t)next * nb + slot) : HN_EMPTY;
+                        }
+                    }
+                }
+            }
+            uint32_t r0 = 0, r1 = 0;       // new entries better than my new entries
+            if (oldn <= 128) {
+                uint64_t ok[4];
+                uint32_t lo[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ok[t] = (uint32_t)lane + 32u * t < oldn ? Q[1 + lane + 32 * t] : 0ull;   // 0 = no entry (never better)
+                uint32_t c0 = 0, c1 = 0;   // old entries better than my new entries (lane j & 31 keeps the count of new entry j)
+                // the first 8 new keys (nearly always all of them) are fetched together and handled without a loop-carried
+                // load; key 0 = "no entry" contributes nothing
+                uint64_t nkr[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) nkr[j] = (uint32_t)j < nc ? m.nkeys[j] : 0ull;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t nk = nkr[j];
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {   // keys are unique and "no entry" is 0: ok[t] > nk  <=>  !(nk > ok[t])
+                        const bool gt = nk > ok[t];
+                        lo[t] += gt;
+                        cnt += 32u - (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, gt));
+                    }
+                    r0 += nk > mynk0;
+                    r1 += nk > mynk1;
+                    if (lane == j) c0 = cnt;
+                }
+                for (uint32_t j = 8; j < nc; ++j) {
+                    const uint64_t nk = m.nkeys[j];
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const bool gt = nk > ok[t];
+                        lo[t] += gt;
+                        cnt += 32u - (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, gt));
+                    }
+                    r0 += nk > mynk0;
+                    r1 += nk > mynk1;
+                    if (lane == (int)(j & 31)) { if (j < 32) c0 = cnt; else c1 = cnt; }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t i = (uint32_t)lane + 32u * t;
+                    const uint32_t pos = i + lo[t];
+                    if (i < oldn && pos < cap) { D[pos] = ok[t]; DN[pos] = QN[1 + i]; }
+                }
+                if ((uint32_t)lane < nc && r0 + c0 < cap) { D[r0 + c0] = mynk0; DN[r0 + c0] = m.nnodes[lane]; }
+                if ((uint32_t)lane + 32u < nc && r1 + c1 < cap) { D[r1 + c1] = mynk1; DN[r1 + c1] = m.nnodes[lane + 32]; }
+            } else {
+                for (uint32_t i = lane; i < oldn; i += 32) {
+                    const uint64_t k = Q[1 + i];
+                    uint32_t lo = 0;
+                    for (uint32_t j = 0; j < nc; ++j) lo += m.nkeys[j] > k;
+                    const uint32_t pos = i + lo;
+                    if (pos < cap) { D[pos] = k; DN[pos] = QN[1 + i]; }
+                }
+                for (uint32_t j = 0; j < nc; ++j) { const uint64_t nk = m.nkeys[j]; r0 += nk > mynk0; r1 += nk > mynk1; }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t p = (uint32_t)lane + 32u * h;
+                    if (p < nc) {
+                        const uint64_t k = h ? mynk1 : mynk0;
+                        uint32_t lo = 0, hi = oldn;  // number of old entries better than k (the old queue is sorted)
+                        while (lo < hi) { const uint32_t md = (lo + hi) >> 1; if (Q[1 + md] > k) lo = md + 1; else hi = md; }
+                        const uint32_t pos = (h ? r1 : r0) + lo;
+                        if (pos < cap) { D[pos] = k; DN[pos] = m.nnodes[p]; }
+                    }
+                }
+            }
+            qlen = min(oldn + nc, cap);
+            cur ^= 1;
+            ++visited;
+        }
+        __syncwarp();
+        if (PROF) {
+            const long long t5 = clock64();
+            st.prof[0] += t2 - t1; st.prof[1] += t3 - t2; st.prof[5] += t5 - t4;
+        }
+    }
+    long long t6 = 0;
+    if (PROF) t6 = clock64();
+    uint32_t P = 1;
+    while (P < rlen) P <<= 1;
+    hw_sort_desc(m.rkeys, m.rnodes, rlen, P, lane);
+    st.rlen = rlen;
+    if (PROF) { const long long t7 = clock64(); st.prof[6] += t7 - t6; st.prof[7] += t7 - t0; }
+}
+
+template <bool F16FAST, bool PROF>
+__global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarve cv) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x;
+    const uint32_t qi = blockIdx.x;
+    HwSmem m;
+    m.qs = smem;
+    m.q32 = reinterpret_cast<float *>(smem + cv.off_q32);
+    m.qkeys = reinterpret_cast<uint64_t *>(smem + cv.off_qkeys);
+    m.rkeys = reinterpret_cast<uint64_t *>(smem + cv.off_rkeys);
+    m.nkeys = reinterpret_cast<uint64_t *>(smem + cv.off_nkeys);
+    m.fs = reinterpret_cast<uint32_t *>(smem + cv.off_fs);
+    m.bar = hw_smem_u32(smem + cv.off_bar);
+    m.qnodes = reinterpret_cast<uint32_t *>(smem + cv.off_qnodes);
+    m.rnodes = reinterpret_cast<uint32_t *>(smem + cv.off_rnodes);
+    m.nnodes = reinterpret_cast<uint32_t *>(smem + cv.off_nnodes);
+    m.nrow = reinterpret_cast<uint32_t *>(smem + cv.off_nrow);
+    m.stage = smem + cv.off_stage;
+    m.EFP = cv.EFP; m.stage_pitch = cv.stage_pitch; m.stage_rows = cv.stage_rows;
+
+    for (uint32_t i = lane; i < a.row_pitch / 4; i += 32)
+        reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[i];
+    __syncwarp();
+    if (F16FAST)
+        for (uint32_t i = lane; i < a.dim; i += 32) m.q32[i] = __half2float(reinterpret_cast<const __half *>(m.qs)[i]);
+    const float qmag = a.qmags[qi];
+    const HnScoreCtx sc{a.rows, a.row_pitch, a.mags, a.dim, a.st, a.metric, a.g.root_row};
+    if (lane == 0) hw_mbar_init(m.bar, 1);
+    HwState st;
+    st.err = 0; st.rlen = 0; st.evals = 0; st.pops = 0; st.bar_phase = 0;
+#pragma unroll
+    for (int i = 0; i < HW_PROF_SLOTS; ++i) st.prof[i] = 0;
+    uint32_t entry = a.g.entry, out_total = 0;
+    __syncwarp();
+
+    // ann_search (vector_store.rs:256-402): fresh fixed set and ef budget per level, results of all levels
+    // concatenated, child of the best result is the entry of the next level
+    for (int level = (int)a.g.num_levels; level >= 0; --level) {
+        const uint32_t nb = level == 0 ? a.g.nbrs0 : a.g.nbrs;
+        const uint32_t take = min(min(a.shortlist, nb), HN_MAX_TAKE);
+        const uint32_t *node_row = ((a.g.identity_mask >> level) & 1u) ? nullptr : a.g.node_row[level];
+        hw_traverse_level<F16FAST, PROF>(node_row, a.g.adj[level], nb, take, sc, m, qmag, HN_QUERY_ID, a.ef, entry, st, lane, a.flags);
+        if (st.err) break;
+        const uint32_t keep = min(st.rlen, HW_FINAL_LEN);
+        for (uint32_t i = lane; i < keep; i += 32) {
+            const uint32_t slot = out_total + i;
+            if (slot < a.out_cap) {
+                const uint32_t nd = m.rnodes[i];
+                a.out_rows[(size_t)qi * a.out_cap + slot] = node_row ? node_row[nd] : nd;
+                a.out_scores[(size_t)qi * a.out_cap + slot] = __uint_as_float(key_to_bits(a.metric, (uint32_t)(m.rkeys[i] >> 32)));
+            }
+        }
+        out_total += keep;
+        if (level > 0) entry = a.g.child[level][m.rnodes[0]];
+        __syncwarp();
+    }
+    if (lane == 0) {
+        a.out_n[qi] = st.err ? 0u : min(out_total, a.out_cap);
+        if (st.err) atomicOr(a.err32 + qi, st.err);
+        if (a.counters) { atomicAdd(a.counters, st.evals); atomicAdd(a.counters + 1, st.pops); }
+        if (PROF && a.prof) {
+            st.prof[8] = (long long)st.pops;
+            for (int i = 0; i < HW_PROF_SLOTS; ++i) atomicAdd(a.prof + i, (unsigned long long)st.prof[i]);
+        }
+    }
+}
+
+size_t hnsw_warp_smem(uint32_t row_pitch, uint32_t dim, uint32_t ef, int st, int metric) {
+    const bool f16fast = st == CDB_ST_F16 && (metric == CDB_METRIC_COSINE || metric == CDB_METRIC_DOT_PRODUCT);
+    return hw_carve(row_pitch, dim, ef, f16fast).total;
+}
+
+template <bool F16FAST, bool PROF>
+static cdb_status launch_warp(const HnswArgs &a, const HwCarve &cv, cudaStream_t s) {
+    auto kern = hnsw_search_warp_kernel<F16FAST, PROF>;
+    CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total));
+    kern<<<a.nq, 32, cv.total, s>>>(a, cv);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+cdb_status hnsw_search_warp_device(const HnswArgs &a, cudaStream_t s) {
+    if (!a.nq) return CDB_OK;
+    if (a.ef == 0 || a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
+    const bool f16fast = a.st == CDB_ST_F16 && (a.metric == CDB_METRIC_COSINE || a.metric == CDB_METRIC_DOT_PRODUCT);
+    const HwCarve cv = hw_carve(a.row_pitch, a.dim, a.ef, f16fast);
+    if (cv.total > 200 * 1024) { set_error("hnsw: ef_search / row size too large for shared memory"); return CDB_INVALID_PARAMS; }
+    const bool prof = a.prof != nullptr;
+    if (f16fast) return prof ? launch_warp<true, true>(a, cv, s) : launch_warp<true, false>(a, cv, s);
+    return prof ? launch_warp<false, true>(a, cv, s) : launch_warp<false, false>(a, cv, s);
+}
+
+}  // namespace cdb

@@ -11,13 +11,18 @@
 //                 every "link" is a byte offset into nodes.ptr (u32::MAX = null); an empty neighbour slot is 13 x 0xFF
 //                 (serializer/hnsw/neighbors.rs:21-60).
 // The two entry links (root_vec_ptr_offset / pseudo_root_vec_ptr_offset) live in LMDB next to the index parameters
-// (types.rs:899-945) and are passed in by the caller.  Only the non-versioned layout (nodes.ptr) is read; with
-// enable_context_history the links are split over "<region>-<version>.ptr" files (cache_loader.rs:97-112), not handled here.
+// (types.rs:899-945) and are passed in by the caller.  With enable_context_history the link image is not one file: every
+// flush writes each dirty 8192-byte region in full to "<region>-<version>.ptr" (cache_loader.rs:91-113,
+// buffered_io.rs:779-797) and the loader takes, per region, the file of the highest version <= the current one
+// (FilelessBufferManager::from_versioned, buffered_io.rs:524-570; file-name rule types.rs:820-842).  Both layouts are read:
+// nodes.ptr when it exists, else the region files (cdb_hnsw_files_open_versioned picks the version).
 //
 // Flattening: breadth first from the entry links over neighbour, child and parent links; level-local indices in discovery order
 // (the root is index 0 of every level it exists on).  node_row = ordinal of the node's Storage record in prop.data (the row
 // cdb_index_append_prop_file gives it), node_id = replica id when the node has Metadata, else the Storage record's id
 // (ProbNode::get_id).  Nodes that no link reaches are unreachable for the reference's search as well and are left out.
+#include <dirent.h>
+
 #include <algorithm>
 #include <deque>
 #include <map>
@@ -75,7 +80,51 @@ struct NodeRec {
 
 struct Reader {
     std::string dir, err;
-    Mapped links;
+    struct { const uint8_t *p = nullptr; size_t len = 0; } links;
+    Mapped links_file;                 // nodes.ptr, or
+    std::vector<uint8_t> links_image;  // the image assembled from "<region>-<version>.ptr" files
+    // "latest version links" of the index directory; latest_version bounds the versioned layout
+    cdb_status open_links(uint32_t latest_version) {
+        struct stat sb;
+        const std::string flat = dir + "/nodes.ptr";
+        if (::stat(flat.c_str(), &sb) == 0) {
+            cdb_status rc = links_file.open(flat.c_str());
+            if (rc) return rc;
+            links.p = links_file.p; links.len = links_file.len;
+            return CDB_OK;
+        }
+        const size_t REGION = 8192;    // buffer size of latest_version_links_bufman (types.rs:819-821)
+        std::map<uint64_t, std::pair<uint32_t, std::string>> best;   // region -> (version, file)
+        DIR *d = opendir(dir.c_str());
+        if (!d) { set_error("cannot open index directory " + dir); return CDB_INVALID_PARAMS; }
+        while (struct dirent *e = readdir(d)) {
+            // "<region>-<version>.ptr": exactly one '.', exactly one '-', both parts decimal (types.rs:823-842)
+            const std::string name = e->d_name;
+            const size_t dot = name.find('.'), dash = name.find('-');
+            if (dot == std::string::npos || name.find('.', dot + 1) != std::string::npos || name.substr(dot) != ".ptr") continue;
+            if (dash == std::string::npos || dash == 0 || dash + 1 >= dot || name.find('-', dash + 1) != std::string::npos) continue;
+            const std::string rs = name.substr(0, dash), vs = name.substr(dash + 1, dot - dash - 1);
+            if (rs.find_first_not_of("0123456789") != std::string::npos || vs.find_first_not_of("0123456789") != std::string::npos) continue;
+            if (rs.size() > 18 || vs.size() > 10) continue;
+            const uint64_t region = std::stoull(rs), ver64 = std::stoull(vs);
+            if (ver64 > 0xFFFFFFFFull || ver64 > latest_version) continue;
+            auto it = best.find(region);
+            if (it != best.end() && it->second.first > (uint32_t)ver64) continue;
+            best[region] = {(uint32_t)ver64, dir + "/" + name};
+        }
+        closedir(d);
+        if (best.empty()) { set_error("no nodes.ptr and no <region>-<version>.ptr files in " + dir); return CDB_INVALID_PARAMS; }
+        for (auto &kv : best) {
+            Mapped f;
+            cdb_status rc = f.open(kv.second.second.c_str());
+            if (rc) return rc;
+            const size_t n = std::min(f.len, REGION), off = (size_t)kv.first * REGION;
+            if (links_image.size() < off + n) links_image.resize(off + n, 0xFF);   // holes = null links
+            if (n) memcpy(links_image.data() + off, f.p, n);
+        }
+        links.p = links_image.data(); links.len = links_image.size();
+        return CDB_OK;
+    }
     std::map<uint32_t, std::unique_ptr<Mapped>> files;
 
     bool fail(const std::string &m) { if (err.empty()) err = m; return false; }
@@ -104,13 +153,13 @@ struct Reader {
     }
 };
 
-cdb_status flatten(const char *index_dir, uint32_t root_link, uint32_t pseudo_link, cdb_hnsw_files &out) {
+cdb_status flatten(const char *index_dir, uint32_t root_link, uint32_t pseudo_link, uint32_t latest_version, cdb_hnsw_files &out) {
     PropIndex pi;
     cdb_status rc = load_prop_index(std::string(index_dir) + "/prop.data", pi);
     if (rc) return rc;
     Reader rd;
     rd.dir = index_dir;
-    if ((rc = rd.links.open((rd.dir + "/nodes.ptr").c_str()))) return rc;
+    if ((rc = rd.open_links(latest_version))) return rc;
     auto bad = [&](const std::string &m) { set_error("hnsw index files: " + (rd.err.empty() ? m : rd.err)); return CDB_INVALID_PARAMS; };
 
     std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> where;   // link -> (level, local index)
@@ -198,13 +247,17 @@ using namespace cdb;
 
 extern "C" {
 
-cdb_status cdb_hnsw_files_open(const char *index_dir, uint32_t root_link_offset, uint32_t pseudo_root_link_offset, cdb_hnsw_files **out) {
+cdb_status cdb_hnsw_files_open_versioned(const char *index_dir, uint32_t root_link_offset, uint32_t pseudo_root_link_offset,
+                                         uint32_t latest_version, cdb_hnsw_files **out) {
     if (!index_dir || !out) { set_error("null argument"); return CDB_INVALID_PARAMS; }
     std::unique_ptr<cdb_hnsw_files> h(new cdb_hnsw_files());
-    const cdb_status rc = flatten(index_dir, root_link_offset, pseudo_root_link_offset, *h);
+    const cdb_status rc = flatten(index_dir, root_link_offset, pseudo_root_link_offset, latest_version, *h);
     if (rc) return rc;
     *out = h.release();
     return CDB_OK;
+}
+cdb_status cdb_hnsw_files_open(const char *index_dir, uint32_t root_link_offset, uint32_t pseudo_root_link_offset, cdb_hnsw_files **out) {
+    return cdb_hnsw_files_open_versioned(index_dir, root_link_offset, pseudo_root_link_offset, 0xFFFFFFFFu, out);
 }
 
 cdb_status cdb_hnsw_files_close(cdb_hnsw_files *h) {

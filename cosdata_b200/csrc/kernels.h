@@ -94,6 +94,7 @@ cdb_status pack_keys_device(int metric, const uint32_t *d_ids, const float *d_sc
 // ---- hnsw.cu
 struct GraphDev {
     uint32_t num_levels, nbrs, nbrs0, entry, root_row;
+    uint32_t identity_mask;           // bit L: node_row[L][i] == i for every node of level L (the lookup is skipped)
     const uint32_t *const *node_row;  // device arrays of device pointers, [num_levels+1]
     const uint32_t *const *adj;
     const uint32_t *const *child;
@@ -114,8 +115,17 @@ struct HnswArgs {
     uint32_t *out_n;
     uint32_t *err32;
     unsigned long long *counters;
+    unsigned long long *prof;         // null, or clock64 sums (hnsw_warp.cu)
+    uint32_t flags;                   // CDB_HNSW_F_* variant switches of the warp kernel
 };
-cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s);
+// variant switches of hnsw_search_warp_kernel (cdb_debug_set_hnsw_flags; the default is the best measured combination)
+constexpr uint32_t CDB_HNSW_F_PRELOAD = 2;   // load the next head's adjacency slots while the queue merge runs
+constexpr uint32_t CDB_HNSW_F_ATOMFS = 4;    // fixed-set walk through atomicOr return values (slot-order loop only on aliasing)
+constexpr uint32_t CDB_HNSW_F_CTA = 8;       // round-1 kernel: one CTA per query
+constexpr uint32_t CDB_HNSW_F_DEFAULT = CDB_HNSW_F_PRELOAD | CDB_HNSW_F_ATOMFS;
+extern std::atomic<uint32_t> g_hnsw_flags;
+cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s);        // one CTA per query (round-1 kernel; A/B runs)
+cdb_status hnsw_search_warp_device(const HnswArgs &a, cudaStream_t s);   // one warp per query (hnsw_warp.cu)
 cdb_status hnsw_dedup_device(const uint32_t *d_rows, const float *d_scores, const uint32_t *d_n, uint32_t in_cap, int metric,
                              uint32_t root_row, uint32_t id_base, uint32_t k5, uint32_t nq, uint32_t *d_cand, uint32_t *d_cand_cnt,
                              cudaStream_t s);

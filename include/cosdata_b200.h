@@ -270,6 +270,12 @@ cdb_status cdb_index_set_graph(cdb_index *index, const cdb_graph_desc *graph);
  *            the fixed set and the reported ids are the reference's InternalIds; searches go through the metadata-aware kernel). */
 typedef struct cdb_hnsw_files cdb_hnsw_files;
 cdb_status cdb_hnsw_files_open(const char *index_dir, uint32_t root_link_offset, uint32_t pseudo_root_link_offset, cdb_hnsw_files **out);
+/* same for indexes written with enable_context_history: the link image is split over "<region>-<version>.ptr" files
+ * (src/models/cache_loader.rs:91-113); per 8192-byte region the file with the highest version <= latest_version counts
+ * (FilelessBufferManager::from_versioned, src/models/buffered_io.rs:524-570).  cdb_hnsw_files_open reads nodes.ptr when it
+ * exists and otherwise this layout with latest_version = u32::MAX. */
+cdb_status cdb_hnsw_files_open_versioned(const char *index_dir, uint32_t root_link_offset, uint32_t pseudo_root_link_offset,
+                                         uint32_t latest_version, cdb_hnsw_files **out);
 cdb_status cdb_hnsw_files_close(cdb_hnsw_files *files);
 cdb_status cdb_hnsw_files_info(const cdb_hnsw_files *files, uint32_t *info8, uint32_t *level_counts);
 cdb_status cdb_hnsw_files_level(const cdb_hnsw_files *files, uint32_t level, uint32_t *node_row, uint32_t *node_id, uint32_t *node_md,
@@ -362,6 +368,18 @@ cdb_status cdb_rerank_f32(cdb_index *index, const float *query, const uint32_t *
 cdb_status cdb_merge_topk_device(int32_t device, int32_t metric, const uint32_t *d_ids, const float *d_scores,
                                  uint32_t n_shards, uint32_t n_queries, uint32_t k,
                                  uint32_t *d_out_ids, float *d_out_scores, void *stream);
+
+/* per-phase clock64 sums of the HNSW search kernel (lane 0 of every query, summed over the queries of all searches since
+ * profiling was enabled): out[0..9) = {pop + adjacency loads, fixed-set walk + compaction, issue of the row copies, wait for
+ * the rows, distance chains, queue merge, end-of-level result sort, whole levels, pops}; the remaining slots are 0.
+ * enable != 0 zeroes the sums and switches the instrumented kernel variant on; 0 switches it off.  out (may be NULL,
+ * CDB_HNSW_PROF_SLOTS entries) receives the sums accumulated so far.  Synchronizes the device. */
+#define CDB_HNSW_PROF_SLOTS 16
+cdb_status cdb_index_hnsw_profile(cdb_index *index, int32_t enable, uint64_t *out);
+/* measurement switch: kernel variant of CDB_MODE_HNSW searches (results are identical for every value).  Bits: 1 cooperative
+ * f16 conversion, 2 next-head adjacency preload, 4 fixed-set walk through atomics, 8 round-1 CTA-per-query kernel;
+ * 0xFFFFFFFF restores the default.  Process-wide. */
+cdb_status cdb_debug_set_hnsw_flags(uint32_t flags);
 
 /* ----------------------------------------------------- instrumentation
  * number of kernels launched by this library since process start (bench.py

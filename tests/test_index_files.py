@@ -185,3 +185,38 @@ def test_index_files_without_metadata_and_damage(tmp_path):
     with pytest.raises(cdb.CosdataError) as e:
         cdb.HnswFiles(d2, rl)
     assert "Storage record" in str(e.value)
+
+
+def test_versioned_link_files_of_enable_context_history(tmp_path):
+    # enable_context_history: no nodes.ptr; every flush writes each dirty 8192-byte region of the link image in full to
+    # "<region>-<version>.ptr" and the loader takes the highest version <= the current one per region
+    # (cache_loader.rs:91-113, buffered_io.rs:524-570)
+    vecs, mg = mdgraph.build(n=1500, dim=16, md_dims=6, levels=3, nb=8, nb0=16, storage_type=4, metric=0, seed=13)
+    flat_dir, ver_dir = str(tmp_path / "flat"), str(tmp_path / "versioned")
+    root_link, pseudo_link = write_index_dir(flat_dir, vecs, mg, seed=5)
+    write_index_dir(ver_dir, vecs, mg, seed=5)
+    image = open(os.path.join(ver_dir, "nodes.ptr"), "rb").read()
+    os.remove(os.path.join(ver_dir, "nodes.ptr"))
+    assert len(image) > 2 * 8192                                          # several regions
+    rng = np.random.default_rng(2)
+    for r in range((len(image) + 8191) // 8192):
+        chunk = image[r * 8192:(r + 1) * 8192]
+        open(os.path.join(ver_dir, f"{r}-3.ptr"), "wb").write(chunk)                      # the current state
+        stale = bytearray(chunk)
+        stale[: len(stale) // 2] = bytes(rng.integers(0, 256, len(stale) // 2, dtype=np.uint8))
+        open(os.path.join(ver_dir, f"{r}-1.ptr"), "wb").write(bytes(stale))               # an older flush of the region
+        if r % 2 == 0:
+            open(os.path.join(ver_dir, f"{r}-9.ptr"), "wb").write(bytes(len(chunk)))      # a version after "current"
+    open(os.path.join(ver_dir, "notes-1.ptr.bak"), "wb").write(b"x")                      # names the loader ignores
+    open(os.path.join(ver_dir, "a-b.ptr"), "wb").write(b"x")
+    a = cdb.HnswFiles(flat_dir, root_link, pseudo_link)
+    b = cdb.HnswFiles(ver_dir, root_link, pseudo_link, latest_version=3)
+    assert (a.num_levels, a.entry, a.pseudo_entry, a.root_row) == (b.num_levels, b.entry, b.pseudo_entry, b.root_row)
+    for lv in range(a.num_levels + 1):
+        for name in ("node_row", "node_id", "node_md", "adj", "child"):
+            assert np.array_equal(getattr(a, name)[lv], getattr(b, name)[lv]), (lv, name)
+    a.close(); b.close()
+    with pytest.raises(cdb.CosdataError):                                 # version 9 zeroed the even regions: links lead nowhere valid
+        cdb.HnswFiles(ver_dir, root_link, pseudo_link)
+    with pytest.raises(cdb.CosdataError):                                 # nothing at or below version 0
+        cdb.HnswFiles(ver_dir, root_link, pseudo_link, latest_version=0)
