@@ -142,6 +142,14 @@ PROTOTYPES = {
     "cdb_search_batch_device": (C.c_int32, [C.c_void_p, c_f32p, C.c_uint32, C.POINTER(SearchParams), c_u32p, c_f32p, c_u32p, c_u8p, C.c_void_p]),
     "cdb_score_ids": (C.c_int32, [C.c_void_p, c_f32p, c_u32p, C.c_uint32, c_f32p, c_i32p]),
     "cdb_rerank_f32": (C.c_int32, [C.c_void_p, c_f32p, c_u32p, C.c_uint32, C.c_uint32, c_u32p, c_f32p, c_u32p]),
+    "cdb_nccl_unique_id": (C.c_int32, [C.c_void_p]),
+    "cdb_shard_group_create": (C.c_int32, [C.c_void_p, C.c_uint32, c_vp]),
+    "cdb_shard_group_create_rank": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, c_vp]),
+    "cdb_shard_group_destroy": (C.c_int32, [C.c_void_p]),
+    "cdb_shard_group_attach": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cdb_shard_group_world": (C.c_uint32, [C.c_void_p]),
+    "cdb_search_batch_sharded": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cdb_search_batch_sharded_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdb_merge_topk_device": (C.c_int32, [C.c_int32, C.c_int32, c_u32p, c_f32p, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_f32p, C.c_void_p]),
     "cdb_kernel_launch_count": (C.c_uint64, []),
     "cdb_index_last_kernel_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -133,6 +133,9 @@ struct cdb_index {
     std::vector<const uint32_t *> g_nr, g_ad, g_ch;  // host copies of the per-level device pointers
     DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags, hn_prof;
     bool hn_prof_on = false;
+    // sharded searches (shard_group.cu): the final kernels also write the packed selection keys of every query here
+    // ([nq][k], 0 = empty slot) -- straight into the collective's send buffer.  cur_keys = the current chunk's slice.
+    uint64_t *keys_out = nullptr, *cur_keys = nullptr;
 };
 
 #define CDB_REQUIRE(cond, msg)                              \
@@ -578,12 +581,14 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
         a.sel_mode = 1;
         if ((rc = scan_topk_device(a, s))) return rc;
         if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 1,
-                                        a.sel_grid, scan_sel_qb(a))))
+                                        a.sel_grid, scan_sel_qb(a), ix->cur_keys)))
             return rc;
         a.sel_mode = 0;
     }
     if ((rc = scan_topk_device(a, s))) return rc;
-    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 0))) return rc;
+    if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 0, 0, 0,
+                                    ix->cur_keys)))
+        return rc;
     if (d_err) {
         err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq, qsel);
         CDB_LAUNCH_CHECK();
@@ -676,7 +681,7 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
         if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
                                     ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
                                     ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s,
-                                    ix->hn_labels.as<uint32_t>())))
+                                    ix->hn_labels.as<uint32_t>(), ix->cur_keys)))
             return rc;
     } else {
         // one warp per query (hnsw_warp.cu); CDB_HNSW_F_CTA selects the round-1 CTA-per-query kernel for A/B measurements
@@ -689,7 +694,8 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
             return rc;
         if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
                                     ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
-                                    ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
+                                    ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s, nullptr,
+                                    ix->cur_keys)))
             return rc;
     }
     if (d_err) {
@@ -767,7 +773,7 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(),
                                     pitch / 4, ix->q_mags.as<float>(), nq, ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(),
-                                    cap, p->k, d.id_base, d_ids, d_scores, d_counts, s)))
+                                    cap, p->k, d.id_base, d_ids, d_scores, d_counts, s, nullptr, ix->cur_keys)))
             return rc;
         if ((rc = select_fallback_device(ix->cand_cnt.as<uint32_t>(), cap, ix->q_mags.as<float>(), nq, ix->qsel.as<uint32_t>(), flags, s)))
             return rc;
@@ -802,7 +808,7 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
         if ((rc = tensor_u8_scan_device(u8_rows, ix->qh.as<uint8_t>(), upitch, ix->size, nq, d.dim, p->k, metric, ix->d_mags,
                                         ix->q_mags.as<float>(), d.id_base, ix->gthr.as<int>(), ix->cand.as<uint64_t>(),
                                         ix->cand_cnt.as<uint32_t>(), cap, ix->err32.as<uint32_t>(), ix->progress.as<uint32_t>(),
-                                        d_ids, d_scores, d_counts, ix->sm_count, s)))
+                                        d_ids, d_scores, d_counts, ix->sm_count, s, ix->cur_keys)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = select_fallback_device(ix->cand_cnt.as<uint32_t>(), cap, nullptr, nq, ix->qsel.as<uint32_t>(), flags, s))) return rc;
@@ -838,12 +844,32 @@ static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, ui
     const uint32_t CH = 2048;
     for (uint32_t off = 0; off < nq; off += CH) {
         const uint32_t m = nq - off < CH ? nq - off : CH;
+        ix->cur_keys = ix->keys_out ? ix->keys_out + (size_t)off * p->k : nullptr;
         cdb_status rc = search_chunk_locked(ix, d_queries + (size_t)off * ix->desc.dim, m, p, d_ids + (size_t)off * p->k,
                                             d_scores + (size_t)off * p->k, d_counts + off, d_err ? d_err + off : nullptr, s);
         if (rc) return rc;
     }
     return CDB_OK;
 }
+
+}  // extern "C"
+namespace cdb {
+// shard_group.cu: search one shard with device buffers on `s`; d_keys ([nq][k], may be null) receives the packed keys
+cdb_status index_search_device_keys(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p, uint32_t *d_ids,
+                                    float *d_scores, uint32_t *d_counts, uint8_t *d_err, uint64_t *d_keys, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
+    ix->keys_out = d_keys;
+    const cdb_status rc = search_device_locked(ix, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
+    ix->keys_out = ix->cur_keys = nullptr;
+    return rc;
+}
+int index_device(const cdb_index *ix) { return ix->desc.device; }
+uint32_t index_dim(const cdb_index *ix) { return ix->desc.dim; }
+int index_result_metric(const cdb_index *ix, int mode) { return mode == CDB_MODE_BRUTE_CODES ? ix->desc.metric : CDB_METRIC_COSINE; }
+}  // namespace cdb
+extern "C" {
 
 cdb_status cdb_search_batch_device(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                    uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, void *stream) {

@@ -180,7 +180,7 @@ struct HwState {
 // row runs the reference chain.  Returns the (position << 8 | flag) of the first failing evaluation, 0xFFFFFFFF if none.
 template <bool F16FAST, bool PROF>
 __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const HwSmem &m, float qmag, uint32_t pp, uint32_t first,
-                                                   uint32_t n, int lane, HwState &st, bool pre_issued) {
+                                                   uint32_t n, int lane, HwState &st) {
     uint32_t err_first = 0xFFFFFFFFu;
     for (uint32_t g0 = 0; g0 < n; g0 += m.stage_rows) {
         const uint32_t gn = min(m.stage_rows, n - g0);
@@ -188,14 +188,11 @@ __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const H
         if (PROF) ts = clock64();
         uint32_t row = 0;
         float rmag = 0.0f;
-        if (!(pre_issued && g0 == 0)) {   // the traversal issues the first group's copies itself, straight from the fixed-set walk
-            if (lane == 0) hw_mbar_expect(m.bar, gn * sc.row_pitch);
-            __syncwarp();
-        }
+        // (a copy may complete before the expect_tx is posted: the phase cannot end before lane 0's arrive)
+        if (lane == 0) hw_mbar_expect(m.bar, gn * sc.row_pitch);
         if ((uint32_t)lane < gn) {
             row = m.nrow[first + g0 + lane];
-            if (!(pre_issued && g0 == 0))
-                hw_bulk_g2s(hw_smem_u32(m.stage + (size_t)lane * m.stage_pitch), sc.rows + (size_t)row * sc.row_pitch, sc.row_pitch, m.bar);
+            hw_bulk_g2s(hw_smem_u32(m.stage + (size_t)lane * m.stage_pitch), sc.rows + (size_t)row * sc.row_pitch, sc.row_pitch, m.bar);
             rmag = sc.mags[row];   // in flight together with the rows
         }
         if (PROF) ti = clock64();
@@ -251,7 +248,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
     if (lane == 0) { m.nnodes[0] = entry; m.nrow[0] = node_row ? node_row[entry] : entry; }
     __syncwarp();
     {
-        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, 1, lane, st, false);
+        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, 1, lane, st);
         st.evals += 1;
         if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; return; }
         if (lane == 0) {
@@ -298,17 +295,6 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                 bk[h] = (((id >> 6) & bmask) << 6) | (id & 0x3f);
             }
         }
-        // speculative: the runner-up is the next head unless a new neighbour beats it; its adjacency slots travel while this
-        // pop's rows are fetched and scored
-        uint32_t spec_node = HN_EMPTY, spec_nbl[2] = {HN_EMPTY, HN_EMPTY};
-        if (f_preload && qlen > 1) {
-            spec_node = QN[1];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t slot = (uint32_t)lane + 32u * h;
-                spec_nbl[h] = slot < take ? __ldg(adj + (size_t)spec_node * nb + slot) : HN_EMPTY;
-            }
-        }
         if (PROF) t2 = clock64();
         // ---- the walk through the lossy fixed set, slot order: a slot is scored iff its bit is not yet set AND no
         // earlier non-empty slot of this pop maps to the same bit (that one either set it or found it set).
@@ -318,22 +304,20 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
         bool accept[2];
         uint32_t nc = 0;
         {
+            const bool two = take > 32;   // levels >= 1 examine <= 32 slots (neighbors_count 32): the second half is skipped there
             bool clear[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                clear[h] = nbl[h] != HN_EMPTY && ((m.fs[bk[h] >> 5] >> (bk[h] & 31)) & 1u) == 0;
-            const uint32_t cand0 = __ballot_sync(0xFFFFFFFFu, clear[0]), cand1 = __ballot_sync(0xFFFFFFFFu, clear[1]);
+            clear[0] = nbl[0] != HN_EMPTY && ((m.fs[bk[0] >> 5] >> (bk[0] & 31)) & 1u) == 0;
+            clear[1] = two && nbl[1] != HN_EMPTY && ((m.fs[bk[1] >> 5] >> (bk[1] & 31)) & 1u) == 0;
+            const uint32_t cand0 = __ballot_sync(0xFFFFFFFFu, clear[0]);
+            const uint32_t cand1 = two ? __ballot_sync(0xFFFFFFFFu, clear[1]) : 0u;
             accept[0] = clear[0]; accept[1] = clear[1];
             bool resolve = true;   // apply the slot-order rule explicitly
             if (f_atomfs) {
-                bool won[2] = {false, false};
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if (clear[h]) {
-                        const uint32_t bit = 1u << (bk[h] & 31);
-                        won[h] = (atomicOr(&m.fs[bk[h] >> 5], bit) & bit) == 0;
-                    }
-                const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, won[0]), w1 = __ballot_sync(0xFFFFFFFFu, won[1]);
+                bool won0 = false, won1 = false;
+                if (clear[0]) { const uint32_t bit = 1u << (bk[0] & 31); won0 = (atomicOr(&m.fs[bk[0] >> 5], bit) & bit) == 0; }
+                if (clear[1]) { const uint32_t bit = 1u << (bk[1] & 31); won1 = (atomicOr(&m.fs[bk[1] >> 5], bit) & bit) == 0; }
+                const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, won0);
+                const uint32_t w1 = two ? __ballot_sync(0xFFFFFFFFu, won1) : 0u;
                 resolve = __popc(w0) + __popc(w1) != __popc(cand0) + __popc(cand1);
             }
             if (resolve) {
@@ -354,18 +338,17 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                         if (accept[h]) atomicOr(&m.fs[bk[h] >> 5], 1u << (bk[h] & 31));
                 }
             }
-            const uint32_t ball0 = __ballot_sync(0xFFFFFFFFu, accept[0]), ball1 = __ballot_sync(0xFFFFFFFFu, accept[1]);
+            // without a conflict the accepted slots are exactly the candidates: no further ballot needed
+            const uint32_t ball0 = resolve ? __ballot_sync(0xFFFFFFFFu, accept[0]) : cand0;
+            const uint32_t ball1 = resolve ? __ballot_sync(0xFFFFFFFFu, accept[1]) : cand1;
             const uint32_t n0 = (uint32_t)__popc(ball0);
             nc = n0 + (uint32_t)__popc(ball1);
-            if (nc && lane == 0) hw_mbar_expect(m.bar, min(nc, m.stage_rows) * sc.row_pitch);
 #pragma unroll
             for (int h = 0; h < 2; ++h)
                 if (accept[h]) {
                     const uint32_t pos = (h ? n0 : 0u) + (uint32_t)__popc((h ? ball1 : ball0) & lt);   // compacted in slot order
                     m.nnodes[pos] = nbl[h];
                     m.nrow[pos] = row[h];
-                    if (pos < m.stage_rows)   // first group: the row copy starts here, no round trip through shared memory
-                        hw_bulk_g2s(hw_smem_u32(m.stage + (size_t)pos * m.stage_pitch), sc.rows + (size_t)row[h] * sc.row_pitch, sc.row_pitch, m.bar);
                     // the next head is often one of these: pull their adjacency rows towards L2 while the chains run
                     const uint8_t *ap = reinterpret_cast<const uint8_t *>(adj + (size_t)nbl[h] * nb);
                     hw_prefetch_l2(ap);
@@ -375,7 +358,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
         }
         if (PROF) t3 = clock64();
         // ---- score the new neighbours
-        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st, true);
+        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st);
         st.evals += nc;
         if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; st.rlen = rlen; return; }
         if (PROF) t4 = clock64();
@@ -392,57 +375,41 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
             // the loads complete while the merge below runs
             pre_node = HN_EMPTY;
             if (f_preload && cap > 0 && oldn + nc > 0) {
-                const uint64_t best = oldn ? Q[1] : 0ull;
-                pre_node = spec_node; pre_nbl[0] = spec_nbl[0]; pre_nbl[1] = spec_nbl[1];   // (HN_EMPTY when the queue had no runner-up)
+                uint64_t best = oldn ? Q[1] : 0ull;
+                uint32_t next = oldn ? QN[1] : HN_EMPTY;
                 if (nc) {
                     // max of the (unique) 64-bit keys: two 32-bit warp reductions (REDUX) instead of a shuffle tree
                     const uint64_t loc = mynk0 > mynk1 ? mynk0 : mynk1;
                     const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(loc >> 32));
                     const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(loc >> 32) == hi ? (uint32_t)loc : 0u);
                     const uint64_t mx = ((uint64_t)hi << 32) | lo;
-                    if (mx > best) {   // a new neighbour becomes the head: its adjacency loads overlap the merge below
+                    if (mx > best) {
                         const uint32_t who0 = __ballot_sync(0xFFFFFFFFu, mynk0 == mx), who1 = __ballot_sync(0xFFFFFFFFu, mynk1 == mx);
-                        const uint32_t next = m.nnodes[who0 ? (uint32_t)__ffs(who0) - 1u : 32u + (uint32_t)__ffs(who1) - 1u];
-                        pre_node = next;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint32_t slot = (uint32_t)lane + 32u * h;
-                            pre_nbl[h] = slot < take ? __ldg(adj + (size_t)next * nb + slot) : HN_EMPTY;
-                        }
+                        next = m.nnodes[who0 ? (uint32_t)__ffs(who0) - 1u : 32u + (uint32_t)__ffs(who1) - 1u];
+                        best = mx;
                     }
+                }
+                pre_node = next;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t slot = (uint32_t)lane + 32u * h;
+                    pre_nbl[h] = slot < take ? __ldg(adj + (size_t)next * nb + slot) : HN_EMPTY;
                 }
             }
             uint32_t r0 = 0, r1 = 0;       // new entries better than my new entries
             if (oldn <= 128) {
+                // every lane keeps 4 old entries in registers; one pass over the few new keys (broadcast reads) yields, for the
+                // old entries, how far they move down and, through ballots, how many old entries beat each new one
                 uint64_t ok[4];
                 uint32_t lo[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) ok[t] = (uint32_t)lane + 32u * t < oldn ? Q[1 + lane + 32 * t] : 0ull;   // 0 = no entry (never better)
                 uint32_t c0 = 0, c1 = 0;   // old entries better than my new entries (lane j & 31 keeps the count of new entry j)
-                // the first 8 new keys (nearly always all of them) are fetched together and handled without a loop-carried
-                // load; key 0 = "no entry" contributes nothing
-                uint64_t nkr[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) nkr[j] = (uint32_t)j < nc ? m.nkeys[j] : 0ull;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint64_t nk = nkr[j];
-                    uint32_t cnt = 0;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {   // keys are unique and "no entry" is 0: ok[t] > nk  <=>  !(nk > ok[t])
-                        const bool gt = nk > ok[t];
-                        lo[t] += gt;
-                        cnt += 32u - (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, gt));
-                    }
-                    r0 += nk > mynk0;
-                    r1 += nk > mynk1;
-                    if (lane == j) c0 = cnt;
-                }
-                for (uint32_t j = 8; j < nc; ++j) {
+                for (uint32_t j = 0; j < nc; ++j) {
                     const uint64_t nk = m.nkeys[j];
                     uint32_t cnt = 0;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
+                    for (int t = 0; t < 4; ++t) {   // keys are unique and "no entry" is 0: ok[t] > nk  <=>  !(nk > ok[t])
                         const bool gt = nk > ok[t];
                         lo[t] += gt;
                         cnt += 32u - (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, gt));
@@ -460,6 +427,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                 if ((uint32_t)lane < nc && r0 + c0 < cap) { D[r0 + c0] = mynk0; DN[r0 + c0] = m.nnodes[lane]; }
                 if ((uint32_t)lane + 32u < nc && r1 + c1 < cap) { D[r1 + c1] = mynk1; DN[r1 + c1] = m.nnodes[lane + 32]; }
             } else {
+                // long queues (ef_search > 128): counting for the old entries, binary search in the sorted old queue for the new
                 for (uint32_t i = lane; i < oldn; i += 32) {
                     const uint64_t k = Q[1 + i];
                     uint32_t lo = 0;
@@ -473,7 +441,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                     const uint32_t p = (uint32_t)lane + 32u * h;
                     if (p < nc) {
                         const uint64_t k = h ? mynk1 : mynk0;
-                        uint32_t lo = 0, hi = oldn;  // number of old entries better than k (the old queue is sorted)
+                        uint32_t lo = 0, hi = oldn;  // number of old entries better than k
                         while (lo < hi) { const uint32_t md = (lo + hi) >> 1; if (Q[1 + md] > k) lo = md + 1; else hi = md; }
                         const uint32_t pos = (h ? r1 : r0) + lo;
                         if (pos < cap) { D[pos] = k; DN[pos] = m.nnodes[p]; }

@@ -46,7 +46,8 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
                              uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
                              const uint32_t *d_cand, const uint32_t *d_cand_counts, uint32_t ncand, uint32_t k, uint32_t id_base,
                              uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s,
-                             const uint32_t *d_labels = nullptr);   // labels: ids reported instead of the candidate ids (replica ids)
+                             const uint32_t *d_labels = nullptr,    // labels: ids reported instead of the candidate ids (replica ids)
+                             uint64_t *d_out_keys = nullptr);       // [nq][k] packed selection keys as well (shard merge)
 
 // ---- scan.cu
 struct ScanArgs {
@@ -83,7 +84,8 @@ cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s);
 // partial [nq][nsplit][k] -> ids/scores/counts
 cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
                                  uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s,
-                                 const uint32_t *qsel = nullptr, uint32_t sel_cap = 0, int sel_mode = 0, uint32_t sel_grid = 0, uint32_t sel_qb = 0);
+                                 const uint32_t *qsel = nullptr, uint32_t sel_cap = 0, int sel_mode = 0, uint32_t sel_grid = 0, uint32_t sel_qb = 0,
+                                 uint64_t *d_out_keys = nullptr);
 // grid of the selective scan (CTAs) and its query block; the partial buffer needs SCAN_SEL_CAP * grid * k keys
 uint32_t scan_sel_grid(int sm_count, uint32_t k);
 uint32_t scan_sel_qb(const ScanArgs &a);
@@ -180,6 +182,7 @@ cdb_status unpack_digits_device(const uint8_t *d_codes, uint32_t row_pitch, uint
 cdb_status tensor_u8_scan_device(const uint8_t *d_x, const uint8_t *d_q, uint32_t pitch, uint64_t n_rows, uint32_t nq, uint32_t dim,
                                  uint32_t k, int metric, const float *d_mags, const float *d_qmags, uint32_t id_base, int *d_gthr,
                                  uint64_t *d_cand, uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_err32, uint32_t *d_progress,
-                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, int sm_count, cudaStream_t s);
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, int sm_count, cudaStream_t s,
+                                 uint64_t *d_out_keys = nullptr);
 
 }  // namespace cdb

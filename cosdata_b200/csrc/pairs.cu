@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
     uint32_t dim, const float *__restrict__ q, uint32_t q_pitch_elems, const float *__restrict__ qmags,
     const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_counts, uint32_t cand_stride, uint32_t k, uint32_t id_base,
     uint32_t *__restrict__ out_ids, float *__restrict__ out_scores, uint32_t *__restrict__ out_counts,
-    const uint32_t *__restrict__ labels) {
+    const uint32_t *__restrict__ labels, uint64_t *__restrict__ out_keys) {
     extern __shared__ __align__(16) uint8_t smem[];
     float *qs = reinterpret_cast<float *>(smem);
     uint64_t *keys = reinterpret_cast<uint64_t *>(qs + round_up(dim, 4));
@@ -124,7 +124,11 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
     const uint32_t b = blockIdx.x;
     const uint32_t ncand = cand_counts ? min(cand_counts[b], cand_stride) : cand_stride;
     for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) qs[c] = q[(size_t)b * q_pitch_elems + c];
-    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { out_ids[(size_t)b * k + j] = CDB_INVALID_ID; out_scores[(size_t)b * k + j] = 0.0f; }
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        out_ids[(size_t)b * k + j] = CDB_INVALID_ID;
+        out_scores[(size_t)b * k + j] = 0.0f;
+        if (out_keys) out_keys[(size_t)b * k + j] = 0ull;   // packed selection keys for the shard merge (0 = empty slot)
+    }
     if (threadIdx.x == 0) { nvalid = 0; ndup = 0; }
     __syncthreads();
     const float mag_q = qmags[b];
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(RERANK_THREADS) rerank_f32_kernel(
         if (!dup && o < nout) {
             out_ids[(size_t)b * k + o] = key64_id(key);
             out_scores[(size_t)b * k + o] = __uint_as_float(key_to_bits(CDB_METRIC_COSINE, (uint32_t)(key >> 32)));
+            if (out_keys) out_keys[(size_t)b * k + o] = key;
         }
     }
     if (threadIdx.x == 0 && out_counts) out_counts[b] = nout;
@@ -186,7 +191,7 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
                              uint32_t dim, const float *d_q, uint32_t q_pitch_elems, const float *d_qmags, uint32_t nq,
                              const uint32_t *d_cand, const uint32_t *d_cand_counts, uint32_t ncand, uint32_t k, uint32_t id_base,
                              uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts, cudaStream_t s,
-                             const uint32_t *d_labels) {
+                             const uint32_t *d_labels, uint64_t *d_out_keys) {
     if (!nq) return CDB_OK;
     if (k == 0 || k > 1024) { set_error("rerank: k must be in 1..1024"); return CDB_INVALID_PARAMS; }
     uint32_t pcap = 64;
@@ -196,7 +201,7 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
     if (smem > 200 * 1024) { set_error("rerank: dimension too large"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(rerank_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_f32_kernel<<<nq, RERANK_THREADS, smem, s>>>(d_raw, pitch_elems, d_raw_mags, n_rows, dim, d_q, q_pitch_elems,
-                                                        d_qmags, d_cand, d_cand_counts, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts, d_labels);
+                                                        d_qmags, d_cand, d_cand_counts, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts, d_labels, d_out_keys);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

@@ -362,7 +362,7 @@ cdb_status scan_topk_device(const ScanArgs &a, cudaStream_t s) {
 __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ partial, uint32_t nlists, uint32_t k,
                                       uint32_t *__restrict__ ids, float *__restrict__ scores, uint32_t *__restrict__ counts,
                                       const uint32_t *__restrict__ qsel, uint32_t sel_cap, int sel_mode, uint32_t sel_grid,
-                                      uint32_t sel_qb) {
+                                      uint32_t sel_qb, uint64_t *__restrict__ out_keys) {
     uint32_t q = blockIdx.x, stride = nlists;
     if (sel_mode) {
         const uint32_t n_sel = qsel[0];
@@ -379,7 +379,11 @@ __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ p
     const uint32_t M = nlists * k;
     const uint64_t *src = partial + (size_t)blockIdx.x * stride * k;
     if (threadIdx.x == 0) nvalid = 0;
-    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { ids[(size_t)q * k + j] = CDB_INVALID_ID; scores[(size_t)q * k + j] = 0.0f; }
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        ids[(size_t)q * k + j] = CDB_INVALID_ID;
+        scores[(size_t)q * k + j] = 0.0f;
+        if (out_keys) out_keys[(size_t)q * k + j] = 0ull;
+    }
     __syncthreads();
     int local = 0;
     for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
@@ -397,6 +401,7 @@ __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ p
         if (rank < k) {
             ids[(size_t)q * k + rank] = key64_id(key);
             scores[(size_t)q * k + rank] = __uint_as_float(key_to_bits(metric, (uint32_t)(key >> 32)));
+            if (out_keys) out_keys[(size_t)q * k + rank] = key;
         }
     }
     if (threadIdx.x == 0 && counts) counts[q] = (uint32_t)nvalid < k ? (uint32_t)nvalid : k;
@@ -404,13 +409,13 @@ __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ p
 
 cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t nq, uint32_t nlists, uint32_t k,
                                  uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s, const uint32_t *qsel,
-                                 uint32_t sel_cap, int sel_mode, uint32_t sel_grid, uint32_t sel_qb) {
+                                 uint32_t sel_cap, int sel_mode, uint32_t sel_grid, uint32_t sel_qb, uint64_t *d_out_keys) {
     if (nq == 0) return CDB_OK;
     size_t smem = (size_t)(sel_mode ? sel_grid : nlists) * k * 8;
     if (smem > 200 * 1024) { set_error("merge: too many partial candidates"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_partials_kernel<<<sel_mode ? sel_cap : nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts, qsel,
-                                                                      sel_cap, sel_mode, sel_grid, sel_qb);
+                                                                      sel_cap, sel_mode, sel_grid, sel_qb, d_out_keys);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

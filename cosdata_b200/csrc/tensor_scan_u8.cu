@@ -268,14 +268,19 @@ tensor_scan_u8_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 // ------------------------------------------------------------------ final selection: sort the emitted keys
 __global__ void __launch_bounds__(256) select_keys_kernel(const uint64_t *__restrict__ cand, const uint32_t *__restrict__ cand_cnt,
                                                           uint32_t cap, int metric, uint32_t k, uint32_t *__restrict__ ids,
-                                                          float *__restrict__ scores, uint32_t *__restrict__ counts) {
+                                                          float *__restrict__ scores, uint32_t *__restrict__ counts,
+                                                          uint64_t *__restrict__ out_keys) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *keys = reinterpret_cast<uint64_t *>(smem);
     const uint32_t q = blockIdx.x, n = min(cand_cnt[q], cap);
     uint32_t P = 1;
     while (P < n) P <<= 1;
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < n ? cand[(size_t)q * cap + i] : 0ull;
-    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) { ids[(size_t)q * k + j] = CDB_INVALID_ID; scores[(size_t)q * k + j] = 0.0f; }
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        ids[(size_t)q * k + j] = CDB_INVALID_ID;
+        scores[(size_t)q * k + j] = 0.0f;
+        if (out_keys) out_keys[(size_t)q * k + j] = 0ull;
+    }
     __syncthreads();
     for (uint32_t size = 2; size <= P; size <<= 1)
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -291,6 +296,7 @@ __global__ void __launch_bounds__(256) select_keys_kernel(const uint64_t *__rest
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
         ids[(size_t)q * k + i] = key64_id(keys[i]);
         scores[(size_t)q * k + i] = __uint_as_float(key_to_bits(metric, (uint32_t)(keys[i] >> 32)));
+        if (out_keys) out_keys[(size_t)q * k + i] = keys[i];
     }
     if (threadIdx.x == 0 && counts) counts[q] = m;
 }
@@ -358,7 +364,8 @@ static cdb_status launch_u8(const CUtensorMap &mq, const CUtensorMap &mx, const 
 cdb_status tensor_u8_scan_device(const uint8_t *d_x, const uint8_t *d_q, uint32_t pitch, uint64_t n_rows, uint32_t nq, uint32_t dim,
                                  uint32_t k, int metric, const float *d_mags, const float *d_qmags, uint32_t id_base, int *d_gthr,
                                  uint64_t *d_cand, uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_err32, uint32_t *d_progress,
-                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, int sm_count, cudaStream_t s) {
+                                 uint32_t *d_ids, float *d_scores, uint32_t *d_counts, int sm_count, cudaStream_t s,
+                                 uint64_t *d_out_keys) {
     TensorU8Args a{};
     a.n_rows = n_rows;
     a.n_queries = nq;
@@ -411,7 +418,7 @@ cdb_status tensor_u8_scan_device(const uint8_t *d_x, const uint8_t *d_q, uint32_
     while (P < cand_cap) P <<= 1;
     const size_t ssm = (size_t)P * 8;
     CDB_CUDA_TRY(cudaFuncSetAttribute(select_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-    select_keys_kernel<<<nq, 256, ssm, s>>>(d_cand, d_cand_cnt, cand_cap, metric, k, d_ids, d_scores, d_counts);
+    select_keys_kernel<<<nq, 256, ssm, s>>>(d_cand, d_cand_cnt, cand_cap, metric, k, d_ids, d_scores, d_counts, d_out_keys);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

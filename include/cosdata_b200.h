@@ -362,6 +362,34 @@ cdb_status cdb_score_ids(cdb_index *index, const float *query, const uint32_t *i
 cdb_status cdb_rerank_f32(cdb_index *index, const float *query, const uint32_t *cand_ids, uint32_t n,
                           uint32_t k, uint32_t *out_ids, float *out_scores, uint32_t *out_count);
 
+/* ------------------------------------------------ multi-GPU: row-sharded search
+ * The reference runs IndexOps::batch_search in one process (src/indexes/mod.rs:260-272).  Here the corpus is row-partitioned
+ * into one cdb_index per GPU (contiguous id ranges, cdb_index_desc.id_base = first global id of the shard); every shard
+ * searches the same query batch and ONE ncclAllGather of B*k packed 64-bit keys (+ B error bytes) per rank is merged with
+ * the common ordering rule (better score, then smaller id).  NCCL is bound at run time (dlopen libnccl.so.2).
+ *   cdb_shard_group_create       one process drives n devices (ncclCommInitAll over device_ordinals[]); a device listed
+ *                                twice selects a copy-based loopback gather (single-GPU tests of the same code path)
+ *   cdb_nccl_unique_id + cdb_shard_group_create_rank   one process per GPU: rank 0 creates the id, every rank passes it in
+ *   cdb_shard_group_attach       local slot i <- the shard living on that slot's device
+ *   cdb_search_batch_sharded     host queries in, merged host results out (every local device gets the batch); in a
+ *                                per-rank group every rank must call it with the same batch and receives the same result
+ *   cdb_search_batch_sharded_device   per-rank groups only: device buffers, asynchronous on `stream`
+ * Results are those cdb_search_batch would return on the concatenated corpus (exact modes), resp. the merge of the
+ * per-shard HNSW results (one independent graph per shard). */
+#define CDB_NCCL_UNIQUE_ID_BYTES 128
+typedef struct cdb_shard_group cdb_shard_group;
+cdb_status cdb_nccl_unique_id(uint8_t *out_id128);
+cdb_status cdb_shard_group_create(const int32_t *device_ordinals, uint32_t n_devices, cdb_shard_group **out);
+cdb_status cdb_shard_group_create_rank(const uint8_t *id128, uint32_t world, uint32_t rank, int32_t device, cdb_shard_group **out);
+cdb_status cdb_shard_group_destroy(cdb_shard_group *group);
+cdb_status cdb_shard_group_attach(cdb_shard_group *group, uint32_t local_slot, cdb_index *shard);
+uint32_t cdb_shard_group_world(const cdb_shard_group *group);
+cdb_status cdb_search_batch_sharded(cdb_shard_group *group, const float *queries, uint32_t n_queries, const cdb_search_params *params,
+                                    uint32_t *out_ids, float *out_scores, uint32_t *out_counts, uint8_t *err_flags);
+cdb_status cdb_search_batch_sharded_device(cdb_shard_group *group, const float *d_queries, uint32_t n_queries,
+                                           const cdb_search_params *params, uint32_t *d_out_ids, float *d_out_scores,
+                                           uint32_t *d_out_counts, uint8_t *d_err_flags, void *stream);
+
 /* ------------------------------------------------ multi-GPU shard merge (5e)
  * d_ids/d_scores: [n_shards][n_queries][k] gathered per-shard results (device);
  * writes the global top-k per query with the same ordering rule. */
