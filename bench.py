@@ -45,8 +45,9 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--exact-only", action="store_true", help="pure FFMA scan (no tensor-core prefilter)")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_250_000)
-    ap.add_argument("--cpu-sample-queries", type=int, default=16)
+    ap.add_argument("--cpu-sample-queries", type=int, default=0, help="0 = max(16, host cores): one query per host thread like rayon")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (other BASELINE.json shapes) of the N=1 line")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "hnsw"],
                     help="c2 (default, the headline): brute cosine 10Mx768 f32; c4: quaternary inner product 50Mx1024, batch 4096; "
                          "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools/build_hnsw_graph.py)")
@@ -64,15 +65,16 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=50):
         self.gpu = gpu_index
+        self.period_ms = period_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", str(self.period_ms)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -109,19 +111,28 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_queries(args):
+    """the reference runs one query per rayon worker (indexes/mod.rs:268): give every host core a query"""
+    cores = os.cpu_count() or 1
+    return max(16, cores) if args.cpu_sample_queries <= 0 else args.cpu_sample_queries
+
+
 def cpu_baseline(rows_full, dim, k, sample_rows, sample_queries, threads):
+    """-> (qps scaled to the full corpus, seconds, description, (ids, scores) of the sample search for the parity gate)"""
     import oracle as orc
     sample_rows = min(sample_rows, rows_full)
     corpus = orc.synth_matrix(SEED_CORPUS, sample_rows, dim)
     queries = orc.synth_matrix(SEED_QUERY, sample_queries, dim)
     orc.brute_topk_f32(corpus[: min(sample_rows, 20000)], queries[:1], k, threads=threads)  # warm
     t0 = time.perf_counter()
-    orc.brute_topk_f32(corpus, queries, k, threads=threads)
+    ids, scores = orc.brute_topk_f32(corpus, queries, k, threads=threads)
     dt = time.perf_counter() - t0
     qps_sample = sample_queries / dt
     qps_full = qps_sample * (sample_rows / rows_full)
-    return qps_full, dt, f"oracle port (C/AVX2+FMA, {threads} threads, one query per thread) on {sample_rows}x{dim} rows " \
-                         f"(1/{rows_full // sample_rows} of the corpus) x {sample_queries} queries in {dt:.2f}s, scaled linearly in rows"
+    busy = min(threads, sample_queries)
+    desc = (f"oracle port (C/AVX2+FMA), one query per thread like rayon: {sample_queries} queries on {busy} of {threads} host threads, "
+            f"{sample_rows}x{dim} rows (1/{max(1, rows_full // sample_rows)} of the corpus) in {dt:.2f}s, scaled linearly in rows")
+    return qps_full, dt, desc, (ids, scores), busy
 
 
 def run_reference(args, rank, world):
@@ -129,9 +140,10 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     import oracle as orc
+    nqs = cpu_queries(args)
     sample_rows = min(args.cpu_sample_rows, args.rows)
     corpus = orc.synth_matrix(SEED_CORPUS, sample_rows, args.dim)
-    queries = orc.synth_matrix(SEED_QUERY, args.cpu_sample_queries, args.dim)
+    queries = orc.synth_matrix(SEED_QUERY, nqs, args.dim)
     for _ in range(max(0, min(args.warmup, 1))):
         orc.brute_topk_f32(corpus[: min(sample_rows, 50000)], queries, args.k, threads=threads)
     times = []
@@ -140,15 +152,16 @@ def run_reference(args, rank, world):
         orc.brute_topk_f32(corpus, queries, args.k, threads=threads)
         times.append(time.perf_counter() - t0)
     dt = float(np.sum(times))
-    qps = args.steps * args.cpu_sample_queries / dt * (sample_rows / args.rows)
-    sample = (f"each step = {args.cpu_sample_queries} queries x {sample_rows}x{args.dim} rows "
-              f"(1/{args.rows // sample_rows} of the corpus), scaled linearly in rows")
+    qps = args.steps * nqs / dt * (sample_rows / args.rows)
+    busy = min(threads, nqs)
+    sample = (f"each step = {nqs} queries (one per thread, {busy} of {threads} host threads busy) x {sample_rows}x{args.dim} rows "
+              f"(1/{max(1, args.rows // sample_rows)} of the corpus), scaled linearly in rows")
     line = {
         "impl": "reference", "metric": "queries/sec, brute-force cosine top-10", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": busy, "host_threads": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -163,10 +176,17 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------- our arm
+def parity_abort(what):
+    sys.stderr.write(f"bench.py: PARITY GATE FAILED: {what}\n")
+    sys.stdout.flush()
+    os._exit(3)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import cosdata_b200 as cdb
+    from cosdata_b200.sharding import ShardGroup, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -175,7 +195,6 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from cosdata_b200.sharding import cuda_merge_fn, gather_and_merge, shard_range
     row0, rows_local = shard_range(args.rows, world, rank)
     B, D, k = args.batch, args.dim, args.k
 
@@ -184,73 +203,101 @@ def run_ours(args, rank, world, local_rank):
     # same global synthetic corpus for every world size: shard r holds rows [row0, row0+rows_local)
     ix.append_synthetic(SEED_CORPUS, rows_local, first_row=row0)
 
+    # multi-GPU: the shard group behind the C ABI owns the NCCL communicator, the gather buffers and the merge
+    # (csrc/shard_group.cu); torch.distributed only carries the 128-byte NCCL id to the other ranks and the barriers
+    group = None
+    if world > 1:
+        box = [ShardGroup.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        group = ShardGroup.rank(box[0], world, rank, local_rank)
+        group.attach(0, ix)
+
     q_host = cdb.synth_matrix(SEED_QUERY, B, D)
-    q_pinned = torch.from_numpy(q_host).pin_memory()
-    d_q = q_pinned.to(dev)
+    d_q = torch.from_numpy(q_host).to(dev)
     d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
     d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
     d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    if world > 1:
-        g_ids = torch.empty((world, B, k), dtype=torch.int32, device=dev)
-        g_scores = torch.empty((world, B, k), dtype=torch.float32, device=dev)
-    out_ids = torch.empty((B, k), dtype=torch.int32).pin_memory()
-    out_scores = torch.empty((B, k), dtype=torch.float32).pin_memory()
 
     stream = torch.cuda.Stream(dev)   # a real (non-default) stream: the ABI treats NULL as "use the handle's own stream"
     torch.cuda.set_stream(stream)
 
     def step_device():
-        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
-                               stream.cuda_stream, exact_only=args.exact_only)
-        def all_gather(x):
-            out = g_ids if x.dtype == torch.int32 else g_scores
-            dist.all_gather_into_tensor(out.view(-1), x.view(-1))
-            return out
-
-        return gather_and_merge(d_ids, d_scores, world, all_gather, cuda_merge_fn(ix._lib, local_rank, 0, stream.cuda_stream))
+        if group is None:
+            ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                                   stream.cuda_stream, exact_only=args.exact_only)
+        else:   # local search -> ONE ncclAllGather of packed keys -> merge, all enqueued by one C call
+            group.search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                                stream.cuda_stream, exact_only=args.exact_only)
 
     def step_e2e():
-        # host queries in, host results out, through the public C-ABI call with HOST buffers
-        if world == 1:
-            ids, scores, counts, err = ix.batch_search(q_host, k, exact_only=args.exact_only)
-            return ids, scores
-        d_q.copy_(q_pinned, non_blocking=True)
-        r_ids, r_scores = step_device()
-        out_ids.copy_(r_ids, non_blocking=True)
-        out_scores.copy_(r_scores, non_blocking=True)
-        stream.synchronize()
-        return out_ids, out_scores
+        # host queries in, host results out, through the public C-ABI call with HOST buffers (copies inside the call)
+        if group is None:
+            return ix.batch_search(q_host, k, exact_only=args.exact_only)[:2]
+        return group.search(q_host, k, exact_only=args.exact_only)[:2]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- parity gate BEFORE any timing: the path that will be timed must return exactly what the exact scan
+    # returns on the resident rows.  (At N = 1 the CPU oracle leg below adds an independent check.)
+    gate_q = min(64, B)
+    got_ids, got_scores, _, _ = ix.batch_search(q_host[:gate_q], k, exact_only=args.exact_only)
+    ex_ids, ex_scores, _, _ = ix.batch_search(q_host[:gate_q], k, exact_only=True)
+    if not (np.array_equal(got_ids, ex_ids) and np.array_equal(got_scores.view(np.uint32), ex_scores.view(np.uint32))):
+        parity_abort("prefilter path differs from the exact scan on the resident shard")
+    parity = {"prefilter_vs_exact_scan": {"queries": gate_q, "rows": rows_local, "bit_identical": True}}
+    if group is not None:   # sharded merge against the same queries: every rank holds the merged result
+        m_ids, m_scores = group.search(q_host[:gate_q], k, exact_only=args.exact_only)[:2]
+        l_keys = None
+        from cosdata_b200.sharding import pack_keys, merge_packed
+        mine = torch.from_numpy(pack_keys(ex_ids, ex_scores).view(np.int64)).to(dev)
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        w_ids, w_scores, _ = merge_packed(np.stack([t.cpu().numpy().view(np.uint64) for t in allk]), k)
+        if not (np.array_equal(m_ids, w_ids) and np.array_equal(m_scores.view(np.uint32), w_scores.view(np.uint32))):
+            parity_abort("sharded search differs from the merge of the per-shard exact scans")
+        parity["sharded_vs_merged_exact_scans"] = {"queries": gate_q, "shards": world, "bit_identical": True}
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
+        l0 = cdb.kernel_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
             fn()
         e1.record(stream)
         barrier()
+        launches = cdb.kernel_launch_count() - l0
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    def timed_host(fn, steps, warmup):
+        """host-blocking calls: wall clock between barriers (the call returns when the results are in host memory)"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([(time.perf_counter() - t0) * 1000.0], dtype=torch.float64, device=dev)
+        barrier()
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
     sampler = ClockSampler(local_rank)
-    launches0 = cdb.kernel_launch_count()
     sampler.start()
-    total_ms = timed(step_device, args.steps, max(args.warmup, 3))
+    total_ms, launches_timed = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop()
-    launches = cdb.kernel_launch_count() - launches0
-    # launches counted over warm-up + timed steps; per timed region:
-    launches_timed = launches * args.steps // (args.steps + max(args.warmup, 3))
     scan_ms = ix.scan_ms_history(args.steps)
-    e2e_ms = timed(step_e2e, args.steps, 1)
+    e2e_ms = timed_host(step_e2e, args.steps, 2)
 
     value = args.steps * B / (total_ms / 1000.0)
     e2e_value = args.steps * B / (e2e_ms / 1000.0)
@@ -259,29 +306,27 @@ def run_ours(args, rank, world, local_rank):
     #   flops = 2*rows*D*B ; bytes = rows*(D*4+4) + B*D*4 (fp32 corpus) -- the tcgen05 prefilter reads the
     #   fp16 shadow instead (rows*D*2 bytes), reported as shadow_bytes.
     stats = ix.stats()
-    tensor_path = stats["tensor_searches"] > 0 and stats["fallbacks"] == 0
+    tensor_path = stats["tensor_searches"] > 0 and stats["fallback_queries"] == 0
     alg_bytes = rows_local * (D * 4 + 4) + B * D * 4
     alg_flops = 2.0 * rows_local * D * B
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = _peaks()
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tc_peak = float(peaks.get("bf16_tflops", 1590.0))
     scan_avg_ms = float(np.mean(scan_ms)) if len(scan_ms) else float("nan")
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("tensor_scan_kernel" if tensor_path else "scan_f32_kernel", {}).get("dram_bytes_per_launch")
+        ent = tj.get("tensor_scan_kernel" if tensor_path else "scan_f32_kernel", {})
+        if ent.get("rows") == rows_local and ent.get("batch") == B:      # only a capture of THIS launch shape counts
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
     except Exception:
         pass
     if tensor_path:
         achieved = alg_flops / (scan_avg_ms / 1000.0) / 1e12
         cand = ix.last_candidate_counts(B)
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak,
-                    "traffic": traffic, "peak_source": peak_src + ", dense bf16/fp16 burst",
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + ", dense bf16/fp16 burst",
                     "kernel": "tensor_scan_kernel (tcgen05 fp16 prefilter, threshold epilogue)", "kernel_ms": scan_avg_ms,
                     "alg_flops_per_launch": alg_flops, "shadow_bytes_per_launch": rows_local * D * 2,
                     "hbm_gbs_on_shadow": rows_local * D * 2 / (scan_avg_ms / 1000.0) / 1e9,
@@ -290,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         achieved = alg_bytes / (scan_avg_ms / 1000.0) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "kernel": "scan_f32_kernel (exact FFMA scan, fused top-k)", "kernel_ms": scan_avg_ms,
                     "alg_bytes_per_launch": alg_bytes, "fp32_tflops": alg_flops / (scan_avg_ms / 1000.0) / 1e12,
                     "note": "HBM-bound only for small per-pass batches; at large B the exact FP32 scan is FFMA/L2-bound"}
@@ -301,19 +346,149 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 8 + B * 5,
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches_timed), "roofline": roofline,
-        "recall_at_10": 1.0, "recall_note": "exact search: ids bit-identical to the CPU oracle (tests/test_gpu_parity.py)",
+                "ms_per_step": e2e_ms / args.steps, "timing": "host wall clock around the blocking C-ABI call, max over ranks"},
+        "gpu_launches": int(launches_timed), "roofline": roofline, "parity_checked": parity,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt, sample = cpu_baseline(args.rows, D, k, args.cpu_sample_rows, args.cpu_sample_queries, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample}
+        nqs = cpu_queries(args)
+        v, dt, sample, (o_ids, o_scores), busy = cpu_baseline(args.rows, D, k, args.cpu_sample_rows, nqs, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": busy, "host_threads": threads, "kind": "port", "sample": sample}
+        # oracle leg of the parity gate: the same sample (rows [0, sample_rows) x nqs queries) through the CUDA path
+        srows = min(args.cpu_sample_rows, args.rows)
+        sm = cdb.DenseIndex(dim=D, capacity=srows, device=local_rank)
+        sm.append_synthetic(SEED_CORPUS, srows)
+        g_ids, g_scores, _, _ = sm.batch_search(cdb.synth_matrix(SEED_QUERY, nqs, D), k, exact_only=args.exact_only)
+        took_tensor = sm.stats()["tensor_searches"] > 0
+        sm.close()
+        if not (np.array_equal(g_ids, o_ids) and np.array_equal(g_scores.view(np.uint32), o_scores.view(np.uint32))):
+            parity_abort("CUDA path differs from the CPU oracle on the sample shard")
+        line["parity_checked"]["cuda_vs_cpu_oracle"] = {"queries": nqs, "rows": srows, "bit_identical": True, "tensor_path": took_tensor}
+        line["recall_at_10"] = float(np.mean([len(set(g_ids[i]) & set(o_ids[i])) / k for i in range(nqs)]))
+        line["recall_note"] = "computed in this run: CUDA top-10 vs the CPU oracle's exact top-10 on the sample shard"
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            line["secondary"] = secondary_records(args, ix, cdb, torch, stream, dev, q_host)
+        except Exception as e:            # a secondary record must never take the headline down
+            line["secondary"] = [{"error": repr(e)}]
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if group is not None:
+        group.close()
     ix.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_records(args, ix, cdb, torch, stream, dev, q_host):
+    """small, fast extra measurements on the same box (each < ~2 s): the other BASELINE.json shapes the driver cannot run
+    separately, with their own rooflines and clock samples"""
+    out = []
+    pk = _peaks()
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    B, D, k, rows = args.batch, args.dim, args.k, ix.size
+
+    def run(fn, n, flush=None):
+        torch.cuda.synchronize()
+        sam = ClockSampler(dev.index, period_ms=20)
+        sam.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if flush is None:
+            e0.record(stream)
+            for _ in range(n):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+        else:                      # cold: L2 flushed before every launch, each launch timed on its own
+            tot = 0.0
+            for _ in range(n):
+                flush()
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            ms = tot / n
+        return ms, sam.stop()
+
+    d_q = torch.from_numpy(q_host).to(dev)
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_sc = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_cn = torch.empty((B,), dtype=torch.int32, device=dev)
+    # ---- the headline corpus at small batches: HBM-bound (north_star: ">= 70 % of the HBM roofline on batched cosine")
+    for nb_, exact in ((1, True), (8, True), (8, False)):
+        def fn():
+            ix.batch_search_device(d_q.data_ptr(), nb_, k, d_ids.data_ptr(), d_sc.data_ptr(), d_cn.data_ptr(), None,
+                                   stream.cuda_stream, exact_only=exact)
+        for _ in range(3):
+            fn()
+        nl_ = 50 if exact else 150        # >= ~0.3 s of back-to-back launches so that nvidia-smi gets samples
+        ms, clk = run(fn, nl_)
+        kms = float(np.mean(ix.scan_ms_history(50)))
+        f32_bytes = rows * (D * 4 + 4) + nb_ * D * 4
+        sh_bytes = rows * D * 2 + nb_ * D * 2
+        alg = f32_bytes if exact else sh_bytes
+        out.append({"name": f"brute-force cosine {rows}x{D}, batch={nb_}, " + ("exact f32 scan" if exact else "fp16 prefilter + exact re-rank"),
+                    "value": nb_ / (ms / 1000.0), "unit": "queries/s", "ms_per_step": ms, "launches_timed": nl_, "clocks": clk,
+                    "roofline": {"bound": "hbm", "achieved": alg / (kms / 1000.0) / 1e9, "peak": hbm, "unit": "GB/s",
+                                 "frac": alg / (kms / 1000.0) / 1e9 / hbm, "kernel_ms": kms, "alg_bytes_per_launch": alg,
+                                 "peak_note": "peak = measured device copy (read + write); a read-only stream can exceed it slightly",
+                                 "kernel": "scan_f32_kernel (f32 rows)" if exact else "tensor_scan_kernel (fp16 shadow rows)"}})
+    # ---- BASELINE.json configs[0]: 100k x 128 fp32, batch = 1 (the reference's own CPU-runnable case), warm and cold L2
+    c1 = cdb.DenseIndex(dim=128, capacity=100_000, device=dev.index)
+    c1.append_synthetic(0xC05DA7A + 1, 100_000)
+    q1 = torch.from_numpy(cdb.synth_matrix(0xC05DA7A + 101, 1, 128)).to(dev)
+
+    def fn1():
+        c1.batch_search_device(q1.data_ptr(), 1, k, d_ids.data_ptr(), d_sc.data_ptr(), d_cn.data_ptr(), None, stream.cuda_stream)
+    for _ in range(5):
+        fn1()
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    warm_ms, clk_w = run(fn1, 200)
+    cold_ms, clk_c = run(fn1, 30, flush=lambda: scratch.zero_())
+    c1.close()
+    del scratch
+    c1_bytes = 100_000 * (128 * 4 + 4) + 128 * 4
+    out.append({"name": "brute-force cosine 100000x128 fp32, batch=1 (BASELINE.json configs[0])", "value": 1000.0 / warm_ms,
+                "unit": "queries/s", "ms_per_step": warm_ms, "cold_l2_ms_per_step": cold_ms, "clocks": clk_w,
+                "roofline": {"bound": "hbm", "achieved": c1_bytes / (cold_ms / 1000.0) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": c1_bytes / (cold_ms / 1000.0) / 1e9 / hbm, "alg_bytes_per_launch": c1_bytes,
+                             "note": "51 MB per query: warm = L2-resident + launch latency bound; cold = L2 flushed (256 MB write) before every launch, "
+                                     "whole step timed (quantize + scan + merge launches), so the HBM fraction is a latency figure"}})
+    # ---- BASELINE.json configs[3] on a 5M shard: quaternary inner product, batch 4096, exact integer scores on tcgen05 kind::i8
+    try:
+        i8_tops, _ = cdb.tensor_peak(True, dev.index)
+        f16_tops, _ = cdb.tensor_peak(False, dev.index)
+        r4, D4, B4 = 5_000_000, 1024, 4096
+        c4 = cdb.DenseIndex(dim=D4, storage_type=cdb.StorageType.SubByte2, metric=cdb.DistanceMetricKind.DotProduct, capacity=r4, device=dev.index)
+        c4.append_synthetic(0xC05DA7A + 4, r4)
+        q4 = torch.from_numpy(cdb.synth_matrix(0xC05DA7A + 104, B4, D4)).to(dev)
+        i4 = torch.empty((B4, k), dtype=torch.int32, device=dev)
+        s4 = torch.empty((B4, k), dtype=torch.float32, device=dev)
+        n4 = torch.empty((B4,), dtype=torch.int32, device=dev)
+
+        def fn4():
+            c4.batch_search_device(q4.data_ptr(), B4, k, i4.data_ptr(), s4.data_ptr(), n4.data_ptr(), None, stream.cuda_stream,
+                                   mode=cdb.SearchMode.BRUTE_CODES)
+        for _ in range(2):
+            fn4()
+        ms4, clk4 = run(fn4, 5)
+        kms4 = float(np.sum(c4.scan_ms_history(5 * ((B4 + 2047) // 2048)))) / 5
+        ops4 = 2.0 * r4 * D4 * B4
+        st4 = c4.stats()
+        c4.close()
+        out.append({"name": f"quaternary-quantized inner product {r4}x{D4}, batch={B4} (BASELINE.json configs[3] on a 1/10 shard)",
+                    "value": B4 / (ms4 / 1000.0), "unit": "queries/s", "ms_per_step": ms4, "clocks": clk4,
+                    "roofline": {"bound": "tensor", "achieved": ops4 / (kms4 / 1000.0) / 1e12, "peak": i8_tops, "unit": "TOP/s",
+                                 "frac": ops4 / (kms4 / 1000.0) / 1e12 / i8_tops, "kernel_ms": kms4, "alg_ops_per_launch": ops4,
+                                 "peak_source": "measured in this run: dense tcgen05 kind::i8 issue-rate probe (csrc/tc_probe.cu); "
+                                                f"the same probe with kind::f16 gives {f16_tops:.0f} TFLOP/s next to the cuBLAS bf16 "
+                                                f"{float(pk.get('bf16_tflops', 0)):.0f}",
+                                 "kernel": "tensor_scan_u8_kernel (tcgen05 kind::i8, exact)", "tensor_path": st4}})
+    except Exception as e:
+        out.append({"name": "quaternary-quantized inner product (configs[3] shard)", "error": repr(e)})
+    return out
 
 
 # ----------------------------------------------------------------------------- secondary workloads (reporting modes)

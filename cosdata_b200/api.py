@@ -43,6 +43,7 @@ class StorageType(enum.IntEnum):
     SubByte3 = 3
     HalfPrecisionFP = 4
     FullPrecisionFP = 5
+    BFloat16 = 6          # labelled extension (CDB_ST_BF16), not a reference StorageType
 
 
 class DistanceMetricKind(enum.IntEnum):
@@ -92,6 +93,13 @@ def device_count():
 def debug_set_hnsw_flags(flags=0xFFFFFFFF):
     """kernel-variant switch of CDB_MODE_HNSW searches (measurement only; results are identical); default restores"""
     _check(_lib.load().cdb_debug_set_hnsw_flags(flags & 0xFFFFFFFF))
+
+
+def tensor_peak(kind_i8=True, device=0, iters=0):
+    """dense tcgen05 issue-rate probe -> (TOP/s or TFLOP/s, ms); the measured peak of kind::i8 / kind::f16 MMAs"""
+    tops, ms = C.c_double(0), C.c_float(0)
+    _check(_lib.load().cdb_debug_tensor_peak(device, 1 if kind_i8 else 0, iters, C.byref(tops), C.byref(ms)))
+    return tops.value, ms.value
 
 
 def kernel_launch_count():
@@ -383,6 +391,22 @@ class DenseIndex:
         _check(self._lib.cdb_index_append_itoe(self._h, os.fsencode(collection_dir), _ptr(ids) if max_ids else None, max_ids, C.byref(n)))
         return n.value, ids[: min(n.value, max_ids)]
 
+    def set_raw(self, first_row, vectors):
+        """raw f32 rows for rows that were appended as codes (keep_raw_f32 index)"""
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        _check(self._lib.cdb_index_set_raw_f32(self._h, first_row, _ptr(v), v.shape[0]))
+
+    @property
+    def raw_missing(self):
+        return int(self._lib.cdb_index_raw_missing(self._h))
+
+    def fill_raw_from_itoe(self, collection_dir, row_ids):
+        """row r <- embedding of internal id row_ids[r] (INVALID_ID: none by design) -> (filled, missing)"""
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint32)
+        f, m = C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.cdb_index_fill_raw_from_itoe(self._h, os.fsencode(collection_dir), _ptr(ids), ids.size, C.byref(f), C.byref(m)))
+        return f.value, m.value
+
     def append_synthetic(self, seed, n, first_row=None):
         """rows [first_row, first_row+n) of synthetic stream `seed` (default: continue at len(self))"""
         first_row = len(self) if first_row is None else first_row
@@ -395,6 +419,10 @@ class DenseIndex:
         return codes, mags
 
     # -- S1
+    @property
+    def size(self):
+        return int(self._lib.cdb_index_size(self._h))
+
     def params(self, k, mode=SearchMode.BRUTE_RAW, ef_search=256, shortlist_size=64, exact_only=False, prefilter_k=0):
         return SearchParams(k, int(mode), ef_search, shortlist_size, 1 if exact_only else 0, prefilter_k, 0, 0)
 

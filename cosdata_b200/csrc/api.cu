@@ -1,9 +1,12 @@
 // api.cu -- the extern "C" boundary declared in include/cosdata_b200.h.
 // Host-side orchestration only: device buffers, streams, launch order.  No torch,
 // no CPU compute path -- without a CUDA device every entry point fails.
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <vector>
 
 #include "kernels.h"
@@ -35,12 +38,12 @@ struct DevBuf {
 
 // (metric, storage) arms of DistanceMetric::calculate: OK / StorageMismatch / unimplemented!()
 static cdb_status arm_status(int metric, int st) {
-    if (st < CDB_ST_U8 || st > CDB_ST_F32) return CDB_INVALID_PARAMS;
+    if (st < CDB_ST_U8 || st > CDB_ST_LAST) return CDB_INVALID_PARAMS;
     switch (metric) {
     case CDB_METRIC_COSINE: return CDB_OK;                                                        // cosine.rs:104-216
     case CDB_METRIC_DOT_PRODUCT: return st == CDB_ST_F32 ? CDB_STORAGE_MISMATCH : CDB_OK;          // dotproduct.rs:20-63
     case CDB_METRIC_EUCLIDEAN:                                                                      // euclidean.rs:17-39
-        if (st == CDB_ST_U8 || st == CDB_ST_F16) return CDB_OK;
+        if (st == CDB_ST_U8 || st == CDB_ST_F16 || st == CDB_ST_BF16) return CDB_OK;
         return st == CDB_ST_F32 ? CDB_STORAGE_MISMATCH : CDB_UNSUPPORTED;
     case CDB_METRIC_HAMMING: return st == CDB_ST_F32 ? CDB_STORAGE_MISMATCH : CDB_OK;              // hamming.rs:21-57
     default: return CDB_INVALID_PARAMS;
@@ -52,7 +55,7 @@ static size_t host_code_bytes(int st, uint32_t dim) {
     switch (st) {
     case CDB_ST_U8: return dim;
     case CDB_ST_SUB1: case CDB_ST_SUB2: case CDB_ST_SUB3: return (size_t)st * plane_bytes(dim);
-    case CDB_ST_F16: return (size_t)dim * 2;
+    case CDB_ST_F16: case CDB_ST_BF16: return (size_t)dim * 2;
     case CDB_ST_F32: return (size_t)dim * 4;
     default: return 0;
     }
@@ -88,6 +91,40 @@ __global__ void err32_to_u8_kernel(const uint32_t *e, uint8_t *out, uint32_t n, 
 
 using namespace cdb;
 
+// Per-call scratch of a search: every buffer a search writes, its own stream and events.  A handle keeps a small pool of
+// these, so concurrent cdb_search_* calls on one handle (several host threads, several streams) do not serialise on a
+// single arena -- the index data itself is read-only during a search (the ABI is re-entrant per handle).
+struct Scratch {
+    DevBuf q_codes, q_mags, partial, err32, io_ids, io_scores, io_counts, io_err, io_q, misc;
+    DevBuf qh, gthr, cand, cand_cnt, flags, progress, qsel;
+    DevBuf hn_rows, hn_scores, hn_n, qraw, qraw_mags, hn_ids, hn_labels, flt_off, flt_dims, flt_has;
+    cudaStream_t stream = nullptr;         // used by the host-buffer entry points
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    cudaStream_t last_stream = nullptr;    // stream of the previous search on this set (stream-ordered hand-over of the buffers)
+    // sharded searches (shard_group.cu): the final kernels also write the packed selection keys of every query here
+    // ([nq][k], 0 = empty slot) -- straight into the collective's send buffer.  cur_keys = the current chunk's slice.
+    uint64_t *keys_out = nullptr, *cur_keys = nullptr;
+    bool busy = false;
+    cdb_status init() {
+        CDB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto &e : ev) CDB_CUDA_TRY(cudaEventCreate(&e));
+        cdb_status rc = flags.ensure(16);
+        if (rc) return rc;
+        CDB_CUDA_TRY(cudaMemset(flags.p, 0, 16));
+        return CDB_OK;
+    }
+    void destroy() {
+        if (stream) cudaStreamSynchronize(stream);
+        for (DevBuf *b : {&q_codes, &q_mags, &partial, &err32, &io_ids, &io_scores, &io_counts, &io_err, &io_q, &misc, &qh, &gthr, &cand,
+                          &cand_cnt, &flags, &progress, &qsel, &hn_rows, &hn_scores, &hn_n, &qraw, &qraw_mags, &hn_ids, &hn_labels,
+                          &flt_off, &flt_dims, &flt_has})
+            b->release();
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct cdb_index {
     cdb_index_desc desc{};
     int sm_count = 0;
@@ -106,17 +143,24 @@ struct cdb_index {
     uint64_t n_allzero_rows = 0;   // degenerate rows (tensor_scan.cu): all-zero rows score NaN against every query = last
     uint64_t n_odd_rows = 0;       // other degenerate rows (norm 0/inf/NaN/out of range): ride on every candidate list
     uint32_t *h_flags = nullptr;   // pinned host staging (16 words)
-    uint64_t stat_tensor_searches = 0;
-    cudaStream_t stream = nullptr;
+    std::atomic<uint64_t> stat_tensor_searches{0};
+    cudaStream_t stream = nullptr; // ingest / build stream (exclusive operations)
     static constexpr int EV_RING = 64;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ring0[EV_RING] = {}, ring1[EV_RING] = {};  // per-search (before scan, after scan)
-    uint64_t n_search = 0;
-    bool ev_valid = false;
-    cudaStream_t last_stream = nullptr;  // stream of the previous search: scratch buffers are shared between searches
-    std::mutex mu;
-    DevBuf q_codes, q_mags, partial, err32, stage, io_ids, io_scores, io_counts, io_err, io_q, misc;
-    DevBuf qh, gthr, cand, cand_cnt, flags, progress, deg, qsel;
+    std::atomic<uint64_t> n_search{0};
+    // searches hold the lock shared, operations that change the index (append, graph upload / build) exclusively
+    std::shared_mutex rw;
+    // scratch pool: sets are created on demand (at most POOL_MAX), a search leases one for its duration
+    static constexpr size_t POOL_MAX = 4;
+    std::vector<std::unique_ptr<Scratch>> pool;
+    std::mutex pool_mu;
+    std::condition_variable pool_cv;
+    Scratch *last = nullptr;       // set of the most recently finished search (stats / timing queries)
+    DevBuf stage, deg;             // ingest staging; degenerate-row bookkeeping (read-only during searches)
+    // rows appended as codes into a keep_raw_f32 index have no raw f32 row yet (cold start from prop.data): searches that
+    // re-rank with raw rows are refused until cdb_index_set_raw_f32 / cdb_index_fill_raw_from_itoe supplied them
+    std::vector<bool> raw_have;
+    uint64_t raw_missing = 0;
     // HNSW graph (cdb_index_set_graph)
     bool has_graph = false;
     GraphDev graph{};
@@ -128,15 +172,41 @@ struct cdb_index {
     const int32_t *md_bits = nullptr;
     const float *md_mags = nullptr;
     uint32_t md_dims = 0, md_pseudo_entry = 0;
-    DevBuf hn_ids, hn_labels, flt_off, flt_dims, flt_has;
     std::vector<uint32_t> g_cnt;
     std::vector<const uint32_t *> g_nr, g_ad, g_ch;  // host copies of the per-level device pointers
-    DevBuf hn_rows, hn_scores, hn_n, hn_counters, qraw, qraw_mags, hn_prof;
+    DevBuf hn_counters, hn_prof;   // cumulative device counters (atomics: shared by concurrent searches)
     bool hn_prof_on = false;
-    // sharded searches (shard_group.cu): the final kernels also write the packed selection keys of every query here
-    // ([nq][k], 0 = empty slot) -- straight into the collective's send buffer.  cur_keys = the current chunk's slice.
-    uint64_t *keys_out = nullptr, *cur_keys = nullptr;
 };
+
+// a leased scratch set; returned to the pool (and remembered as "last") on destruction
+struct Lease {
+    cdb_index *ix = nullptr;
+    Scratch *sc = nullptr;
+    ~Lease() {
+        if (!sc) return;
+        std::lock_guard<std::mutex> g(ix->pool_mu);
+        sc->busy = false;
+        ix->last = sc;
+        ix->pool_cv.notify_one();
+    }
+};
+static cdb_status lease_scratch(cdb_index *ix, Lease &l) {
+    std::unique_lock<std::mutex> g(ix->pool_mu);
+    for (;;) {
+        for (auto &u : ix->pool)
+            if (!u->busy) { u->busy = true; l.ix = ix; l.sc = u.get(); return CDB_OK; }
+        if (ix->pool.size() < cdb_index::POOL_MAX) {
+            std::unique_ptr<Scratch> u(new Scratch());
+            cdb_status rc = u->init();
+            if (rc) { u->destroy(); return rc; }
+            u->busy = true;
+            l.ix = ix; l.sc = u.get();
+            ix->pool.push_back(std::move(u));
+            return CDB_OK;
+        }
+        ix->pool_cv.wait(g);
+    }
+}
 
 #define CDB_REQUIRE(cond, msg)                              \
     do {                                                    \
@@ -168,7 +238,7 @@ size_t cdb_code_bytes(int32_t st, uint32_t dim) { return host_code_bytes(st, dim
 
 cdb_status cdb_quantize_batch(int32_t device, int32_t st, float lo, float hi, const float *vecs, uint64_t n, uint32_t dim,
                               void *out_codes, float *out_mags) {
-    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_F32, "bad storage type");
+    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_LAST, "bad storage type");
     CDB_REQUIRE(dim > 0 && (vecs || !n) && (out_codes || !n) && (out_mags || !n), "bad arguments");
     CDB_CUDA_TRY(cudaSetDevice(device));
     const uint32_t pitch = row_pitch_bytes(st, dim);
@@ -250,7 +320,7 @@ cdb_status cdb_sample_values_range(int32_t device, const float *vecs, uint64_t n
 cdb_status cdb_distance_pairs(int32_t device, int32_t metric, int32_t st, uint32_t dim, const void *x_codes,
                               const float *x_mags, const void *y_codes, const float *y_mags, uint64_t n, float *out,
                               int32_t *out_status) {
-    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_F32 && metric >= 0 && metric <= 3 && dim > 0, "bad metric/storage/dim");
+    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_LAST && metric >= 0 && metric <= 3 && dim > 0, "bad metric/storage/dim");
     if (!n) return CDB_OK;
     CDB_REQUIRE(x_codes && y_codes && x_mags && y_mags && out && out_status, "null buffer");
     CDB_CUDA_TRY(cudaSetDevice(device));
@@ -281,7 +351,7 @@ done:
 
 cdb_status cdb_distance_pairs_md(int32_t device, int32_t metric, int32_t st, uint32_t dim, uint32_t M, const cdb_vector_data_batch *x,
                                  const cdb_vector_data_batch *y, uint64_t n, float *out, int32_t *out_status) {
-    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_F32 && metric >= 0 && metric <= 3 && dim > 0, "bad metric/storage/dim");
+    CDB_REQUIRE(st >= CDB_ST_U8 && st <= CDB_ST_LAST && metric >= 0 && metric <= 3 && dim > 0, "bad metric/storage/dim");
     CDB_REQUIRE(x && y, "null argument");
     if (!n) return CDB_OK;
     CDB_REQUIRE(x->codes && y->codes && x->mags && y->mags && out && out_status, "null buffer");
@@ -332,7 +402,7 @@ cdb_status cdb_distance_pairs_md(int32_t device, int32_t metric, int32_t st, uin
 
 cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
     CDB_REQUIRE(d && out, "null argument");
-    CDB_REQUIRE(d->dim > 0 && d->storage_type >= CDB_ST_U8 && d->storage_type <= CDB_ST_F32, "bad dim/storage type");
+    CDB_REQUIRE(d->dim > 0 && d->storage_type >= CDB_ST_U8 && d->storage_type <= CDB_ST_LAST, "bad dim/storage type");
     CDB_REQUIRE(d->metric >= CDB_METRIC_COSINE && d->metric <= CDB_METRIC_DOT_PRODUCT, "bad metric");
     CDB_REQUIRE(d->capacity > 0 && d->capacity < 0xFFFFFFFFull, "capacity must be in 1..2^32-2");
     CDB_CUDA_TRY(cudaSetDevice(d->device));
@@ -350,8 +420,6 @@ cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
     };
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
-    for (auto &ev : ix->ev)
-        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail(e, "event");
     for (int i = 0; i < cdb_index::EV_RING; ++i)
         if ((e = cudaEventCreate(&ix->ring0[i])) != cudaSuccess || (e = cudaEventCreate(&ix->ring1[i])) != cudaSuccess) return fail(e, "event");
     if ((e = cudaMalloc(&ix->d_codes, (size_t)d->capacity * ix->row_pitch)) != cudaSuccess) return fail(e, "cudaMalloc(codes)");
@@ -382,8 +450,6 @@ cdb_status cdb_index_create(const cdb_index_desc *d, cdb_index **out) {
         if ((e = cudaMemsetAsync(ix->d_digits, 0, (size_t)d->capacity * ix->digit_pitch, ix->stream)) != cudaSuccess) return fail(e, "memset");
     }
     if ((e = cudaMallocHost(&ix->h_flags, 64)) != cudaSuccess) return fail(e, "cudaMallocHost");
-    if (ix->flags.ensure(16) != CDB_OK) return fail(cudaErrorMemoryAllocation, "flags");
-    if ((e = cudaMemsetAsync(ix->flags.p, 0, 16, ix->stream)) != cudaSuccess) return fail(e, "memset");
     if (ix->deg.ensure(TS_DEG_WORDS * 4) != CDB_OK) return fail(cudaErrorMemoryAllocation, "deg");
     if ((e = cudaMemsetAsync(ix->deg.p, 0, TS_DEG_WORDS * 4, ix->stream)) != cudaSuccess) return fail(e, "memset");
     if ((e = cudaStreamSynchronize(ix->stream)) != cudaSuccess) return fail(e, "sync");
@@ -404,12 +470,9 @@ cdb_status cdb_index_destroy(cdb_index *ix) {
     for (void *g : ix->graph_allocs) cudaFree(g);
     for (void *g : ix->md_allocs) cudaFree(g);
     if (ix->h_flags) cudaFreeHost(ix->h_flags);
-    for (DevBuf *b : {&ix->q_codes, &ix->q_mags, &ix->partial, &ix->err32, &ix->stage, &ix->io_ids, &ix->io_scores,
-                      &ix->io_counts, &ix->io_err, &ix->io_q, &ix->misc, &ix->qh, &ix->gthr, &ix->cand, &ix->cand_cnt, &ix->flags, &ix->progress, &ix->deg, &ix->qsel, &ix->hn_rows, &ix->hn_scores, &ix->hn_n, &ix->hn_counters, &ix->hn_prof,
-                      &ix->qraw, &ix->qraw_mags, &ix->hn_ids, &ix->hn_labels, &ix->flt_off, &ix->flt_dims, &ix->flt_has})
-        b->release();
-    for (auto &ev : ix->ev)
-        if (ev) cudaEventDestroy(ev);
+    for (auto &u : ix->pool) u->destroy();
+    ix->pool.clear();
+    for (DevBuf *b : {&ix->stage, &ix->deg, &ix->hn_counters, &ix->hn_prof}) b->release();
     for (int i = 0; i < cdb_index::EV_RING; ++i) {
         if (ix->ring0[i]) cudaEventDestroy(ix->ring0[i]);
         if (ix->ring1[i]) cudaEventDestroy(ix->ring1[i]);
@@ -456,7 +519,7 @@ static cdb_status index_after_append(cdb_index *ix, uint64_t first, uint64_t n) 
 static cdb_status append_f32_locked(cdb_index *ix, const float *vecs, uint64_t n);
 cdb_status cdb_index_append_f32(cdb_index *ix, const float *vecs, uint64_t n) {
     CDB_REQUIRE(ix && (vecs || !n), "null argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     return append_f32_locked(ix, vecs, n);
 }
 static cdb_status append_f32_locked(cdb_index *ix, const float *vecs, uint64_t n) {
@@ -484,7 +547,7 @@ static cdb_status append_f32_locked(cdb_index *ix, const float *vecs, uint64_t n
 
 cdb_status cdb_index_append_f32_device(cdb_index *ix, const float *d_vecs, uint64_t n) {
     CDB_REQUIRE(ix && (d_vecs || !n), "null argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     if (!n) return CDB_OK;
@@ -502,22 +565,67 @@ cdb_status cdb_index_append_f32_device(cdb_index *ix, const float *d_vecs, uint6
 
 cdb_status cdb_index_append_codes(cdb_index *ix, const void *codes, const float *mags, uint64_t n) {
     CDB_REQUIRE(ix && ((codes && mags) || !n), "null argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
-    CDB_REQUIRE(!ix->raw_owned, "append_codes cannot populate raw f32 rows (keep_raw_f32 index)");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     cdb_status rc = copy_codes(ix->d_codes + ix->size * ix->row_pitch, codes, ix->desc.storage_type, ix->desc.dim, n, true, ix->stream);
     if (rc) return rc;
     CDB_CUDA_TRY(cudaMemcpyAsync(ix->d_mags + ix->size, mags, n * 4, cudaMemcpyHostToDevice, ix->stream));
-    if ((rc = index_after_append(ix, ix->size, n))) return rc;
+    if (ix->raw_owned) {
+        // keep_raw_f32 index: the raw rows arrive later (cdb_index_set_raw_f32 / cdb_index_fill_raw_from_itoe); until then the
+        // rows stay zero and are counted as missing.  Digits are derived from the codes and can be built now.
+        if (ix->d_digits && (rc = unpack_digits_device(ix->d_codes + ix->size * ix->row_pitch, ix->row_pitch, n, ix->desc.dim,
+                                                       ix->desc.storage_type, ix->d_digits + ix->size * ix->digit_pitch, ix->digit_pitch, ix->stream)))
+            return rc;
+        if (ix->raw_have.size() < ix->size) ix->raw_have.resize(ix->size, true);
+        ix->raw_have.resize(ix->size + n, false);
+        ix->raw_missing += n;
+    } else if ((rc = index_after_append(ix, ix->size, n))) {
+        return rc;
+    }
     CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
     ix->size += n;
     return CDB_OK;
 }
 
+cdb_status cdb_index_set_raw_f32(cdb_index *ix, uint64_t first_row, const float *vecs, uint64_t n) {
+    CDB_REQUIRE(ix && (vecs || !n), "null argument");
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
+    CDB_REQUIRE(ix->raw_owned, "the index keeps no separate raw f32 rows (F32 storage or keep_raw_f32 = 0)");
+    CDB_REQUIRE(first_row + n <= ix->size, "row range out of bounds");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    const uint32_t dim = ix->desc.dim;
+    const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / ((size_t)dim * 4));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t m = std::min(chunk, n - off), first = first_row + off;
+        CDB_CUDA_TRY(cudaMemcpy2DAsync(ix->d_raw + first * ix->raw_pitch_elems, (size_t)ix->raw_pitch_elems * 4, vecs + off * dim,
+                                       (size_t)dim * 4, (size_t)dim * 4, m, cudaMemcpyHostToDevice, ix->stream));
+        cdb_status rc;
+        if (ix->raw_mags_owned &&
+            (rc = raw_mags_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, m, dim, ix->d_raw_mags + first, ix->stream)))
+            return rc;
+        if (ix->d_xh) {
+            if ((rc = normalize_f16_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, ix->d_raw_mags + first, m, dim,
+                                           (uint8_t *)ix->d_xh + first * ix->xh_pitch * 2, ix->xh_pitch, ix->stream)) ||
+                (rc = classify_rows_device(ix->d_raw + first * ix->raw_pitch_elems, ix->raw_pitch_elems, ix->d_raw_mags + first, m, dim,
+                                           (uint32_t)first, ix->deg.as<uint32_t>(), ix->stream)))
+                return rc;
+            CDB_CUDA_TRY(cudaMemcpyAsync(ix->h_flags + 4, ix->deg.p, 8, cudaMemcpyDeviceToHost, ix->stream));
+        }
+        CDB_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        if (ix->d_xh) { ix->n_allzero_rows = ix->h_flags[4]; ix->n_odd_rows = ix->h_flags[5]; }
+    }
+    if (ix->raw_have.size() < ix->size) ix->raw_have.resize(ix->size, true);
+    for (uint64_t r = first_row; r < first_row + n; ++r)
+        if (!ix->raw_have[r]) { ix->raw_have[r] = true; --ix->raw_missing; }
+    return CDB_OK;
+}
+
+uint64_t cdb_index_raw_missing(const cdb_index *ix) { return ix ? ix->raw_missing : 0; }
+
 cdb_status cdb_index_append_synthetic(cdb_index *ix, uint64_t seed, uint64_t first_row, uint64_t n) {
     CDB_REQUIRE(ix, "null index");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(ix->size + n <= ix->desc.capacity, "append exceeds capacity");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     uint64_t first = ix->size;
@@ -546,10 +654,10 @@ cdb_status cdb_index_read_codes(const cdb_index *ix, uint64_t first, uint64_t n,
 
 // ------------------------------------------------------------------ S1 search
 
-// prepared (quantized) queries live in ix->q_codes / ix->q_mags.
+// prepared (quantized) queries live in sc->q_codes / sc->q_mags.
 // qsel == null: unconditional scan of the whole batch.  Otherwise the device decides (ScanArgs): a selective scan of the
 // <= SCAN_SEL_CAP queries the tensor-core path could not answer, or -- if there are more -- the whole batch again.
-static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric, uint32_t pitch, uint32_t nq, uint32_t k,
+static cdb_status exact_scan_locked(cdb_index *ix, Scratch *sc, bool raw, int st, int metric, uint32_t pitch, uint32_t nq, uint32_t k,
                                     uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s,
                                     const uint32_t *qsel = nullptr) {
     const cdb_index_desc &d = ix->desc;
@@ -563,8 +671,8 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
     a.st = st;
     a.metric = metric;
     a.raw_mode = raw ? 1 : 0;
-    a.q = ix->q_codes.as<uint8_t>();
-    a.qmags = ix->q_mags.as<float>();
+    a.q = sc->q_codes.as<uint8_t>();
+    a.qmags = sc->q_mags.as<float>();
     a.nq = nq;
     a.k = k;
     a.id_base = d.id_base;
@@ -573,21 +681,21 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
     a.sel_cap = SCAN_SEL_CAP;
     a.sel_grid = scan_sel_grid(ix->sm_count, k);
     const size_t part_full = (size_t)nq * a.nsplit * k * 8, part_sel = qsel ? (size_t)SCAN_SEL_CAP * a.sel_grid * k * 8 : 0;
-    if ((rc = ix->partial.ensure(std::max(part_full, part_sel))) || (rc = ix->err32.ensure((size_t)nq * 4))) return rc;
-    a.partial = ix->partial.as<uint64_t>();
-    a.err32 = ix->err32.as<uint32_t>();
+    if ((rc = sc->partial.ensure(std::max(part_full, part_sel))) || (rc = sc->err32.ensure((size_t)nq * 4))) return rc;
+    a.partial = sc->partial.as<uint64_t>();
+    a.err32 = sc->err32.as<uint32_t>();
     if (!qsel) CDB_CUDA_TRY(cudaMemsetAsync(a.err32, 0, (size_t)nq * 4, s));   // the tensor-core path prepared it otherwise
     if (qsel) {
         a.sel_mode = 1;
         if ((rc = scan_topk_device(a, s))) return rc;
         if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 1,
-                                        a.sel_grid, scan_sel_qb(a), ix->cur_keys)))
+                                        a.sel_grid, scan_sel_qb(a), sc->cur_keys)))
             return rc;
         a.sel_mode = 0;
     }
     if ((rc = scan_topk_device(a, s))) return rc;
     if ((rc = merge_partials_device(metric, a.partial, nq, a.nsplit, k, d_ids, d_scores, d_counts, s, qsel, a.sel_cap, 0, 0, 0,
-                                    ix->cur_keys)))
+                                    sc->cur_keys)))
         return rc;
     if (d_err) {
         err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq, qsel);
@@ -598,13 +706,14 @@ static cdb_status exact_scan_locked(cdb_index *ix, bool raw, int st, int metric,
 
 // search_internal (hnsw/mod.rs:390-440): quantized ann_search on the uploaded graph, then
 // remove_duplicates_and_filter and the exact f32 re-rank of finalize_ann_results.
-static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+static cdb_status hnsw_search_locked(cdb_index *ix, Scratch *sc, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                      uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s,
                                      const uint32_t *d_foff = nullptr, const int8_t *d_fdims = nullptr, const uint8_t *d_fhas = nullptr) {
     const cdb_index_desc &d = ix->desc;
     CDB_REQUIRE(ix->has_graph, "CDB_MODE_HNSW needs cdb_index_set_graph");
     CDB_REQUIRE(ix->has_md || !d_fhas, "metadata filters need cdb_index_set_graph_metadata");
     CDB_REQUIRE(ix->d_raw, "HNSW search re-ranks with raw f32 rows (F32 storage or keep_raw_f32)");
+    CDB_REQUIRE(ix->raw_missing == 0, "rows appended as codes still lack their raw f32 rows (cdb_index_set_raw_f32 / cdb_index_fill_raw_from_itoe)");
     CDB_REQUIRE(p->shortlist_size >= 1 && p->shortlist_size <= 64, "shortlist_size must be in 1..64");
     CDB_REQUIRE(p->ef_search >= 1 && p->ef_search <= 4096, "ef_search must be in 1..4096");
     cdb_status rc;
@@ -615,25 +724,25 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
     const uint32_t out_cap = (ix->graph.num_levels + 1) * 100;
     const uint32_t k5 = 5 * p->k;
     const uint32_t rpitch = ix->raw_pitch_elems * 4;
-    if ((rc = ix->q_codes.ensure((size_t)nq * ix->row_pitch)) || (rc = ix->q_mags.ensure((size_t)nq * 4)) ||
-        (rc = ix->qraw.ensure((size_t)nq * rpitch)) || (rc = ix->qraw_mags.ensure((size_t)nq * 4)) ||
-        (rc = ix->hn_rows.ensure((size_t)nq * out_cap * 4)) || (rc = ix->hn_scores.ensure((size_t)nq * out_cap * 4)) ||
-        (rc = ix->hn_n.ensure((size_t)nq * 4)) || (rc = ix->err32.ensure((size_t)nq * 4)) ||
-        (rc = ix->cand.ensure((size_t)nq * k5 * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)))
+    if ((rc = sc->q_codes.ensure((size_t)nq * ix->row_pitch)) || (rc = sc->q_mags.ensure((size_t)nq * 4)) ||
+        (rc = sc->qraw.ensure((size_t)nq * rpitch)) || (rc = sc->qraw_mags.ensure((size_t)nq * 4)) ||
+        (rc = sc->hn_rows.ensure((size_t)nq * out_cap * 4)) || (rc = sc->hn_scores.ensure((size_t)nq * out_cap * 4)) ||
+        (rc = sc->hn_n.ensure((size_t)nq * 4)) || (rc = sc->err32.ensure((size_t)nq * 4)) ||
+        (rc = sc->cand.ensure((size_t)nq * k5 * 4)) || (rc = sc->cand_cnt.ensure((size_t)nq * 4)))
         return rc;
-    if (ix->has_md && ((rc = ix->hn_ids.ensure((size_t)nq * out_cap * 4)) || (rc = ix->hn_labels.ensure((size_t)nq * k5 * 4)))) return rc;
+    if (ix->has_md && ((rc = sc->hn_ids.ensure((size_t)nq * out_cap * 4)) || (rc = sc->hn_labels.ensure((size_t)nq * k5 * 4)))) return rc;
     if (!ix->hn_counters.p) {
         if ((rc = ix->hn_counters.ensure(16))) return rc;
         CDB_CUDA_TRY(cudaMemsetAsync(ix->hn_counters.p, 0, 16, s));
     }
-    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)nq * ix->row_pitch, s));
-    CDB_CUDA_TRY(cudaMemsetAsync(ix->qraw.p, 0, (size_t)nq * rpitch, s));
-    CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(sc->q_codes.p, 0, (size_t)nq * ix->row_pitch, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(sc->qraw.p, 0, (size_t)nq * rpitch, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(sc->err32.p, 0, (size_t)nq * 4, s));
     // the query is quantized like a stored vector (hnsw/mod.rs:399-403); the re-rank uses the raw query
-    if ((rc = quantize_rows_device(d_queries, nq, d.dim, d.storage_type, d.range_lo, d.range_hi, ix->q_codes.as<uint8_t>(),
-                                   ix->row_pitch, ix->q_mags.as<float>(), nullptr, 0, s)) ||
-        (rc = quantize_rows_device(d_queries, nq, d.dim, CDB_ST_F32, 0.f, 0.f, ix->qraw.as<uint8_t>(), rpitch,
-                                   ix->qraw_mags.as<float>(), nullptr, 0, s)))
+    if ((rc = quantize_rows_device(d_queries, nq, d.dim, d.storage_type, d.range_lo, d.range_hi, sc->q_codes.as<uint8_t>(),
+                                   ix->row_pitch, sc->q_mags.as<float>(), nullptr, 0, s)) ||
+        (rc = quantize_rows_device(d_queries, nq, d.dim, CDB_ST_F32, 0.f, 0.f, sc->qraw.as<uint8_t>(), rpitch,
+                                   sc->qraw_mags.as<float>(), nullptr, 0, s)))
         return rc;
     HnswArgs a{};
     a.g = ix->graph;
@@ -643,20 +752,19 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
     a.dim = d.dim;
     a.st = d.storage_type;
     a.metric = d.metric;
-    a.q = ix->q_codes.as<uint8_t>();
-    a.qmags = ix->q_mags.as<float>();
+    a.q = sc->q_codes.as<uint8_t>();
+    a.qmags = sc->q_mags.as<float>();
     a.nq = nq;
     a.ef = p->ef_search;
     a.shortlist = p->shortlist_size;
     a.out_cap = out_cap;
-    a.out_rows = ix->hn_rows.as<uint32_t>();
-    a.out_scores = ix->hn_scores.as<float>();
-    a.out_n = ix->hn_n.as<uint32_t>();
-    a.err32 = ix->err32.as<uint32_t>();
+    a.out_rows = sc->hn_rows.as<uint32_t>();
+    a.out_scores = sc->hn_scores.as<float>();
+    a.out_n = sc->hn_n.as<uint32_t>();
+    a.err32 = sc->err32.as<uint32_t>();
     a.counters = ix->hn_counters.as<unsigned long long>();
-    const int slot = (int)(ix->n_search % cdb_index::EV_RING);
-    ix->n_search++;
-    CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
+    const int slot = (int)(ix->n_search.fetch_add(1) % cdb_index::EV_RING);
+    CDB_CUDA_TRY(cudaEventRecord(sc->ev[0], s));
     CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
     if (ix->has_md) {
         // graph with replica nodes: metadata-aware traversal (hnsw_md.cu); results carry replica ids, the re-rank scores
@@ -672,16 +780,16 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
         ma.filter_offsets = d_foff;
         ma.filter_dims = d_fdims;
         ma.has_filter = d_fhas;
-        ma.out_ids = ix->hn_ids.as<uint32_t>();
+        ma.out_ids = sc->hn_ids.as<uint32_t>();
         if ((rc = hnsw_search_md_device(ma, s))) return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = hnsw_dedup_md_device(ma.out_ids, a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, d.id_base, k5, nq,
-                                       ix->cand.as<uint32_t>(), ix->hn_labels.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
+                                       sc->cand.as<uint32_t>(), sc->hn_labels.as<uint32_t>(), sc->cand_cnt.as<uint32_t>(), s)))
             return rc;
-        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
-                                    ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
-                                    ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s,
-                                    ix->hn_labels.as<uint32_t>(), ix->cur_keys)))
+        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, sc->qraw.as<float>(),
+                                    ix->raw_pitch_elems, sc->qraw_mags.as<float>(), nq, sc->cand.as<uint32_t>(),
+                                    sc->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s,
+                                    sc->hn_labels.as<uint32_t>(), sc->cur_keys)))
             return rc;
     } else {
         // one warp per query (hnsw_warp.cu); CDB_HNSW_F_CTA selects the round-1 CTA-per-query kernel for A/B measurements
@@ -690,21 +798,21 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
         if ((rc = (a.flags & CDB_HNSW_F_CTA) ? hnsw_search_device(a, s) : hnsw_search_warp_device(a, s))) return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
         if ((rc = hnsw_dedup_device(a.out_rows, a.out_scores, a.out_n, out_cap, d.metric, ix->graph.root_row, d.id_base, k5, nq,
-                                    ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), s)))
+                                    sc->cand.as<uint32_t>(), sc->cand_cnt.as<uint32_t>(), s)))
             return rc;
-        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->qraw.as<float>(),
-                                    ix->raw_pitch_elems, ix->qraw_mags.as<float>(), nq, ix->cand.as<uint32_t>(),
-                                    ix->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s, nullptr,
-                                    ix->cur_keys)))
+        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, sc->qraw.as<float>(),
+                                    ix->raw_pitch_elems, sc->qraw_mags.as<float>(), nq, sc->cand.as<uint32_t>(),
+                                    sc->cand_cnt.as<uint32_t>(), k5, p->k, d.id_base, d_ids, d_scores, d_counts, s, nullptr,
+                                    sc->cur_keys)))
             return rc;
     }
     if (d_err) {
         err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(a.err32, d_err, nq);
         CDB_LAUNCH_CHECK();
     }
-    CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
-    CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
-    ix->ev_valid = true;
+    CDB_CUDA_TRY(cudaEventRecord(sc->ev[1], s));
+    CDB_CUDA_TRY(cudaEventRecord(sc->ev[2], s));
+    sc->ev_valid = true;
     return CDB_OK;
 }
 
@@ -712,19 +820,20 @@ static cdb_status hnsw_search_locked(cdb_index *ix, const float *d_queries, uint
 // (two fp16 roundings, fp32 tensor accumulation, f32 norms)
 static float prefilter_eps(uint32_t dim) { return 1.0e-3f + 8.0e-7f * (float)dim; }
 
-static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+static cdb_status search_chunk_locked(cdb_index *ix, Scratch *sc, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                       uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
     const cdb_index_desc &d = ix->desc;
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
     if (nq == 0) return CDB_OK;
     cdb_status rc;
-    if (p->mode == CDB_MODE_HNSW) return hnsw_search_locked(ix, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
+    if (p->mode == CDB_MODE_HNSW) return hnsw_search_locked(ix, sc, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
     if (p->mode != CDB_MODE_BRUTE_RAW && p->mode != CDB_MODE_BRUTE_CODES) {
         set_error("unknown search mode");
         return CDB_INVALID_PARAMS;
     }
     const bool raw = p->mode == CDB_MODE_BRUTE_RAW;
     if (raw) CDB_REQUIRE(ix->d_raw, "BRUTE_RAW needs raw f32 rows (F32 storage or keep_raw_f32)");
+    if (raw) CDB_REQUIRE(ix->raw_missing == 0, "rows appended as codes still lack their raw f32 rows (cdb_index_set_raw_f32 / cdb_index_fill_raw_from_itoe)");
     const int st = raw ? CDB_ST_F32 : d.storage_type;
     const int metric = raw ? CDB_METRIC_COSINE : d.metric;
     if (!raw && (rc = arm_status(metric, st)) != CDB_OK) {
@@ -732,56 +841,55 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
         return rc;
     }
     const uint32_t pitch = raw ? ix->raw_pitch_elems * 4 : ix->row_pitch;
-    // search_internal: quantize the query with the index's storage type and range (hnsw/mod.rs:399-403);
-    // raw mode keeps f32 and |q| = sequential fold (vector_store.rs:412)
-    if ((rc = ix->q_codes.ensure((size_t)nq * pitch)) || (rc = ix->q_mags.ensure((size_t)nq * 4))) return rc;
-    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)nq * pitch, s));
-    if ((rc = quantize_rows_device(d_queries, nq, d.dim, st, d.range_lo, d.range_hi, ix->q_codes.as<uint8_t>(), pitch,
-                                   ix->q_mags.as<float>(), nullptr, 0, s)))
-        return rc;
-    const int slot = (int)(ix->n_search % cdb_index::EV_RING);
-    ix->n_search++;
-    CDB_CUDA_TRY(cudaEventRecord(ix->ev[0], s));
-
     // ---- tcgen05 prefilter + exact re-rank: identical results, far fewer exact dot products.
     // Needs k proper (non-degenerate) rows for the bound to exist, and few enough odd degenerate rows to carry them on
     // every candidate list (tensor_scan.cu).
     const bool tensor_ok = raw && ix->d_xh && !p->exact_only && nq >= 4 && ix->size >= 16384 && p->k <= 64 &&
                            ix->n_odd_rows <= TS_MAX_ODD && ix->size - ix->n_allzero_rows - ix->n_odd_rows >= p->k &&
                            tensor_scan_smem_bytes(p->k) <= 227 * 1024 && (nq + 127) / 128 <= (uint32_t)ix->sm_count;
+    // search_internal: quantize the query with the index's storage type and range (hnsw/mod.rs:399-403);
+    // raw mode keeps f32 and |q| = sequential fold (vector_store.rs:412)
+    if ((rc = sc->q_codes.ensure((size_t)nq * pitch)) || (rc = sc->q_mags.ensure((size_t)nq * 4))) return rc;
+    if (!tensor_ok) {   // (the prefilter path prepares its queries in one fused launch below)
+        CDB_CUDA_TRY(cudaMemsetAsync(sc->q_codes.p, 0, (size_t)nq * pitch, s));
+        if ((rc = quantize_rows_device(d_queries, nq, d.dim, st, d.range_lo, d.range_hi, sc->q_codes.as<uint8_t>(), pitch,
+                                       sc->q_mags.as<float>(), nullptr, 0, s)))
+            return rc;
+    }
+    const int slot = (int)(ix->n_search.fetch_add(1) % cdb_index::EV_RING);
+    CDB_CUDA_TRY(cudaEventRecord(sc->ev[0], s));
+
     const uint32_t *qsel = nullptr;
     if (tensor_ok) {
         const uint32_t mt = (nq + 127) / 128;
         // candidate slots per query (<= 64 MB in total): long lists only arise for few queries, and a query whose list
         // overflows is re-done alone by the selective exact scan
         const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 32768u : (nq <= 1024 ? 16384u : 8192u));
-        if ((rc = ix->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = ix->gthr.ensure((size_t)mt * 128 * 64 * 4)) ||
-            (rc = ix->cand.ensure((size_t)nq * cap * 4)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) ||
-            (rc = ix->progress.ensure(4096)) || (rc = ix->qsel.ensure((size_t)(nq + 1) * 4)))
+        if ((rc = sc->qh.ensure((size_t)mt * 128 * ix->xh_pitch * 2)) || (rc = sc->gthr.ensure((size_t)mt * 128 * 64 * 4)) ||
+            (rc = sc->cand.ensure((size_t)nq * cap * 4)) || (rc = sc->cand_cnt.ensure((size_t)nq * 4)) ||
+            (rc = sc->progress.ensure(8192)) || (rc = sc->qsel.ensure((size_t)(nq + 1) * 4)) || (rc = sc->err32.ensure((size_t)nq * 4)))
             return rc;
-        uint32_t *flags = ix->flags.as<uint32_t>();  // [0] queries of the last search that needed the exact scan, [3] searches with a fallback
-        CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * ix->xh_pitch * 2, s));
-        if ((rc = normalize_f16_device(ix->q_codes.as<float>(), pitch / 4, ix->q_mags.as<float>(), nq, d.dim, ix->qh.p,
-                                       ix->xh_pitch, s)))
+        uint32_t *flags = sc->flags.as<uint32_t>();  // [0] queries of the last search that needed the exact scan, [3] searches with a fallback
+        const bool has_deg = ix->n_allzero_rows + ix->n_odd_rows > 0;
+        if ((rc = prep_queries_device(d_queries, nq, d.dim, sc->q_codes.as<float>(), pitch / 4, sc->q_mags.as<float>(), sc->qh.p,
+                                      ix->xh_pitch, sc->gthr.as<int>(), ix->deg.as<uint32_t>(), has_deg, d.id_base,
+                                      sc->cand.as<uint32_t>(), cap, sc->cand_cnt.as<uint32_t>(), sc->err32.as<uint32_t>(), d_err,
+                                      sc->progress.as<uint32_t>(), s)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-        const bool has_deg = ix->n_allzero_rows + ix->n_odd_rows > 0;
-        if ((rc = tensor_scan_device(ix->d_xh, ix->qh.p, ix->xh_pitch, ix->size, nq, d.dim, p->k, 2.0f * prefilter_eps(d.dim),
-                                     d.id_base, ix->gthr.as<int>(), ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(), cap,
-                                     ix->progress.as<uint32_t>(), ix->deg.as<uint32_t>(), has_deg, ix->sm_count, s)))
+        if ((rc = tensor_scan_device(ix->d_xh, sc->qh.p, ix->xh_pitch, ix->size, nq, d.dim, p->k, 2.0f * prefilter_eps(d.dim),
+                                     d.id_base, sc->gthr.as<int>(), sc->cand.as<uint32_t>(), sc->cand_cnt.as<uint32_t>(), cap,
+                                     sc->progress.as<uint32_t>(), ix->deg.as<uint32_t>(), has_deg, ix->sm_count, s, /*prepared=*/true)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
-        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(),
-                                    pitch / 4, ix->q_mags.as<float>(), nq, ix->cand.as<uint32_t>(), ix->cand_cnt.as<uint32_t>(),
-                                    cap, p->k, d.id_base, d_ids, d_scores, d_counts, s, nullptr, ix->cur_keys)))
+        if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, sc->q_codes.as<float>(),
+                                    pitch / 4, sc->q_mags.as<float>(), nq, sc->cand.as<uint32_t>(), sc->cand_cnt.as<uint32_t>(),
+                                    cap, p->k, d.id_base, d_ids, d_scores, d_counts, s, nullptr, sc->cur_keys)))
             return rc;
-        if ((rc = select_fallback_device(ix->cand_cnt.as<uint32_t>(), cap, ix->q_mags.as<float>(), nq, ix->qsel.as<uint32_t>(), flags, s)))
+        if ((rc = select_fallback_device(sc->cand_cnt.as<uint32_t>(), cap, sc->q_mags.as<float>(), nq, sc->qsel.as<uint32_t>(), flags, s)))
             return rc;
-        if ((rc = ix->err32.ensure((size_t)nq * 4))) return rc;
-        CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
-        if (d_err) CDB_CUDA_TRY(cudaMemsetAsync(d_err, 0, nq, s));
         ix->stat_tensor_searches++;
-        qsel = ix->qsel.as<uint32_t>();  // the exact scan below only runs (on the device's own decision) for the queries listed there
+        qsel = sc->qsel.as<uint32_t>();  // the exact scan below only runs (on the device's own decision) for the queries listed there
     }
     // ---- exact integer scoring on tcgen05 kind::i8: u8 codes in place, sub-byte codes through the digit copy
     const uint8_t *u8_rows = !raw ? (st == CDB_ST_U8 ? ix->d_codes : ix->d_digits) : nullptr;
@@ -792,60 +900,60 @@ static cdb_status search_chunk_locked(cdb_index *ix, const float *d_queries, uin
         const uint32_t mt = (nq + 127) / 128;
         const uint32_t upitch = st == CDB_ST_U8 ? ix->row_pitch : ix->digit_pitch;
         const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 4096u : 2048u));
-        if ((rc = ix->qh.ensure((size_t)mt * 128 * upitch)) || (rc = ix->gthr.ensure((size_t)nq * 4)) ||
-            (rc = ix->cand.ensure((size_t)nq * cap * 8)) || (rc = ix->cand_cnt.ensure((size_t)nq * 4)) ||
-            (rc = ix->progress.ensure(4096)) || (rc = ix->err32.ensure((size_t)nq * 4)))
+        if ((rc = sc->qh.ensure((size_t)mt * 128 * upitch)) || (rc = sc->gthr.ensure((size_t)nq * 4)) ||
+            (rc = sc->cand.ensure((size_t)nq * cap * 8)) || (rc = sc->cand_cnt.ensure((size_t)nq * 4)) ||
+            (rc = sc->progress.ensure(4096)) || (rc = sc->err32.ensure((size_t)nq * 4)))
             return rc;
-        if ((rc = ix->qsel.ensure((size_t)(nq + 1) * 4))) return rc;
-        uint32_t *flags = ix->flags.as<uint32_t>();
-        CDB_CUDA_TRY(cudaMemsetAsync(ix->err32.p, 0, (size_t)nq * 4, s));
-        CDB_CUDA_TRY(cudaMemsetAsync(ix->qh.p, 0, (size_t)mt * 128 * upitch, s));
+        if ((rc = sc->qsel.ensure((size_t)(nq + 1) * 4))) return rc;
+        uint32_t *flags = sc->flags.as<uint32_t>();
+        CDB_CUDA_TRY(cudaMemsetAsync(sc->err32.p, 0, (size_t)nq * 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(sc->qh.p, 0, (size_t)mt * 128 * upitch, s));
         if (st == CDB_ST_U8)
-            CDB_CUDA_TRY(cudaMemcpyAsync(ix->qh.p, ix->q_codes.p, (size_t)nq * upitch, cudaMemcpyDeviceToDevice, s));
-        else if ((rc = unpack_digits_device(ix->q_codes.as<uint8_t>(), pitch, nq, d.dim, st, ix->qh.as<uint8_t>(), upitch, s)))
+            CDB_CUDA_TRY(cudaMemcpyAsync(sc->qh.p, sc->q_codes.p, (size_t)nq * upitch, cudaMemcpyDeviceToDevice, s));
+        else if ((rc = unpack_digits_device(sc->q_codes.as<uint8_t>(), pitch, nq, d.dim, st, sc->qh.as<uint8_t>(), upitch, s)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-        if ((rc = tensor_u8_scan_device(u8_rows, ix->qh.as<uint8_t>(), upitch, ix->size, nq, d.dim, p->k, metric, ix->d_mags,
-                                        ix->q_mags.as<float>(), d.id_base, ix->gthr.as<int>(), ix->cand.as<uint64_t>(),
-                                        ix->cand_cnt.as<uint32_t>(), cap, ix->err32.as<uint32_t>(), ix->progress.as<uint32_t>(),
-                                        d_ids, d_scores, d_counts, ix->sm_count, s, ix->cur_keys)))
+        if ((rc = tensor_u8_scan_device(u8_rows, sc->qh.as<uint8_t>(), upitch, ix->size, nq, d.dim, p->k, metric, ix->d_mags,
+                                        sc->q_mags.as<float>(), d.id_base, sc->gthr.as<int>(), sc->cand.as<uint64_t>(),
+                                        sc->cand_cnt.as<uint32_t>(), cap, sc->err32.as<uint32_t>(), sc->progress.as<uint32_t>(),
+                                        d_ids, d_scores, d_counts, ix->sm_count, s, sc->cur_keys)))
             return rc;
         CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
-        if ((rc = select_fallback_device(ix->cand_cnt.as<uint32_t>(), cap, nullptr, nq, ix->qsel.as<uint32_t>(), flags, s))) return rc;
+        if ((rc = select_fallback_device(sc->cand_cnt.as<uint32_t>(), cap, nullptr, nq, sc->qsel.as<uint32_t>(), flags, s))) return rc;
         if (d_err) {
-            err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(ix->err32.as<uint32_t>(), d_err, nq);
+            err32_to_u8_kernel<<<(nq + 255) / 256, 256, 0, s>>>(sc->err32.as<uint32_t>(), d_err, nq);
             CDB_LAUNCH_CHECK();
         }
         ix->stat_tensor_searches++;
-        qsel = ix->qsel.as<uint32_t>();
+        qsel = sc->qsel.as<uint32_t>();
     }
     {
         // exact scan: unconditional when no tensor-core path applies, otherwise a device-side conditional fallback
         // (its kernels return immediately unless qsel lists queries the tensor-core path could not answer) -- no host sync
         const bool fast = qsel != nullptr;
         if (!fast) CDB_CUDA_TRY(cudaEventRecord(ix->ring0[slot], s));
-        if ((rc = exact_scan_locked(ix, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s, qsel))) return rc;
+        if ((rc = exact_scan_locked(ix, sc, raw, st, metric, pitch, nq, p->k, d_ids, d_scores, d_counts, d_err, s, qsel))) return rc;
         if (!fast) CDB_CUDA_TRY(cudaEventRecord(ix->ring1[slot], s));
     }
-    CDB_CUDA_TRY(cudaEventRecord(ix->ev[1], s));
-    CDB_CUDA_TRY(cudaEventRecord(ix->ev[2], s));
-    ix->ev_valid = true;
+    CDB_CUDA_TRY(cudaEventRecord(sc->ev[1], s));
+    CDB_CUDA_TRY(cudaEventRecord(sc->ev[2], s));
+    sc->ev_valid = true;
     return CDB_OK;
 }
 
 // Batches are processed in chunks of <= 2048 queries (16 query tiles of 128): 148 SMs then split into 9 whole
 // CTA groups (144 CTAs) for the tensor-core kernels, and per-chunk scratch stays bounded.
-static cdb_status search_device_locked(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
+static cdb_status search_device_locked(cdb_index *ix, Scratch *sc, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                        uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, cudaStream_t s) {
     // the handle's scratch arena is reused by every search: a search enqueued on a different stream than the previous
     // one must wait for it (stream-ordered hand-over, no host sync)
-    if (ix->ev_valid && ix->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, ix->ev[2], 0));
-    ix->last_stream = s;
+    if (sc->ev_valid && sc->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[2], 0));
+    sc->last_stream = s;
     const uint32_t CH = 2048;
     for (uint32_t off = 0; off < nq; off += CH) {
         const uint32_t m = nq - off < CH ? nq - off : CH;
-        ix->cur_keys = ix->keys_out ? ix->keys_out + (size_t)off * p->k : nullptr;
-        cdb_status rc = search_chunk_locked(ix, d_queries + (size_t)off * ix->desc.dim, m, p, d_ids + (size_t)off * p->k,
+        sc->cur_keys = sc->keys_out ? sc->keys_out + (size_t)off * p->k : nullptr;
+        cdb_status rc = search_chunk_locked(ix, sc, d_queries + (size_t)off * ix->desc.dim, m, p, d_ids + (size_t)off * p->k,
                                             d_scores + (size_t)off * p->k, d_counts + off, d_err ? d_err + off : nullptr, s);
         if (rc) return rc;
     }
@@ -857,12 +965,16 @@ namespace cdb {
 // shard_group.cu: search one shard with device buffers on `s`; d_keys ([nq][k], may be null) receives the packed keys
 cdb_status index_search_device_keys(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p, uint32_t *d_ids,
                                     float *d_scores, uint32_t *d_counts, uint8_t *d_err, uint64_t *d_keys, cudaStream_t s) {
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::shared_lock<std::shared_mutex> lock(ix->rw);
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
-    ix->keys_out = d_keys;
-    const cdb_status rc = search_device_locked(ix, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
-    ix->keys_out = ix->cur_keys = nullptr;
+    Lease l;
+    cdb_status rc = lease_scratch(ix, l);
+    if (rc) return rc;
+    Scratch *sc = l.sc;
+    sc->keys_out = d_keys;
+    rc = search_device_locked(ix, sc, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s ? s : sc->stream);
+    sc->keys_out = sc->cur_keys = nullptr;
     return rc;
 }
 int index_device(const cdb_index *ix) { return ix->desc.device; }
@@ -874,38 +986,46 @@ extern "C" {
 cdb_status cdb_search_batch_device(cdb_index *ix, const float *d_queries, uint32_t nq, const cdb_search_params *p,
                                    uint32_t *d_ids, float *d_scores, uint32_t *d_counts, uint8_t *d_err, void *stream) {
     CDB_REQUIRE(ix && p && (d_queries || !nq) && (d_ids || !nq) && (d_scores || !nq), "null argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::shared_lock<std::shared_mutex> lock(ix->rw);
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
-    cdb_status rc;
+    Lease l;
+    cdb_status rc = lease_scratch(ix, l);
+    if (rc) return rc;
+    Scratch *sc = l.sc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : sc->stream;
     if (!d_counts) {
-        if ((rc = ix->io_counts.ensure((size_t)nq * 4))) return rc;
-        d_counts = ix->io_counts.as<uint32_t>();
+        if ((rc = sc->io_counts.ensure((size_t)nq * 4))) return rc;
+        d_counts = sc->io_counts.as<uint32_t>();
     }
-    return search_device_locked(ix, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
+    // asynchronous: the set goes back to the pool when this call returns; the next search that leases it orders itself
+    // behind this one on the device (event hand-over in search_device_locked)
+    return search_device_locked(ix, sc, d_queries, nq, p, d_ids, d_scores, d_counts, d_err, s);
 }
 
 cdb_status cdb_search_batch(cdb_index *ix, const float *queries, uint32_t nq, const cdb_search_params *p, uint32_t *out_ids,
                             float *out_scores, uint32_t *out_counts, uint8_t *err_flags) {
     CDB_REQUIRE(ix && p && (queries || !nq) && (out_ids || !nq) && (out_scores || !nq), "null argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::shared_lock<std::shared_mutex> lock(ix->rw);
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     if (!nq) return CDB_OK;
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
-    cudaStream_t s = ix->stream;
-    const size_t nk = (size_t)nq * p->k;
-    cdb_status rc;
-    if ((rc = ix->io_q.ensure((size_t)nq * ix->desc.dim * 4)) || (rc = ix->io_ids.ensure(nk * 4)) ||
-        (rc = ix->io_scores.ensure(nk * 4)) || (rc = ix->io_counts.ensure((size_t)nq * 4)) || (rc = ix->io_err.ensure(nq)))
-        return rc;
-    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, queries, (size_t)nq * ix->desc.dim * 4, cudaMemcpyHostToDevice, s));
-    rc = search_device_locked(ix, ix->io_q.as<float>(), nq, p, ix->io_ids.as<uint32_t>(), ix->io_scores.as<float>(),
-                              ix->io_counts.as<uint32_t>(), ix->io_err.as<uint8_t>(), s);
+    Lease l;
+    cdb_status rc = lease_scratch(ix, l);
     if (rc) return rc;
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, nk * 4, cudaMemcpyDeviceToHost, s));
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, ix->io_scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
-    if (out_counts) CDB_CUDA_TRY(cudaMemcpyAsync(out_counts, ix->io_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-    if (err_flags) CDB_CUDA_TRY(cudaMemcpyAsync(err_flags, ix->io_err.p, nq, cudaMemcpyDeviceToHost, s));
+    Scratch *sc = l.sc;
+    cudaStream_t s = sc->stream;
+    const size_t nk = (size_t)nq * p->k;
+    if ((rc = sc->io_q.ensure((size_t)nq * ix->desc.dim * 4)) || (rc = sc->io_ids.ensure(nk * 4)) ||
+        (rc = sc->io_scores.ensure(nk * 4)) || (rc = sc->io_counts.ensure((size_t)nq * 4)) || (rc = sc->io_err.ensure(nq)))
+        return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(sc->io_q.p, queries, (size_t)nq * ix->desc.dim * 4, cudaMemcpyHostToDevice, s));
+    rc = search_device_locked(ix, sc, sc->io_q.as<float>(), nq, p, sc->io_ids.as<uint32_t>(), sc->io_scores.as<float>(),
+                              sc->io_counts.as<uint32_t>(), sc->io_err.as<uint8_t>(), s);
+    if (rc) return rc;
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->io_ids.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, sc->io_scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    if (out_counts) CDB_CUDA_TRY(cudaMemcpyAsync(out_counts, sc->io_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    if (err_flags) CDB_CUDA_TRY(cudaMemcpyAsync(err_flags, sc->io_err.p, nq, cudaMemcpyDeviceToHost, s));
     CDB_CUDA_TRY(cudaStreamSynchronize(s));
     return CDB_OK;
 }
@@ -916,16 +1036,19 @@ cdb_status cdb_search_batch_filtered(cdb_index *ix, const float *queries, uint32
     CDB_REQUIRE(ix && p && (queries || !nq) && (out_ids || !nq) && (out_scores || !nq), "null argument");
     CDB_REQUIRE(p->mode == CDB_MODE_HNSW, "metadata filters apply to CDB_MODE_HNSW");
     CDB_REQUIRE(!has_filter || filter_offsets, "has_filter needs filter_offsets");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::shared_lock<std::shared_mutex> lock(ix->rw);
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     if (!nq) return CDB_OK;
     CDB_REQUIRE(p->k >= 1 && p->k <= 1024, "k must be in 1..1024");
     CDB_REQUIRE(ix->has_md, "metadata filters need cdb_index_set_graph_metadata");
-    cudaStream_t s = ix->stream;
+    Lease l;
+    cdb_status rc = lease_scratch(ix, l);
+    if (rc) return rc;
+    Scratch *sc = l.sc;
+    cudaStream_t s = sc->stream;
     const size_t nk = (size_t)nq * p->k;
-    cdb_status rc;
-    if ((rc = ix->io_q.ensure((size_t)nq * ix->desc.dim * 4)) || (rc = ix->io_ids.ensure(nk * 4)) ||
-        (rc = ix->io_scores.ensure(nk * 4)) || (rc = ix->io_counts.ensure((size_t)nq * 4)) || (rc = ix->io_err.ensure(nq)))
+    if ((rc = sc->io_q.ensure((size_t)nq * ix->desc.dim * 4)) || (rc = sc->io_ids.ensure(nk * 4)) ||
+        (rc = sc->io_scores.ensure(nk * 4)) || (rc = sc->io_counts.ensure((size_t)nq * 4)) || (rc = sc->io_err.ensure(nq)))
         return rc;
     const uint32_t *d_off = nullptr;
     const int8_t *d_dims = nullptr;
@@ -938,29 +1061,29 @@ cdb_status cdb_search_batch_filtered(cdb_index *ix, const float *queries, uint32
         }
         total = filter_offsets[nq];
         CDB_REQUIRE(filter_dims || !total, "null filter_dims");
-        if ((rc = ix->flt_off.ensure((size_t)(nq + 1) * 4)) || (rc = ix->flt_has.ensure(nq)) ||
-            (rc = ix->flt_dims.ensure((size_t)total * ix->md_dims + 1)))
+        if ((rc = sc->flt_off.ensure((size_t)(nq + 1) * 4)) || (rc = sc->flt_has.ensure(nq)) ||
+            (rc = sc->flt_dims.ensure((size_t)total * ix->md_dims + 1)))
             return rc;
-        CDB_CUDA_TRY(cudaMemcpyAsync(ix->flt_off.p, filter_offsets, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
-        CDB_CUDA_TRY(cudaMemcpyAsync(ix->flt_has.p, has_filter, nq, cudaMemcpyHostToDevice, s));
-        if (total) CDB_CUDA_TRY(cudaMemcpyAsync(ix->flt_dims.p, filter_dims, (size_t)total * ix->md_dims, cudaMemcpyHostToDevice, s));
-        d_off = ix->flt_off.as<uint32_t>(); d_dims = ix->flt_dims.as<int8_t>(); d_has = ix->flt_has.as<uint8_t>();
+        CDB_CUDA_TRY(cudaMemcpyAsync(sc->flt_off.p, filter_offsets, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s));
+        CDB_CUDA_TRY(cudaMemcpyAsync(sc->flt_has.p, has_filter, nq, cudaMemcpyHostToDevice, s));
+        if (total) CDB_CUDA_TRY(cudaMemcpyAsync(sc->flt_dims.p, filter_dims, (size_t)total * ix->md_dims, cudaMemcpyHostToDevice, s));
+        d_off = sc->flt_off.as<uint32_t>(); d_dims = sc->flt_dims.as<int8_t>(); d_has = sc->flt_has.as<uint8_t>();
     }
-    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, queries, (size_t)nq * ix->desc.dim * 4, cudaMemcpyHostToDevice, s));
-    if (ix->ev_valid && ix->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, ix->ev[2], 0));
-    ix->last_stream = s;
+    CDB_CUDA_TRY(cudaMemcpyAsync(sc->io_q.p, queries, (size_t)nq * ix->desc.dim * 4, cudaMemcpyHostToDevice, s));
+    if (sc->ev_valid && sc->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[2], 0));
+    sc->last_stream = s;
     const uint32_t CH = 2048;
     for (uint32_t q0 = 0; q0 < nq; q0 += CH) {
         const uint32_t m = std::min(CH, nq - q0);
-        rc = hnsw_search_locked(ix, ix->io_q.as<float>() + (size_t)q0 * ix->desc.dim, m, p, ix->io_ids.as<uint32_t>() + (size_t)q0 * p->k,
-                                ix->io_scores.as<float>() + (size_t)q0 * p->k, ix->io_counts.as<uint32_t>() + q0,
-                                ix->io_err.as<uint8_t>() + q0, s, d_off ? d_off + q0 : nullptr, d_dims, d_has ? d_has + q0 : nullptr);
+        rc = hnsw_search_locked(ix, sc, sc->io_q.as<float>() + (size_t)q0 * ix->desc.dim, m, p, sc->io_ids.as<uint32_t>() + (size_t)q0 * p->k,
+                                sc->io_scores.as<float>() + (size_t)q0 * p->k, sc->io_counts.as<uint32_t>() + q0,
+                                sc->io_err.as<uint8_t>() + q0, s, d_off ? d_off + q0 : nullptr, d_dims, d_has ? d_has + q0 : nullptr);
         if (rc) return rc;
     }
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, nk * 4, cudaMemcpyDeviceToHost, s));
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, ix->io_scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
-    if (out_counts) CDB_CUDA_TRY(cudaMemcpyAsync(out_counts, ix->io_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
-    if (err_flags) CDB_CUDA_TRY(cudaMemcpyAsync(err_flags, ix->io_err.p, nq, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->io_ids.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, sc->io_scores.p, nk * 4, cudaMemcpyDeviceToHost, s));
+    if (out_counts) CDB_CUDA_TRY(cudaMemcpyAsync(out_counts, sc->io_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    if (err_flags) CDB_CUDA_TRY(cudaMemcpyAsync(err_flags, sc->io_err.p, nq, cudaMemcpyDeviceToHost, s));
     CDB_CUDA_TRY(cudaStreamSynchronize(s));
     return CDB_OK;
 }
@@ -969,30 +1092,36 @@ cdb_status cdb_search_batch_filtered(cdb_index *ix, const float *queries, uint32
 
 cdb_status cdb_score_ids(cdb_index *ix, const float *query, const uint32_t *ids, uint32_t n, float *out, int32_t *out_status) {
     CDB_REQUIRE(ix && query && (ids || !n) && (out || !n) && (out_status || !n), "null argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::shared_lock<std::shared_mutex> lock(ix->rw);
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     if (!n) return CDB_OK;
     const cdb_index_desc &d = ix->desc;
-    cudaStream_t s = ix->stream;
-    cdb_status rc;
-    if ((rc = ix->io_q.ensure((size_t)d.dim * 4)) || (rc = ix->q_codes.ensure(ix->row_pitch)) || (rc = ix->q_mags.ensure(4)) ||
-        (rc = ix->io_ids.ensure((size_t)n * 4)) || (rc = ix->io_scores.ensure((size_t)n * 4)) || (rc = ix->misc.ensure((size_t)n * 4)))
+    Lease l;
+    cdb_status rc = lease_scratch(ix, l);
+    if (rc) return rc;
+    Scratch *sc = l.sc;
+    cudaStream_t s = sc->stream;
+    // the set's buffers may still be read by an asynchronous search enqueued on a caller stream: order behind it
+    if (sc->ev_valid && sc->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[2], 0));
+    sc->last_stream = s;
+    if ((rc = sc->io_q.ensure((size_t)d.dim * 4)) || (rc = sc->q_codes.ensure(ix->row_pitch)) || (rc = sc->q_mags.ensure(4)) ||
+        (rc = sc->io_ids.ensure((size_t)n * 4)) || (rc = sc->io_scores.ensure((size_t)n * 4)) || (rc = sc->misc.ensure((size_t)n * 4)))
         return rc;
-    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, query, (size_t)d.dim * 4, cudaMemcpyHostToDevice, s));
-    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, ix->row_pitch, s));
-    if ((rc = quantize_rows_device(ix->io_q.as<float>(), 1, d.dim, d.storage_type, d.range_lo, d.range_hi,
-                                   ix->q_codes.as<uint8_t>(), ix->row_pitch, ix->q_mags.as<float>(), nullptr, 0, s)))
+    CDB_CUDA_TRY(cudaMemcpyAsync(sc->io_q.p, query, (size_t)d.dim * 4, cudaMemcpyHostToDevice, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(sc->io_ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(sc->q_codes.p, 0, ix->row_pitch, s));
+    if ((rc = quantize_rows_device(sc->io_q.as<float>(), 1, d.dim, d.storage_type, d.range_lo, d.range_hi,
+                                   sc->q_codes.as<uint8_t>(), ix->row_pitch, sc->q_mags.as<float>(), nullptr, 0, s)))
         return rc;
     float qmag = 0.0f;
-    CDB_CUDA_TRY(cudaMemcpyAsync(&qmag, ix->q_mags.p, 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(&qmag, sc->q_mags.p, 4, cudaMemcpyDeviceToHost, s));
     CDB_CUDA_TRY(cudaStreamSynchronize(s));
-    if ((rc = score_ids_device(d.metric, d.storage_type, d.dim, ix->q_codes.as<uint8_t>(), qmag, ix->d_codes, ix->d_mags,
-                               ix->row_pitch, ix->size, ix->io_ids.as<uint32_t>(), n, ix->io_scores.as<float>(),
-                               ix->misc.as<int32_t>(), s)))
+    if ((rc = score_ids_device(d.metric, d.storage_type, d.dim, sc->q_codes.as<uint8_t>(), qmag, ix->d_codes, ix->d_mags,
+                               ix->row_pitch, ix->size, sc->io_ids.as<uint32_t>(), n, sc->io_scores.as<float>(),
+                               sc->misc.as<int32_t>(), s)))
         return rc;
-    CDB_CUDA_TRY(cudaMemcpyAsync(out, ix->io_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_status, ix->misc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out, sc->io_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_status, sc->misc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CDB_CUDA_TRY(cudaStreamSynchronize(s));
     return CDB_OK;
 }
@@ -1000,30 +1129,36 @@ cdb_status cdb_score_ids(cdb_index *ix, const float *query, const uint32_t *ids,
 cdb_status cdb_rerank_f32(cdb_index *ix, const float *query, const uint32_t *cand_ids, uint32_t n, uint32_t k,
                           uint32_t *out_ids, float *out_scores, uint32_t *out_count) {
     CDB_REQUIRE(ix && query && (cand_ids || !n) && out_ids && out_scores && k >= 1, "bad argument");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::shared_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(ix->d_raw, "re-rank needs raw f32 rows (F32 storage or keep_raw_f32)");
+    CDB_REQUIRE(ix->raw_missing == 0, "rows appended as codes still lack their raw f32 rows (cdb_index_set_raw_f32 / cdb_index_fill_raw_from_itoe)");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     const cdb_index_desc &d = ix->desc;
-    cudaStream_t s = ix->stream;
-    cdb_status rc;
+    Lease l;
+    cdb_status rc = lease_scratch(ix, l);
+    if (rc) return rc;
+    Scratch *sc = l.sc;
+    cudaStream_t s = sc->stream;
+    if (sc->ev_valid && sc->last_stream != s) CDB_CUDA_TRY(cudaStreamWaitEvent(s, sc->ev[2], 0));
+    sc->last_stream = s;
     const uint32_t qpitch = ix->raw_pitch_elems;
-    if ((rc = ix->io_q.ensure((size_t)d.dim * 4)) || (rc = ix->q_codes.ensure((size_t)qpitch * 4)) || (rc = ix->q_mags.ensure(4)) ||
-        (rc = ix->misc.ensure((size_t)(n ? n : 1) * 4)) || (rc = ix->io_ids.ensure((size_t)k * 4)) ||
-        (rc = ix->io_scores.ensure((size_t)k * 4)) || (rc = ix->io_counts.ensure(4)))
+    if ((rc = sc->io_q.ensure((size_t)d.dim * 4)) || (rc = sc->q_codes.ensure((size_t)qpitch * 4)) || (rc = sc->q_mags.ensure(4)) ||
+        (rc = sc->misc.ensure((size_t)(n ? n : 1) * 4)) || (rc = sc->io_ids.ensure((size_t)k * 4)) ||
+        (rc = sc->io_scores.ensure((size_t)k * 4)) || (rc = sc->io_counts.ensure(4)))
         return rc;
-    CDB_CUDA_TRY(cudaMemcpyAsync(ix->io_q.p, query, (size_t)d.dim * 4, cudaMemcpyHostToDevice, s));
-    if (n) CDB_CUDA_TRY(cudaMemcpyAsync(ix->misc.p, cand_ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    CDB_CUDA_TRY(cudaMemsetAsync(ix->q_codes.p, 0, (size_t)qpitch * 4, s));
-    if ((rc = quantize_rows_device(ix->io_q.as<float>(), 1, d.dim, CDB_ST_F32, 0.f, 0.f, ix->q_codes.as<uint8_t>(), qpitch * 4,
-                                   ix->q_mags.as<float>(), nullptr, 0, s)))
+    CDB_CUDA_TRY(cudaMemcpyAsync(sc->io_q.p, query, (size_t)d.dim * 4, cudaMemcpyHostToDevice, s));
+    if (n) CDB_CUDA_TRY(cudaMemcpyAsync(sc->misc.p, cand_ids, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(sc->q_codes.p, 0, (size_t)qpitch * 4, s));
+    if ((rc = quantize_rows_device(sc->io_q.as<float>(), 1, d.dim, CDB_ST_F32, 0.f, 0.f, sc->q_codes.as<uint8_t>(), qpitch * 4,
+                                   sc->q_mags.as<float>(), nullptr, 0, s)))
         return rc;
-    if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, ix->q_codes.as<float>(), qpitch,
-                                ix->q_mags.as<float>(), 1, ix->misc.as<uint32_t>(), nullptr, n, k, d.id_base, ix->io_ids.as<uint32_t>(),
-                                ix->io_scores.as<float>(), ix->io_counts.as<uint32_t>(), s)))
+    if ((rc = rerank_f32_device(ix->d_raw, ix->raw_pitch_elems, ix->d_raw_mags, ix->size, d.dim, sc->q_codes.as<float>(), qpitch,
+                                sc->q_mags.as<float>(), 1, sc->misc.as<uint32_t>(), nullptr, n, k, d.id_base, sc->io_ids.as<uint32_t>(),
+                                sc->io_scores.as<float>(), sc->io_counts.as<uint32_t>(), s)))
         return rc;
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, ix->io_ids.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
-    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, ix->io_scores.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
-    if (out_count) CDB_CUDA_TRY(cudaMemcpyAsync(out_count, ix->io_counts.p, 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->io_ids.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
+    CDB_CUDA_TRY(cudaMemcpyAsync(out_scores, sc->io_scores.p, (size_t)k * 4, cudaMemcpyDeviceToHost, s));
+    if (out_count) CDB_CUDA_TRY(cudaMemcpyAsync(out_count, sc->io_counts.p, 4, cudaMemcpyDeviceToHost, s));
     CDB_CUDA_TRY(cudaStreamSynchronize(s));
     return CDB_OK;
 }
@@ -1048,11 +1183,12 @@ cdb_status cdb_index_last_kernel_ms(const cdb_index *ix, float *scan_ms, float *
     CDB_REQUIRE(ix, "null index");
     if (scan_ms) *scan_ms = 0.f;
     if (total_ms) *total_ms = 0.f;
-    if (!ix->ev_valid) return CDB_OK;
+    const Scratch *sc = ix->last;           // set of the most recently finished search
+    if (!sc || !sc->ev_valid) return CDB_OK;
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
-    CDB_CUDA_TRY(cudaEventSynchronize(ix->ev[2]));
-    if (scan_ms) CDB_CUDA_TRY(cudaEventElapsedTime(scan_ms, ix->ev[0], ix->ev[1]));
-    if (total_ms) CDB_CUDA_TRY(cudaEventElapsedTime(total_ms, ix->ev[0], ix->ev[2]));
+    CDB_CUDA_TRY(cudaEventSynchronize(sc->ev[2]));
+    if (scan_ms) CDB_CUDA_TRY(cudaEventElapsedTime(scan_ms, sc->ev[0], sc->ev[1]));
+    if (total_ms) CDB_CUDA_TRY(cudaEventElapsedTime(total_ms, sc->ev[0], sc->ev[2]));
     return CDB_OK;
 }
 
@@ -1062,7 +1198,7 @@ cdb_status cdb_index_set_graph(cdb_index *ix, const cdb_graph_desc *gd) {
     CDB_REQUIRE(gd->num_levels <= 31, "too many levels");
     CDB_REQUIRE(gd->neighbors_count >= 1 && gd->neighbors_count <= 64 && gd->level0_neighbors_count >= 1 &&
                     gd->level0_neighbors_count <= 64, "neighbour counts must be in 1..64");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(gd->level_counts[0] >= 1, "level 0 is empty");
     CDB_REQUIRE(gd->root_row < ix->size, "root_row out of range");
     CDB_REQUIRE(gd->entry < gd->level_counts[gd->num_levels], "entry out of range");
@@ -1134,7 +1270,7 @@ cdb_status cdb_index_set_graph_metadata(cdb_index *ix, const cdb_graph_metadata 
     CDB_REQUIRE(ix && md && md->node_id && md->node_md, "null argument");
     CDB_REQUIRE(md->md_dims >= 1 && md->md_dims <= 4096, "md_dims must be in 1..4096");
     CDB_REQUIRE((md->md_bits && md->md_mags) || !md->n_md, "null metadata table");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(ix->has_graph, "cdb_index_set_graph_metadata needs cdb_index_set_graph first");
     const uint32_t L1 = ix->graph.num_levels + 1;
     CDB_REQUIRE(md->pseudo_entry < ix->g_cnt[L1 - 1], "pseudo_entry out of range");
@@ -1180,7 +1316,7 @@ cdb_status cdb_index_build_graph(cdb_index *ix, const cdb_build_params *bp) {
                     bp->level0_neighbors_count <= 64, "neighbour counts must be in 1..64");
     CDB_REQUIRE(bp->ef_construction >= 1 && bp->ef_construction <= 4096 && bp->shortlist_size >= 1 && bp->shortlist_size <= 64 &&
                     bp->num_levels <= 15, "bad build parameters");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_REQUIRE(ix->size >= 1 && ix->size + 1 <= ix->desc.capacity, "build needs >= 1 row and capacity for the root row");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     cdb_status rc;
@@ -1243,7 +1379,7 @@ cdb_status cdb_debug_set_hnsw_flags(uint32_t flags) {
 
 cdb_status cdb_index_hnsw_profile(cdb_index *ix, int32_t enable, uint64_t *out) {
     CDB_REQUIRE(ix, "null index");
-    std::lock_guard<std::mutex> lock(ix->mu);
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
     CDB_CUDA_TRY(cudaDeviceSynchronize());
     if (out) {
@@ -1259,15 +1395,26 @@ cdb_status cdb_index_hnsw_profile(cdb_index *ix, int32_t enable, uint64_t *out) 
     return CDB_OK;
 }
 
+// cumulative fallback count = sum over the pool's sets; "last" values come from the most recently finished search
+static cdb_status read_pool_flags(const cdb_index *ix, uint64_t *fallbacks, uint64_t *last_fallback_queries) {
+    *fallbacks = 0; *last_fallback_queries = 0;
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    CDB_CUDA_TRY(cudaDeviceSynchronize());
+    for (const auto &u : ix->pool) {
+        uint32_t fl[4] = {0, 0, 0, 0};
+        if (u->flags.p) CDB_CUDA_TRY(cudaMemcpy(fl, u->flags.p, 16, cudaMemcpyDeviceToHost));
+        *fallbacks += fl[3];
+        if (u.get() == ix->last) *last_fallback_queries = fl[0];
+    }
+    return CDB_OK;
+}
+
 cdb_status cdb_index_stats(const cdb_index *ix, uint64_t *out4) {
     CDB_REQUIRE(ix && out4, "null argument");
-    uint32_t fb = 0;
-    if (ix->flags.p) {
-        CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
-        CDB_CUDA_TRY(cudaDeviceSynchronize());
-        CDB_CUDA_TRY(cudaMemcpy(&fb, ix->flags.as<uint32_t>() + 3, 4, cudaMemcpyDeviceToHost));
-    }
-    out4[0] = ix->stat_tensor_searches;
+    uint64_t fb = 0, lq = 0;
+    cdb_status rc = read_pool_flags(ix, &fb, &lq);
+    if (rc) return rc;
+    out4[0] = ix->stat_tensor_searches.load();
     out4[1] = fb;
     out4[2] = ix->n_allzero_rows + ix->n_odd_rows;
     out4[3] = ix->d_xh ? 1 : 0;
@@ -1276,33 +1423,32 @@ cdb_status cdb_index_stats(const cdb_index *ix, uint64_t *out4) {
 
 cdb_status cdb_index_stats_ex(const cdb_index *ix, uint64_t *out, uint32_t n) {
     CDB_REQUIRE(ix && (out || !n), "null argument");
-    uint32_t fl[4] = {0, 0, 0, 0};
-    if (ix->flags.p) {
-        CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
-        CDB_CUDA_TRY(cudaDeviceSynchronize());
-        CDB_CUDA_TRY(cudaMemcpy(fl, ix->flags.p, 16, cudaMemcpyDeviceToHost));
-    }
-    const uint64_t v[CDB_STATS_FIELDS] = {ix->stat_tensor_searches, fl[3], ix->n_allzero_rows, ix->n_odd_rows,
-                                          ix->d_xh ? 1ull : 0ull, fl[0]};
+    uint64_t fb = 0, lq = 0;
+    cdb_status rc = read_pool_flags(ix, &fb, &lq);
+    if (rc) return rc;
+    const uint64_t v[CDB_STATS_FIELDS] = {ix->stat_tensor_searches.load(), fb, ix->n_allzero_rows, ix->n_odd_rows,
+                                          ix->d_xh ? 1ull : 0ull, lq};
     for (uint32_t i = 0; i < n && i < CDB_STATS_FIELDS; ++i) out[i] = v[i];
     return CDB_OK;
 }
 
 cdb_status cdb_index_last_candidate_counts(const cdb_index *ix, uint32_t n, uint32_t *out) {
     CDB_REQUIRE(ix && out, "null argument");
-    CDB_REQUIRE(ix->cand_cnt.p && (size_t)n * 4 <= ix->cand_cnt.cap, "no prefilter search of that size has run");
+    const Scratch *sc = ix->last;
+    CDB_REQUIRE(sc && sc->cand_cnt.p && (size_t)n * 4 <= sc->cand_cnt.cap, "no prefilter search of that size has run");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
-    CDB_CUDA_TRY(cudaMemcpy(out, ix->cand_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CDB_CUDA_TRY(cudaMemcpy(out, sc->cand_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return CDB_OK;
 }
 
 cdb_status cdb_index_scan_ms_history(const cdb_index *ix, uint32_t n, float *out, uint32_t *out_n) {
     CDB_REQUIRE(ix && out && out_n, "null argument");
     CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
-    uint64_t have = ix->n_search < (uint64_t)cdb_index::EV_RING ? ix->n_search : (uint64_t)cdb_index::EV_RING;
+    const uint64_t ns = ix->n_search.load();
+    uint64_t have = ns < (uint64_t)cdb_index::EV_RING ? ns : (uint64_t)cdb_index::EV_RING;
     uint32_t m = n < have ? n : (uint32_t)have;
     for (uint32_t i = 0; i < m; ++i) {  // oldest of the last m first
-        int slot = (int)((ix->n_search - m + i) % cdb_index::EV_RING);
+        int slot = (int)((ns - m + i) % cdb_index::EV_RING);
         CDB_CUDA_TRY(cudaEventSynchronize(ix->ring1[slot]));
         CDB_CUDA_TRY(cudaEventElapsedTime(out + i, ix->ring0[slot], ix->ring1[slot]));
     }

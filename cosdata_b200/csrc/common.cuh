@@ -47,10 +47,19 @@ __host__ __device__ inline uint32_t row_pitch_bytes(int st, uint32_t dim) {
     switch (st) {
     case CDB_ST_U8: return round_up(dim, 16);
     case CDB_ST_SUB1: case CDB_ST_SUB2: case CDB_ST_SUB3: return (uint32_t)st * plane_pitch(dim);
-    case CDB_ST_F16: return round_up(dim * 2, 16);
+    case CDB_ST_F16: case CDB_ST_BF16: return round_up(dim * 2, 16);
     case CDB_ST_F32: return round_up(dim * 4, 16);
     default: return 0;
     }
+}
+
+// ---------------------------------------------------------------- bfloat16 (labelled extension, CDB_ST_BF16)
+// half::bf16::from_f32: round to nearest even on the upper 16 bits; NaN keeps its sign and top payload bits, quiet bit set
+__host__ __device__ inline uint16_t f32_to_bf16_bits(uint32_t x) {
+    if ((x & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((x >> 16) | 0x0040u);
+    const uint32_t round_bit = 0x00008000u;
+    if ((x & round_bit) != 0 && (x & (3u * round_bit - 1u)) != 0) return (uint16_t)((x >> 16) + 1u);
+    return (uint16_t)(x >> 16);
 }
 
 // ---------------------------------------------------------------- ordering

@@ -149,6 +149,44 @@ __device__ __forceinline__ float hw_dot_f16_q32(const float *__restrict__ q, con
     return s;
 }
 
+// bfloat16 rows (labelled extension CDB_ST_BF16): widening is a 16-bit shift / mask on the integer pipe, so the FMA pipe only
+// sees the one FFMA per element
+__device__ __forceinline__ float hw_chain8_bf16(float s, const uint4 &vb, const float4 &qa, const float4 &qb) {
+    s = __fmaf_rn(qa.x, bf16_lo(vb.x), s);
+    s = __fmaf_rn(qa.y, bf16_hi(vb.x), s);
+    s = __fmaf_rn(qa.z, bf16_lo(vb.y), s);
+    s = __fmaf_rn(qa.w, bf16_hi(vb.y), s);
+    s = __fmaf_rn(qb.x, bf16_lo(vb.z), s);
+    s = __fmaf_rn(qb.y, bf16_hi(vb.z), s);
+    s = __fmaf_rn(qb.z, bf16_lo(vb.w), s);
+    s = __fmaf_rn(qb.w, bf16_hi(vb.w), s);
+    return s;
+}
+__device__ __forceinline__ float hw_dot_bf16_q32(const float *__restrict__ q, const uint8_t *__restrict__ row, uint32_t n) {
+    float s = 0.0f;
+    const uint32_t n16 = n & ~15u;
+    uint32_t i = 0;
+    if (n16) {
+        HwBlk16 cur = hw_ld16(q, row, 0);
+        for (; i + 16 < n16; i += 16) {
+            const HwBlk16 nxt = hw_ld16(q, row, i + 16);
+            s = hw_chain8_bf16(s, cur.r0, cur.q0, cur.q1);
+            s = hw_chain8_bf16(s, cur.r1, cur.q2, cur.q3);
+            cur = nxt;
+        }
+        s = hw_chain8_bf16(s, cur.r0, cur.q0, cur.q1);
+        s = hw_chain8_bf16(s, cur.r1, cur.q2, cur.q3);
+        i = n16;
+    }
+    if (i + 8 <= n) {
+        s = hw_chain8_bf16(s, *reinterpret_cast<const uint4 *>(row + 2 * i), *reinterpret_cast<const float4 *>(q + i),
+                           *reinterpret_cast<const float4 *>(q + i + 4));
+        i += 8;
+    }
+    for (; i < n; ++i) s = __fmaf_rn(q[i], __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(row)[i] << 16), s);
+    return s;
+}
+
 // warp bitonic sort, descending, n keys padded to P (power of two) with zeros
 __device__ inline void hw_sort_desc(uint64_t *keys, uint32_t *vals, uint32_t n, uint32_t P, int lane) {
     for (uint32_t i = n + lane; i < P; i += 32) { keys[i] = 0ull; vals[i] = 0; }
@@ -178,7 +216,7 @@ struct HwState {
 // Score the compacted neighbours nnodes/nrow[first .. first+n) into nkeys (slot order kept).  Rows are staged through
 // shared memory (one TMA bulk copy per row, all in flight together: one memory round trip per group), then one lane per
 // row runs the reference chain.  Returns the (position << 8 | flag) of the first failing evaluation, 0xFFFFFFFF if none.
-template <bool F16FAST, bool PROF>
+template <int FAST, bool PROF>
 __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const HwSmem &m, float qmag, uint32_t pp, uint32_t first,
                                                    uint32_t n, int lane, HwState &st) {
     uint32_t err_first = 0xFFFFFFFFu;
@@ -204,8 +242,8 @@ __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const H
             const uint32_t pos = first + g0 + lane;
             const uint8_t *code = m.stage + (size_t)lane * m.stage_pitch;
             float d = 0.0f;
-            if (F16FAST) {
-                const float dot = hw_dot_f16_q32(m.q32, code, sc.dim);
+            if (FAST) {
+                const float dot = FAST == 1 ? hw_dot_f16_q32(m.q32, code, sc.dim) : hw_dot_bf16_q32(m.q32, code, sc.dim);
                 if (sc.metric == CDB_METRIC_COSINE) {
                     const float denom = __fmul_rn(qmag, rmag);
                     if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
@@ -232,7 +270,7 @@ __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const H
 
 // One level (traverse_find_nearest).  All 32 lanes call it with warp-uniform arguments.  On return (st.err == 0)
 // rkeys/rnodes[0..st.rlen) hold every popped entry sorted best first.
-template <bool F16FAST, bool PROF>
+template <int FAST, bool PROF>
 __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null: identity */, const uint32_t *__restrict__ adj,
                                   uint32_t nb, uint32_t take, const HnScoreCtx &sc, const HwSmem &m, float qmag, uint32_t self_id,
                                   uint32_t ef, uint32_t entry, HwState &st, int lane, uint32_t flags) {
@@ -248,7 +286,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
     if (lane == 0) { m.nnodes[0] = entry; m.nrow[0] = node_row ? node_row[entry] : entry; }
     __syncwarp();
     {
-        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, 1, lane, st);
+        const uint32_t e = hw_score_group<FAST, PROF>(sc, m, qmag, pp, 0, 1, lane, st);
         st.evals += 1;
         if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; return; }
         if (lane == 0) {
@@ -358,7 +396,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
         }
         if (PROF) t3 = clock64();
         // ---- score the new neighbours
-        const uint32_t e = hw_score_group<F16FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st);
+        const uint32_t e = hw_score_group<FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st);
         st.evals += nc;
         if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; st.rlen = rlen; return; }
         if (PROF) t4 = clock64();
@@ -467,7 +505,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
     if (PROF) { const long long t7 = clock64(); st.prof[6] += t7 - t6; st.prof[7] += t7 - t0; }
 }
 
-template <bool F16FAST, bool PROF>
+template <int FAST, bool PROF>
 __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarve cv) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x;
@@ -490,8 +528,10 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarv
     for (uint32_t i = lane; i < a.row_pitch / 4; i += 32)
         reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[i];
     __syncwarp();
-    if (F16FAST)
+    if (FAST == 1)
         for (uint32_t i = lane; i < a.dim; i += 32) m.q32[i] = __half2float(reinterpret_cast<const __half *>(m.qs)[i]);
+    if (FAST == 2)
+        for (uint32_t i = lane; i < a.dim; i += 32) m.q32[i] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(m.qs)[i] << 16);
     const float qmag = a.qmags[qi];
     const HnScoreCtx sc{a.rows, a.row_pitch, a.mags, a.dim, a.st, a.metric, a.g.root_row};
     if (lane == 0) hw_mbar_init(m.bar, 1);
@@ -508,7 +548,7 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarv
         const uint32_t nb = level == 0 ? a.g.nbrs0 : a.g.nbrs;
         const uint32_t take = min(min(a.shortlist, nb), HN_MAX_TAKE);
         const uint32_t *node_row = ((a.g.identity_mask >> level) & 1u) ? nullptr : a.g.node_row[level];
-        hw_traverse_level<F16FAST, PROF>(node_row, a.g.adj[level], nb, take, sc, m, qmag, HN_QUERY_ID, a.ef, entry, st, lane, a.flags);
+        hw_traverse_level<FAST, PROF>(node_row, a.g.adj[level], nb, take, sc, m, qmag, HN_QUERY_ID, a.ef, entry, st, lane, a.flags);
         if (st.err) break;
         const uint32_t keep = min(st.rlen, HW_FINAL_LEN);
         for (uint32_t i = lane; i < keep; i += 32) {
@@ -534,14 +574,17 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarv
     }
 }
 
+static int hw_fast_kind(int st, int metric) {   // 1: f16 chain, 2: bf16 chain, 0: generic pair_distance
+    if (metric != CDB_METRIC_COSINE && metric != CDB_METRIC_DOT_PRODUCT) return 0;
+    return st == CDB_ST_F16 ? 1 : (st == CDB_ST_BF16 ? 2 : 0);
+}
 size_t hnsw_warp_smem(uint32_t row_pitch, uint32_t dim, uint32_t ef, int st, int metric) {
-    const bool f16fast = st == CDB_ST_F16 && (metric == CDB_METRIC_COSINE || metric == CDB_METRIC_DOT_PRODUCT);
-    return hw_carve(row_pitch, dim, ef, f16fast).total;
+    return hw_carve(row_pitch, dim, ef, hw_fast_kind(st, metric) != 0).total;
 }
 
-template <bool F16FAST, bool PROF>
+template <int FAST, bool PROF>
 static cdb_status launch_warp(const HnswArgs &a, const HwCarve &cv, cudaStream_t s) {
-    auto kern = hnsw_search_warp_kernel<F16FAST, PROF>;
+    auto kern = hnsw_search_warp_kernel<FAST, PROF>;
     CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total));
     kern<<<a.nq, 32, cv.total, s>>>(a, cv);
     CDB_LAUNCH_CHECK();
@@ -551,12 +594,13 @@ static cdb_status launch_warp(const HnswArgs &a, const HwCarve &cv, cudaStream_t
 cdb_status hnsw_search_warp_device(const HnswArgs &a, cudaStream_t s) {
     if (!a.nq) return CDB_OK;
     if (a.ef == 0 || a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
-    const bool f16fast = a.st == CDB_ST_F16 && (a.metric == CDB_METRIC_COSINE || a.metric == CDB_METRIC_DOT_PRODUCT);
-    const HwCarve cv = hw_carve(a.row_pitch, a.dim, a.ef, f16fast);
+    const int fast = hw_fast_kind(a.st, a.metric);
+    const HwCarve cv = hw_carve(a.row_pitch, a.dim, a.ef, fast != 0);
     if (cv.total > 200 * 1024) { set_error("hnsw: ef_search / row size too large for shared memory"); return CDB_INVALID_PARAMS; }
     const bool prof = a.prof != nullptr;
-    if (f16fast) return prof ? launch_warp<true, true>(a, cv, s) : launch_warp<true, false>(a, cv, s);
-    return prof ? launch_warp<false, true>(a, cv, s) : launch_warp<false, false>(a, cv, s);
+    if (fast == 1) return prof ? launch_warp<1, true>(a, cv, s) : launch_warp<1, false>(a, cv, s);
+    if (fast == 2) return prof ? launch_warp<2, true>(a, cv, s) : launch_warp<2, false>(a, cv, s);
+    return prof ? launch_warp<0, true>(a, cv, s) : launch_warp<0, false>(a, cv, s);
 }
 
 }  // namespace cdb

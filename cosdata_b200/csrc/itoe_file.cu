@@ -276,4 +276,45 @@ cdb_status cdb_index_append_itoe(cdb_index *index, const char *collection_dir, u
     return CDB_OK;
 }
 
+// Cold start, second half: rows appended from prop.data (cdb_index_append_prop_file) carry only the quantized payload; the raw
+// f32 embeddings the exact re-rank reads live in the itoe store, keyed by internal id.  row_ids[r] = the id whose embedding
+// belongs to row r (what cdb_index_append_prop_file returned; for collections with a metadata schema the caller maps a
+// replica id to its base id first, collection.rs:368-384).  CDB_INVALID_ID marks rows that have no embedding by design
+// (the root vector, id u32::MAX, vector_store.rs:57-67): they stay zero and count as filled.
+cdb_status cdb_index_fill_raw_from_itoe(cdb_index *index, const char *collection_dir, const uint32_t *row_ids, uint64_t n_rows,
+                                        uint64_t *out_filled, uint64_t *out_missing) {
+    if (!index || !collection_dir || (!row_ids && n_rows)) { set_error("null argument"); return CDB_INVALID_PARAMS; }
+    cdb_index_desc desc;
+    cdb_status rc = cdb_index_describe(index, &desc);
+    if (rc) return rc;
+    ItoeStore s;
+    if (!s.open(collection_dir)) return store_error(s);
+    const uint64_t CH = std::max<uint64_t>(1, (64ull << 20) / ((uint64_t)desc.dim * 4));
+    std::vector<float> buf;
+    uint64_t filled = 0, missing = 0;
+    for (uint64_t r0 = 0; r0 < n_rows; r0 += CH) {
+        const uint64_t m = std::min<uint64_t>(CH, n_rows - r0);
+        buf.assign(m * desc.dim, 0.0f);
+        for (uint64_t i = 0; i < m; ++i) {
+            const uint32_t id = row_ids[r0 + i];
+            if (id == CDB_INVALID_ID) { ++filled; continue; }
+            Entry e;
+            bool hit = false;
+            if (!s.lookup(id, e, hit)) return store_error(s);
+            if (!hit || e.dense_len == 0) { ++missing; continue; }
+            if (e.dense_len != desc.dim) {
+                set_error("itoe store: internal id " + std::to_string(id) + " has " + std::to_string(e.dense_len) + " dense values, index dim is " + std::to_string(desc.dim));
+                return CDB_STORAGE_MISMATCH;
+            }
+            s.copy_dense(e, buf.data() + i * desc.dim);
+            ++filled;
+        }
+        if ((rc = cdb_index_set_raw_f32(index, r0, buf.data(), m))) return rc;
+    }
+    if (out_filled) *out_filled = filled;
+    if (out_missing) *out_missing = missing;
+    if (missing) { set_error(std::to_string(missing) + " rows have no embedding in the itoe store (their raw rows are zero)"); return CDB_INVALID_PARAMS; }
+    return CDB_OK;
+}
+
 }  // extern "C"

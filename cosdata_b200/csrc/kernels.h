@@ -169,8 +169,13 @@ cdb_status classify_rows_device(const float *d_raw, uint32_t pitch_elems, const 
 size_t tensor_scan_smem_bytes(uint32_t k);
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
                               uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_ggm, uint32_t *d_cand,
-                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, const uint32_t *d_deg, bool has_deg,
-                              int sm_count, cudaStream_t s);
+                              uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress /* 2048 words */, const uint32_t *d_deg,
+                              bool has_deg, int sm_count, cudaStream_t s, bool prepared = false);
+// one launch: raw + fp16-normalised query copies, |q|, and every per-search initialisation of the prefilter path
+cdb_status prep_queries_device(const float *d_q, uint32_t nq, uint32_t dim, float *d_q_raw, uint32_t raw_pitch_elems, float *d_q_mags,
+                               void *d_qh, uint32_t qh_pitch_halfs, int *d_ggm, const uint32_t *d_deg, bool has_deg, uint32_t id_base,
+                               uint32_t *d_cand, uint32_t cand_cap, uint32_t *d_cand_cnt, uint32_t *d_err32, uint8_t *d_err8,
+                               uint32_t *d_progress, cudaStream_t s);
 // queries whose candidate list overflowed (or whose norm is degenerate, d_qmags may be null) -> d_qsel = {n, indices...}
 cdb_status select_fallback_device(const uint32_t *d_cnt, uint32_t cap, const float *d_qmags, uint32_t n, uint32_t *d_qsel,
                                   uint32_t *d_flags, cudaStream_t s);

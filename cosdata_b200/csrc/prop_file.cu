@@ -146,37 +146,49 @@ cdb_status cdb_index_append_prop_file(cdb_index *index, const char *path, uint32
     Mapped f;
     if ((rc = f.open(path))) return rc;
     const size_t want = cdb_code_bytes(st_index, dim);
+    if (out_appended) *out_appended = 0;
+    // pass 1: validate the whole file -- nothing is committed to the index unless every record parses and matches it
+    // (a half-loaded index would silently break the row = record-ordinal mapping the graph flattener relies on)
+    {
+        Cur c{f.p, f.p + f.len};
+        Record r;
+        uint64_t idx = 0;
+        while (c.p < c.end) {
+            const size_t off = (size_t)(c.p - f.p);
+            if (peek_is_metadata(c)) { if (!skip_item(c)) return record_error(c, idx, off); continue; }
+            if (!parse_record(c, r)) return record_error(c, idx, off);
+            if (r.st != st_index || r.code.size() != want) {
+                set_error("prop file record " + std::to_string(idx) + ": Storage variant / length does not match the index (StorageMismatch)");
+                return CDB_STORAGE_MISMATCH;
+            }
+            ++idx;
+        }
+    }
+    // pass 2: append in chunks; *out_appended always reports the rows committed so far (a device error can still stop it)
     const uint64_t CH = 16384;
     std::vector<uint8_t> codes;
     std::vector<float> mags;
     codes.reserve(CH * want); mags.reserve(CH);
     Cur c{f.p, f.p + f.len};
     Record r;
-    uint64_t idx = 0;
+    uint64_t idx = 0, committed = 0;
     auto flush = [&]() -> cdb_status {
         if (mags.empty()) return CDB_OK;
         cdb_status e = cdb_index_append_codes(index, codes.data(), mags.data(), mags.size());
+        if (e == CDB_OK) { committed += mags.size(); if (out_appended) *out_appended = committed; }
         codes.clear(); mags.clear();
         return e;
     };
     while (c.p < c.end) {
-        const size_t off = (size_t)(c.p - f.p);
-        if (peek_is_metadata(c)) { if (!skip_item(c)) { flush(); return record_error(c, idx, off); } continue; }
-        if (!parse_record(c, r)) { flush(); return record_error(c, idx, off); }
-        if (r.st != st_index || r.code.size() != want) {
-            flush();
-            set_error("prop file record " + std::to_string(idx) + ": Storage variant / length does not match the index (StorageMismatch)");
-            return CDB_STORAGE_MISMATCH;
-        }
+        if (peek_is_metadata(c)) { skip_item(c); continue; }
+        parse_record(c, r);
         codes.insert(codes.end(), r.code.begin(), r.code.end());
         mags.push_back(r.mag);
         if (out_ids && idx < max_ids) out_ids[idx] = r.id;
         ++idx;
         if (mags.size() == CH && (rc = flush())) return rc;
     }
-    if ((rc = flush())) return rc;
-    if (out_appended) *out_appended = idx;
-    return CDB_OK;
+    return flush();
 }
 
 }  // extern "C"

@@ -85,6 +85,11 @@ __global__ void quantize_codes_kernel(Src src, uint64_t n, uint32_t dim, int st,
         for (uint32_t e = 0; e < cnt; ++e) h[e] = __float2half_rn(v[e]);
         break;
     }
+    case CDB_ST_BF16: {
+        uint16_t *h = reinterpret_cast<uint16_t *>(out) + c0;
+        for (uint32_t e = 0; e < cnt; ++e) h[e] = f32_to_bf16_bits(__float_as_uint(v[e]));
+        break;
+    }
     case CDB_ST_F32: {
         float *f = reinterpret_cast<float *>(out) + c0;
         for (uint32_t e = 0; e < cnt; ++e) f[e] = v[e];
@@ -117,6 +122,41 @@ __global__ void mags_kernel(Src src, uint64_t n, uint32_t dim, int st, float lo,
     }
 }
 
+// Few rows (a query batch): one CTA per row.  The per-row fold is sequential (`iter().map(|x| x*x).sum()`), but the squares
+// are produced by the whole CTA with coalesced loads and the chain thread reads them from shared memory -- the
+// thread-per-row form above walks global memory element by element (55 us for 1024 x 768 queries, a fixed cost of every
+// HNSW / exact search).  u8 magnitudes are a wrapping integer sum: any order.
+template <class Src>
+__global__ void __launch_bounds__(128) mags_cta_kernel(Src src, uint64_t n, uint32_t dim, int st, float lo, float hi, float *__restrict__ mags) {
+    extern __shared__ float sq[];
+    __shared__ uint32_t isum;
+    const uint64_t row = blockIdx.x;
+    const uint32_t tid = threadIdx.x;
+    if (st == CDB_ST_U8) {
+        if (tid == 0) isum = 0;
+        __syncthreads();
+        uint32_t ss = 0;
+        for (uint32_t c = tid; c < dim; c += 128) {
+            const uint32_t q = quant_u8(src.get(row, c), lo, hi);
+            ss += q * q;
+        }
+        atomicAdd(&isum, ss);
+        __syncthreads();
+        if (tid == 0) mags[row] = __fsqrt_rn((float)isum);
+        return;
+    }
+    for (uint32_t c = tid; c < dim; c += 128) {
+        const float x = src.get(row, c);
+        sq[c] = __fmul_rn(x, x);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (uint32_t c = 0; c < dim; ++c) s = __fadd_rn(s, sq[c]);
+        mags[row] = __fsqrt_rn(s);
+    }
+}
+
 template <class Src>
 static cdb_status run_quantize(Src src, uint64_t n, uint32_t dim, int st, float lo, float hi, uint8_t *codes,
                                uint32_t row_pitch, float *mags, float *raw, uint32_t raw_pitch_elems, cudaStream_t s) {
@@ -126,7 +166,10 @@ static cdb_status run_quantize(Src src, uint64_t n, uint32_t dim, int st, float 
     uint32_t blocks = (uint32_t)((total + 255) / 256);
     quantize_codes_kernel<Src><<<blocks, 256, 0, s>>>(src, n, dim, st, lo, hi, codes, row_pitch, raw, raw_pitch_elems);
     CDB_LAUNCH_CHECK();
-    mags_kernel<Src><<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(src, n, dim, st, lo, hi, mags);
+    if (n <= 8192 && (size_t)dim * 4 <= 48 * 1024)
+        mags_cta_kernel<Src><<<(uint32_t)n, 128, (size_t)dim * 4, s>>>(src, n, dim, st, lo, hi, mags);
+    else
+        mags_kernel<Src><<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(src, n, dim, st, lo, hi, mags);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }

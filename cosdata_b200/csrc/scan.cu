@@ -58,43 +58,43 @@ __device__ inline void topk_offer(const TopK &t, int b, uint64_t key) {
         t.buf[(size_t)b * t.cap + pos] = key;
     }
 }
-// one warp: keep the best min(n,k) keys of buffer b, sorted best-first
-__device__ inline void topk_compact_warp(const TopK &t, int b, int lane) {
+// whole CTA: keep the best min(n,k) keys of buffer b, sorted best-first (rank selection: keys are unique).  All threads
+// of the block must call it; buffers are processed one after the other with all 256 threads on each -- a single warp per
+// buffer made the final compaction of a short scan (few passes per CTA, cold threshold, ~700 entries) cost more than the
+// scan itself (84 us for 100k x 128 at batch 1).
+__device__ inline void topk_compact_block(const TopK &t, int b) {
     const int n = t.cnt[b];
     uint64_t *B = t.buf + (size_t)b * t.cap;
     uint64_t *T = t.tmp + (size_t)b * t.k;
-    for (int idx = lane; idx < n; idx += 32) {
+    for (int idx = threadIdx.x; idx < n; idx += SCAN_THREADS) {
         const uint64_t key = B[idx];
         uint32_t rank = 0;
         for (int j = 0; j < n; ++j) rank += (B[j] > key);
         if (rank < t.k) T[rank] = key;
     }
-    __syncwarp();
+    __syncthreads();
     const int m = n < (int)t.k ? n : (int)t.k;
-    for (int idx = lane; idx < m; idx += 32) B[idx] = T[idx];
-    __syncwarp();
-    if (lane == 0) {
+    for (int idx = threadIdx.x; idx < m; idx += SCAN_THREADS) B[idx] = T[idx];
+    if (threadIdx.x == 0) {
         t.cnt[b] = m;
         if (n >= (int)t.k) t.thr[b] = T[t.k - 1];
     }
+    __syncthreads();
 }
 // end of a pass: compacts when a buffer could overflow during the next pass.
 // A reader may miss appends of the current pass (<= RPP), hence the slack in topk_cap().
 __device__ inline void topk_end_pass(const TopK &t, uint32_t qb) {
     int pred = (threadIdx.x < qb) ? (t.cnt[threadIdx.x] > (int)(t.k + RPP)) : 0;
     if (__syncthreads_or(pred)) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (uint32_t b = warp; b < qb; b += SCAN_THREADS / 32) topk_compact_warp(t, b, lane);
-        __syncthreads();
+        for (uint32_t b = 0; b < qb; ++b)
+            if (t.cnt[b] > (int)t.k) topk_compact_block(t, (int)b);   // block-uniform condition (shared memory, after the barrier)
     }
 }
 // qslot0 = first slot of this CTA's queries in the partial buffer; err goes to the real query index (qidx, may be null)
 __device__ inline void topk_finish(const TopK &t, uint32_t qb, uint32_t nqv, uint32_t qslot0, uint32_t split,
                                    uint32_t nsplit, uint64_t *partial, uint32_t *err32, const uint32_t *qidx) {
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint32_t b = warp; b < qb; b += SCAN_THREADS / 32) topk_compact_warp(t, b, lane);
-    __syncthreads();
+    for (uint32_t b = 0; b < qb; ++b) topk_compact_block(t, (int)b);
     for (uint32_t idx = threadIdx.x; idx < nqv * t.k; idx += blockDim.x) {
         uint32_t b = idx / t.k, j = idx % t.k;
         partial[((size_t)(qslot0 + b) * nsplit + split) * t.k + j] = (int)j < t.cnt[b] ? t.buf[(size_t)b * t.cap + j] : 0ull;
@@ -336,7 +336,7 @@ static cdb_status launch_scan(const ScanArgs &a, uint32_t sel_grid, cudaStream_t
 }
 
 uint32_t scan_sel_grid(int sm_count, uint32_t k) {   // the merge holds grid*k keys in shared memory
-    const uint32_t lim = 20480u / (k ? k : 1u);
+    const uint32_t lim = 16384u / (k ? k : 1u);   // padded to a power of two for the bitonic merge: <= 128 KB
     const uint32_t g = 2u * (uint32_t)sm_count;
     return g < lim ? g : (lim ? lim : 1u);
 }
@@ -393,15 +393,42 @@ __global__ void merge_partials_kernel(int metric, const uint64_t *__restrict__ p
     }
     if (local) atomicAdd(&nvalid, local);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
-        const uint64_t key = keys[i];
-        if (!key) continue;
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < M; ++j) rank += keys[j] > key;
-        if (rank < k) {
-            ids[(size_t)q * k + rank] = key64_id(key);
-            scores[(size_t)q * k + rank] = __uint_as_float(key_to_bits(metric, (uint32_t)(key >> 32)));
-            if (out_keys) out_keys[(size_t)q * k + rank] = key;
+    if (M <= 768) {
+        // rank selection: O(M^2 / threads)
+        for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+            const uint64_t key = keys[i];
+            if (!key) continue;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < M; ++j) rank += keys[j] > key;
+            if (rank < k) {
+                ids[(size_t)q * k + rank] = key64_id(key);
+                scores[(size_t)q * k + rank] = __uint_as_float(key_to_bits(metric, (uint32_t)(key >> 32)));
+                if (out_keys) out_keys[(size_t)q * k + rank] = key;
+            }
+        }
+    } else {
+        // many lists (a short scan split over every SM): bitonic sort in shared memory, O(M log^2 M / threads) -- the
+        // quadratic selection took 342 us for 391 lists x 10 (batch 1 over 100k rows)
+        uint32_t P = 1;
+        while (P < M) P <<= 1;
+        for (uint32_t i = M + threadIdx.x; i < P; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        for (uint32_t size = 2; size <= P; size <<= 1)
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                    const uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                    const bool desc = (lo & size) == 0;
+                    const uint64_t x = keys[lo], y = keys[hi];
+                    if ((x < y) == desc) { keys[lo] = y; keys[hi] = x; }
+                }
+                __syncthreads();
+            }
+        const uint32_t nout = min((uint32_t)nvalid, k);
+        for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+            const uint64_t key = keys[i];
+            ids[(size_t)q * k + i] = key64_id(key);
+            scores[(size_t)q * k + i] = __uint_as_float(key_to_bits(metric, (uint32_t)(key >> 32)));
+            if (out_keys) out_keys[(size_t)q * k + i] = key;
         }
     }
     if (threadIdx.x == 0 && counts) counts[q] = (uint32_t)nvalid < k ? (uint32_t)nvalid : k;
@@ -411,7 +438,9 @@ cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t
                                  uint32_t *d_ids, float *d_scores, uint32_t *d_counts, cudaStream_t s, const uint32_t *qsel,
                                  uint32_t sel_cap, int sel_mode, uint32_t sel_grid, uint32_t sel_qb, uint64_t *d_out_keys) {
     if (nq == 0) return CDB_OK;
-    size_t smem = (size_t)(sel_mode ? sel_grid : nlists) * k * 8;
+    size_t M = (size_t)(sel_mode ? sel_grid : nlists) * k, P = 1;
+    while (P < M) P <<= 1;
+    size_t smem = (M <= 768 ? M : P) * 8;
     if (smem > 200 * 1024) { set_error("merge: too many partial candidates"); return CDB_INVALID_PARAMS; }
     CDB_CUDA_TRY(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_partials_kernel<<<sel_mode ? sel_cap : nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts, qsel,

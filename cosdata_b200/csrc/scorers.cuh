@@ -130,6 +130,38 @@ __device__ inline float dot_f16_seq(const __half *__restrict__ a, const __half *
     return s;
 }
 
+// ------------------------------------------------------------------ bf16 (labelled extension)
+// same sequential fold as dot_f16_seq; a bf16 widens to f32 by a 16-bit shift, products of two bf16 are exact in f32
+// (PRMT keeps the widening on the integer pipe; ptxas turns `w << 16` into an IMAD on the FMA pipe)
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0u, 0x1044)); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ inline float dot_bf16_seq(const uint16_t *__restrict__ a, const uint16_t *__restrict__ b, uint32_t n) {
+    float s = 0.0f;
+    uint32_t i = 0;
+    if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
+        for (; i + 8 <= n; i += 8) {
+            const uint4 va = *reinterpret_cast<const uint4 *>(a + i);
+            const uint4 vb = *reinterpret_cast<const uint4 *>(b + i);
+            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                s = __fadd_rn(s, __fmul_rn(bf16_lo(wa[e]), bf16_lo(wb[e])));
+                s = __fadd_rn(s, __fmul_rn(bf16_hi(wa[e]), bf16_hi(wb[e])));
+            }
+        }
+    }
+    for (; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__uint_as_float((uint32_t)a[i] << 16), __uint_as_float((uint32_t)b[i] << 16)));
+    return s;
+}
+__device__ inline float euclid_bf16_seq(const uint16_t *a, const uint16_t *b, uint32_t n) {
+    float s = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float d = __fsub_rn(__uint_as_float((uint32_t)a[i] << 16), __uint_as_float((uint32_t)b[i] << 16));
+        s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    return __fsqrt_rn(s);
+}
+
 // ------------------------------------------------------------------ u8
 __device__ inline uint64_t dot_u8_int(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, uint32_t n) {
     uint64_t total = 0;
@@ -244,6 +276,7 @@ __device__ inline int pair_distance(int metric, int st, uint32_t dim,
         case CDB_ST_SUB2: dot = (float)dot_quaternary_int((const uint8_t *)x, x_pp, (const uint8_t *)y, y_pp, nb); have_dot = true; break;
         case CDB_ST_SUB3: dot = (float)dot_octal_int((const uint8_t *)x, x_pp, (const uint8_t *)y, y_pp, nb); have_dot = true; break;
         case CDB_ST_F16: dot = dot_f16_seq((const __half *)x, (const __half *)y, dim); have_dot = true; break;
+        case CDB_ST_BF16: dot = dot_bf16_seq((const uint16_t *)x, (const uint16_t *)y, dim); have_dot = true; break;
         case CDB_ST_F32:
             if (metric == CDB_METRIC_DOT_PRODUCT) return CDB_STORAGE_MISMATCH;  // dotproduct.rs:62
             dot = dot_f32_avx_order_1t((const float *)x, (const float *)y, dim); have_dot = true; break;
@@ -263,6 +296,7 @@ __device__ inline int pair_distance(int metric, int st, uint32_t dim,
         switch (st) {
         case CDB_ST_U8: *out = canon_nan(euclid_u8_seq((const uint8_t *)x, (const uint8_t *)y, dim)); return CDB_OK;
         case CDB_ST_F16: *out = canon_nan(euclid_f16_seq((const __half *)x, (const __half *)y, dim)); return CDB_OK;
+        case CDB_ST_BF16: *out = canon_nan(euclid_bf16_seq((const uint16_t *)x, (const uint16_t *)y, dim)); return CDB_OK;
         case CDB_ST_SUB1: case CDB_ST_SUB2: case CDB_ST_SUB3: return CDB_UNSUPPORTED;  // euclidean.rs:34-37 unimplemented!()
         default: return CDB_STORAGE_MISMATCH;
         }
@@ -276,7 +310,8 @@ __device__ inline int pair_distance(int metric, int st, uint32_t dim,
             *out = (float)s;
             return CDB_OK;
         }
-        case CDB_ST_F16: *out = (float)hamming_bytes((const uint8_t *)x, (const uint8_t *)y, dim * 2, 0xFFFFFFFFu); return CDB_OK;
+        case CDB_ST_F16: case CDB_ST_BF16:
+            *out = (float)hamming_bytes((const uint8_t *)x, (const uint8_t *)y, dim * 2, 0xFFFFFFFFu); return CDB_OK;
         default: return CDB_STORAGE_MISMATCH;
         }
     default: return CDB_INVALID_PARAMS;

@@ -99,69 +99,94 @@ __device__ __forceinline__ void sort_desc(float (&v)[NG]) {
 // They must not tighten the bound: accumulators that are exactly 0.0f are left out of the class maxima (dropping values
 // from a maximum only loosens a lower bound, so a proper row that happens to score 0.0f is harmless).  Degenerate rows
 // that are not all-zero are put on every candidate list by the host side (api.cu), all-zero rows are provably worst.
-template <int STAGES, int NG, bool HAS_DEG>
+// CTAS = 2: two CTAs of a cluster (one TPC) work as a pair on query tiles 2p and 2p+1 against the same corpus tile:
+// tcgen05.mma.cta_group::2 with M = 256 (each CTA's 128 queries stay in its own shared memory and TMEM) and N = 256 corpus
+// rows of which each CTA stages only HALF (128 rows).  Per SM and k-block the shared-memory traffic drops from 96 KB
+// (fill 48 + operand reads 48) to 64 KB (fill 32 + reads 32) against 542 tensor-pipe cycles of work -- the single-CTA form
+// is bound by the 128 B/clk shared-memory port.  Barriers of the pair live in the leader (even) CTA:
+// both CTAs' TMA loads complete on its full barrier, its MMA thread issues for both, commits multicast to both CTAs'
+// empty / accumulator-full barriers, and both epilogues release the accumulator stage on its accumulator-empty barrier.
+template <int STAGES, int NG, bool HAS_DEG, int CTAS>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TensorScanArgs a) {
+    constexpr uint32_t B_ROWS = TS_BLOCK_N / CTAS;                          // corpus rows staged by this CTA
+    constexpr uint32_t B_BYTES = B_ROWS * TS_BLOCK_K * 2;
+    constexpr uint32_t STAGE_BYTES = TS_A_BYTES + B_BYTES;                  // 48 KB, resp. 32 KB per CTA of a pair
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TS_BLOCK_N >> 3) << 17) | ((uint32_t)((TS_BLOCK_M * CTAS) >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *tiles = smem;
-    uint32_t *lstage = reinterpret_cast<uint32_t *>(tiles + STAGES * TS_STAGE_BYTES);       // [128][TS_LSTAGE+1]
+    uint32_t *lstage = reinterpret_cast<uint32_t *>(tiles + STAGES * STAGE_BYTES);           // [128][TS_LSTAGE+1]
     uint64_t *bars = reinterpret_cast<uint64_t *>(lstage + TS_BLOCK_M * (TS_LSTAGE + 2));     // 8-byte aligned
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = CTAS == 2 ? cluster_ctarank() : 0u;              // 0 = leader of the pair
+    const bool leader = crank == 0;
 
     // work assignment: CTA c owns query tile c % mtiles and every G-th corpus tile
     // gridDim.x is a multiple of mtiles: the mtiles CTAs of group g walk the same corpus tiles g, g+G, ...
     // and are kept within `window` tiles of each other, so a corpus tile is fetched from HBM once and
-    // served to the other query tiles from L2.
+    // served to the other query tiles from L2.  (Pairs: mtiles is even, CTAs 2j and 2j+1 of a group are one cluster.)
     const uint32_t mt = blockIdx.x % a.mtiles;
     const uint32_t g = blockIdx.x / a.mtiles;
     const uint32_t G = gridDim.x / a.mtiles;
+    const uint32_t issuers = a.mtiles / CTAS;                               // MMA issuers per group (progress counter units)
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128 * CTAS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TS_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TS_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TS_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();               // barriers of both CTAs initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (one per CTA) =====================
         if (lane == 0) {
             uint32_t s = 0, phase = 0, t = 0;
             for (uint32_t nt = g; nt < a.ntiles; nt += G, ++t) {
                 if (a.mtiles > 1 && t >= a.window) {
-                    // bounded drift: every CTA of the group must have issued tile t - window
-                    const uint32_t need = (t - a.window + 1) * a.mtiles;
+                    // bounded drift: every issuer of the group must have issued tile t - window
+                    const uint32_t need = (t - a.window + 1) * issuers;
                     // bounded spin: if a peer CTA is not resident (GPU shared with another stream) we only lose locality
                     for (int spin = 0; spin < 20000 && *reinterpret_cast<volatile uint32_t *>(a.progress + g) < need; ++spin) __nanosleep(64);
                 }
                 for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
-                    mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);
+                    mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1);          // own stage free (commit multicast reaches both CTAs)
                     const uint32_t fb = smem_u32(&full_bar[s]);
-                    mbar_expect_tx(fb, TS_STAGE_BYTES);
-                    const uint32_t sa = smem_u32(tiles + (size_t)s * TS_STAGE_BYTES);
-                    tma_load_2d(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
-                    tma_load_2d(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N));
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+                    if (CTAS == 2) {
+                        if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);     // the leader's barrier counts both CTAs' bytes
+                        tma_load_2d_pair(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
+                        tma_load_2d_pair(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N + crank * B_ROWS));
+                    } else {
+                        mbar_expect_tx(fb, STAGE_BYTES);
+                        tma_load_2d(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
+                        tma_load_2d(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N));
+                    }
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (the leader issues for the pair) =====================
+        if (lane == 0 && leader) {
             uint32_t s = 0, phase = 0, as = 0, aphase = 0;
             for (uint32_t nt = g; nt < a.ntiles; nt += G) {
                 mbar_wait(smem_u32(&tempty_bar[as]), aphase ^ 1);
@@ -170,15 +195,19 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 for (uint32_t kb = 0; kb < a.kblocks; ++kb) {
                     mbar_wait(smem_u32(&full_bar[s]), phase);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(tiles + (size_t)s * TS_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TS_A_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < TS_BLOCK_K / 16; ++kk)  // +32 bytes along K = +2 in the encoded start address
-                        tcgen05_mma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, TS_IDESC, (kb | kk) != 0);
-                    tcgen05_commit(smem_u32(&empty_bar[s]));  // frees the smem stage when these MMAs retire
+                    for (int kk = 0; kk < TS_BLOCK_K / 16; ++kk) {  // +32 bytes along K = +2 in the encoded start address
+                        if (CTAS == 2) tcgen05_mma_f16_pair(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                        else tcgen05_mma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                    }
+                    // frees the smem stage (of both CTAs) when these MMAs retire
+                    if (CTAS == 2) tcgen05_commit_pair(smem_u32(&empty_bar[s])); else tcgen05_commit(smem_u32(&empty_bar[s]));
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
-                tcgen05_commit(smem_u32(&tfull_bar[as]));  // accumulator complete
+                // accumulator complete (in both CTAs' TMEM)
+                if (CTAS == 2) tcgen05_commit_pair(smem_u32(&tfull_bar[as])); else tcgen05_commit(smem_u32(&tfull_bar[as]));
                 if (a.mtiles > 1) atomicAdd(a.progress + g, 1u);  // all loads of this tile have landed in smem
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
@@ -274,7 +303,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[as]));  // the accumulator stage is free: the MMA warp can run ahead
+            // the accumulator stage is free: the MMA warp can run ahead (pairs: both CTAs' epilogues report to the leader)
+            if (CTAS == 2) mbar_arrive_leader(smem_u32(&tempty_bar[as])); else mbar_arrive(smem_u32(&tempty_bar[as]));
             if (++as == 2) { as = 0; aphase ^= 1; }
             // refresh the shared bound: every tile early on (and in the seeding pass), then every 8th tile
             if (qvalid && (t < 8 || (t & a.refresh_mask) == a.refresh_mask || !a.emit)) {
@@ -306,10 +336,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // pairs: no CTA leaves while its peer may still touch its barriers / smem
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS) : "memory");
+        if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TS_TMEM_COLS) : "memory");
     }
 }
 
@@ -362,6 +393,74 @@ cdb_status classify_rows_device(const float *d_raw, uint32_t pitch_elems, const 
                                 uint32_t first_row, uint32_t *d_deg, cudaStream_t s) {
     if (!n) return CDB_OK;
     classify_rows_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(d_raw, pitch_elems, d_mags, n, dim, first_row, d_deg);
+    CDB_LAUNCH_CHECK();
+    return CDB_OK;
+}
+
+// One launch prepares everything a prefilter search needs from the raw query batch (it replaces eleven memsets / small
+// kernels whose launch gaps were a fixed ~0.1 ms per batch -- the limiter of strong scaling once the scan itself takes 1.6 ms):
+//   q_raw   f32 copy in the index's pitched layout (operand of the exact re-rank), zero padded
+//   q_mags  |q| = sqrt of the SEQUENTIAL fold of x*x (vector_store.rs:412), one thread, squares staged in shared memory
+//   qh      fp16 copy of q / |q| (zero row for a degenerate norm and for the padding rows up to mtiles*128)
+//   ggm     class maxima of the query := -inf;  cand_cnt := number of pre-seeded odd rows (+ their ids);  err := 0
+//   progress counters of the seeding and of the main pass := 0
+// One CTA of 128 threads per query slot (mtiles*128 slots).
+__global__ void __launch_bounds__(128) prep_queries_kernel(const float *__restrict__ q, uint32_t nq, uint32_t dim, float *__restrict__ q_raw,
+                                                           uint32_t raw_pitch_elems, float *__restrict__ q_mags, __half *__restrict__ qh,
+                                                           uint32_t qh_pitch, int *__restrict__ ggm, const uint32_t *__restrict__ deg,
+                                                           uint32_t has_deg, uint32_t id_base, uint32_t *__restrict__ cand,
+                                                           uint32_t cand_cap, uint32_t *__restrict__ cand_cnt, uint32_t *__restrict__ err32,
+                                                           uint8_t *__restrict__ err8, uint32_t *__restrict__ progress) {
+    extern __shared__ float sq[];     // [dim] squares
+    __shared__ float s_mag;
+    const uint32_t slot = blockIdx.x, tid = threadIdx.x;
+    if (slot == 0) for (uint32_t i = tid; i < 2048; i += 128) progress[i] = 0u;
+    // class maxima: layout [tile][class][128]
+    if (tid < (uint32_t)TS_GROUPS) ggm[((size_t)(slot >> 7) * TS_GROUPS + tid) * TS_BLOCK_M + (slot & 127u)] = (int)0x807FFFFF;   // f2ord(-inf)
+    __half *hrow = qh + (size_t)slot * qh_pitch;
+    if (slot >= nq) {
+        for (uint32_t c = tid; c < qh_pitch; c += 128) hrow[c] = __float2half_rn(0.0f);
+        return;
+    }
+    const float *src = q + (size_t)slot * dim;
+    float *dst = q_raw + (size_t)slot * raw_pitch_elems;
+    for (uint32_t c = tid; c < raw_pitch_elems; c += 128) {
+        const float v = c < dim ? src[c] : 0.0f;
+        dst[c] = v;
+        if (c < dim) sq[c] = __fmul_rn(v, v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (uint32_t c = 0; c < dim; ++c) s = __fadd_rn(s, sq[c]);
+        const float m = __fsqrt_rn(s);
+        s_mag = m;
+        q_mags[slot] = m;
+        err32[slot] = 0u;
+        if (err8) err8[slot] = 0;
+        uint32_t n_odd = 0;
+        if (has_deg) {
+            n_odd = min(min(deg[1], (uint32_t)TS_MAX_ODD), cand_cap);
+            for (uint32_t i = 0; i < n_odd; ++i) cand[(size_t)slot * cand_cap + i] = id_base + deg[2 + i];
+        }
+        cand_cnt[slot] = n_odd;
+    }
+    __syncthreads();
+    const float m = s_mag;
+    const bool ok = norm_is_proper(m);
+    for (uint32_t c = tid; c < qh_pitch; c += 128)
+        hrow[c] = __float2half_rn((ok && c < dim) ? __fdiv_rn(src[c], m) : 0.0f);
+}
+
+cdb_status prep_queries_device(const float *d_q, uint32_t nq, uint32_t dim, float *d_q_raw, uint32_t raw_pitch_elems, float *d_q_mags,
+                               void *d_qh, uint32_t qh_pitch_halfs, int *d_ggm, const uint32_t *d_deg, bool has_deg, uint32_t id_base,
+                               uint32_t *d_cand, uint32_t cand_cap, uint32_t *d_cand_cnt, uint32_t *d_err32, uint8_t *d_err8,
+                               uint32_t *d_progress, cudaStream_t s) {
+    const uint32_t mtiles = (nq + TS_BLOCK_M - 1) / TS_BLOCK_M;
+    prep_queries_kernel<<<mtiles * TS_BLOCK_M, 128, (size_t)dim * 4, s>>>(d_q, nq, dim, d_q_raw, raw_pitch_elems, d_q_mags,
+                                                                          reinterpret_cast<__half *>(d_qh), qh_pitch_halfs, d_ggm, d_deg,
+                                                                          has_deg ? 1u : 0u, id_base, d_cand, cand_cap, d_cand_cnt, d_err32,
+                                                                          d_err8, d_progress);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }
@@ -432,36 +531,54 @@ static int tensor_scan_stages(uint32_t k) {
     if (k > (uint32_t)TS_GROUPS) return 0;  // the class-maximum bound needs k <= 64 disjoint classes
     return TS_STAGES;
 }
+constexpr int TS_STAGES_PAIR = 6;   // 32 KB per stage and CTA in the pair form: a deeper ring fits
+static size_t tensor_scan_smem(int stages, uint32_t stage_bytes) {
+    return 1024 + (size_t)stages * stage_bytes + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * stages + 4) * 8 + 16;
+}
 size_t tensor_scan_smem_bytes(uint32_t k) {
     if (!tensor_scan_stages(k)) return (size_t)1 << 30;
-    return 1024 + (size_t)TS_STAGES * TS_STAGE_BYTES + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * TS_STAGES + 4) * 8 + 16;
+    return tensor_scan_smem(TS_STAGES, TS_STAGE_BYTES);
 }
 
-template <int STAGES, int NG, bool HAS_DEG>
-static cdb_status launch_tensor_scan_gd(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
-                                        size_t smem, cudaStream_t s) {
-    auto kern = tensor_scan_kernel<STAGES, NG, HAS_DEG>;
+template <int STAGES, int NG, bool HAS_DEG, int CTAS>
+static cdb_status launch_tensor_scan_gdc(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
+                                         cudaStream_t s) {
+    auto kern = tensor_scan_kernel<STAGES, NG, HAS_DEG, CTAS>;
+    const size_t smem = tensor_scan_smem(STAGES, TS_A_BYTES + TS_B_BYTES / CTAS);
     CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
+    if (CTAS == 1) {
+        kern<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TS_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CDB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mq, mx, a));
+    }
     CDB_LAUNCH_CHECK();
     return CDB_OK;
 }
 
-template <int STAGES, int NG>
-static cdb_status launch_tensor_scan_g(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
-                                       size_t smem, cudaStream_t s) {
-    return a.has_deg ? launch_tensor_scan_gd<STAGES, NG, true>(mq, mx, a, grid, smem, s)
-                     : launch_tensor_scan_gd<STAGES, NG, false>(mq, mx, a, grid, smem, s);
+template <int NG, int CTAS>
+static cdb_status launch_tensor_scan_g(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid, cudaStream_t s) {
+    constexpr int ST = CTAS == 2 ? TS_STAGES_PAIR : TS_STAGES;
+    return a.has_deg ? launch_tensor_scan_gdc<ST, NG, true, CTAS>(mq, mx, a, grid, s)
+                     : launch_tensor_scan_gdc<ST, NG, false, CTAS>(mq, mx, a, grid, s);
 }
 
 // fewer classes = cheaper bound refresh (the sort network grows as NG log^2 NG); the bound stays within ~1.5x of the
 // exact k-th best as long as k is well below NG
-template <int STAGES>
-static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
-                                     size_t smem, cudaStream_t s) {
-    if (a.k <= 12) return launch_tensor_scan_g<STAGES, 16>(mq, mx, a, grid, smem, s);
-    if (a.k <= 28) return launch_tensor_scan_g<STAGES, 32>(mq, mx, a, grid, smem, s);
-    return launch_tensor_scan_g<STAGES, 64>(mq, mx, a, grid, smem, s);
+template <int CTAS>
+static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid, cudaStream_t s) {
+    if (a.k <= 12) return launch_tensor_scan_g<16, CTAS>(mq, mx, a, grid, s);
+    if (a.k <= 28) return launch_tensor_scan_g<32, CTAS>(mq, mx, a, grid, s);
+    return launch_tensor_scan_g<64, CTAS>(mq, mx, a, grid, s);
 }
 
 // d_xh: fp16 normalised corpus [n_rows][pitch_halfs]; d_qh: fp16 normalised queries, padded with zero
@@ -469,7 +586,7 @@ static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &m
 cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch_halfs, uint64_t n_rows, uint32_t nq,
                               uint32_t dim, uint32_t k, float two_eps, uint32_t id_base, int *d_ggm, uint32_t *d_cand,
                               uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_progress, const uint32_t *d_deg, bool has_deg,
-                              int sm_count, cudaStream_t s) {
+                              int sm_count, cudaStream_t s, bool prepared) {
     TensorScanArgs a{};
     a.has_deg = has_deg ? 1u : 0u;
     a.progress = d_progress;
@@ -491,18 +608,23 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     a.cand_cap = cand_cap;
     const int stages = tensor_scan_stages(k);
     if (!stages) { set_error("tensor scan: k too large for shared memory"); return CDB_INVALID_PARAMS; }
-    const size_t smem = tensor_scan_smem_bytes(k);
+    // CTA pairs (cta_group::2) need an even number of query tiles; CDB_TS_PAIR=0 forces the single-CTA form (A/B runs)
+    static const bool pair_allowed = !(getenv("CDB_TS_PAIR") && atoi(getenv("CDB_TS_PAIR")) == 0);
+    const bool pair = pair_allowed && a.mtiles % 2 == 0;
     CUtensorMap mq, mx;
     cdb_status rc;
     if ((rc = make_map_f16(&mq, d_qh, (uint64_t)a.mtiles * TS_BLOCK_M, dim, pitch_halfs, TS_BLOCK_M))) return rc;
-    if ((rc = make_map_f16(&mx, d_xh, n_rows, dim, pitch_halfs, TS_BLOCK_N))) return rc;
-    fill_i32_kernel<<<(a.mtiles * TS_BLOCK_M * TS_GROUPS + 255) / 256, 256, 0, s>>>(d_ggm, (int)0x807FFFFF /* f2ord(-inf) */, a.mtiles * TS_BLOCK_M * TS_GROUPS);
-    CDB_LAUNCH_CHECK();
-    if (has_deg) {
-        seed_candidates_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_deg, id_base, nq, d_cand, cand_cap, d_cand_cnt);
+    if ((rc = make_map_f16(&mx, d_xh, n_rows, dim, pitch_halfs, pair ? TS_BLOCK_N / 2 : TS_BLOCK_N))) return rc;
+    if (!prepared) {   // prep_queries_kernel did all of this already
+        fill_i32_kernel<<<(a.mtiles * TS_BLOCK_M * TS_GROUPS + 255) / 256, 256, 0, s>>>(d_ggm, (int)0x807FFFFF /* f2ord(-inf) */, a.mtiles * TS_BLOCK_M * TS_GROUPS);
         CDB_LAUNCH_CHECK();
-    } else {
-        CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
+        if (has_deg) {
+            seed_candidates_kernel<<<(nq + 255) / 256, 256, 0, s>>>(d_deg, id_base, nq, d_cand, cand_cap, d_cand_cnt);
+            CDB_LAUNCH_CHECK();
+        } else {
+            CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
+        }
+        CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 8192, s));
     }
 
     // 1. seeding pass over a prefix of the corpus: a few CTAs per query tile, no emission, only gthr.
@@ -514,11 +636,11 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
         sa.emit = 0;
         sa.ntiles = seed_tiles;
         sa.n_rows = std::min<uint64_t>(n_rows, (uint64_t)seed_tiles * TS_BLOCK_N);
-        uint32_t per_m = std::max<uint32_t>(1, std::min<uint32_t>(8, (uint32_t)sm_count / a.mtiles));
-        per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 8));
+        // as many CTAs per query tile as the SMs allow, >= 2 corpus tiles each: the pass is a latency-bound prologue
+        uint32_t per_m = std::max<uint32_t>(1, (uint32_t)sm_count / a.mtiles);
+        per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 2));
         const uint32_t sgrid = a.mtiles * per_m;
-        CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 4096, s));
-        rc = launch_tensor_scan<TS_STAGES>(mq, mx, sa, sgrid, smem, s);
+        rc = pair ? launch_tensor_scan<2>(mq, mx, sa, sgrid, s) : launch_tensor_scan<1>(mq, mx, sa, sgrid, s);
         if (rc) return rc;
     }
     // 2. main pass.  Every CTA should own several corpus tiles, so tiny corpora are not shredded over all SMs.
@@ -527,8 +649,8 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count, std::max<uint64_t>(1, total_tiles / 4));
     grid = std::max<uint32_t>(1, grid / a.mtiles) * a.mtiles;  // whole groups only (148 SMs, 8 query tiles -> 144 CTAs)
     if (grid > (uint32_t)sm_count) { set_error("tensor scan: more query tiles than SMs"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 4096, s));
-    return launch_tensor_scan<TS_STAGES>(mq, mx, a, grid, smem, s);
+    a.progress = d_progress + 1024;   // the seeding pass used the first 1024 counters
+    return pair ? launch_tensor_scan<2>(mq, mx, a, grid, s) : launch_tensor_scan<1>(mq, mx, a, grid, s);
 }
 
 cdb_status select_fallback_device(const uint32_t *d_cnt, uint32_t cap, const float *d_qmags, uint32_t n, uint32_t *d_qsel,

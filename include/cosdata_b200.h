@@ -57,8 +57,15 @@ enum {
     CDB_ST_SUB2 = 2,
     CDB_ST_SUB3 = 3,
     CDB_ST_F16 = 4,
-    CDB_ST_F32 = 5
+    CDB_ST_F32 = 5,
+    /* LABELLED EXTENSION, not a reference storage type: bfloat16 codes.  BASELINE.json configs[2] says "bf16" while the
+     * reference only has IEEE f16 (StorageType::HalfPrecisionFP); this arm is what that variant would compute with
+     * half::bf16 in place of half::f16 -- bf16::from_f32 rounding (nearest even, NaN keeps sign and is quieted), the same
+     * sequential f32 dot product (products of two bf16 are exact in f32), the same metric arms as f16.  Parity for it is
+     * defined against the oracle's restatement only. */
+    CDB_ST_BF16 = 6
 };
+#define CDB_ST_LAST CDB_ST_BF16
 
 /* DistanceMetric (src/models/types.rs:460-467). */
 enum {
@@ -130,7 +137,7 @@ cdb_status cdb_device_count(int32_t *out);
 cdb_status cdb_synth_fill_host(uint64_t seed, uint64_t first_idx, uint64_t n, float *out);
 
 /* ------------------------------------------------- Quantization::quantize
- * bytes per code: u8 D | sub r*ceil(D/8) (planes [r][ceil(D/8)], plane 0 first) | f16 2D | f32 4D */
+ * bytes per code: u8 D | sub r*ceil(D/8) (planes [r][ceil(D/8)], plane 0 first) | f16 2D | f32 4D | bf16 2D */
 size_t cdb_code_bytes(int32_t storage_type, uint32_t dim);
 cdb_status cdb_quantize_batch(int32_t device, int32_t storage_type, float range_lo, float range_hi,
                               const float *vecs, uint64_t n, uint32_t dim,
@@ -211,6 +218,18 @@ cdb_status cdb_itoe_load(const char *collection_dir, uint64_t first_entry, uint6
 cdb_status cdb_itoe_get(const char *collection_dir, uint32_t internal_id, float *out_vector, uint32_t capacity, uint32_t *out_len);
 cdb_status cdb_index_append_itoe(cdb_index *index, const char *collection_dir, uint32_t *out_internal_ids, uint64_t max_ids,
                                  uint64_t *out_appended);
+/* Raw f32 rows for rows that were appended as codes (cdb_index_append_codes / cdb_index_append_prop_file) into a keep_raw_f32
+ * index: such rows are searchable by BRUTE_CODES at once, but HNSW / BRUTE_RAW / re-rank are refused (CDB_INVALID_PARAMS)
+ * until every row has its raw embedding -- what the reference reads from internal_to_external_map (collection.rs:368-384).
+ *   cdb_index_set_raw_f32        rows [first_row, first_row+n) <- vecs (n x dim f32); also builds the fp16 shadow rows
+ *   cdb_index_raw_missing        rows still lacking a raw embedding
+ *   cdb_index_fill_raw_from_itoe row r <- embedding of internal id row_ids[r] from the itoe store (CDB_INVALID_ID = the row
+ *                                has none by design, e.g. the root vector).  Cold start of a quantized on-disk index:
+ *                                append_prop_file -> fill_raw_from_itoe(ids it returned) -> set_graph_from_files. */
+cdb_status cdb_index_set_raw_f32(cdb_index *index, uint64_t first_row, const float *vecs, uint64_t n);
+uint64_t cdb_index_raw_missing(const cdb_index *index);
+cdb_status cdb_index_fill_raw_from_itoe(cdb_index *index, const char *collection_dir, const uint32_t *row_ids, uint64_t n_rows,
+                                        uint64_t *out_filled, uint64_t *out_missing);
 /* generate rows [first_row, first_row+n) of synthetic stream `seed` ON DEVICE and append
  * them (exactly what cdb_index_append_f32 would store for the same values) */
 cdb_status cdb_index_append_synthetic(cdb_index *index, uint64_t seed, uint64_t first_row, uint64_t n);
@@ -404,6 +423,11 @@ cdb_status cdb_merge_topk_device(int32_t device, int32_t metric, const uint32_t 
  * CDB_HNSW_PROF_SLOTS entries) receives the sums accumulated so far.  Synchronizes the device. */
 #define CDB_HNSW_PROF_SLOTS 16
 cdb_status cdb_index_hnsw_profile(cdb_index *index, int32_t enable, uint64_t *out);
+/* dense tcgen05 issue-rate probe (csrc/tc_probe.cu): every SM issues M128 x N256 MMAs on shared-memory-resident operands,
+ * no loads, no epilogue.  kind_i8 != 0: kind::i8 (u8 x u8 -> s32), else kind::f16.  out_tops = 2*M*N*K*count / time in
+ * TOP/s resp. TFLOP/s: the measured roofline denominator of the integer tensor path (MEASURED_PEAKS.json only has bf16).
+ * iters = 0 -> default length (~10 ms). */
+cdb_status cdb_debug_tensor_peak(int32_t device, int32_t kind_i8, uint32_t iters, double *out_tops, float *out_ms);
 /* measurement switch: kernel variant of CDB_MODE_HNSW searches (results are identical for every value).  Bits: 1 cooperative
  * f16 conversion, 2 next-head adjacency preload, 4 fixed-set walk through atomics, 8 round-1 CTA-per-query kernel;
  * 0xFFFFFFFF restores the default.  Process-wide. */

@@ -153,6 +153,32 @@ float orc_dot_f16(const uint16_t *a, const uint16_t *b, size_t n) {
     return s;
 }
 
+/* ---- LABELLED EXTENSION (not in the reference): bfloat16 storage, what StorageType::HalfPrecisionFP would compute with
+ * half::bf16 in place of half::f16 (BASELINE.json configs[2] says "bf16").  half 2.4 `bf16::from_f32`: round to nearest
+ * even on the upper 16 bits, NaN keeps its sign and is quieted. */
+uint16_t orc_f32_to_bf16(float v) {
+    uint32_t x;
+    memcpy(&x, &v, 4);
+    if ((x & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((x >> 16) | 0x0040u);
+    const uint32_t round_bit = 0x00008000u;
+    if ((x & round_bit) != 0 && (x & (3u * round_bit - 1u)) != 0) return (uint16_t)((x >> 16) + 1u);
+    return (uint16_t)(x >> 16);
+}
+float orc_bf16_to_f32(uint16_t h) {
+    uint32_t x = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &x, 4);
+    return f;
+}
+float orc_dot_bf16(const uint16_t *a, const uint16_t *b, size_t n) {
+    float s = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float p = orc_bf16_to_f32(a[i]) * orc_bf16_to_f32(b[i]);
+        s = s + p;
+    }
+    return s;
+}
+
 /* src/models/dot_product.rs:59-62 */
 float orc_dot_f32_scalar(const float *a, const float *b, size_t n) {
     float s = 0.0f;
@@ -350,7 +376,7 @@ size_t orc_code_bytes(int st, size_t dim) {
     switch (st) {
     case ORC_ST_U8: return dim;
     case ORC_ST_SUB1: case ORC_ST_SUB2: case ORC_ST_SUB3: return (size_t)st * ((dim + 7) / 8);
-    case ORC_ST_F16: return dim * 2;
+    case ORC_ST_F16: case ORC_ST_BF16: return dim * 2;
     case ORC_ST_F32: return dim * 4;
     default: return 0;
     }
@@ -408,6 +434,12 @@ int orc_quantize(int st, float lo, float hi, const float *v, size_t dim, void *o
         *out_mag = orc_mag_f32(v, dim);
         return ORC_OK;
     }
+    case ORC_ST_BF16: {
+        uint16_t *q = (uint16_t *)out_code;
+        for (size_t i = 0; i < dim; ++i) q[i] = orc_f32_to_bf16(v[i]);
+        *out_mag = orc_mag_f32(v, dim);
+        return ORC_OK;
+    }
     case ORC_ST_F32:
         memcpy(out_code, v, dim * 4);
         *out_mag = orc_mag_f32(v, dim);
@@ -436,6 +468,7 @@ static int storage_dot(int st, size_t dim, const void *x, const void *y, float *
     case ORC_ST_SUB2: *dot = orc_dot_quaternary_avx2((const uint8_t *)x, (const uint8_t *)y, nb); return ORC_OK;
     case ORC_ST_SUB3: *dot = orc_dot_octal_avx2((const uint8_t *)x, (const uint8_t *)y, nb); return ORC_OK;
     case ORC_ST_F16: *dot = orc_dot_f16((const uint16_t *)x, (const uint16_t *)y, dim); return ORC_OK;
+    case ORC_ST_BF16: *dot = orc_dot_bf16((const uint16_t *)x, (const uint16_t *)y, dim); return ORC_OK;
     case ORC_ST_F32: *dot = orc_dot_f32_simd((const float *)x, (const float *)y, dim); return ORC_OK;
     default: return ORC_INVALID;
     }
@@ -485,6 +518,15 @@ static float hamming_subbyte(const uint8_t *x, const uint8_t *y, size_t nbytes, 
     }
     return total;
 }
+static float euclid_bf16(const uint16_t *x, const uint16_t *y, size_t n) {
+    float s = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float d = orc_bf16_to_f32(x[i]) - orc_bf16_to_f32(y[i]);
+        float p = d * d;
+        s = s + p;
+    }
+    return sqrtf(s);
+}
 static float hamming_f16(const uint16_t *x, const uint16_t *y, size_t n) {
     float s = 0.0f;
     for (size_t i = 0; i < n; ++i) s = s + (float)__builtin_popcount((unsigned)(x[i] ^ y[i]));
@@ -514,6 +556,7 @@ int orc_distance(int metric, int st, size_t dim, const void *x, float x_mag,
         switch (st) {
         case ORC_ST_U8: *out = euclid_u8((const uint8_t *)x, (const uint8_t *)y, dim); return ORC_OK;
         case ORC_ST_F16: *out = euclid_f16((const uint16_t *)x, (const uint16_t *)y, dim); return ORC_OK;
+        case ORC_ST_BF16: *out = euclid_bf16((const uint16_t *)x, (const uint16_t *)y, dim); return ORC_OK;
         case ORC_ST_SUB1: case ORC_ST_SUB2: case ORC_ST_SUB3: return ORC_UNIMPLEMENTED; /* euclidean.rs:34-37 */
         default: return ORC_STORAGE_MISMATCH;
         }
@@ -522,7 +565,7 @@ int orc_distance(int metric, int st, size_t dim, const void *x, float x_mag,
         case ORC_ST_U8: *out = hamming_bytes_masked((const uint8_t *)x, (const uint8_t *)y, dim, 0xFF); return ORC_OK;
         case ORC_ST_SUB1: case ORC_ST_SUB2: case ORC_ST_SUB3:
             *out = hamming_subbyte((const uint8_t *)x, (const uint8_t *)y, nb, (unsigned)st); return ORC_OK;
-        case ORC_ST_F16: *out = hamming_f16((const uint16_t *)x, (const uint16_t *)y, dim); return ORC_OK;
+        case ORC_ST_F16: case ORC_ST_BF16: *out = hamming_f16((const uint16_t *)x, (const uint16_t *)y, dim); return ORC_OK;
         default: return ORC_STORAGE_MISMATCH;
         }
     default: return ORC_INVALID;

@@ -46,7 +46,8 @@ enum {
     ORC_ST_SUB2 = 2,
     ORC_ST_SUB3 = 3,
     ORC_ST_F16 = 4,
-    ORC_ST_F32 = 5
+    ORC_ST_F32 = 5,
+    ORC_ST_BF16 = 6   /* labelled extension (bfloat16), see cosdata_oracle.c */
 };
 
 /* DistanceMetric (src/models/types.rs:460-467). */

@@ -13,6 +13,7 @@ _SO = os.path.join(_HERE, "libcosdata_oracle.so")
 
 OK, STORAGE_MISMATCH, CALCULATION_ERROR, INVALID, UNIMPLEMENTED = 0, 1, 2, 3, 6
 ST_U8, ST_SUB1, ST_SUB2, ST_SUB3, ST_F16, ST_F32 = range(6)
+ST_BF16 = 6   # labelled extension (bfloat16); not a reference StorageType
 METRIC_COSINE, METRIC_EUCLIDEAN, METRIC_HAMMING, METRIC_DOT = range(4)
 
 

@@ -38,7 +38,8 @@ def build_both(vecs, st, metric, levels=5, nb=16, nb0=32, efc=64, seed=5):
 
 @pytest.mark.parametrize("st,metric", [(ST.HalfPrecisionFP, MK.Cosine), (ST.UnsignedByte, MK.Cosine),
                                         (ST.SubByte2, MK.DotProduct), (ST.FullPrecisionFP, MK.Cosine),
-                                        (ST.SubByte3, MK.Cosine), (ST.HalfPrecisionFP, MK.DotProduct)])
+                                        (ST.SubByte3, MK.Cosine), (ST.HalfPrecisionFP, MK.DotProduct),
+                                        (ST.BFloat16, MK.Cosine), (ST.BFloat16, MK.DotProduct)])
 @pytest.mark.parametrize("ef", [16, 64, 256])
 def test_hnsw_search_matches_oracle(st, metric, ef):
     n, dim, k = 2500, 48, 10

@@ -223,7 +223,7 @@ def test_score_ids_matches_oracle(st):
     ix.close()
 
 
-@pytest.mark.parametrize("st", [ST.FullPrecisionFP, ST.UnsignedByte, ST.HalfPrecisionFP, ST.SubByte2])
+@pytest.mark.parametrize("st", [ST.FullPrecisionFP, ST.UnsignedByte, ST.HalfPrecisionFP, ST.SubByte2, ST.BFloat16])
 def test_rerank_matches_oracle(st):
     dim, n = 768, 400
     corpus = orc.synth_matrix(1200, n, dim)
@@ -307,3 +307,35 @@ def test_append_from_device_memory_and_timing_history():
         hist = ix.scan_ms_history(4)
         assert hist.size >= 1 and (hist > 0).all()
         ix.close()
+
+
+def test_searches_on_one_handle_are_reentrant():
+    """the ABI is re-entrant per handle.  Eight host threads search one index at the same time (every call leases its
+    own scratch set: buffers, stream, events); each must get exactly what a serial call returns."""
+    import threading
+    dim, n, k = 96, 60000, 10
+    corpus = orc.synth_matrix(7100, n, dim)
+    ix = cdb.DenseIndex(dim=dim, capacity=n)
+    ix.append(corpus)
+    batches = [orc.synth_matrix(7200 + t, 5 + 17 * t, dim) for t in range(8)]        # 5 .. 124 queries: exact and prefilter paths
+    want = [ix.batch_search(b, k) for b in batches]
+    got, errors = [None] * 8, []
+
+    def work(t):
+        try:
+            for _ in range(6):
+                got[t] = ix.batch_search(batches[t], k)
+        except Exception as e:                                                       # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(8):
+        assert np.array_equal(got[t][0], want[t][0]) and np.array_equal(got[t][1].view(np.uint32), want[t][1].view(np.uint32))
+        o_ids, o_scores = orc.brute_topk_f32(corpus, batches[t], k)
+        assert np.array_equal(got[t][0], o_ids) and np.array_equal(got[t][1].view(np.uint32), o_scores.view(np.uint32))
+    ix.close()

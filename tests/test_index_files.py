@@ -220,3 +220,51 @@ def test_versioned_link_files_of_enable_context_history(tmp_path):
         cdb.HnswFiles(ver_dir, root_link, pseudo_link)
     with pytest.raises(cdb.CosdataError):                                 # nothing at or below version 0
         cdb.HnswFiles(ver_dir, root_link, pseudo_link, latest_version=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("st,metric", [(0, 0), (4, 0)])
+def test_cold_start_from_a_collection_directory_end_to_end(tmp_path, st, metric):
+    """ADVICE r1 (medium): prop.data -> rows (quantized payloads), itoe store -> their raw f32 rows, index files -> graph;
+    then a filtered HNSW search on the GPU must equal the oracle's on the source graph.  Storage is U8 / F16, i.e. the raw
+    rows are NOT derivable from the codes -- the case the documented cold start could not serve before."""
+    from tests.test_itoe_file import TreeMapWriter, raw_embedding
+    vecs, mg = mdgraph.build(n=500, dim=24, md_dims=6, levels=3, nb=8, nb0=16, storage_type=st, metric=metric, seed=17)
+    fg = mg.fg
+    idx_dir, coll_dir = str(tmp_path / "coll" / "idx"), str(tmp_path / "coll")
+    os.makedirs(coll_dir)
+    root_link, pseudo_link = write_index_dir(idx_dir, vecs, mg, seed=2)
+    n = fg.n
+    w = TreeMapWriter()
+    for row in range(n):                                                  # raw embeddings are keyed by the base id of the row
+        w.insert(row % 3, row * 4, raw_embedding(f"vec-{row}", vecs[row]))
+    w.serialize(coll_dir)
+
+    ix = cdb.DenseIndex(dim=24, storage_type=cdb.StorageType(st), metric=cdb.DistanceMetricKind(metric), capacity=vecs.shape[0],
+                        keep_raw_f32=True)
+    cnt, ids = ix.append_prop_file(os.path.join(idx_dir, "prop.data"), max_ids=vecs.shape[0])
+    assert cnt == vecs.shape[0] and ix.raw_missing == cnt
+    with pytest.raises(cdb.CosdataError):                                 # no raw rows yet: the re-ranking modes are refused
+        ix.batch_search(vecs[:2], 3)
+    row_ids = ids.copy()
+    row_ids[n:] = cdb.INVALID_ID                                          # the two root vectors have no embedding by design
+    assert np.array_equal(row_ids[:n], np.arange(n, dtype=np.uint32) * 4)
+    filled, missing = ix.fill_raw_from_itoe(coll_dir, row_ids)
+    assert (filled, missing) == (vecs.shape[0], 0) and ix.raw_missing == 0
+    hf = cdb.HnswFiles(idx_dir, root_link, pseudo_link)
+    hf.apply(ix)
+    hf.close()
+    q, filters = mdgraph.make_queries(vecs, mg, 48, seed=5)
+    got = ix.batch_search_filtered(q, filters, 5, ef_search=24, shortlist_size=64)
+    want = pymeta.search_batch_md(mg, vecs, q, filters, 5, ef_search=24)
+    for g, w_ in zip(got, want[:4]):
+        assert np.array_equal(np.asarray(g).view(np.uint8), np.asarray(w_).view(np.uint8))
+    # a row whose id is unknown to the store is reported, not silently zero-filled
+    bad = row_ids.copy()
+    bad[3] = 999_999
+    ix2 = cdb.DenseIndex(dim=24, storage_type=cdb.StorageType(st), metric=cdb.DistanceMetricKind(metric), capacity=vecs.shape[0],
+                         keep_raw_f32=True)
+    ix2.append_prop_file(os.path.join(idx_dir, "prop.data"))
+    with pytest.raises(cdb.CosdataError):
+        ix2.fill_raw_from_itoe(coll_dir, bad)
+    ix.close(); ix2.close()

@@ -346,3 +346,38 @@ def test_brute_codes_zero_norm_sets_error_flag():
     assert rc == 0 and err.tolist() == [1, 1] and 7 not in ids
     rc, ids, scores, err = orc.brute_topk_codes(orc.METRIC_DOT, orc.ST_SUB2, dim, codes, mags, qc, qm, 5)
     assert rc == 0 and err.tolist() == [0, 0]
+
+
+# ------------------------------------------------------------------ bfloat16 (labelled extension, ST_BF16)
+def test_bf16_extension_conversion_and_dot_against_independent_restatements():
+    """not a reference storage type: what HalfPrecisionFP would compute with half::bf16.  Conversion = round to nearest
+    even on the upper 16 bits (NaN keeps its sign, quiet bit set); dot = sequential f32 fold of exact products."""
+    rng = np.random.default_rng(77)
+    v = np.concatenate([rng.normal(size=4000).astype(np.float32), orc.synth_matrix(5, 1, 4000)[0],
+                        np.array([0.0, -0.0, 1.0, -1.0, 1e-40, -1e-40, 3.3895314e38, np.inf, -np.inf, 65504.0,
+                                  1.00390625, 1.005859375, 1.01171875], dtype=np.float32)])
+    code, mag = orc.quantize_batch(orc.ST_BF16, v[None])
+    got = code.view(np.uint16)[0]
+    x = v.view(np.uint32).astype(np.uint64)
+    want = ((x + 0x7FFF + ((x >> 16) & 1)) >> 16).astype(np.uint16)          # RNE restated arithmetically
+    assert np.array_equal(got, want)
+    bits = lambda a_: np.ascontiguousarray(a_, dtype=np.float32).view(np.uint32)
+    nan = np.array([np.float32("nan"), -np.float32("nan")], dtype=np.float32)
+    ncode, _ = orc.quantize_batch(orc.ST_BF16, nan[None])
+    nb = ncode.view(np.uint16)[0]
+    assert ((nb & 0x7F80) == 0x7F80).all() and ((nb & 0x0040) != 0).all() and (nb[0] >> 15) != (nb[1] >> 15)
+    # dot: exact products (8-bit significands), sequential f32 adds
+    a, b = orc.synth_matrix(6, 1, 333)[0], orc.synth_matrix(7, 1, 333)[0]
+    ac, am = orc.quantize_batch(orc.ST_BF16, a[None])
+    bc, bm = orc.quantize_batch(orc.ST_BF16, b[None])
+    fa = (ac.view(np.uint16)[0].astype(np.uint32) << 16).view(np.float32)
+    fb = (bc.view(np.uint16)[0].astype(np.uint32) << 16).view(np.float32)
+    s = np.float32(0)
+    for i in range(333):
+        p = np.float64(fa[i]) * np.float64(fb[i])
+        assert np.float64(np.float32(p)) == p                                # the product is exact in f32
+        s = np.float32(s + np.float32(p))
+    rc, d = orc.distance(orc.METRIC_DOT, orc.ST_BF16, 333, ac[0], am[0], bc[0], bm[0])
+    assert rc == orc.OK and bits(np.array([d], np.float32))[0] == bits(np.array([s], np.float32))[0]
+    rc, c = orc.distance(orc.METRIC_COSINE, orc.ST_BF16, 333, ac[0], am[0], bc[0], bm[0])
+    assert rc == orc.OK and bits(np.array([c], np.float32))[0] == bits(np.array([s / np.float32(am[0] * bm[0])], np.float32))[0]

@@ -1,7 +1,7 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: shard ranges, global id offsets, the
-all-gather layout and the merge rule.  Per-shard searches and the merge are done by the CPU oracle
-/ numpy here (test infrastructure); on GPUs the same functions run cdb_search_batch_device and
-cdb_merge_topk_device (bench.py, tests/test_gpu_parity.py::test_merge_topk_device)."""
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: shard ranges, global id offsets, the packed-key
+all-gather layout and the merge rule.  Per-shard searches are done by the CPU oracle and the merge by the numpy mirror in
+cosdata_b200/sharding.py (test infrastructure); on GPUs the same steps run inside cdb_search_batch_sharded
+(csrc/shard_group.cu, NCCL; tests/test_gpu_sharded.py)."""
 import os
 import socket
 
@@ -15,21 +15,6 @@ from cosdata_b200.sharding import gather_and_merge, shard_range
 INVALID = 0xFFFFFFFF
 
 
-def numpy_merge(g_ids, g_scores):
-    """reference merge: better score (total order) first, then smaller id; INVALID ids ignored"""
-    import oracle as orc
-    world, b, k = g_ids.shape
-    out_ids = np.full((b, k), INVALID, dtype=np.uint32)
-    out_scores = np.zeros((b, k), dtype=np.float32)
-    for q in range(b):
-        items = [((orc.order_key(0, float(g_scores[w, q, j])) << 32) | ((~int(g_ids[w, q, j])) & 0xFFFFFFFF), int(g_ids[w, q, j]), g_scores[w, q, j])
-                 for w in range(world) for j in range(k) if int(g_ids[w, q, j]) != INVALID]
-        items.sort(key=lambda t: -t[0])
-        for j, (_, i, s) in enumerate(items[:k]):
-            out_ids[q, j], out_scores[q, j] = i, s
-    return out_ids, out_scores
-
-
 def _worker(rank, world, port, n, dim, b, k, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -41,13 +26,18 @@ def _worker(rank, world, port, n, dim, b, k, ret):
     ids, scores = orc.brute_topk_f32(corpus[row0:row0 + nloc], queries, k, threads=2)
     ids = np.where(ids == INVALID, INVALID, ids + row0).astype(np.uint32)      # id_base = row0
 
-    def all_gather(x):
-        t = torch.from_numpy(np.ascontiguousarray(x).view(np.int32))
+    calls = []
+
+    def all_gather(x):                                    # ONE collective of B*k packed u64 keys per rank
+        assert x.dtype == np.uint64
+        calls.append(x.shape)
+        t = torch.from_numpy(np.ascontiguousarray(x).view(np.int64))
         out = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(out, t)
-        return np.stack([o.numpy().view(x.dtype) for o in out])
+        return np.stack([o.numpy().view(np.uint64) for o in out])
 
-    m_ids, m_scores = gather_and_merge(ids, scores, world, all_gather, numpy_merge)
+    m_ids, m_scores = gather_and_merge(ids, scores, world, all_gather)
+    assert len(calls) == 1
     want_ids, want_scores = orc.brute_topk_f32(corpus, queries, k, threads=2)
     ok = np.array_equal(m_ids, want_ids) and np.array_equal(m_scores.view(np.uint32), want_scores.view(np.uint32))
     ret[rank] = bool(ok)
