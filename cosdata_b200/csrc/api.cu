@@ -19,6 +19,24 @@ void set_error(const std::string &msg) { t_last_error = msg; }
 std::atomic<uint64_t> g_launch_count{0};
 std::atomic<uint32_t> g_hnsw_flags{CDB_HNSW_F_DEFAULT};
 
+cudaError_t allow_max_dynamic_smem(const void *kernel) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void *>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> g(mu);
+    for (const auto &d : done)
+        if (d.first == dev && d.second == kernel) return cudaSuccess;
+    int optin = 0;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes)) != cudaSuccess) return e;
+    done.emplace_back(dev, kernel);
+    return cudaSuccess;
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -894,15 +912,15 @@ static cdb_status search_chunk_locked(cdb_index *ix, Scratch *sc, const float *d
     // ---- exact integer scoring on tcgen05 kind::i8: u8 codes in place, sub-byte codes through the digit copy
     const uint8_t *u8_rows = !raw ? (st == CDB_ST_U8 ? ix->d_codes : ix->d_digits) : nullptr;
     const bool u8_ok = u8_rows && !p->exact_only && (metric == CDB_METRIC_COSINE || metric == CDB_METRIC_DOT_PRODUCT) &&
-                       ix->size >= 16384 && p->k <= 128 && tensor_u8_smem_bytes(p->k) <= 227 * 1024 &&
+                       ix->size >= 16384 && p->k <= 64 && tensor_u8_smem_bytes(p->k) <= 227 * 1024 &&
                        (nq + 127) / 128 <= (uint32_t)ix->sm_count;
     if (u8_ok) {
         const uint32_t mt = (nq + 127) / 128;
         const uint32_t upitch = st == CDB_ST_U8 ? ix->row_pitch : ix->digit_pitch;
         const uint32_t cap = p->prefilter_k ? p->prefilter_k : (nq <= 256 ? 16384u : (nq <= 1024 ? 4096u : 2048u));
-        if ((rc = sc->qh.ensure((size_t)mt * 128 * upitch)) || (rc = sc->gthr.ensure((size_t)nq * 4)) ||
+        if ((rc = sc->qh.ensure((size_t)mt * 128 * upitch)) || (rc = sc->gthr.ensure((size_t)mt * 128 * 64 * 4)) ||
             (rc = sc->cand.ensure((size_t)nq * cap * 8)) || (rc = sc->cand_cnt.ensure((size_t)nq * 4)) ||
-            (rc = sc->progress.ensure(4096)) || (rc = sc->err32.ensure((size_t)nq * 4)))
+            (rc = sc->progress.ensure(8192)) || (rc = sc->err32.ensure((size_t)nq * 4)))
             return rc;
         if ((rc = sc->qsel.ensure((size_t)(nq + 1) * 4))) return rc;
         uint32_t *flags = sc->flags.as<uint32_t>();

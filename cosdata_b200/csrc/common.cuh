@@ -35,6 +35,17 @@ extern std::atomic<uint64_t> g_launch_count;
         }                                                                                      \
     } while (0)
 
+// Opt a kernel in to the device's maximum dynamic shared memory ONCE (per device and kernel).  Setting the attribute to
+// the size of the launch at hand, as every launch site used to, races when searches run concurrently on one handle: a
+// thread lowers the limit between another thread's cudaFuncSetAttribute and its launch ("invalid argument").  The carve-out
+// limit does not affect occupancy -- that follows the dynamic size actually requested at launch.
+cudaError_t allow_max_dynamic_smem(const void *kernel);
+#define CDB_ALLOW_SMEM(kern, bytes)                                                            \
+    do {                                                                                       \
+        (void)(bytes);                                                                         \
+        CDB_CUDA_TRY(::cdb::allow_max_dynamic_smem(reinterpret_cast<const void *>(kern)));     \
+    } while (0)
+
 // ---------------------------------------------------------------- layout
 // One stored row = code bytes padded to a 16-byte multiple (row_pitch).
 //   u8 : D bytes            sub r: r planes of ceil(D/8) bytes, plane p at p*plane_pitch

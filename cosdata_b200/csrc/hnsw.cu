@@ -123,7 +123,7 @@ cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s) {
     if (a.ef == 0 || a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
     const size_t smem = hnsw_search_smem(a.row_pitch, a.ef);
     if (smem > 200 * 1024) { set_error("hnsw: ef_search too large for shared memory"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(hnsw_search_kernel, smem);
     hnsw_search_kernel<<<a.nq, HN_THREADS, smem, s>>>(a);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
@@ -137,7 +137,7 @@ cdb_status hnsw_dedup_device(const uint32_t *d_rows, const float *d_scores, cons
     while (P < in_cap) P <<= 1;
     const size_t smem = (size_t)P * 12 + (size_t)in_cap * 4 + 16;
     if (smem > 200 * 1024) { set_error("hnsw dedup: too many levels"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(hnsw_dedup_kernel, smem);
     hnsw_dedup_kernel<<<nq, 256, smem, s>>>(d_rows, d_scores, d_n, in_cap, metric, root_row, id_base, k5, d_cand, d_cand_cnt);
     CDB_LAUNCH_CHECK();
     return CDB_OK;

@@ -266,7 +266,7 @@ cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n /* data rows; root
     CDB_CUDA_TRY(cudaMalloc(&z_n, (size_t)max_batch * L1 * 4));
     CDB_CUDA_TRY(cudaMalloc(&failed, max_batch));
     const size_t smem = hn_smem_bytes(sc.row_pitch, ef_construction);
-    CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_build_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(hnsw_build_search_kernel, smem);
     BuildArgs a{};
     a.g = bg.g;
     a.sc = sc;

@@ -199,7 +199,7 @@ cdb_status hnsw_search_md_device(const HnswMdArgs &a, cudaStream_t s) {
     if (a.a.ef == 0 || a.a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
     const size_t smem = round_up((uint32_t)hn_smem_bytes(a.a.row_pitch, a.a.ef), 16) + (size_t)HNM_Z * 12 + (size_t)a.M * 4 + 16;
     if (smem > 200 * 1024) { set_error("hnsw: ef_search / metadata dims too large for shared memory"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_search_md_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(hnsw_search_md_kernel, smem);
     hnsw_search_md_kernel<<<a.a.nq, HN_THREADS, smem, s>>>(a);
     CDB_LAUNCH_CHECK();
     return CDB_OK;
@@ -213,7 +213,7 @@ cdb_status hnsw_dedup_md_device(const uint32_t *d_ids, const uint32_t *d_rows, c
     while (P < in_cap) P <<= 1;
     const size_t smem = (size_t)P * 12 + (size_t)in_cap * 4 + 16;
     if (smem > 200 * 1024) { set_error("hnsw dedup: too many levels"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(hnsw_dedup_md_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(hnsw_dedup_md_kernel, smem);
     hnsw_dedup_md_kernel<<<nq, 256, smem, s>>>(d_ids, d_rows, d_scores, d_n, in_cap, metric, id_base, k5, d_cand, d_labels, d_cand_cnt);
     CDB_LAUNCH_CHECK();
     return CDB_OK;

@@ -276,7 +276,9 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                                   uint32_t ef, uint32_t entry, HwState &st, int lane, uint32_t flags) {
     const uint32_t pp = plane_pitch(sc.dim);
     const bool f_preload = (flags & CDB_HNSW_F_PRELOAD) != 0, f_atomfs = (flags & CDB_HNSW_F_ATOMFS) != 0;
+    const bool f_pool = (flags & CDB_HNSW_F_POOL) != 0;
     const uint32_t EFP = m.EFP;
+    const uint32_t CAPQ = 2 * EFP;      // pool form: both queue buffers are one unsorted pool
     const uint32_t bmask = nb - 1u;
     const uint32_t lt = (1u << lane) - 1u;
     long long t0 = 0;
@@ -302,14 +304,22 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
     uint32_t qlen = 1, cur = 0, visited = 0, rlen = 0;
     // adjacency slots of the head, loaded one pop ahead (while the previous pop's queue merge runs)
     uint32_t pre_node = HN_EMPTY, pre_nbl[2] = {HN_EMPTY, HN_EMPTY};
-    while (qlen > 0 && visited < ef) {
+    // POOL form (CDB_HNSW_F_POOL): the candidates are an UNSORTED pool in shared memory and the head is found by an
+    // arg-max (8 slots per lane, two 32-bit REDUX) instead of keeping a sorted queue that every pop has to merge into.
+    // The pop order is the same: the head is the best entry present, and an entry is only ever dropped when at least
+    // (pops still to come) better entries exist, so it could never have been popped.
+    uint64_t hkey = f_pool ? m.qkeys[0] : 0ull;
+    uint32_t hnode = entry;
+    bool have_head = true;
+    if (f_pool) qlen = 0;
+    while ((f_pool ? have_head : qlen > 0) && visited < ef) {
         uint64_t *Q = m.qkeys + cur * EFP;
         uint32_t *QN = m.qnodes + cur * EFP;
         long long t1 = 0, t2 = 0, t3 = 0, t4 = 0;
         if (PROF) t1 = clock64();
         // ---- pop
-        const uint32_t bn = QN[0];
-        if (lane == 0) { m.rkeys[rlen] = Q[0]; m.rnodes[rlen] = bn; }
+        const uint32_t bn = f_pool ? hnode : QN[0];
+        if (lane == 0) { m.rkeys[rlen] = f_pool ? hkey : Q[0]; m.rnodes[rlen] = bn; }
         ++rlen;
         st.pops += 1;
         // ---- adjacency: slots lane and lane + 32; ids and fixed-set bit positions
@@ -400,6 +410,85 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
         st.evals += nc;
         if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; st.rlen = rlen; return; }
         if (PROF) t4 = clock64();
+        if (f_pool) {
+            uint64_t *P = m.qkeys;
+            uint32_t *PN = m.qnodes;
+            // ---- append the new entries, pick the next head, keep the pool bounded
+            if ((uint32_t)lane < nc) { P[qlen + lane] = m.nkeys[lane]; PN[qlen + lane] = m.nnodes[lane]; }
+            if ((uint32_t)lane + 32u < nc) { P[qlen + lane + 32] = m.nkeys[lane + 32]; PN[qlen + lane + 32] = m.nnodes[lane + 32]; }
+            qlen += nc;
+            ++visited;
+            __syncwarp();
+            const uint32_t R = ef - visited;   // pops still to come
+            have_head = false;
+            pre_node = HN_EMPTY;
+            if (R > 0 && qlen > 0) {
+                uint64_t best = 0ull;
+                uint32_t bidx = 0;
+                for (uint32_t i = lane; i < qlen; i += 32) { const uint64_t k = P[i]; if (k > best) { best = k; bidx = i; } }
+                const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(best >> 32));
+                const uint32_t lo = __reduce_max_sync(0xFFFFFFFFu, (uint32_t)(best >> 32) == hi ? (uint32_t)best : 0u);
+                const uint64_t mx = ((uint64_t)hi << 32) | lo;
+                const uint32_t who = __ballot_sync(0xFFFFFFFFu, best == mx);
+                const uint32_t idx = __shfl_sync(0xFFFFFFFFu, bidx, __ffs(who) - 1);
+                hkey = mx;
+                hnode = PN[idx];
+                have_head = true;
+                if (f_preload) {   // its adjacency slots travel while the pool is tidied up
+                    pre_node = hnode;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t slot = (uint32_t)lane + 32u * h;
+                        pre_nbl[h] = slot < take ? __ldg(adj + (size_t)hnode * nb + slot) : HN_EMPTY;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && idx != qlen - 1) { P[idx] = P[qlen - 1]; PN[idx] = PN[qlen - 1]; }   // remove: last entry fills the hole
+                --qlen;
+                __syncwarp();
+                if (qlen + HN_MAX_TAKE > CAPQ) {
+                    // the next pop's up to 64 new entries might not fit: drop entries that can never be popped.  T is raised
+                    // to pivots that still have >= R better entries; anything <= T is droppable.
+                    uint64_t T = 0ull;
+                    uint32_t kept = qlen;
+                    for (uint32_t it = 0; it < 12 && kept + HN_MAX_TAKE + 32 > CAPQ; ++it) {
+                        const uint64_t pivot = P[(visited * 7u + it * 61u) % qlen];
+                        if (pivot <= T) continue;
+                        uint32_t c = 0;
+                        for (uint32_t i = lane; i < qlen; i += 32) c += P[i] > pivot;
+                        c = __reduce_add_sync(0xFFFFFFFFu, c);
+                        if (c >= R) { T = pivot; kept = c; }
+                    }
+                    if (kept + HN_MAX_TAKE > CAPQ) {
+                        // unlucky pivots: exact selection of the R best (rank by counting), slow but always sufficient (R <= EFP)
+                        for (uint32_t i0 = 0; i0 < qlen; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            const uint64_t k = i < qlen ? P[i] : 0ull;
+                            uint32_t rank = 0;
+                            for (uint32_t j = 0; j < qlen; ++j) rank += P[j] > k;
+                            const uint32_t cand = (i < qlen && rank == R - 1) ? 1u : 0u;   // the R-th best key
+                            const uint32_t b = __ballot_sync(0xFFFFFFFFu, cand);
+                            if (b) { const uint64_t kk = __shfl_sync(0xFFFFFFFFu, k, __ffs(b) - 1); T = kk - 1; }
+                        }
+                        if (qlen < R) T = 0ull;
+                    }
+                    // in-place stream compaction (destinations never overtake the rows still to be read)
+                    uint32_t dst = 0;
+                    for (uint32_t i0 = 0; i0 < qlen; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const uint64_t k = i < qlen ? P[i] : 0ull;
+                        const uint32_t nd = i < qlen ? PN[i] : 0u;
+                        const bool keep = i < qlen && k > T;
+                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, keep);
+                        __syncwarp();
+                        if (keep) { const uint32_t d = dst + (uint32_t)__popc(b & lt); P[d] = k; PN[d] = nd; }
+                        dst += (uint32_t)__popc(b);
+                        __syncwarp();
+                    }
+                    qlen = dst;
+                }
+            }
+        } else
         // ---- merge the old queue (minus the popped head) with the new entries, keep what can still be popped.
         // Final position of an entry = number of entries of the union that are better; no sort of the new entries needed.
         {
@@ -585,7 +674,7 @@ size_t hnsw_warp_smem(uint32_t row_pitch, uint32_t dim, uint32_t ef, int st, int
 template <int FAST, bool PROF>
 static cdb_status launch_warp(const HnswArgs &a, const HwCarve &cv, cudaStream_t s) {
     auto kern = hnsw_search_warp_kernel<FAST, PROF>;
-    CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cv.total));
+    CDB_ALLOW_SMEM(kern, cv.total);
     kern<<<a.nq, 32, cv.total, s>>>(a, cv);
     CDB_LAUNCH_CHECK();
     return CDB_OK;

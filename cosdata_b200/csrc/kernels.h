@@ -124,6 +124,7 @@ struct HnswArgs {
 constexpr uint32_t CDB_HNSW_F_PRELOAD = 2;   // load the next head's adjacency slots while the queue merge runs
 constexpr uint32_t CDB_HNSW_F_ATOMFS = 4;    // fixed-set walk through atomicOr return values (slot-order loop only on aliasing)
 constexpr uint32_t CDB_HNSW_F_CTA = 8;       // round-1 kernel: one CTA per query
+constexpr uint32_t CDB_HNSW_F_POOL = 16;     // candidates as an unsorted pool + arg-max pops instead of a sorted queue + merges
 constexpr uint32_t CDB_HNSW_F_DEFAULT = CDB_HNSW_F_PRELOAD | CDB_HNSW_F_ATOMFS;
 extern std::atomic<uint32_t> g_hnsw_flags;
 cdb_status hnsw_search_device(const HnswArgs &a, cudaStream_t s);        // one CTA per query (round-1 kernel; A/B runs)
@@ -176,6 +177,10 @@ cdb_status prep_queries_device(const float *d_q, uint32_t nq, uint32_t dim, floa
                                void *d_qh, uint32_t qh_pitch_halfs, int *d_ggm, const uint32_t *d_deg, bool has_deg, uint32_t id_base,
                                uint32_t *d_cand, uint32_t cand_cap, uint32_t *d_cand_cnt, uint32_t *d_err32, uint8_t *d_err8,
                                uint32_t *d_progress, cudaStream_t s);
+cdb_status tensor_scan_i8_device(const uint8_t *d_x, const uint8_t *d_q, uint32_t pitch, uint64_t n_rows, uint32_t nq, uint32_t dim,
+                                 uint32_t k, int metric, const float *d_mags, const float *d_qmags, uint32_t id_base, int *d_ggm,
+                                 uint64_t *d_cand64, uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_err32,
+                                 uint32_t *d_progress /* 2048 words */, int sm_count, cudaStream_t s);
 // queries whose candidate list overflowed (or whose norm is degenerate, d_qmags may be null) -> d_qsel = {n, indices...}
 cdb_status select_fallback_device(const uint32_t *d_cnt, uint32_t cap, const float *d_qmags, uint32_t n, uint32_t *d_qsel,
                                   uint32_t *d_flags, cudaStream_t s);

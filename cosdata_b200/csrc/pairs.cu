@@ -199,7 +199,7 @@ cdb_status rerank_f32_device(const float *d_raw, uint32_t pitch_elems, const flo
     if (ncand > pcap) pcap = RERANK_BUF;
     size_t smem = (size_t)round_up(dim, 4) * 4 + (size_t)pcap * 8;
     if (smem > 200 * 1024) { set_error("rerank: dimension too large"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(rerank_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(rerank_f32_kernel, smem);
     rerank_f32_kernel<<<nq, RERANK_THREADS, smem, s>>>(d_raw, pitch_elems, d_raw_mags, n_rows, dim, d_q, q_pitch_elems,
                                                         d_qmags, d_cand, d_cand_counts, ncand, k, id_base, d_out_ids, d_out_scores, d_out_counts, d_labels, d_out_keys);
     CDB_LAUNCH_CHECK();

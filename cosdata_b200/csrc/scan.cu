@@ -324,11 +324,11 @@ static cdb_status launch_scan(const ScanArgs &a, uint32_t sel_grid, cudaStream_t
     const bool f32path = (a.st == CDB_ST_F32 && a.metric == CDB_METRIC_COSINE);
     if (f32path) {
         auto kern = scan_f32_kernel<QB, 2>;
-        CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CDB_ALLOW_SMEM(kern, smem);
         kern<<<grid, SCAN_THREADS, smem, s>>>(a);
     } else {
         auto kern = scan_generic_kernel<QB>;
-        CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CDB_ALLOW_SMEM(kern, smem);
         kern<<<grid, SCAN_THREADS, smem, s>>>(a);
     }
     CDB_LAUNCH_CHECK();
@@ -442,7 +442,7 @@ cdb_status merge_partials_device(int metric, const uint64_t *d_partial, uint32_t
     while (P < M) P <<= 1;
     size_t smem = (M <= 768 ? M : P) * 8;
     if (smem > 200 * 1024) { set_error("merge: too many partial candidates"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(merge_partials_kernel, smem);
     merge_partials_kernel<<<sel_mode ? sel_cap : nq, 256, smem, s>>>(metric, d_partial, nlists, k, d_ids, d_scores, d_counts, qsel,
                                                                       sel_cap, sel_mode, sel_grid, sel_qb, d_out_keys);
     CDB_LAUNCH_CHECK();

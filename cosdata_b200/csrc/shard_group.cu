@@ -306,7 +306,7 @@ static cdb_status sharded_enqueue(cdb_shard_group *g, uint32_t nq, const cdb_sea
     cudaStream_t s0 = (nl == 1 && out_stream) ? out_stream : g->stream[0];
     const size_t smem = (size_t)g->world * k * 8;
     if (smem > 200 * 1024) { set_error("sharded merge: world * k too large"); return CDB_INVALID_PARAMS; }
-    CDB_CUDA_TRY(cudaFuncSetAttribute(merge_gathered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(merge_gathered_kernel, smem);
     merge_gathered_kernel<<<nq, 128, smem, s0>>>(reinterpret_cast<const uint64_t *>(g->gather[0].p), g->world, nq, k, words,
                                                   index_result_metric(g->shard[0], p->mode), d_ids, d_scores, d_counts, d_err);
     CDB_LAUNCH_CHECK();

@@ -68,7 +68,7 @@ template <bool I8>
 static cdb_status run_probe(int sm_count, uint32_t iters, float *ms) {
     auto kern = tc_probe_kernel<I8>;
     const size_t smem = 1024 + PR_A_BYTES + PR_B_BYTES + 64;
-    CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(kern, smem);
     cudaEvent_t e0, e1;
     CDB_CUDA_TRY(cudaEventCreate(&e0));
     CDB_CUDA_TRY(cudaEventCreate(&e1));

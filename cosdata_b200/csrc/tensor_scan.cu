@@ -56,6 +56,13 @@ struct TensorScanArgs {
     uint32_t window;     // a CTA may run at most `window` tiles ahead of the slowest CTA of its group
     uint32_t refresh_mask;  // the shared bound is refreshed when (tile & mask) == mask (and for the first tiles)
     uint32_t has_deg;       // the corpus holds degenerate rows: kernel variant that keeps zero accumulators out of the bound
+    // ---- integer form (KIND 1: exact scoring of u8 codes / sub-byte digits on kind::i8, tensor_scan_u8.cu)
+    int metric;             // CDB_METRIC_COSINE or CDB_METRIC_DOT_PRODUCT
+    const float *mags;      // [n_rows] stored magnitudes (cosine)
+    const float *qmags;     // [n_queries]
+    uint64_t *cand64;       // [n_queries][cand_cap] emitted selection keys (exact scores)
+    uint32_t *err32;        // [n_queries] error bits
+    float rel;              // threshold = bound * rel - two_eps (1 for the f16 form and for the dot product; 1 - 2^-18 for cosine)
 };
 
 constexpr uint32_t TS_LSTAGE = 32;  // thread-private candidate staging slots (shared memory), slot 0 = count
@@ -69,6 +76,27 @@ __device__ __noinline__ void epi_emit(const TensorScanArgs &a, uint32_t qi, uint
         const uint32_t pos = atomicAdd(a.cand_cnt + qi, c);
         for (uint32_t i = 0; i < c; ++i)
             if (pos + i < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos + i] = stage[1 + i];
+        c = 0;
+    }
+    stage[0] = c;
+}
+
+// integer form: a value passed the filter -> its EXACT score (dp as f32, or dp / (|q| * |row|), cosine.rs:120, 223-235) becomes
+// a selection key; 16 keys are staged per thread, slot 0 of the stage = count
+constexpr uint32_t TS_KSTAGE = 16;
+__device__ __noinline__ void epi_emit_key(const TensorScanArgs &a, uint32_t qi, uint64_t *stage, int dp, uint64_t row, float qmag) {
+    float score = __int2float_rn(dp);   // u64 -> f32 of the reference; dp < 2^31 so the conversion is the same RNE
+    if (a.metric == CDB_METRIC_COSINE) {
+        const float denom = __fmul_rn(qmag, a.mags[row]);
+        if (denom == 0.0f) return;      // Err(CalculationError): flagged per tile / per query in the epilogue, the row is skipped
+        score = __fdiv_rn(score, denom);
+    }
+    uint32_t c = (uint32_t)stage[0];
+    stage[1 + c] = make_key64(order_key(a.metric, __float_as_uint(score)), a.id_base + (uint32_t)row);
+    if (++c == TS_KSTAGE) {
+        const uint32_t pos = atomicAdd(a.cand_cnt + qi, c);
+        for (uint32_t i = 0; i < c; ++i)
+            if (pos + i < a.cand_cap) a.cand64[(size_t)qi * a.cand_cap + pos + i] = stage[1 + i];
         c = 0;
     }
     stage[0] = c;
@@ -106,13 +134,20 @@ __device__ __forceinline__ void sort_desc(float (&v)[NG]) {
 // is bound by the 128 B/clk shared-memory port.  Barriers of the pair live in the leader (even) CTA:
 // both CTAs' TMA loads complete on its full barrier, its MMA thread issues for both, commits multicast to both CTAs'
 // empty / accumulator-full barriers, and both epilogues release the accumulator stage on its accumulator-empty barrier.
-template <int STAGES, int NG, bool HAS_DEG, int CTAS>
+// KIND = 1: the same pipeline on tcgen05.mma.kind::i8 (u8 x u8 -> s32, exact): operand rows are 128 BYTES of K per stage
+// (128 u8 elements instead of 64 halfs -- identical tile bytes, descriptors and swizzle), and the epilogue's values are
+// exact integer dot products: the class-maximum bound works on f32(dp) (dot product) or on f32(dp) / |row| (cosine, the
+// per-row reciprocals staged in shared memory per tile), the filter keeps a 2^-18 relative margin for the cosine form and
+// none for the dot product, and whatever passes is scored EXACTLY (epi_emit_key) -- final selection keys, not candidates.
+template <int STAGES, int NG, bool HAS_DEG, int CTAS, int KIND>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TensorScanArgs a) {
     constexpr uint32_t B_ROWS = TS_BLOCK_N / CTAS;                          // corpus rows staged by this CTA
-    constexpr uint32_t B_BYTES = B_ROWS * TS_BLOCK_K * 2;
+    constexpr uint32_t B_BYTES = B_ROWS * TS_BLOCK_K * 2;                   // 128 bytes of K per row in either form
     constexpr uint32_t STAGE_BYTES = TS_A_BYTES + B_BYTES;                  // 48 KB, resp. 32 KB per CTA of a pair
-    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TS_BLOCK_N >> 3) << 17) | ((uint32_t)((TS_BLOCK_M * CTAS) >> 4) << 24);
+    constexpr uint32_t K_ELEMS = KIND == 1 ? 2 * TS_BLOCK_K : TS_BLOCK_K;   // elements per 128-byte row: 128 u8 / 64 halfs
+    // instruction descriptor: D format (1 = F32, 2 = S32) | A/B formats (0 = F16 resp. UINT8) | N >> 3 | M >> 4
+    constexpr uint32_t IDESC = ((KIND == 1 ? 2u : 1u) << 4) | ((uint32_t)(TS_BLOCK_N >> 3) << 17) | ((uint32_t)((TS_BLOCK_M * CTAS) >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -121,6 +156,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     uint64_t *bars = reinterpret_cast<uint64_t *>(lstage + TS_BLOCK_M * (TS_LSTAGE + 2));     // 8-byte aligned
     uint64_t *full_bar = bars, *empty_bar = bars + STAGES, *tfull_bar = bars + 2 * STAGES, *tempty_bar = bars + 2 * STAGES + 2;
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    float *rinv_s = reinterpret_cast<float *>(tmem_ptr_smem + 4);           // KIND 1 cosine: [2][256] reciprocal row magnitudes
+    uint32_t *zflag_s = reinterpret_cast<uint32_t *>(rinv_s + 2 * TS_BLOCK_N);   // [2] a valid row of the tile has |row| = 0
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = CTAS == 2 ? cluster_ctarank() : 0u;              // 0 = leader of the pair
@@ -173,12 +210,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
                     if (CTAS == 2) {
                         if (leader) mbar_expect_tx(fb, 2 * STAGE_BYTES);     // the leader's barrier counts both CTAs' bytes
-                        tma_load_2d_pair(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
-                        tma_load_2d_pair(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N + crank * B_ROWS));
+                        tma_load_2d_pair(sa, &map_q, fb, (int)(kb * K_ELEMS), (int)(mt * TS_BLOCK_M));
+                        tma_load_2d_pair(sa + TS_A_BYTES, &map_x, fb, (int)(kb * K_ELEMS), (int)(nt * TS_BLOCK_N + crank * B_ROWS));
                     } else {
                         mbar_expect_tx(fb, STAGE_BYTES);
-                        tma_load_2d(sa, &map_q, fb, (int)(kb * TS_BLOCK_K), (int)(mt * TS_BLOCK_M));
-                        tma_load_2d(sa + TS_A_BYTES, &map_x, fb, (int)(kb * TS_BLOCK_K), (int)(nt * TS_BLOCK_N));
+                        tma_load_2d(sa, &map_q, fb, (int)(kb * K_ELEMS), (int)(mt * TS_BLOCK_M));
+                        tma_load_2d(sa + TS_A_BYTES, &map_x, fb, (int)(kb * K_ELEMS), (int)(nt * TS_BLOCK_N));
                     }
                     if (++s == STAGES) { s = 0; phase ^= 1; }
                 }
@@ -199,8 +236,13 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + TS_A_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < TS_BLOCK_K / 16; ++kk) {  // +32 bytes along K = +2 in the encoded start address
-                        if (CTAS == 2) tcgen05_mma_f16_pair(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
-                        else tcgen05_mma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                        if (KIND == 1) {
+                            if (CTAS == 2) tcgen05_mma_i8_pair(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                            else tcgen05_mma_i8(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                        } else {
+                            if (CTAS == 2) tcgen05_mma_f16_pair(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                            else tcgen05_mma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (kb | kk) != 0);
+                        }
                     }
                     // frees the smem stage (of both CTAs) when these MMAs retire
                     if (CTAS == 2) tcgen05_commit_pair(smem_u32(&empty_bar[s])); else tcgen05_commit(smem_u32(&empty_bar[s]));
@@ -224,7 +266,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         // ggm[query][64] (class sets of different CTAs are disjoint too), which makes the bound GLOBAL: about as
         // tight as the exact running k-th best, at one FMNMX per value.
         uint32_t *stage = lstage + (size_t)ql * (TS_LSTAGE + 1);
-        stage[0] = 0;
+        uint64_t *kstage = reinterpret_cast<uint64_t *>(lstage) + (size_t)ql * (TS_KSTAGE + 1);   // KIND 1: same bytes, 16 keys
+        if (KIND == 1) kstage[0] = 0ull; else stage[0] = 0;
+        const bool cosine = KIND == 1 && a.metric == CDB_METRIC_COSINE;
+        const float qmag = (KIND == 1 && qvalid) ? a.qmags[qi] : 0.0f;
+        uint32_t err = (cosine && qvalid && qmag == 0.0f && a.n_rows > 0) ? (uint32_t)CDB_ERRFLAG_CALCULATION : 0u;
+        const uint32_t et = threadIdx.x - 64;                  // 0..127 within the epilogue warps
         float gm[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) gm[i] = -INFINITY;
@@ -237,13 +284,28 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             sort_desc<NG>(g2);
 #pragma unroll
             for (int i = 0; i < NG; ++i) if ((uint32_t)i == a.k - 1) bound = g2[i];
-            thr = bound - a.two_eps;
+            thr = KIND == 1 ? bound * a.rel : bound - a.two_eps;
         }
         uint32_t as = 0, aphase = 0, t = 0;
         for (uint32_t nt = g; nt < a.ntiles; nt += G, ++t) {
+            const uint64_t row0 = (uint64_t)nt * TS_BLOCK_N;
+            const float *rs = rinv_s + as * TS_BLOCK_N;
+            if (cosine) {
+                // reciprocal magnitudes of this tile's rows -> shared memory (double buffered by accumulator stage); a zero
+                // magnitude is an Err for every query that meets the row (cosine.rs:230-231)
+                if (et == 0) zflag_s[as] = 0u;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (uint32_t c = et; c < (uint32_t)TS_BLOCK_N; c += 128) {
+                    const bool valid = row0 + c < a.n_rows;
+                    const float mg = valid ? a.mags[row0 + c] : 0.0f;
+                    rinv_s[as * TS_BLOCK_N + c] = mg > 0.0f ? __frcp_rn(mg) : 0.0f;
+                    if (valid && mg == 0.0f) zflag_s[as] = 1u;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (qvalid && zflag_s[as]) err |= (uint32_t)CDB_ERRFLAG_CALCULATION;
+            }
             mbar_wait(smem_u32(&tfull_bar[as]), aphase);
             tcgen05_fence_after();
-            const uint64_t row0 = (uint64_t)nt * TS_BLOCK_N;
             const bool full_tile = row0 + TS_BLOCK_N <= a.n_rows;  // only the corpus' last tile can be partial (TMA zero fill)
 #pragma unroll 1
             for (int c = 0; c < TS_BLOCK_N / 64; ++c) {
@@ -259,10 +321,16 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     float cm[NG];
 #pragma unroll
                     for (int i = 0; i < NG; ++i) cm[i] = -INFINITY;
-#pragma unroll
                     float zmax = -INFINITY;   // HAS_DEG: 0.0f if some accumulator of the chunk is exactly zero
+#pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r1[j]);
+                        float v0, v1;
+                        if (KIND == 1) {      // exact integer dot -> f32 (dot product) or -> f32 / |row| (cosine filter value)
+                            v0 = __int2float_rn((int)r0[j]); v1 = __int2float_rn((int)r1[j]);
+                            if (cosine) { v0 *= rs[c * 64 + j]; v1 *= rs[c * 64 + 32 + j]; }
+                        } else {
+                            v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
+                        }
                         if (HAS_DEG) {
                             zmax = (v0 == 0.0f || v1 == 0.0f) ? 0.0f : zmax;
                             v0 = v0 == 0.0f ? -INFINITY : v0;
@@ -277,15 +345,28 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                     if (cmax >= thr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            m0 |= (__uint_as_float(r0[j]) >= thr ? 1u : 0u) << j;
-                            m1 |= (__uint_as_float(r1[j]) >= thr ? 1u : 0u) << j;
+                            float v0, v1;
+                            if (KIND == 1) {
+                                v0 = __int2float_rn((int)r0[j]); v1 = __int2float_rn((int)r1[j]);
+                                if (cosine) { v0 *= rs[c * 64 + j]; v1 *= rs[c * 64 + 32 + j]; }
+                            } else {
+                                v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
+                            }
+                            m0 |= (v0 >= thr ? 1u : 0u) << j;
+                            m1 |= (v1 >= thr ? 1u : 0u) << j;
                         }
                     }
                 } else {
                     const uint64_t left = a.n_rows > row0 + c * 64 ? a.n_rows - (row0 + c * 64) : 0;  // valid columns in this chunk
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v0 = __uint_as_float(r0[j]), v1 = __uint_as_float(r1[j]);
+                        float v0, v1;
+                        if (KIND == 1) {
+                            v0 = __int2float_rn((int)r0[j]); v1 = __int2float_rn((int)r1[j]);
+                            if (cosine) { v0 *= rs[c * 64 + j]; v1 *= rs[c * 64 + 32 + j]; }
+                        } else {
+                            v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
+                        }
                         const bool ok0 = (uint64_t)j < left, ok1 = (uint64_t)(32 + j) < left;
                         m0 |= ((ok0 && v0 >= thr) ? 1u : 0u) << j;
                         m1 |= ((ok1 && v1 >= thr) ? 1u : 0u) << j;
@@ -296,10 +377,16 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 if (qvalid && a.emit && (m0 | m1)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if ((m0 >> j) & 1u) epi_emit(a, qi, stage, a.id_base + (uint32_t)(row0 + c * 64 + j));
+                        if ((m0 >> j) & 1u) {
+                            if (KIND == 1) epi_emit_key(a, qi, kstage, (int)r0[j], row0 + c * 64 + j, qmag);
+                            else epi_emit(a, qi, stage, a.id_base + (uint32_t)(row0 + c * 64 + j));
+                        }
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if ((m1 >> j) & 1u) epi_emit(a, qi, stage, a.id_base + (uint32_t)(row0 + c * 64 + 32 + j));
+                        if ((m1 >> j) & 1u) {
+                            if (KIND == 1) epi_emit_key(a, qi, kstage, (int)r1[j], row0 + c * 64 + 32 + j, qmag);
+                            else epi_emit(a, qi, stage, a.id_base + (uint32_t)(row0 + c * 64 + 32 + j));
+                        }
                 }
             }
             tcgen05_fence_before();
@@ -321,18 +408,22 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 float nb = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < NG; ++i) if ((uint32_t)i == a.k - 1) nb = g2[i];
-                if (nb > bound) { bound = nb; thr = bound - a.two_eps; }
+                if (nb > bound) { bound = nb; thr = KIND == 1 ? bound * a.rel : bound - a.two_eps; }
             }
         }
         if (qvalid) {  // final publish + flush of the staged candidates
 #pragma unroll
             for (int i = 0; i < NG; ++i) atomicMax(ggm_q + (size_t)i * TS_BLOCK_M, f2ord(gm[i]));
-            const uint32_t c = stage[0];
+            const uint32_t c = KIND == 1 ? (uint32_t)kstage[0] : stage[0];
             if (a.emit && c) {
                 const uint32_t pos = atomicAdd(a.cand_cnt + qi, c);
                 for (uint32_t i = 0; i < c; ++i)
-                    if (pos + i < a.cand_cap) a.cand[(size_t)qi * a.cand_cap + pos + i] = stage[1 + i];
+                    if (pos + i < a.cand_cap) {
+                        if (KIND == 1) a.cand64[(size_t)qi * a.cand_cap + pos + i] = kstage[1 + i];
+                        else a.cand[(size_t)qi * a.cand_cap + pos + i] = stage[1 + i];
+                    }
             }
+            if (KIND == 1 && err) atomicOr(a.err32 + qi, err);
         }
     }
     tcgen05_fence_before();
@@ -533,19 +624,21 @@ static int tensor_scan_stages(uint32_t k) {
 }
 constexpr int TS_STAGES_PAIR = 6;   // 32 KB per stage and CTA in the pair form: a deeper ring fits
 static size_t tensor_scan_smem(int stages, uint32_t stage_bytes) {
-    return 1024 + (size_t)stages * stage_bytes + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * stages + 4) * 8 + 16;
+    // tiles + per-thread staging + barriers + tmem pointer + (integer form) reciprocal magnitudes of two tiles + flags
+    return 1024 + (size_t)stages * stage_bytes + (size_t)TS_BLOCK_M * (TS_LSTAGE + 2) * 4 + (2 * stages + 4) * 8 + 16 +
+           2 * TS_BLOCK_N * 4 + 16;
 }
 size_t tensor_scan_smem_bytes(uint32_t k) {
     if (!tensor_scan_stages(k)) return (size_t)1 << 30;
     return tensor_scan_smem(TS_STAGES, TS_STAGE_BYTES);
 }
 
-template <int STAGES, int NG, bool HAS_DEG, int CTAS>
+template <int STAGES, int NG, bool HAS_DEG, int CTAS, int KIND>
 static cdb_status launch_tensor_scan_gdc(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid,
                                          cudaStream_t s) {
-    auto kern = tensor_scan_kernel<STAGES, NG, HAS_DEG, CTAS>;
+    auto kern = tensor_scan_kernel<STAGES, NG, HAS_DEG, CTAS, KIND>;
     const size_t smem = tensor_scan_smem(STAGES, TS_A_BYTES + TS_B_BYTES / CTAS);
-    CDB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CDB_ALLOW_SMEM(kern, smem);
     if (CTAS == 1) {
         kern<<<grid, TS_THREADS, smem, s>>>(mq, mx, a);
     } else {
@@ -565,20 +658,59 @@ static cdb_status launch_tensor_scan_gdc(const CUtensorMap &mq, const CUtensorMa
     return CDB_OK;
 }
 
-template <int NG, int CTAS>
+template <int NG, int CTAS, int KIND>
 static cdb_status launch_tensor_scan_g(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid, cudaStream_t s) {
     constexpr int ST = CTAS == 2 ? TS_STAGES_PAIR : TS_STAGES;
-    return a.has_deg ? launch_tensor_scan_gdc<ST, NG, true, CTAS>(mq, mx, a, grid, s)
-                     : launch_tensor_scan_gdc<ST, NG, false, CTAS>(mq, mx, a, grid, s);
+    if (KIND == 1) return launch_tensor_scan_gdc<ST, NG, false, CTAS, KIND>(mq, mx, a, grid, s);   // exact scores: no degenerate-row variant
+    return a.has_deg ? launch_tensor_scan_gdc<ST, NG, true, CTAS, 0>(mq, mx, a, grid, s)
+                     : launch_tensor_scan_gdc<ST, NG, false, CTAS, 0>(mq, mx, a, grid, s);
 }
 
 // fewer classes = cheaper bound refresh (the sort network grows as NG log^2 NG); the bound stays within ~1.5x of the
 // exact k-th best as long as k is well below NG
-template <int CTAS>
+template <int CTAS, int KIND>
 static cdb_status launch_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, const TensorScanArgs &a, uint32_t grid, cudaStream_t s) {
-    if (a.k <= 12) return launch_tensor_scan_g<16, CTAS>(mq, mx, a, grid, s);
-    if (a.k <= 28) return launch_tensor_scan_g<32, CTAS>(mq, mx, a, grid, s);
-    return launch_tensor_scan_g<64, CTAS>(mq, mx, a, grid, s);
+    if (a.k <= 12) return launch_tensor_scan_g<16, CTAS, KIND>(mq, mx, a, grid, s);
+    if (a.k <= 28) return launch_tensor_scan_g<32, CTAS, KIND>(mq, mx, a, grid, s);
+    return launch_tensor_scan_g<64, CTAS, KIND>(mq, mx, a, grid, s);
+}
+
+// seeding pass over a prefix of the corpus, then the main pass (both forms)
+template <int KIND>
+static cdb_status run_tensor_scan(const CUtensorMap &mq, const CUtensorMap &mx, TensorScanArgs a, bool pair, uint64_t n_rows,
+                                  uint32_t *d_progress, int sm_count, cudaStream_t s) {
+    cdb_status rc;
+    // 1. seeding pass over a prefix of the corpus: a few CTAs per query tile, no emission, only the class maxima.
+    //    Afterwards every CTA of the main pass starts from the k-th best of ~16K rows instead of from
+    //    -inf, which removes the per-CTA warm-up bursts from the candidate lists.
+    const uint32_t seed_tiles = std::min<uint32_t>(a.ntiles, 64);
+    a.progress = d_progress;
+    if (a.ntiles > 8) {
+        TensorScanArgs sa = a;
+        sa.emit = 0;
+        sa.ntiles = seed_tiles;
+        sa.n_rows = std::min<uint64_t>(n_rows, (uint64_t)seed_tiles * TS_BLOCK_N);
+        // as many CTAs per query tile as the SMs allow, >= 2 corpus tiles each: the pass is a latency-bound prologue
+        uint32_t per_m = std::max<uint32_t>(1, (uint32_t)sm_count / a.mtiles);
+        per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 2));
+        const uint32_t sgrid = a.mtiles * per_m;
+        rc = pair ? launch_tensor_scan<2, KIND>(mq, mx, sa, sgrid, s) : launch_tensor_scan<1, KIND>(mq, mx, sa, sgrid, s);
+        if (rc) return rc;
+    }
+    // 2. main pass.  Every CTA should own several corpus tiles, so tiny corpora are not shredded over all SMs.
+    a.emit = 1;
+    uint64_t total_tiles = (uint64_t)a.mtiles * a.ntiles;
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count, std::max<uint64_t>(1, total_tiles / 4));
+    grid = std::max<uint32_t>(1, grid / a.mtiles) * a.mtiles;  // whole groups only (148 SMs, 8 query tiles -> 144 CTAs)
+    if (grid > (uint32_t)sm_count) { set_error("tensor scan: more query tiles than SMs"); return CDB_INVALID_PARAMS; }
+    a.progress = d_progress + 1024;   // the seeding pass used the first 1024 counters
+    return pair ? launch_tensor_scan<2, KIND>(mq, mx, a, grid, s) : launch_tensor_scan<1, KIND>(mq, mx, a, grid, s);
+}
+
+static bool tensor_scan_pair_ok(uint32_t mtiles) {
+    // CTA pairs (cta_group::2) need an even number of query tiles; CDB_TS_PAIR=0 forces the single-CTA form (A/B runs)
+    static const bool pair_allowed = !(getenv("CDB_TS_PAIR") && atoi(getenv("CDB_TS_PAIR")) == 0);
+    return pair_allowed && mtiles % 2 == 0;
 }
 
 // d_xh: fp16 normalised corpus [n_rows][pitch_halfs]; d_qh: fp16 normalised queries, padded with zero
@@ -608,9 +740,7 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
     a.cand_cap = cand_cap;
     const int stages = tensor_scan_stages(k);
     if (!stages) { set_error("tensor scan: k too large for shared memory"); return CDB_INVALID_PARAMS; }
-    // CTA pairs (cta_group::2) need an even number of query tiles; CDB_TS_PAIR=0 forces the single-CTA form (A/B runs)
-    static const bool pair_allowed = !(getenv("CDB_TS_PAIR") && atoi(getenv("CDB_TS_PAIR")) == 0);
-    const bool pair = pair_allowed && a.mtiles % 2 == 0;
+    const bool pair = tensor_scan_pair_ok(a.mtiles);
     CUtensorMap mq, mx;
     cdb_status rc;
     if ((rc = make_map_f16(&mq, d_qh, (uint64_t)a.mtiles * TS_BLOCK_M, dim, pitch_halfs, TS_BLOCK_M))) return rc;
@@ -627,30 +757,48 @@ cdb_status tensor_scan_device(const void *d_xh, const void *d_qh, uint32_t pitch
         CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 8192, s));
     }
 
-    // 1. seeding pass over a prefix of the corpus: a few CTAs per query tile, no emission, only gthr.
-    //    Afterwards every CTA of the main pass starts from the k-th best of ~16K rows instead of from
-    //    -inf, which removes the per-CTA warm-up bursts from the candidate lists.
-    const uint32_t seed_tiles = std::min<uint32_t>(a.ntiles, 64);
-    if (a.ntiles > 8) {
-        TensorScanArgs sa = a;
-        sa.emit = 0;
-        sa.ntiles = seed_tiles;
-        sa.n_rows = std::min<uint64_t>(n_rows, (uint64_t)seed_tiles * TS_BLOCK_N);
-        // as many CTAs per query tile as the SMs allow, >= 2 corpus tiles each: the pass is a latency-bound prologue
-        uint32_t per_m = std::max<uint32_t>(1, (uint32_t)sm_count / a.mtiles);
-        per_m = std::min<uint32_t>(per_m, std::max<uint32_t>(1, seed_tiles / 2));
-        const uint32_t sgrid = a.mtiles * per_m;
-        rc = pair ? launch_tensor_scan<2>(mq, mx, sa, sgrid, s) : launch_tensor_scan<1>(mq, mx, sa, sgrid, s);
-        if (rc) return rc;
-    }
-    // 2. main pass.  Every CTA should own several corpus tiles, so tiny corpora are not shredded over all SMs.
-    a.emit = 1;
-    uint64_t total_tiles = (uint64_t)a.mtiles * a.ntiles;
-    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sm_count, std::max<uint64_t>(1, total_tiles / 4));
-    grid = std::max<uint32_t>(1, grid / a.mtiles) * a.mtiles;  // whole groups only (148 SMs, 8 query tiles -> 144 CTAs)
-    if (grid > (uint32_t)sm_count) { set_error("tensor scan: more query tiles than SMs"); return CDB_INVALID_PARAMS; }
-    a.progress = d_progress + 1024;   // the seeding pass used the first 1024 counters
-    return pair ? launch_tensor_scan<2>(mq, mx, a, grid, s) : launch_tensor_scan<1>(mq, mx, a, grid, s);
+    a.rel = 1.0f;
+    return run_tensor_scan<0>(mq, mx, a, pair, n_rows, d_progress, sm_count, s);
+}
+
+// Integer form (tensor_scan_u8.cu): d_x u8 operand rows [n_rows][pitch] (u8 codes or unpacked digits), d_q the query operand
+// rows padded with zero rows to a multiple of 128.  Emits exact selection keys into d_cand64; the caller sorts them.
+cdb_status tensor_scan_i8_device(const uint8_t *d_x, const uint8_t *d_q, uint32_t pitch, uint64_t n_rows, uint32_t nq, uint32_t dim,
+                                 uint32_t k, int metric, const float *d_mags, const float *d_qmags, uint32_t id_base, int *d_ggm,
+                                 uint64_t *d_cand64, uint32_t *d_cand_cnt, uint32_t cand_cap, uint32_t *d_err32, uint32_t *d_progress,
+                                 int sm_count, cudaStream_t s) {
+    TensorScanArgs a{};
+    a.window = 3;
+    a.refresh_mask = 15;
+    a.n_rows = n_rows;
+    a.n_queries = nq;
+    a.k = k;
+    a.kblocks = (dim + 2 * TS_BLOCK_K - 1) / (2 * TS_BLOCK_K);   // 128 u8 elements per 128-byte row
+    a.mtiles = (nq + TS_BLOCK_M - 1) / TS_BLOCK_M;
+    a.ntiles = (uint32_t)((n_rows + TS_BLOCK_N - 1) / TS_BLOCK_N);
+    a.two_eps = 0.0f;
+    a.rel = metric == CDB_METRIC_COSINE ? 1.0f - 1.0f / 262144.0f : 1.0f;
+    a.id_base = id_base;
+    a.ggm = d_ggm;
+    a.cand64 = d_cand64;
+    a.cand_cnt = d_cand_cnt;
+    a.cand_cap = cand_cap;
+    a.metric = metric;
+    a.mags = d_mags;
+    a.qmags = d_qmags;
+    a.err32 = d_err32;
+    if (!tensor_scan_stages(k)) { set_error("u8 tensor scan: k too large (class-maximum bound needs k <= 64)"); return CDB_INVALID_PARAMS; }
+    if ((uint32_t)sm_count < a.mtiles) { set_error("u8 tensor scan: more query tiles than SMs"); return CDB_INVALID_PARAMS; }
+    const bool pair = tensor_scan_pair_ok(a.mtiles);
+    CUtensorMap mq, mx;
+    cdb_status rc;
+    if ((rc = make_tensor_map_2d(&mq, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d_q, (uint64_t)a.mtiles * TS_BLOCK_M, dim, pitch, TS_BLOCK_M))) return rc;
+    if ((rc = make_tensor_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d_x, n_rows, dim, pitch, pair ? TS_BLOCK_N / 2 : TS_BLOCK_N))) return rc;
+    fill_i32_kernel<<<(a.mtiles * TS_BLOCK_M * TS_GROUPS + 255) / 256, 256, 0, s>>>(d_ggm, (int)0x807FFFFF /* f2ord(-inf) */, a.mtiles * TS_BLOCK_M * TS_GROUPS);
+    CDB_LAUNCH_CHECK();
+    CDB_CUDA_TRY(cudaMemsetAsync(d_cand_cnt, 0, (size_t)nq * 4, s));
+    CDB_CUDA_TRY(cudaMemsetAsync(d_progress, 0, 8192, s));
+    return run_tensor_scan<1>(mq, mx, a, pair, n_rows, d_progress, sm_count, s);
 }
 
 cdb_status select_fallback_device(const uint32_t *d_cnt, uint32_t cap, const float *d_qmags, uint32_t n, uint32_t *d_qsel,

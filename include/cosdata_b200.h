@@ -348,7 +348,7 @@ cdb_status cdb_index_hnsw_counters(const cdb_index *index, uint64_t *out2);
  * err_flags may be NULL.  k <= 1024.
  * Execution paths (same results, chosen by shape): BRUTE_RAW with an fp16 shadow, >= 4 queries, >= 16384 rows and
  * k <= 64 -> tcgen05 fp16 prefilter + exact re-rank; BRUTE_CODES over u8 / sub-byte codes with cosine or dot product,
- * >= 16384 rows and k <= 128 -> exact tcgen05 kind::i8 scoring; everything else -> exact SIMT scan. */
+ * >= 16384 rows and k <= 64 -> exact tcgen05 kind::i8 scoring; everything else -> exact SIMT scan. */
 cdb_status cdb_search_batch(cdb_index *index, const float *queries, uint32_t n_queries,
                             const cdb_search_params *params,
                             uint32_t *out_ids, float *out_scores, uint32_t *out_counts,
