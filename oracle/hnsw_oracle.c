@@ -2,6 +2,7 @@
  * hnsw_oracle.c -- see hnsw_oracle.h.  TEST INFRASTRUCTURE ONLY.
  */
 #include "hnsw_oracle.h"
+#include "hnsw_build_internal.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -203,16 +204,6 @@ int orc_hnsw_search_batch(const orc_graph *g, const float *raw, const float *que
 }
 
 /* ------------------------------------------------------------------ builder */
-typedef struct {
-    uint32_t cnt, cap, nb;
-    uint32_t *node_row;
-    uint32_t *adj;       /* [cap*nb] local indices */
-    uint32_t *simkey;    /* [cap*nb] order key of the slot's similarity (MetricResult ordering) */
-    uint32_t *child;
-    uint32_t *lowest_idx;
-    uint32_t *lowest_key;
-} blevel;
-
 struct orc_built {
     orc_graph g;
     uint32_t nlevels1;
@@ -222,25 +213,6 @@ struct orc_built {
     uint32_t min_key, max_key; /* MetricResult::min / ::max as order keys (src/models/types.rs:435-457) */
 };
 
-static void lv_reserve(blevel *l, uint32_t want) {
-    if (want <= l->cap) return;
-    uint32_t nc = l->cap ? l->cap * 2 : 64;
-    if (nc < want) nc = want;
-    l->node_row = (uint32_t *)realloc(l->node_row, sizeof(uint32_t) * nc);
-    l->adj = (uint32_t *)realloc(l->adj, sizeof(uint32_t) * (size_t)nc * l->nb);
-    l->simkey = (uint32_t *)realloc(l->simkey, sizeof(uint32_t) * (size_t)nc * l->nb);
-    l->child = (uint32_t *)realloc(l->child, sizeof(uint32_t) * nc);
-    l->lowest_idx = (uint32_t *)realloc(l->lowest_idx, sizeof(uint32_t) * nc);
-    l->lowest_key = (uint32_t *)realloc(l->lowest_key, sizeof(uint32_t) * nc);
-    l->cap = nc;
-}
-static void lv_init_node(orc_built *b, blevel *l, uint32_t idx, uint32_t row) {
-    l->node_row[idx] = row;
-    for (uint32_t s = 0; s < l->nb; ++s) { l->adj[(size_t)idx * l->nb + s] = ORC_EMPTY; l->simkey[(size_t)idx * l->nb + s] = 0; }
-    l->child[idx] = ORC_EMPTY;
-    l->lowest_idx[idx] = 0;             /* ProbNode::new: lowest_index = (0, MetricResult::min) */
-    l->lowest_key[idx] = b->min_key;
-}
 static void refresh_view(orc_built *b) {
     for (uint32_t L = 0; L < b->nlevels1; ++L) {
         b->cnt_arr[L] = b->lv[L].cnt;
@@ -249,32 +221,8 @@ static void refresh_view(orc_built *b) {
         b->child_arr[L] = b->lv[L].child;
     }
 }
-
-/* ProbNode::add_neighbor (src/models/prob_node.rs:210-283); returns slot index or -1 */
 static int add_neighbor(orc_built *b, blevel *l, uint32_t node, uint32_t nbr, uint32_t dkey) {
-    const uint32_t lidx = l->lowest_idx[node], lkey = l->lowest_key[node];
-    if (dkey <= lkey) return -1;
-    uint32_t *slot = &l->adj[(size_t)node * l->nb + lidx];
-    uint32_t *skey = &l->simkey[(size_t)node * l->nb + lidx];
-    int ok = 0;
-    uint32_t old = ORC_EMPTY;
-    if (*slot == ORC_EMPTY) { *slot = nbr; *skey = dkey; ok = 1; }
-    else if (dkey > *skey) { old = *slot; *slot = nbr; *skey = dkey; ok = 1; }
-    /* recompute (lowest_idx, lowest_sim) */
-    uint32_t nidx = 0, nkey = b->max_key;
-    for (uint32_t s = 0; s < l->nb; ++s) {
-        if (l->adj[(size_t)node * l->nb + s] == ORC_EMPTY) { nkey = b->min_key; nidx = s; break; }
-        uint32_t k = l->simkey[(size_t)node * l->nb + s];
-        if (k < nkey) { nkey = k; nidx = s; }
-    }
-    l->lowest_idx[node] = nidx;
-    l->lowest_key[node] = nkey;
-    if (!ok) return -1;
-    if (old != ORC_EMPTY) { /* evicted neighbour drops its back link (remove_neighbor_by_id) */
-        for (uint32_t s = 0; s < l->nb; ++s)
-            if (l->adj[(size_t)old * l->nb + s] == node) { l->adj[(size_t)old * l->nb + s] = ORC_EMPTY; break; }
-    }
-    return (int)lidx;
+    return bl_add_neighbor(b->min_key, b->max_key, l, node, nbr, dkey);
 }
 
 /* create_node_edges (src/vector_store.rs:976-1070), Base nodes only */
@@ -315,16 +263,13 @@ orc_built *orc_hnsw_build(int metric, int st, size_t dim, const void *codes, con
     g->num_levels = num_levels; g->neighbors_count = nbrs; g->level0_neighbors_count = nbrs0; g->n = n;
     g->metric = metric; g->storage_type = st; g->dim = dim; g->codes = codes; g->mags = mags;
     g->cnt = b->cnt_arr; g->node_row = b->node_row_arr; g->adj = b->adj_arr; g->child = b->child_arr;
-    switch (metric) { /* MetricResult::min / max */
-    case ORC_METRIC_COSINE: b->min_key = orc_order_key(metric, -1.0f); b->max_key = orc_order_key(metric, 2.0f); break;
-    default: b->min_key = orc_order_key(metric, -__builtin_inff()); b->max_key = orc_order_key(metric, __builtin_inff()); break;
-    }
+    bl_min_max_keys(metric, &b->min_key, &b->max_key);
     /* root nodes on every level (vector_store.rs:44-140): row n, child links downwards */
     for (uint32_t L = 0; L <= num_levels; ++L) {
         blevel *l = &b->lv[L];
         l->nb = L == 0 ? nbrs0 : nbrs;
-        if (L == 0) { lv_reserve(l, n + 1); l->cnt = n + 1; for (uint32_t i = 0; i <= n; ++i) lv_init_node(b, l, i, i); }
-        else { lv_reserve(l, 64); l->cnt = 1; lv_init_node(b, l, 0, n); l->child[0] = (L == 1) ? n : 0; }
+        if (L == 0) { lv_reserve(l, n + 1); l->cnt = n + 1; for (uint32_t i = 0; i <= n; ++i) lv_init_node(b->min_key, l, i, i); }
+        else { lv_reserve(l, 64); l->cnt = 1; lv_init_node(b->min_key, l, 0, n); l->child[0] = (L == 1) ? n : 0; }
     }
     g->entry = num_levels == 0 ? n : 0;
     /* level 0 nodes exist as slots for every row but are only linked once inserted */
@@ -371,7 +316,7 @@ orc_built *orc_hnsw_build(int metric, int st, size_t dim, const void *codes, con
             if ((uint32_t)level <= max_level) {
                 uint32_t idx;
                 if (level == 0) { idx = r; present0[r] = 1; }
-                else { lv_reserve(l, l->cnt + 1); idx = l->cnt++; lv_init_node(b, l, idx, r); }
+                else { lv_reserve(l, l->cnt + 1); idx = l->cnt++; lv_init_node(b->min_key, l, idx, r); }
                 if (parent != ORC_EMPTY) b->lv[level + 1].child[parent] = idx;
                 node_at[level] = idx;
                 parent = idx;
@@ -392,10 +337,7 @@ const orc_graph *orc_built_graph(const orc_built *b) { return &b->g; }
 
 void orc_built_free(orc_built *b) {
     if (!b) return;
-    for (uint32_t L = 0; L < b->nlevels1; ++L) {
-        free(b->lv[L].node_row); free(b->lv[L].adj); free(b->lv[L].simkey); free(b->lv[L].child);
-        free(b->lv[L].lowest_idx); free(b->lv[L].lowest_key);
-    }
+    for (uint32_t L = 0; L < b->nlevels1; ++L) lv_free(&b->lv[L]);
     free(b->lv); free(b->cnt_arr); free(b->node_row_arr); free(b->adj_arr); free(b->child_arr);
     free(b);
 }

@@ -112,7 +112,8 @@ static mitem pop(mitem *h, size_t *n) {
 /* traverse_find_nearest (vector_store.rs:1112-1204) with fvec metadata `x`; the fixed set is the caller's (shared between
  * the traversals of one level, vector_store.rs:266-271, 277-291) */
 static int traverse_md(const orc_md_graph *mg, uint32_t level, uint32_t entry, const orc_vector_data *x, uint32_t ef,
-                       uint32_t shortlist, uint64_t *fs, mitem *out, uint32_t *out_n, uint64_t *evals, uint64_t *pops) {
+                       uint32_t shortlist, uint32_t final_len, uint64_t *fs, mitem *out, uint32_t *out_n, uint64_t *evals,
+                       uint64_t *pops) {
     const uint32_t nb = mg_nbrs(mg, level);
     const uint32_t *adj = mg->g.adj[level];
     const uint32_t take = shortlist < nb ? shortlist : nb;
@@ -147,7 +148,7 @@ static int traverse_md(const orc_md_graph *mg, uint32_t level, uint32_t entry, c
         }
     }
     qsort(res, rn, sizeof(mitem), cmp_desc);
-    if (rn > 100) rn = 100;
+    if (rn > final_len) rn = final_len; /* 100 for search, 64 while indexing (vector_store.rs:1194) */
     memcpy(out, res, sizeof(mitem) * rn);
     *out_n = (uint32_t)rn;
 done:
@@ -180,7 +181,7 @@ int orc_ann_search_md(const orc_md_graph *mg, const void *qcode, float qmag, con
                 x.md_bits = fbits;
                 x.md_mag = orc_query_filter_mag(filters + f * M, M);
                 uint32_t tn = 0;
-                rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_search, shortlist_size, fs, tmp, &tn, evals, pops);
+                rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_search, shortlist_size, 100, fs, tmp, &tn, evals, pops);
                 if (rc != ORC_OK) break;
                 for (uint32_t i = 0; i < tn; ++i) {
                     if (mg->g.metric == ORC_METRIC_COSINE && tmp[i].score == -1.0f) continue; /* vector_store.rs:294-303 */
@@ -193,7 +194,7 @@ int orc_ann_search_md(const orc_md_graph *mg, const void *qcode, float qmag, con
         } else {
             x.md_bits = NULL;
             uint32_t tn = 0;
-            rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_search, shortlist_size, fs, z, &tn, evals, pops);
+            rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_search, shortlist_size, 100, fs, z, &tn, evals, pops);
             if (rc != ORC_OK) break;
             zn = tn;
         }

@@ -59,6 +59,29 @@ def test_hnsw_search_matches_oracle(st, metric, ef):
     ix.close()
 
 
+@pytest.mark.parametrize("flags,name", [(0, "plain"), (2, "preload"), (4, "atomic fixed set"), (22, "pool + arg-max pops"), (8, "cta per query")])
+@pytest.mark.parametrize("st,ef,nb0", [(ST.HalfPrecisionFP, 128, 32), (ST.HalfPrecisionFP, 300, 64), (ST.UnsignedByte, 40, 32)])
+def test_hnsw_kernel_variants_walk_the_same_path(flags, name, st, ef, nb0):
+    # every variant of the search kernel (cdb_debug_set_hnsw_flags) must pop the same nodes in the same order as the oracle
+    n, dim, k = 3000, 40, 10
+    vecs = clustered(n, dim, 21)
+    fg, ix = build_both(vecs, st, MK.Cosine, levels=4, nb=16, nb0=nb0, efc=48, seed=3)
+    rng = np.random.default_rng(22)
+    queries = (vecs[rng.integers(0, n, 70)] + 0.05 * rng.normal(size=(70, dim))).astype(np.float32)
+    want = pyhnsw.search_batch(fg, vecs, queries, k, ef_search=ef)
+    try:
+        cdb.debug_set_hnsw_flags(flags)
+        ev0, pp0 = ix.hnsw_counters()
+        ids, scores, counts, err = ix.batch_search(queries, k, cdb.SearchMode.HNSW, ef_search=ef, shortlist_size=64)
+        ev1, pp1 = ix.hnsw_counters()
+    finally:
+        cdb.debug_set_hnsw_flags()
+    assert np.array_equal(ids, want[0]) and np.array_equal(bits(scores), bits(want[1])), name
+    assert np.array_equal(counts, want[2]) and np.array_equal(err, want[3])
+    assert (ev1 - ev0, pp1 - pp0) == (want[4], want[5]), name
+    ix.close()
+
+
 def test_hnsw_default_params_recall_and_shortlist():
     # reference defaults (config.toml:19-33): nbrs 32/64, ef_search 256, shortlist 64, 9 layers
     n, dim, k = 4000, 64, 10
