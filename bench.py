@@ -774,7 +774,7 @@ def run_c3(args):
         # same graph, same queries: kernel time (CUDA events around the search kernel) and phase profile of every variant
         variants = []
         ref_ids = ids.copy()
-        for name, fl, nb_ in [("default(preload+atomfs)", 6, B), ("pool+argmax pops (preload+atomfs)", 22, B), ("preload only", 2, B),
+        for name, fl, nb_ in [("default(preload+atomfs)", 6, B), ("speculative scoring (preload+atomfs)", 38, B), ("pool+argmax pops (preload+atomfs)", 22, B), ("preload only", 2, B),
                               ("atomfs only", 4, B), ("plain", 0, B), ("cta-per-query (round 1)", 8, B),
                               ("default, half batch", 6, B // 2), ("default, quarter batch", 6, B // 4)]:
             cdb.debug_set_hnsw_flags(fl)

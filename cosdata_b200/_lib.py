@@ -81,6 +81,16 @@ class BuildParams(C.Structure):
     ]
 
 
+class ReplicaBuild(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint32),
+        ("row", C.c_void_p), ("node_id", C.c_void_p), ("base_id", C.c_void_p), ("md_row", C.c_void_p), ("max_level", C.c_void_p),
+        ("md_dims", C.c_uint32), ("n_md", C.c_uint32),
+        ("md_bits", C.c_void_p), ("md_mags", C.c_void_p),
+        ("main_root_md", C.c_uint32), ("pseudo_root_md", C.c_uint32),
+    ]
+
+
 class SearchParams(C.Structure):
     _fields_ = [
         ("k", C.c_uint32),
@@ -135,6 +145,8 @@ PROTOTYPES = {
     "cdb_index_read_codes": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, c_vp, c_f32p]),
     "cdb_index_set_graph": (C.c_int32, [C.c_void_p, C.POINTER(GraphDesc)]),
     "cdb_index_build_graph": (C.c_int32, [C.c_void_p, C.POINTER(BuildParams)]),
+    "cdb_index_build_graph_replicas": (C.c_int32, [C.c_void_p, C.POINTER(BuildParams), C.POINTER(ReplicaBuild), C.c_void_p]),
+    "cdb_index_read_graph_metadata_level": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "cdb_index_graph_info": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdb_index_read_graph_level": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cdb_index_hnsw_counters": (C.c_int32, [C.c_void_p, C.c_void_p]),

@@ -483,7 +483,8 @@ class DenseIndex:
         _check(self._lib.cdb_index_hnsw_profile(self._h, 1 if enable else 0, _ptr(out)))
         if out is None:
             return None
-        names = ["adjacency", "fixed_set", "stage_issue", "stage_wait", "chains", "merge", "level_sort", "levels_total", "pops"]
+        names = ["adjacency", "fixed_set", "stage_issue", "stage_wait", "chains", "merge", "level_sort", "levels_total", "pops",
+                 "speculation", "chain_phases", "speculative_evals"]
         return {n: int(v) for n, v in zip(names, out)}
 
     def stats(self):
@@ -561,6 +562,38 @@ class DenseIndex:
         bp = BuildParams(num_levels, neighbors_count, level0_neighbors_count, ef_construction, shortlist_size, max_batch, seed)
         _check(self._lib.cdb_index_build_graph(self._h, C.byref(bp)))
 
+    def build_graph_replicas(self, row, node_id, base_id, md_row, max_level, md_bits, md_mags, main_root_md, pseudo_root_md,
+                             num_levels=9, neighbors_count=32, level0_neighbors_count=64, ef_construction=128, shortlist_size=64,
+                             max_batch=4096, seed=1):
+        """GPU-side index_embeddings for a collection with a metadata schema (cdb_index_build_graph_replicas): one entry per
+        graph node to create; row 0xFFFFFFFF = the pseudo root's vector.  -> failed u8[n_nodes]"""
+        from ._lib import ReplicaBuild
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (row, node_id, base_id, md_row)]
+        lv = np.ascontiguousarray(max_level, dtype=np.uint8)
+        bits = np.ascontiguousarray(md_bits, dtype=np.int32)
+        mags = np.ascontiguousarray(md_mags, dtype=np.float32)
+        n = arrs[0].size
+        assert all(a.size == n for a in arrs) and lv.size == n and bits.ndim == 2 and mags.size == bits.shape[0]
+        rb = ReplicaBuild(n, *[a.ctypes.data for a in arrs], lv.ctypes.data, bits.shape[1], bits.shape[0], bits.ctypes.data,
+                          mags.ctypes.data, int(main_root_md) & 0xFFFFFFFF, int(pseudo_root_md))
+        bp = BuildParams(num_levels, neighbors_count, level0_neighbors_count, ef_construction, shortlist_size, max_batch, seed)
+        failed = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(self._lib.cdb_index_build_graph_replicas(self._h, C.byref(bp), C.byref(rb), _ptr(failed)))
+        self.md_dims = bits.shape[1]
+        return failed[:n]
+
+    def read_graph_metadata(self):
+        """-> (node_id[], node_md[]) per level of a graph with replica nodes"""
+        info = np.zeros(5, dtype=np.uint32)
+        counts = np.zeros(32, dtype=np.uint32)
+        _check(self._lib.cdb_index_graph_info(self._h, _ptr(info), _ptr(counts)))
+        ids, mds = [], []
+        for lv in range(int(info[0]) + 1):
+            a, b = np.zeros(int(counts[lv]), np.uint32), np.zeros(int(counts[lv]), np.uint32)
+            _check(self._lib.cdb_index_read_graph_metadata_level(self._h, lv, _ptr(a), _ptr(b)))
+            ids.append(a); mds.append(b)
+        return ids, mds
+
     def read_graph(self):
         """-> dict(num_levels, neighbors_count, level0_neighbors_count, entry, root_row, node_row[], adj[], child[])"""
         info = np.zeros(5, dtype=np.uint32)
@@ -580,3 +613,28 @@ class DenseIndex:
     def append_device(self, d_ptr, n):
         """rows already on the index's device: d_ptr = address of n*dim contiguous f32"""
         _check(self._lib.cdb_index_append_f32_device(self._h, d_ptr, n))
+
+
+# ----------------------------------------------------------------------------- level draws (host side of the builders)
+def level_probs(num_levels, factor=4.0):
+    """generate_level_probs (src/models/common.rs:421-429; factor 4, api_service.rs:109): [(1 - factor^-n, n)] for n = num_levels..0"""
+    return [(1.0 - float(factor) ** (-n), n) for n in range(int(num_levels), -1, -1)]
+
+
+def pseudo_level_probs(num_levels, num_pseudo_nodes):
+    """pseudo_level_probs (src/metadata/mod.rs:182-211): pseudo replicas are spread over the top ilog10(n)+1 levels"""
+    higher = len(str(int(num_pseudo_nodes)))             # ilog10 + 1
+    if higher > num_levels:
+        higher, lower = 0, int(num_levels)
+    else:
+        lower = int(num_levels) - higher
+    out = [(p, lower + lv) for p, lv in level_probs(higher, 10.0) if lv != 0] if higher > 0 else []
+    return out + [(0.0, i) for i in range(lower, -1, -1)]
+
+
+def max_insert_level(x, probs):
+    """get_max_insert_level (src/models/common.rs:373-379): level of the first entry with x >= prob"""
+    for p, lv in probs:
+        if x >= p:
+            return lv
+    raise ValueError("No matching element found")

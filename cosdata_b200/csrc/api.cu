@@ -192,6 +192,7 @@ struct cdb_index {
     uint32_t md_dims = 0, md_pseudo_entry = 0;
     std::vector<uint32_t> g_cnt;
     std::vector<const uint32_t *> g_nr, g_ad, g_ch;  // host copies of the per-level device pointers
+    std::vector<const uint32_t *> g_id, g_md;        // same for node_id / node_md when has_md
     DevBuf hn_counters, hn_prof;   // cumulative device counters (atomics: shared by concurrent searches)
     bool hn_prof_on = false;
 };
@@ -1320,6 +1321,8 @@ cdb_status cdb_index_set_graph_metadata(cdb_index *ix, const cdb_graph_metadata 
         return rc;
     ix->md_node_id = reinterpret_cast<const uint32_t *const *>(t_id);
     ix->md_node_md = reinterpret_cast<const uint32_t *const *>(t_md);
+    ix->g_id.assign(L1, nullptr); ix->g_md.assign(L1, nullptr);
+    for (uint32_t L = 0; L < L1; ++L) { ix->g_id[L] = (const uint32_t *)ids[L]; ix->g_md[L] = (const uint32_t *)mds[L]; }
     ix->md_bits = reinterpret_cast<const int32_t *>(bits);
     ix->md_mags = reinterpret_cast<const float *>(mags);
     ix->md_dims = md->md_dims;
@@ -1360,6 +1363,71 @@ cdb_status cdb_index_build_graph(cdb_index *ix, const cdb_build_params *bp) {
                            &ix->g_ad, &ix->g_ch, ix->stream);
     if (rc) return rc;
     ix->has_graph = true;
+    return CDB_OK;
+}
+
+cdb_status cdb_index_build_graph_replicas(cdb_index *ix, const cdb_build_params *bp, const cdb_replica_build *rb, uint8_t *out_failed) {
+    CDB_REQUIRE(ix && bp && rb, "null argument");
+    CDB_REQUIRE(bp->neighbors_count >= 1 && bp->neighbors_count <= 64 && bp->level0_neighbors_count >= 1 &&
+                    bp->level0_neighbors_count <= 64, "neighbour counts must be in 1..64");
+    CDB_REQUIRE(bp->ef_construction >= 1 && bp->ef_construction <= 4096 && bp->shortlist_size >= 1 && bp->shortlist_size <= 64 &&
+                    bp->num_levels <= 15, "bad build parameters");
+    CDB_REQUIRE(rb->md_dims >= 1 && rb->md_dims <= 4096, "md_dims must be in 1..4096");
+    CDB_REQUIRE((rb->row && rb->node_id && rb->base_id && rb->md_row && rb->max_level) || !rb->n_nodes, "null replica list");
+    CDB_REQUIRE((rb->md_bits && rb->md_mags) || !rb->n_md, "null metadata table");
+    CDB_REQUIRE(rb->pseudo_root_md < rb->n_md, "the pseudo root needs a metadata row");
+    CDB_REQUIRE(rb->main_root_md == CDB_INVALID_ID || rb->main_root_md < rb->n_md, "main_root_md out of range");
+    std::unique_lock<std::shared_mutex> lock(ix->rw);
+    CDB_REQUIRE(ix->size + 2 <= ix->desc.capacity, "build needs capacity for the two root rows");
+    const uint32_t n = (uint32_t)ix->size;
+    for (uint32_t t = 0; t < rb->n_nodes; ++t) {
+        CDB_REQUIRE(rb->row[t] == CDB_INVALID_ID || rb->row[t] < n, "replica row out of range");
+        CDB_REQUIRE(rb->md_row[t] == CDB_INVALID_ID || rb->md_row[t] < rb->n_md, "replica md_row out of range");
+    }
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    cdb_status rc;
+    if ((rc = arm_status(ix->desc.metric, ix->desc.storage_type)) != CDB_OK) {
+        set_error("metric/storage arm is an Err in the reference");
+        return rc;
+    }
+    // main root: uniform in [range_lo, range_hi) (vector_store.rs:57-64); pseudo root: pseudo_node_vector = zeros (metadata/mod.rs:214-216)
+    std::vector<float> roots(2 * (size_t)ix->desc.dim, 0.0f);
+    for (uint32_t c = 0; c < ix->desc.dim; ++c)
+        roots[c] = ix->desc.range_lo + (synth_value(bp->seed ^ 0x526F6F74ull, c) + 1.0f) * 0.5f * (ix->desc.range_hi - ix->desc.range_lo);
+    if ((rc = append_f32_locked(ix, roots.data(), 2))) return rc;
+    for (void *g : ix->md_allocs) cudaFree(g);
+    ix->md_allocs.clear();
+    ix->has_md = false;
+    for (void *g : ix->graph_allocs) cudaFree(g);
+    ix->graph_allocs.clear();
+    ix->has_graph = false;
+    std::vector<uint32_t> rows(rb->row, rb->row + rb->n_nodes);
+    for (auto &r : rows) if (r == CDB_INVALID_ID) r = n + 1;   // pseudo replicas reuse the pseudo root's prop_value (vector_store.rs:661)
+    ReplicaHost rh{rb->n_nodes, rows.data(), rb->node_id, rb->base_id, rb->md_row, rb->max_level, rb->md_dims, rb->n_md,
+                   rb->md_bits, rb->md_mags, n, rb->main_root_md, n + 1, rb->pseudo_root_md};
+    HnScoreCtx sc{ix->d_codes, ix->row_pitch, ix->d_mags, ix->desc.dim, ix->desc.storage_type, ix->desc.metric, n};
+    ReplicaGraphDev mdv{};
+    std::vector<uint8_t> failed;
+    rc = hnsw_build_replicas_device(sc, rh, bp->num_levels, bp->neighbors_count, bp->level0_neighbors_count, bp->ef_construction,
+                                    bp->shortlist_size, bp->max_batch, &ix->graph, &ix->graph_allocs, &ix->g_cnt, &ix->g_nr,
+                                    &ix->g_ad, &ix->g_ch, &mdv, &failed, ix->stream);
+    if (rc) return rc;
+    ix->has_graph = true;
+    ix->md_node_id = mdv.node_id; ix->md_node_md = mdv.node_md;
+    ix->g_id = mdv.h_node_id; ix->g_md = mdv.h_node_md;
+    ix->md_bits = mdv.md_bits; ix->md_mags = mdv.md_mags;
+    ix->md_dims = mdv.md_dims; ix->md_pseudo_entry = mdv.pseudo_entry;
+    ix->has_md = true;   // the arrays live in graph_allocs
+    if (out_failed) std::copy(failed.begin(), failed.end(), out_failed);
+    return CDB_OK;
+}
+
+cdb_status cdb_index_read_graph_metadata_level(const cdb_index *ix, uint32_t level, uint32_t *node_id, uint32_t *node_md) {
+    CDB_REQUIRE(ix && ix->has_graph && ix->has_md && level <= ix->graph.num_levels, "no graph metadata / bad level");
+    CDB_CUDA_TRY(cudaSetDevice(ix->desc.device));
+    const uint32_t cnt = ix->g_cnt[level];
+    if (node_id) CDB_CUDA_TRY(cudaMemcpy(node_id, ix->g_id[level], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+    if (node_md) CDB_CUDA_TRY(cudaMemcpy(node_md, ix->g_md[level], (size_t)cnt * 4, cudaMemcpyDeviceToHost));
     return CDB_OK;
 }
 

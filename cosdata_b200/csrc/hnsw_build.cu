@@ -31,12 +31,26 @@ struct BuildLevel {
     uint32_t *lowest_idx;  // [cnt]
     uint32_t *lowest_key;  // [cnt]
     int *lock;             // [cnt]
+    // replica builds (collections with a metadata schema): [0] main root, [1] pseudo root, then created nodes in list order
+    const uint32_t *node_id;   // [cnt] ProbNode::get_id()
+    const uint32_t *node_md;   // [cnt] metadata table row or HN_EMPTY
+    const uint32_t *node_ins;  // [cnt] position in the replica list (ascending from local 2; roots HN_EMPTY)
 };
 constexpr int BUILD_MAX_LEVELS = 16;
 struct BuildGraph {
     uint32_t num_levels, entry, root_row;
     BuildLevel lv[BUILD_MAX_LEVELS];
     uint32_t min_key, max_key;  // MetricResult::min / ::max as order keys (types.rs:435-457)
+    uint32_t pseudo_entry;      // replica builds: top-level index of the pseudo root
+};
+
+// the flattened IndexableEmbeddings of preprocess_embedding (vector_store.rs:629-712) on the device
+struct ReplicaDev {
+    const uint32_t *row, *id, *base_id, *md;   // [n_nodes]
+    const int32_t *md_bits;                    // [n_md][M]
+    const float *md_mags;
+    uint32_t M;
+    uint32_t key_one, key_minus_one;           // order keys of cs == 1.0 / -1.0 (edge rules, vector_store.rs:1014-1040)
 };
 
 struct BuildArgs {
@@ -49,10 +63,17 @@ struct BuildArgs {
     uint32_t *z_keys;       // [count][num_levels+1][64] order keys
     uint32_t *z_n;          // [count][num_levels+1]
     uint8_t *failed;        // [count]
+    bool replicas;          // rows of the batch are positions of the replica list `rl`
+    ReplicaDev rl;
 };
 
 // local index of `row` at `level` (level 0: the row itself; level >= 1: binary search in the sorted node_row)
-__device__ inline uint32_t build_local(const BuildLevel &l, uint32_t level, uint32_t row) {
+__device__ inline uint32_t build_local(const BuildLevel &l, uint32_t level, uint32_t row, bool replicas = false) {
+    if (replicas) {   // every level lists the created nodes in list order behind the two roots
+        uint32_t lo = 2, hi = l.cnt;
+        while (lo < hi) { const uint32_t md = (lo + hi) >> 1; if (l.node_ins[md] < row) lo = md + 1; else hi = md; }
+        return lo;
+    }
     if (level == 0) return row;
     uint32_t lo = 1, hi = l.cnt;
     while (lo < hi) { const uint32_t md = (lo + hi) >> 1; if (l.node_row[md] < row) lo = md + 1; else hi = md; }
@@ -65,18 +86,34 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_build_search_kernel(BuildArgs
     __shared__ HnShared sh;
     const uint32_t b = blockIdx.x, r = a.first + b;
     const int tid = threadIdx.x;
+    const uint32_t vrow = a.replicas ? a.rl.row[r] : r;
     for (uint32_t i = tid; i < a.sc.row_pitch / 4; i += HN_THREADS)
-        reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.sc.rows + (size_t)r * a.sc.row_pitch)[i];
-    const float qmag = a.sc.mags[r];
+        reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.sc.rows + (size_t)vrow * a.sc.row_pitch)[i];
+    const float qmag = a.sc.mags[vrow];
     const uint32_t max_level = a.levels[r];
     const uint32_t L1 = a.g.num_levels + 1;
-    if (tid == 0) { sh.err = 0; sh.entry = a.g.entry; }
+    // replica builds: the traversal carries the embedding's metadata and prop_value.id (vector_store.rs:809-821); nodes whose
+    // metadata has mag != 0 (Pseudo / Metadata kinds) start at the pseudo root (:461-483, 755-758)
+    HnMdCtx md{};
+    uint32_t self_id = r;
+    bool under_pseudo = false;
+    if (a.replicas) {
+        const uint32_t mrow = a.rl.md[r];
+        md.md_bits = a.rl.md_bits; md.md_mags = a.rl.md_mags; md.M = a.rl.M;
+        md.q_bits = mrow == HN_EMPTY ? nullptr : a.rl.md_bits + (size_t)mrow * a.rl.M;
+        md.q_mag = mrow == HN_EMPTY ? 0.0f : a.rl.md_mags[mrow];
+        md.keep_fs = false; md.q_has_id = true; md.q_id = a.rl.base_id[r];
+        self_id = a.rl.id[r];
+        under_pseudo = md.q_bits && md.q_mag != 0.0f;
+    }
+    if (tid == 0) { sh.err = 0; sh.entry = under_pseudo ? a.g.pseudo_entry : a.g.entry; }
     unsigned long long evals = 0, pops = 0;
     __syncthreads();
     for (int level = (int)a.g.num_levels; level >= 0; --level) {
         const BuildLevel &l = a.g.lv[level];
         const uint32_t take = min(min(a.shortlist, l.nb), HN_MAX_TAKE);
-        hn_traverse_level(l.node_row, l.adj, l.nb, take, a.sc, m, sh, qmag, /*self id*/ r, a.ef, evals, pops);
+        if (a.replicas) { md.node_id = l.node_id; md.node_md = l.node_md; }
+        hn_traverse_level(l.node_row, l.adj, l.nb, take, a.sc, m, sh, qmag, self_id, a.ef, evals, pops, a.replicas ? &md : nullptr);
         if (sh.err) break;
         const uint32_t keep = min(sh.rlen, 64u);  // is_indexing: final_len = 64 (vector_store.rs:1194)
         if ((uint32_t)level <= max_level) {
@@ -133,6 +170,14 @@ __device__ int build_add_neighbor(const BuildGraph &g, const BuildLevel &l, uint
     return (int)lidx;
 }
 
+// ProbNode::replica_node_kind (prob_node.rs:487-496): the node's own id and metadata
+__device__ inline int build_node_kind(const ReplicaDev &rl, const BuildLevel &l, uint32_t node) {
+    const uint32_t mrow = l.node_md[node];
+    if (mrow == HN_EMPTY || rl.md_mags[mrow] == 0.0f) return MD_KIND_BASE;
+    const uint32_t id = l.node_id[node];
+    return id >= MD_PSEUDO_ID_LO && id <= MD_PSEUDO_ID_HI ? MD_KIND_PSEUDO : MD_KIND_METADATA;
+}
+
 // one warp per new vector, lane 0 works (a thread spinning on a lock must not share a warp with its holder)
 __global__ void __launch_bounds__(128) hnsw_build_link_kernel(BuildArgs a) {
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -142,13 +187,20 @@ __global__ void __launch_bounds__(128) hnsw_build_link_kernel(BuildArgs a) {
     const uint32_t top = min((uint32_t)a.levels[r], a.g.num_levels);
     for (uint32_t level = 0; level <= top; ++level) {  // edges are created bottom-up as the recursion unwinds
         const BuildLevel &l = a.g.lv[level];
-        const uint32_t node = build_local(l, level, r);
+        const uint32_t node = build_local(l, level, r, a.replicas);
         const size_t base = ((size_t)b * L1 + level) * 64;
         const uint32_t zn = a.z_n[(size_t)b * L1 + level];
+        const bool rules = a.replicas && a.sc.metric == CDB_METRIC_COSINE;   // the rules match MetricResult::CosineSimilarity only
+        const int nk = rules ? build_node_kind(a.rl, l, node) : MD_KIND_BASE;
         uint32_t successful = 0;
         for (uint32_t i = 0; i < zn; ++i) {
             if (successful >= l.nb) break;
             const uint32_t nbr = a.z_nodes[base + i], dkey = a.z_keys[base + i];
+            if (rules && nk == MD_KIND_METADATA) {   // vector_store.rs:1014-1040
+                const int bk = build_node_kind(a.rl, l, nbr);
+                if (bk == MD_KIND_PSEUDO && dkey != a.rl.key_one) continue;          // pseudo neighbour: perfect match only
+                if (bk == MD_KIND_METADATA && dkey == a.rl.key_minus_one) continue;  // metadata neighbour: not on a strong mismatch
+            }
             const int idx = build_add_neighbor(a.g, l, node, nbr, dkey);
             if (idx >= 0) {
                 const int j = build_add_neighbor(a.g, l, nbr, node, dkey);
@@ -312,6 +364,171 @@ cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n /* data rows; root
     out_graph->node_row = reinterpret_cast<const uint32_t *const *>(tbl[0]);
     out_graph->adj = reinterpret_cast<const uint32_t *const *>(tbl[1]);
     out_graph->child = reinterpret_cast<const uint32_t *const *>(tbl[2]);
+    return CDB_OK;
+}
+
+// ------------------------------------------------------------------ replica lists (collections with a metadata schema)
+// index_embeddings over the flattened IndexableEmbeddings (vector_store.rs:714-780): host arrays, one entry per node to create.
+// Level layout: [0] main root, [1] pseudo root (both on every level, create_root_node / create_pseudo_root_node), then the
+// created nodes in list order.  The same two kernels as above do the work; level draws come from the caller.
+cdb_status hnsw_build_replicas_device(const HnScoreCtx &sc, const ReplicaHost &rh, uint32_t num_levels, uint32_t nbrs, uint32_t nbrs0,
+                                      uint32_t ef_construction, uint32_t shortlist, uint32_t max_batch, GraphDev *out_graph,
+                                      std::vector<void *> *out_allocs, std::vector<uint32_t> *out_counts,
+                                      std::vector<const uint32_t *> *out_nr, std::vector<const uint32_t *> *out_ad,
+                                      std::vector<const uint32_t *> *out_ch, ReplicaGraphDev *out_md, std::vector<uint8_t> *out_failed,
+                                      cudaStream_t s) {
+    if (num_levels + 1 > BUILD_MAX_LEVELS) { set_error("build: too many levels"); return CDB_INVALID_PARAMS; }
+    const uint32_t L1 = num_levels + 1, n = rh.n_nodes;
+    std::vector<uint8_t> levels(n);
+    std::vector<std::vector<uint32_t>> members(L1);   // list positions present on each level
+    for (uint32_t t = 0; t < n; ++t) {
+        levels[t] = (uint8_t)std::min<uint32_t>(rh.max_level[t], num_levels);
+        for (uint32_t L = 0; L <= levels[t]; ++L) members[L].push_back(t);
+    }
+    BuiltGraph bg;
+    bg.g.num_levels = num_levels;
+    bg.g.root_row = rh.main_root_row;
+    bg.g.entry = 0;
+    bg.g.pseudo_entry = 1;
+    switch (sc.metric) {
+    case CDB_METRIC_COSINE: bg.g.min_key = order_key(sc.metric, 0xBF800000u); bg.g.max_key = order_key(sc.metric, 0x40000000u); break;
+    default: bg.g.min_key = order_key(sc.metric, 0xFF800000u); bg.g.max_key = order_key(sc.metric, 0x7F800000u); break;
+    }
+    auto dalloc = [&](void **p, size_t bytes) -> cdb_status {
+        CDB_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 4));
+        out_allocs->push_back(*p);
+        return CDB_OK;
+    };
+    auto upload = [&](const void *src, size_t bytes, void **dst) -> cdb_status {
+        cdb_status rc = dalloc(dst, bytes);
+        if (rc) return rc;
+        if (bytes) CDB_CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return CDB_OK;
+    };
+    cdb_status rc;
+    ReplicaDev rl{};
+    void *p = nullptr;
+    if ((rc = upload(rh.row, (size_t)n * 4, &p))) return rc;
+    rl.row = (const uint32_t *)p;
+    if ((rc = upload(rh.node_id, (size_t)n * 4, &p))) return rc;
+    rl.id = (const uint32_t *)p;
+    if ((rc = upload(rh.base_id, (size_t)n * 4, &p))) return rc;
+    rl.base_id = (const uint32_t *)p;
+    if ((rc = upload(rh.md_row, (size_t)n * 4, &p))) return rc;
+    rl.md = (const uint32_t *)p;
+    if ((rc = upload(rh.md_bits, (size_t)rh.n_md * rh.md_dims * 4, &p))) return rc;
+    rl.md_bits = (const int32_t *)p;
+    if ((rc = upload(rh.md_mags, (size_t)rh.n_md * 4, &p))) return rc;
+    rl.md_mags = (const float *)p;
+    rl.M = rh.md_dims;
+    rl.key_one = order_key(CDB_METRIC_COSINE, 0x3F800000u);
+    rl.key_minus_one = order_key(CDB_METRIC_COSINE, 0xBF800000u);
+    std::vector<const uint32_t *> t_nr(L1), t_ad(L1), t_ch(L1), t_id(L1), t_md(L1);
+    for (uint32_t L = 0; L < L1; ++L) {
+        BuildLevel &l = bg.g.lv[L];
+        const std::vector<uint32_t> &mem = members[L];
+        l.nb = L == 0 ? nbrs0 : nbrs;
+        l.cnt = 2 + (uint32_t)mem.size();
+        std::vector<uint32_t> nr(l.cnt), ch(l.cnt, HN_EMPTY), ni(l.cnt), nm(l.cnt), ins(l.cnt, HN_EMPTY);
+        nr[0] = rh.main_root_row; ni[0] = 0xFFFFFFFFu; nm[0] = rh.main_root_md;
+        nr[1] = rh.pseudo_root_row; ni[1] = MD_PSEUDO_ID_LO; nm[1] = rh.pseudo_root_md;
+        if (L > 0) { ch[0] = 0; ch[1] = 1; }
+        uint32_t j = 0;   // position in the level below (both lists ascend)
+        for (uint32_t i = 0; i < mem.size(); ++i) {
+            const uint32_t t = mem[i];
+            nr[2 + i] = rh.row[t]; ni[2 + i] = rh.node_id[t]; nm[2 + i] = rh.md_row[t]; ins[2 + i] = t;
+            if (L > 0) { while (members[L - 1][j] != t) ++j; ch[2 + i] = 2 + j; }
+        }
+        void *d_nr, *d_ch, *d_ni, *d_nm, *d_ins;
+        if ((rc = upload(nr.data(), (size_t)l.cnt * 4, &d_nr)) || (rc = upload(ch.data(), (size_t)l.cnt * 4, &d_ch)) ||
+            (rc = upload(ni.data(), (size_t)l.cnt * 4, &d_ni)) || (rc = upload(nm.data(), (size_t)l.cnt * 4, &d_nm)) ||
+            (rc = upload(ins.data(), (size_t)l.cnt * 4, &d_ins)))
+            return rc;
+        l.node_row = (uint32_t *)d_nr; l.child = (uint32_t *)d_ch;
+        l.node_id = (const uint32_t *)d_ni; l.node_md = (const uint32_t *)d_nm; l.node_ins = (const uint32_t *)d_ins;
+        if ((rc = dalloc((void **)&l.adj, (size_t)l.cnt * l.nb * 4)) || (rc = dalloc((void **)&l.simkey, (size_t)l.cnt * l.nb * 4)) ||
+            (rc = dalloc((void **)&l.lowest_idx, (size_t)l.cnt * 4)) || (rc = dalloc((void **)&l.lowest_key, (size_t)l.cnt * 4)) ||
+            (rc = dalloc((void **)&l.lock, (size_t)l.cnt * 4)))
+            return rc;
+        const uint64_t slots = (uint64_t)l.cnt * l.nb;
+        fill_u32_kernel<<<(uint32_t)((slots + 255) / 256), 256, 0, s>>>(l.adj, HN_EMPTY, slots);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA_TRY(cudaMemsetAsync(l.simkey, 0, slots * 4, s));
+        CDB_CUDA_TRY(cudaMemsetAsync(l.lowest_idx, 0, (size_t)l.cnt * 4, s));
+        fill_u32_kernel<<<(l.cnt + 255) / 256, 256, 0, s>>>(l.lowest_key, bg.g.min_key, l.cnt);
+        CDB_LAUNCH_CHECK();
+        CDB_CUDA_TRY(cudaMemsetAsync(l.lock, 0, (size_t)l.cnt * 4, s));
+        t_nr[L] = l.node_row; t_ad[L] = l.adj; t_ch[L] = l.child; t_id[L] = l.node_id; t_md[L] = l.node_md;
+    }
+    uint8_t *d_levels = nullptr;
+    if ((rc = upload(levels.data(), n, (void **)&d_levels))) return rc;
+    if (max_batch == 0) max_batch = 4096;
+    max_batch = std::min<uint32_t>(max_batch, std::max<uint32_t>(n, 1));
+    uint32_t *z_nodes = nullptr, *z_keys = nullptr, *z_n = nullptr;
+    uint8_t *failed = nullptr;
+    CDB_CUDA_TRY(cudaMalloc(&z_nodes, (size_t)max_batch * L1 * 64 * 4));
+    CDB_CUDA_TRY(cudaMalloc(&z_keys, (size_t)max_batch * L1 * 64 * 4));
+    CDB_CUDA_TRY(cudaMalloc(&z_n, (size_t)max_batch * L1 * 4));
+    CDB_CUDA_TRY(cudaMalloc(&failed, (size_t)std::max<uint32_t>(n, 1)));
+    const size_t smem = hn_smem_bytes(sc.row_pitch, ef_construction);
+    CDB_ALLOW_SMEM(hnsw_build_search_kernel, smem);
+    BuildArgs a{};
+    a.g = bg.g;
+    a.sc = sc;
+    a.sc.root_row = rh.main_root_row;
+    a.levels = d_levels;
+    a.ef = ef_construction;
+    a.shortlist = shortlist;
+    a.z_nodes = z_nodes; a.z_keys = z_keys; a.z_n = z_n;
+    a.replicas = true;
+    a.rl = rl;
+    for (uint32_t done = 0; done < n;) {
+        uint32_t batch = std::max<uint32_t>(1, std::min<uint32_t>(max_batch, done / 8));
+        batch = std::min<uint32_t>(batch, n - done);
+        a.first = done;
+        a.count = batch;
+        a.failed = failed + done;   // per list position, read back below
+        hnsw_build_search_kernel<<<batch, HN_THREADS, smem, s>>>(a);
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        hnsw_build_link_kernel<<<(batch * 32 + 127) / 128, 128, 0, s>>>(a);
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        done += batch;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && out_failed) {
+        out_failed->assign(n, 0);
+        if (n) e = cudaMemcpy(out_failed->data(), failed, n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(z_nodes); cudaFree(z_keys); cudaFree(z_n); cudaFree(failed);
+    if (e != cudaSuccess) { set_error(std::string("hnsw replica build: ") + cudaGetErrorString(e)); return CDB_CUDA_ERROR; }
+    const std::vector<const uint32_t *> *src[5] = {&t_nr, &t_ad, &t_ch, &t_id, &t_md};
+    const uint32_t *tbl[5];
+    for (int t = 0; t < 5; ++t) {
+        void *q = nullptr;
+        if ((rc = upload(src[t]->data(), L1 * sizeof(void *), &q))) return rc;
+        tbl[t] = (const uint32_t *)q;
+    }
+    out_counts->clear();
+    for (uint32_t L = 0; L < L1; ++L) out_counts->push_back(bg.g.lv[L].cnt);
+    *out_nr = t_nr; *out_ad = t_ad; *out_ch = t_ch;
+    out_graph->num_levels = num_levels;
+    out_graph->nbrs = nbrs;
+    out_graph->nbrs0 = nbrs0;
+    out_graph->entry = 0;
+    out_graph->root_row = rh.main_root_row;
+    out_graph->identity_mask = 0u;
+    out_graph->node_row = reinterpret_cast<const uint32_t *const *>(tbl[0]);
+    out_graph->adj = reinterpret_cast<const uint32_t *const *>(tbl[1]);
+    out_graph->child = reinterpret_cast<const uint32_t *const *>(tbl[2]);
+    out_md->node_id = reinterpret_cast<const uint32_t *const *>(tbl[3]);
+    out_md->node_md = reinterpret_cast<const uint32_t *const *>(tbl[4]);
+    out_md->h_node_id = t_id;
+    out_md->h_node_md = t_md;
+    out_md->md_bits = rl.md_bits;
+    out_md->md_mags = rl.md_mags;
+    out_md->md_dims = rh.md_dims;
+    out_md->pseudo_entry = 1;
     return CDB_OK;
 }
 

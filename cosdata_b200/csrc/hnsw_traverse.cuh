@@ -45,6 +45,8 @@ struct HnMdCtx {
     const int32_t *q_bits;     // query-side Metadata.mbits (shared memory), nullptr = None
     float q_mag;
     bool keep_fs;              // keep the fixed set of the previous traversal of this level (vector_store.rs:266-291)
+    bool q_has_id;             // fvec_data.id: None for queries, Some(prop_value.id) while indexing (vector_store.rs:812, 1131-1135)
+    uint32_t q_id;
 };
 struct HnScoreCtx {
     const uint8_t *rows;
@@ -135,7 +137,7 @@ __device__ __forceinline__ int hn_score_node(const uint32_t *__restrict__ node_r
     }
     *id = md->node_id[local];
     const uint32_t mrow = md->node_md[local];
-    const MdSide x{m.qs, qmag, pp, false, 0u, md->q_bits, md->q_mag};
+    const MdSide x{m.qs, qmag, pp, md->q_has_id, md->q_id, md->q_bits, md->q_mag};
     const MdSide y{code, sc.mags[row], pp, true, *id, mrow == HN_EMPTY ? nullptr : md->md_bits + (size_t)mrow * md->M,
                    mrow == HN_EMPTY ? 0.0f : md->md_mags[mrow]};
     return md_pair_distance(sc.metric, sc.st, sc.dim, md->M, x, y, d);

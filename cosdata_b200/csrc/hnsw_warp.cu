@@ -28,21 +28,26 @@ namespace cdb {
 
 constexpr uint32_t HW_FINAL_LEN = 100;          // vector_store.rs:1194
 constexpr uint32_t HW_STAGE_BYTES = 12800;      // staged neighbour rows per group: 8 rows of f16 x 768, 4 of f32 x 768
+constexpr uint32_t HW_STAGE_BYTES_SPEC = 18700; // speculative form: 12 rows of f16 x 768 (7 warps/SM still fit in shared memory)
+constexpr uint32_t HW_CACHE = 256;              // speculative form: direct-mapped (node -> score key) cache entries per query
+constexpr uint32_t HW_WORK = HN_MAX_TAKE + 32;  // speculative form: rows to score in one pop (misses of the head + fill)
 // clock64 sums per query (lane 0): [0] pop + adjacency (+ node_row) loads, [1] fixed-set walk + compaction + prefetches,
 // [2] issue of the row copies, [3] wait for the rows, [4] distance chains, [5] queue merge, [6] end-of-level result sort,
 // [7] whole levels, [8] pops
-constexpr int HW_PROF_SLOTS = 9;
+// speculative form: [9] cache look-ups + choice of speculative rows, [10] chain phases, [11] speculative evaluations
+constexpr int HW_PROF_SLOTS = 12;
 
 struct HwCarve {
     uint32_t EFP, stage_pitch, stage_rows;
     uint32_t off_q32, off_qkeys, off_rkeys, off_nkeys, off_fs, off_qnodes, off_rnodes, off_nnodes, off_nrow, off_bar, off_stage, total;
+    uint32_t off_cache, off_work;   // speculative form only
 };
 
-__host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, uint32_t ef, bool f16fast) {
+__host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, uint32_t ef, bool f16fast, bool spec = false) {
     HwCarve c;
     c.EFP = hn_efp(ef);
     c.stage_pitch = round_up(row_pitch, 16) + 16;   // + 16 bytes: the lanes' rows start on different banks
-    uint32_t r = HW_STAGE_BYTES / c.stage_pitch;
+    uint32_t r = (spec ? HW_STAGE_BYTES_SPEC : HW_STAGE_BYTES) / c.stage_pitch;
     c.stage_rows = r > 32 ? 32 : (r ? r : 1u);      // one lane scores one staged row
     uint32_t o = round_up(row_pitch, 16);
     c.off_q32 = o;            o += f16fast ? round_up(dim * 4, 16) : 0;
@@ -55,6 +60,14 @@ __host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, ui
     c.off_rnodes = o;         o += c.EFP * 4;
     c.off_nnodes = o;         o += HN_MAX_TAKE * 4;
     c.off_nrow = o;           o += HN_MAX_TAKE * 4;
+    c.off_cache = c.off_work = 0;
+    if (spec) {
+        o = round_up(o, 8);
+        c.off_cache = o;      o += HW_CACHE * 8;
+        // the work list (node, row, destination) reuses the f16 copy of the query once the f32 copy exists
+        if (f16fast && round_up(row_pitch, 16) >= 3 * HW_WORK * 4) c.off_work = 0;
+        else { c.off_work = o; o += 3 * HW_WORK * 4; }
+    }
     c.off_stage = round_up(o, 16);
     c.total = c.off_stage + c.stage_rows * c.stage_pitch;
     return c;
@@ -66,6 +79,8 @@ struct HwSmem {
     uint64_t *qkeys, *rkeys, *nkeys;
     uint32_t *fs;            // PerformantFixedSet as 128 x 32-bit words: bucket b = words 2b, 2b+1 (native 32-bit shared atomics)
     uint32_t *qnodes, *rnodes, *nnodes, *nrow;
+    uint64_t *cache;         // speculative form: (node << 32 | score order key), tag 0xFFFFFFFF = empty
+    uint32_t *wnode, *wrow, *wdst;
     uint8_t *stage;
     uint32_t bar;            // shared-space address of the warp's mbarrier (row copies complete on it)
     uint32_t EFP, stage_pitch, stage_rows;
@@ -268,6 +283,65 @@ __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const H
     return err_first;
 }
 
+__device__ __forceinline__ uint32_t hw_cache_slot(uint32_t node) { return (node * 0x9E3779B1u) >> 24; }   // HW_CACHE = 256
+
+// Speculative form: score the work list wnode/wrow[0 .. nt).  Entries [0, nm) are the head's neighbours whose score is not
+// cached (slot order kept; the key goes to nkeys[wdst]); entries [nm, nt) are neighbours of upcoming heads that fill the
+// otherwise idle lanes of the chain phase -- their score keys go to the cache (an evaluation that fails is simply not cached:
+// the error belongs to the pop that commits it).  Same staging and the same chains as hw_score_group.
+template <int FAST, bool PROF>
+__device__ __forceinline__ uint32_t hw_score_work(const HnScoreCtx &sc, const HwSmem &m, float qmag, uint32_t pp, uint32_t nm,
+                                                  uint32_t nt, int lane, HwState &st) {
+    uint32_t err_first = 0xFFFFFFFFu;
+    for (uint32_t g0 = 0; g0 < nt; g0 += m.stage_rows) {
+        const uint32_t gn = min(m.stage_rows, nt - g0);
+        long long ts = 0, ti = 0, tw = 0;
+        if (PROF) ts = clock64();
+        uint32_t row = 0;
+        float rmag = 0.0f;
+        if (lane == 0) hw_mbar_expect(m.bar, gn * sc.row_pitch);
+        if ((uint32_t)lane < gn) {
+            row = m.wrow[g0 + lane];
+            hw_bulk_g2s(hw_smem_u32(m.stage + (size_t)lane * m.stage_pitch), sc.rows + (size_t)row * sc.row_pitch, sc.row_pitch, m.bar);
+            rmag = sc.mags[row];
+        }
+        if (PROF) ti = clock64();
+        hw_mbar_wait(m.bar, st.bar_phase);
+        st.bar_phase ^= 1u;
+        if (PROF) tw = clock64();
+        int rc = CDB_OK;
+        const uint32_t idx = g0 + (uint32_t)lane;
+        if ((uint32_t)lane < gn) {
+            const uint8_t *code = m.stage + (size_t)lane * m.stage_pitch;
+            float d = 0.0f;
+            if (FAST) {
+                const float dot = FAST == 1 ? hw_dot_f16_q32(m.q32, code, sc.dim) : hw_dot_bf16_q32(m.q32, code, sc.dim);
+                if (sc.metric == CDB_METRIC_COSINE) {
+                    const float denom = __fmul_rn(qmag, rmag);
+                    if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
+                    else d = canon_nan(__fdiv_rn(dot, denom));
+                } else {
+                    d = dot;
+                }
+            } else {
+                rc = pair_distance(sc.metric, sc.st, sc.dim, m.qs, qmag, pp, code, rmag, pp, &d);
+            }
+            const uint32_t okey = order_key(sc.metric, __float_as_uint(d));
+            if (idx < nm) m.nkeys[m.wdst[idx]] = make_key64(okey, hn_id(sc.root_row, row));
+            else if (rc == CDB_OK) { const uint32_t nd = m.wnode[idx]; m.cache[hw_cache_slot(nd)] = ((uint64_t)nd << 32) | okey; }
+        }
+        const uint32_t bad = __ballot_sync(0xFFFFFFFFu, rc != CDB_OK && idx < nm);
+        if (bad && err_first == 0xFFFFFFFFu) {   // the reference stops at the first Err (slot order)
+            const int src_lane = __ffs(bad) - 1;
+            const int flag = __shfl_sync(0xFFFFFFFFu, (int)md_err_flag(rc), src_lane);
+            err_first = ((g0 + (uint32_t)src_lane) << 8) | (uint32_t)flag;
+        }
+        __syncwarp();
+        if (PROF) { const long long te = clock64(); st.prof[2] += ti - ts; st.prof[3] += tw - ti; st.prof[4] += te - tw; st.prof[10] += 1; }
+    }
+    return err_first;
+}
+
 // One level (traverse_find_nearest).  All 32 lanes call it with warp-uniform arguments.  On return (st.err == 0)
 // rkeys/rnodes[0..st.rlen) hold every popped entry sorted best first.
 template <int FAST, bool PROF>
@@ -277,6 +351,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
     const uint32_t pp = plane_pitch(sc.dim);
     const bool f_preload = (flags & CDB_HNSW_F_PRELOAD) != 0, f_atomfs = (flags & CDB_HNSW_F_ATOMFS) != 0;
     const bool f_pool = (flags & CDB_HNSW_F_POOL) != 0;
+    const bool f_spec = (flags & CDB_HNSW_F_SPEC) != 0 && !f_pool;
     const uint32_t EFP = m.EFP;
     const uint32_t CAPQ = 2 * EFP;      // pool form: both queue buffers are one unsorted pool
     const uint32_t bmask = nb - 1u;
@@ -285,6 +360,9 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
     if (PROF) t0 = clock64();
 #pragma unroll
     for (int i = 0; i < 4; ++i) m.fs[lane + 32 * i] = 0u;
+    if (f_spec)   // node indices are level-local: the score cache starts empty on every level
+        for (uint32_t i = lane; i < HW_CACHE; i += 32) m.cache[i] = ~0ull;
+    uint32_t sd0 = HN_EMPTY, sd1 = HN_EMPTY, sd2 = HN_EMPTY, sd3 = HN_EMPTY;   // queue entries whose neighbours are all cached
     if (lane == 0) { m.nnodes[0] = entry; m.nrow[0] = node_row ? node_row[entry] : entry; }
     __syncwarp();
     {
@@ -332,6 +410,28 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                 const uint32_t slot = (uint32_t)lane + 32u * h;
                 nbl[h] = slot < take ? __ldg(adj + (size_t)bn * nb + slot) : HN_EMPTY;
             }
+        }
+        // SPECULATIVE form (CDB_HNSW_F_SPEC): a pop scores ~4 rows, so ~28 lanes idle through a 768-step dependent chain.  The
+        // next heads are already known (the sorted queue), a score is a pure function of (query, node), and the fixed set only
+        // grows: whatever a later pop will score is among the neighbours of that head whose bit is clear NOW.  So the free
+        // lanes of this pop's chain phase score those rows ahead of time into a small cache; the later pop walks its fixed
+        // set exactly as before (same order, same insertions, same evals count) and takes the keys from the cache, and a pop
+        // whose accepted neighbours are all cached has no chain phase at all.
+        uint32_t ssrc[2] = {HN_EMPTY, HN_EMPTY}, snbl[2][2] = {{HN_EMPTY, HN_EMPTY}, {HN_EMPTY, HN_EMPTY}};
+        if (f_spec) {
+            for (uint32_t j = 1; j < qlen && j <= 5; ++j) {
+                const uint32_t nd = QN[j];
+                if (nd == sd0 || nd == sd1 || nd == sd2 || nd == sd3) continue;
+                if (ssrc[0] == HN_EMPTY) ssrc[0] = nd;
+                else { ssrc[1] = nd; break; }
+            }
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t slot = (uint32_t)lane + 32u * h;
+                    if (ssrc[sidx] != HN_EMPTY && slot < take) snbl[sidx][h] = __ldg(adj + (size_t)ssrc[sidx] * nb + slot);
+                }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -406,7 +506,70 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
         }
         if (PROF) t3 = clock64();
         // ---- score the new neighbours
-        const uint32_t e = hw_score_group<FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st);
+        uint32_t e = 0xFFFFFFFFu;
+        if (f_spec) {
+            // keys of accepted neighbours that were scored ahead of time; the others form the work list
+            bool miss[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t pos = (uint32_t)lane + 32u * h;
+                miss[h] = false;
+                if (pos < nc) {
+                    const uint32_t nd = m.nnodes[pos];
+                    const uint64_t ce = m.cache[hw_cache_slot(nd)];
+                    if ((uint32_t)(ce >> 32) == nd) m.nkeys[pos] = make_key64((uint32_t)ce, hn_id(sc.root_row, m.nrow[pos]));
+                    else miss[h] = true;
+                }
+            }
+            const uint32_t mb0 = __ballot_sync(0xFFFFFFFFu, miss[0]);
+            const uint32_t mb1 = nc > 32 ? __ballot_sync(0xFFFFFFFFu, miss[1]) : 0u;
+            const uint32_t nm0 = (uint32_t)__popc(mb0), nm = nm0 + (uint32_t)__popc(mb1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (miss[h]) {
+                    const uint32_t pos = (uint32_t)lane + 32u * h;
+                    const uint32_t w = (h ? nm0 : 0u) + (uint32_t)__popc((h ? mb1 : mb0) & lt);
+                    m.wnode[w] = m.nnodes[pos]; m.wrow[w] = m.nrow[pos]; m.wdst[w] = pos;
+                }
+            uint32_t nt = nm;
+            if (nm > 0 && nm < m.stage_rows) {
+                // one chain phase is due anyway: fill its free lanes with the uncached, not yet visited neighbours of the next heads
+#pragma unroll
+                for (int sidx = 0; sidx < 2; ++sidx) {
+                    const uint32_t room = m.stage_rows - nt;
+                    if (ssrc[sidx] == HN_EMPTY || room == 0) continue;
+                    bool c[2];
+                    uint32_t r[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        c[h] = false; r[h] = 0;
+                        const uint32_t nd = snbl[sidx][h];
+                        if (nd != HN_EMPTY) {
+                            r[h] = node_row ? __ldg(node_row + nd) : nd;
+                            const uint32_t id = hn_id(sc.root_row, r[h]);
+                            const uint32_t b = (((id >> 6) & bmask) << 6) | (id & 0x3f);
+                            if (((m.fs[b >> 5] >> (b & 31)) & 1u) == 0) c[h] = (uint32_t)(m.cache[hw_cache_slot(nd)] >> 32) != nd;
+                        }
+                    }
+                    const uint32_t c0 = __ballot_sync(0xFFFFFFFFu, c[0]);
+                    const uint32_t c1 = take > 32 ? __ballot_sync(0xFFFFFFFFu, c[1]) : 0u;
+                    const uint32_t n0 = (uint32_t)__popc(c0), tot = n0 + (uint32_t)__popc(c1);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (c[h]) {
+                            const uint32_t pch = (h ? n0 : 0u) + (uint32_t)__popc((h ? c1 : c0) & lt);
+                            if (pch < room) { m.wnode[nt + pch] = snbl[sidx][h]; m.wrow[nt + pch] = r[h]; }
+                        }
+                    if (tot <= room) { sd3 = sd2; sd2 = sd1; sd1 = sd0; sd0 = ssrc[sidx]; }   // nothing left to score for this entry
+                    nt += min(tot, room);
+                }
+            }
+            __syncwarp();   // work list visible
+            if (PROF) { const long long tq = clock64(); st.prof[9] += tq - t3; st.prof[11] += nt - nm; t3 = tq; }
+            if (nt) e = hw_score_work<FAST, PROF>(sc, m, qmag, pp, nm, nt, lane, st);
+        } else {
+            e = hw_score_group<FAST, PROF>(sc, m, qmag, pp, 0, nc, lane, st);
+        }
         st.evals += nc;
         if (e != 0xFFFFFFFFu) { st.err = e & 0xFFu; st.rlen = rlen; return; }
         if (PROF) t4 = clock64();
@@ -612,6 +775,10 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarv
     m.nnodes = reinterpret_cast<uint32_t *>(smem + cv.off_nnodes);
     m.nrow = reinterpret_cast<uint32_t *>(smem + cv.off_nrow);
     m.stage = smem + cv.off_stage;
+    m.cache = reinterpret_cast<uint64_t *>(smem + cv.off_cache);
+    m.wnode = reinterpret_cast<uint32_t *>(smem + cv.off_work);
+    m.wrow = m.wnode + HW_WORK;
+    m.wdst = m.wrow + HW_WORK;
     m.EFP = cv.EFP; m.stage_pitch = cv.stage_pitch; m.stage_rows = cv.stage_rows;
 
     for (uint32_t i = lane; i < a.row_pitch / 4; i += 32)
@@ -668,7 +835,7 @@ static int hw_fast_kind(int st, int metric) {   // 1: f16 chain, 2: bf16 chain, 
     return st == CDB_ST_F16 ? 1 : (st == CDB_ST_BF16 ? 2 : 0);
 }
 size_t hnsw_warp_smem(uint32_t row_pitch, uint32_t dim, uint32_t ef, int st, int metric) {
-    return hw_carve(row_pitch, dim, ef, hw_fast_kind(st, metric) != 0).total;
+    return hw_carve(row_pitch, dim, ef, hw_fast_kind(st, metric) != 0, true).total;
 }
 
 template <int FAST, bool PROF>
@@ -684,7 +851,8 @@ cdb_status hnsw_search_warp_device(const HnswArgs &a, cudaStream_t s) {
     if (!a.nq) return CDB_OK;
     if (a.ef == 0 || a.ef > 4096) { set_error("hnsw: ef_search must be in 1..4096"); return CDB_INVALID_PARAMS; }
     const int fast = hw_fast_kind(a.st, a.metric);
-    const HwCarve cv = hw_carve(a.row_pitch, a.dim, a.ef, fast != 0);
+    const bool spec = (a.flags & CDB_HNSW_F_SPEC) != 0 && (a.flags & CDB_HNSW_F_POOL) == 0;
+    const HwCarve cv = hw_carve(a.row_pitch, a.dim, a.ef, fast != 0, spec);
     if (cv.total > 200 * 1024) { set_error("hnsw: ef_search / row size too large for shared memory"); return CDB_INVALID_PARAMS; }
     const bool prof = a.prof != nullptr;
     if (fast == 1) return prof ? launch_warp<1, true>(a, cv, s) : launch_warp<1, false>(a, cv, s);

@@ -124,6 +124,7 @@ struct HnswArgs {
 constexpr uint32_t CDB_HNSW_F_PRELOAD = 2;   // load the next head's adjacency slots while the queue merge runs
 constexpr uint32_t CDB_HNSW_F_ATOMFS = 4;    // fixed-set walk through atomicOr return values (slot-order loop only on aliasing)
 constexpr uint32_t CDB_HNSW_F_CTA = 8;       // round-1 kernel: one CTA per query
+constexpr uint32_t CDB_HNSW_F_SPEC = 32;     // idle lanes of a chain phase score the next heads' neighbours ahead of time (hnsw_warp.cu)
 constexpr uint32_t CDB_HNSW_F_POOL = 16;     // candidates as an unsorted pool + arg-max pops instead of a sorted queue + merges
 constexpr uint32_t CDB_HNSW_F_DEFAULT = CDB_HNSW_F_PRELOAD | CDB_HNSW_F_ATOMFS;
 extern std::atomic<uint32_t> g_hnsw_flags;
@@ -159,6 +160,30 @@ cdb_status hnsw_build_device(const HnScoreCtx &sc, uint32_t n, uint32_t num_leve
                              std::vector<void *> *out_allocs, std::vector<uint32_t> *out_counts,
                              std::vector<const uint32_t *> *out_nr, std::vector<const uint32_t *> *out_ad,
                              std::vector<const uint32_t *> *out_ch, cudaStream_t s);
+
+// replica lists: one entry per graph node to create, host arrays (cdb_replica_build)
+struct ReplicaHost {
+    uint32_t n_nodes;
+    const uint32_t *row, *node_id, *base_id, *md_row;
+    const uint8_t *max_level;
+    uint32_t md_dims, n_md;
+    const int32_t *md_bits;
+    const float *md_mags;
+    uint32_t main_root_row, main_root_md, pseudo_root_row, pseudo_root_md;
+};
+struct ReplicaGraphDev {
+    const uint32_t *const *node_id, *const *node_md;   // device tables of device arrays
+    std::vector<const uint32_t *> h_node_id, h_node_md;   // the same per-level device pointers on the host
+    const int32_t *md_bits;
+    const float *md_mags;
+    uint32_t md_dims, pseudo_entry;
+};
+cdb_status hnsw_build_replicas_device(const HnScoreCtx &sc, const ReplicaHost &rh, uint32_t num_levels, uint32_t nbrs, uint32_t nbrs0,
+                                      uint32_t ef_construction, uint32_t shortlist, uint32_t max_batch, GraphDev *out_graph,
+                                      std::vector<void *> *out_allocs, std::vector<uint32_t> *out_counts,
+                                      std::vector<const uint32_t *> *out_nr, std::vector<const uint32_t *> *out_ad,
+                                      std::vector<const uint32_t *> *out_ch, ReplicaGraphDev *out_md, std::vector<uint8_t> *out_failed,
+                                      cudaStream_t s);
 
 // ---- tensor_scan.cu (tcgen05 prefilter)
 constexpr uint32_t TS_MAX_ODD = 64;   // degenerate rows that are not all-zero ride on every candidate list; more -> no prefilter

@@ -335,6 +335,33 @@ typedef struct {
     uint64_t seed;                    /* level assignment + root vector */
 } cdb_build_params;
 cdb_status cdb_index_build_graph(cdb_index *index, const cdb_build_params *params);
+/* The same build for a collection with a metadata schema (index_embeddings over preprocess_embedding's flattened
+ * IndexableEmbeddings, src/vector_store.rs:629-780): one entry per graph node to create, in insertion order.
+ *   row        vector row of the embedding; CDB_INVALID_ID = the pseudo root's vector (pseudo replicas, :655-667)
+ *   node_id    ProbNode::get_id(): replica id, or prop_value.id without metadata (:803-806)
+ *   base_id    prop_value.id, carried by the traversal's fvec_data (:812)
+ *   md_row     row of the metadata table or CDB_INVALID_ID (prop_metadata None)
+ *   max_level  the caller's get_max_insert_level draw (levels_prob, pseudo_level_probs for pseudo replicas; :749-753)
+ * Nodes whose metadata has mag != 0 are indexed under the pseudo root, the rest under the main root (:461-483); edges follow
+ * create_node_edges including the replica rules (:1014-1040: Metadata node <-> Pseudo neighbour only on cs == 1.0,
+ * Metadata <-> Metadata not on cs == -1.0).  Appends TWO rows (main root: random in values_range, id u32::MAX, metadata
+ * main_root_md; pseudo root: zeros, id u32::MAX - 257, metadata pseudo_root_md).  Every level lists [0] main root,
+ * [1] pseudo root, then the created nodes in list order.  out_failed[n_nodes] (optional): 1 where the reference's insert
+ * would have returned Err / panicked (the node stays unlinked).  The graph and its metadata replace any uploaded ones;
+ * searches then go through cdb_search_batch_filtered / CDB_MODE_HNSW as after cdb_index_set_graph_metadata. */
+typedef struct {
+    uint32_t n_nodes;
+    const uint32_t *row, *node_id, *base_id, *md_row;
+    const uint8_t *max_level;
+    uint32_t md_dims, n_md;
+    const int32_t *md_bits;           /* [n_md x md_dims] Metadata.mbits */
+    const float *md_mags;             /* [n_md] Metadata.mag */
+    uint32_t main_root_md;            /* schema.base_dimensions() with mag 0 (vector_store.rs:79-93), or CDB_INVALID_ID */
+    uint32_t pseudo_root_md;          /* schema.pseudo_root_dimensions(HIGH_WEIGHT) (vector_store.rs:185-187) */
+} cdb_replica_build;
+cdb_status cdb_index_build_graph_replicas(cdb_index *index, const cdb_build_params *params, const cdb_replica_build *replicas,
+                                          uint8_t *out_failed);
+cdb_status cdb_index_read_graph_metadata_level(const cdb_index *index, uint32_t level, uint32_t *node_id, uint32_t *node_md);
 /* read the current graph back: info5 = {num_levels, neighbors_count, level0_neighbors_count, entry, root_row} */
 cdb_status cdb_index_graph_info(const cdb_index *index, uint32_t *info5, uint32_t *level_counts /* [num_levels+1] or NULL */);
 cdb_status cdb_index_read_graph_level(const cdb_index *index, uint32_t level, uint32_t *node_row, uint32_t *adjacency, uint32_t *child);
@@ -362,8 +389,9 @@ cdb_status cdb_search_batch(cdb_index *index, const float *queries, uint32_t n_q
 cdb_status cdb_search_batch_filtered(cdb_index *index, const float *queries, uint32_t n_queries, const cdb_search_params *params,
                                      const uint32_t *filter_offsets, const int8_t *filter_dims, const uint8_t *has_filter,
                                      uint32_t *out_ids, float *out_scores, uint32_t *out_counts, uint8_t *err_flags);
-/* same, every pointer is DEVICE memory on the index's device; asynchronous on `stream`.  Searches on one handle share
- * its scratch arena and are ordered on the device (a search on another stream waits for the previous one). */
+/* same, every pointer is DEVICE memory on the index's device; asynchronous on `stream`.  Each search leases one of the
+ * handle's scratch sets (a small pool, grown on demand): searches on different streams run concurrently, a scratch set is
+ * handed to its next user only behind the event that ends its previous search. */
 cdb_status cdb_search_batch_device(cdb_index *index, const float *d_queries, uint32_t n_queries,
                                    const cdb_search_params *params,
                                    uint32_t *d_out_ids, float *d_out_scores, uint32_t *d_out_counts,
@@ -417,8 +445,9 @@ cdb_status cdb_merge_topk_device(int32_t device, int32_t metric, const uint32_t 
                                  uint32_t *d_out_ids, float *d_out_scores, void *stream);
 
 /* per-phase clock64 sums of the HNSW search kernel (lane 0 of every query, summed over the queries of all searches since
- * profiling was enabled): out[0..9) = {pop + adjacency loads, fixed-set walk + compaction, issue of the row copies, wait for
- * the rows, distance chains, queue merge, end-of-level result sort, whole levels, pops}; the remaining slots are 0.
+ * profiling was enabled): out[0..12) = {pop + adjacency loads, fixed-set walk + compaction, issue of the row copies, wait for
+ * the rows, distance chains, queue merge, end-of-level result sort, whole levels, pops, score-cache look-ups + choice of
+ * speculative rows, chain phases, speculative evaluations} (the last three only with CDB_HNSW_F_SPEC); the remaining slots are 0.
  * enable != 0 zeroes the sums and switches the instrumented kernel variant on; 0 switches it off.  out (may be NULL,
  * CDB_HNSW_PROF_SLOTS entries) receives the sums accumulated so far.  Synchronizes the device. */
 #define CDB_HNSW_PROF_SLOTS 16

@@ -2,6 +2,7 @@
  * metadata_oracle.c -- see metadata_oracle.h.  TEST INFRASTRUCTURE ONLY.
  */
 #include "metadata_oracle.h"
+#include "hnsw_build_internal.h"
 
 #include <float.h>
 #include <math.h>
@@ -305,4 +306,173 @@ int orc_hnsw_search_batch_md(const orc_md_graph *mg, const float *raw, const flo
     if (evals) *evals = ev_total;
     if (pops) *pops = pop_total;
     return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ builder with replica nodes */
+#define ORC_PSEUDO_ROOT_ID (0xFFFFFFFFu - 257u) /* metadata/mod.rs:219-225 */
+
+struct orc_md_built {
+    orc_md_graph mg;
+    uint32_t nlevels1;
+    blevel *lv;
+    uint32_t *cnt_arr;
+    const uint32_t **node_row_arr, **adj_arr, **child_arr, **node_id_arr, **node_md_arr;
+    uint32_t min_key, max_key;
+};
+
+static void md_refresh_view(orc_md_built *b) {
+    for (uint32_t L = 0; L < b->nlevels1; ++L) {
+        b->cnt_arr[L] = b->lv[L].cnt;
+        b->node_row_arr[L] = b->lv[L].node_row;
+        b->adj_arr[L] = b->lv[L].adj;
+        b->child_arr[L] = b->lv[L].child;
+        b->node_id_arr[L] = b->lv[L].node_id;
+        b->node_md_arr[L] = b->lv[L].node_md;
+    }
+}
+
+/* ProbNode::replica_node_kind (prob_node.rs:487-496): VectorData { id: Some(get_id()), metadata } */
+static int node_kind(const orc_md_built *b, const blevel *l, uint32_t node) {
+    orc_vector_data v;
+    memset(&v, 0, sizeof v);
+    const uint32_t md = l->node_md[node];
+    v.has_id = 1;
+    v.id = l->node_id[node];
+    v.md_bits = md == ORC_EMPTY ? NULL : b->mg.md_bits + (size_t)md * b->mg.md_dims;
+    v.md_mag = md == ORC_EMPTY ? 0.0f : b->mg.md_mags[md];
+    return orc_replica_kind(&v);
+}
+
+/* create_node_edges (src/vector_store.rs:976-1070) with the replica rules of :1014-1040 */
+static void md_create_node_edges(orc_md_built *b, blevel *l, uint32_t node, const mitem *z, uint32_t zn) {
+    const int cosine = b->mg.g.metric == ORC_METRIC_COSINE; /* the rules match MetricResult::CosineSimilarity only */
+    const int nk = node_kind(b, l, node);
+    uint32_t successful = 0;
+    for (uint32_t i = 0; i < zn; ++i) {
+        if (successful >= l->nb) break;
+        const uint32_t nbr = z[i].node;
+        if (cosine) {
+            const int bk = node_kind(b, l, nbr);
+            if (bk == ORC_KIND_PSEUDO && nk == ORC_KIND_METADATA && z[i].score != 1.0f) continue;
+            if (bk == ORC_KIND_METADATA && nk == ORC_KIND_METADATA && z[i].score == -1.0f) continue;
+        }
+        const uint32_t dkey = orc_order_key(b->mg.g.metric, z[i].score);
+        const int idx = bl_add_neighbor(b->min_key, b->max_key, l, node, nbr, dkey);
+        if (idx >= 0) {
+            const int j = bl_add_neighbor(b->min_key, b->max_key, l, nbr, node, dkey);
+            if (j >= 0) successful++;
+            else if (l->adj[(size_t)node * l->nb + idx] == nbr) l->adj[(size_t)node * l->nb + idx] = ORC_EMPTY; /* remove_neighbor_by_index_and_id */
+        }
+    }
+}
+
+orc_md_built *orc_hnsw_build_md(int metric, int st, size_t dim, const void *codes, const float *mags, size_t md_dims,
+                                const int32_t *md_bits, const float *md_mags, const orc_replica_list *rl, uint32_t num_levels,
+                                uint32_t nbrs, uint32_t nbrs0, uint32_t ef_construction, uint32_t shortlist, uint8_t *failed_out) {
+    orc_md_built *b = (orc_md_built *)calloc(1, sizeof(orc_md_built));
+    const uint32_t L1 = num_levels + 1;
+    b->nlevels1 = L1;
+    b->lv = (blevel *)calloc(L1, sizeof(blevel));
+    b->cnt_arr = (uint32_t *)calloc(L1, sizeof(uint32_t));
+    b->node_row_arr = (const uint32_t **)calloc(L1, sizeof(uint32_t *));
+    b->adj_arr = (const uint32_t **)calloc(L1, sizeof(uint32_t *));
+    b->child_arr = (const uint32_t **)calloc(L1, sizeof(uint32_t *));
+    b->node_id_arr = (const uint32_t **)calloc(L1, sizeof(uint32_t *));
+    b->node_md_arr = (const uint32_t **)calloc(L1, sizeof(uint32_t *));
+    orc_md_graph *mg = &b->mg;
+    orc_graph *g = &mg->g;
+    g->num_levels = num_levels; g->neighbors_count = nbrs; g->level0_neighbors_count = nbrs0; g->n = rl->main_root_row;
+    g->metric = metric; g->storage_type = st; g->dim = dim; g->codes = codes; g->mags = mags;
+    g->cnt = b->cnt_arr; g->node_row = b->node_row_arr; g->adj = b->adj_arr; g->child = b->child_arr;
+    mg->md_dims = md_dims; mg->md_bits = md_bits; mg->md_mags = md_mags;
+    mg->node_id = b->node_id_arr; mg->node_md = b->node_md_arr;
+    bl_min_max_keys(metric, &b->min_key, &b->max_key);
+    /* both roots exist on every level, linked downwards (vector_store.rs:96-140, 203-250) */
+    for (uint32_t L = 0; L < L1; ++L) {
+        blevel *l = &b->lv[L];
+        l->nb = L == 0 ? nbrs0 : nbrs;
+        lv_reserve(l, 64);
+        l->cnt = 2;
+        lv_init_node(b->min_key, l, 0, rl->main_root_row);
+        l->node_id[0] = ORC_ROOT_ID; l->node_md[0] = rl->main_root_md;
+        lv_init_node(b->min_key, l, 1, rl->pseudo_root_row);
+        l->node_id[1] = ORC_PSEUDO_ROOT_ID; l->node_md[1] = rl->pseudo_root_md;
+        if (L > 0) { l->child[0] = 0; l->child[1] = 1; }
+    }
+    g->entry = 0;
+    mg->pseudo_entry = 1;
+    const uint32_t maxnb = nbrs0 > nbrs ? nbrs0 : nbrs;
+    uint64_t *fs = (uint64_t *)malloc(sizeof(uint64_t) * maxnb);
+    mitem *z = (mitem *)malloc(sizeof(mitem) * 64 * L1);
+    uint32_t *zn = (uint32_t *)malloc(sizeof(uint32_t) * L1);
+    uint32_t *node_at = (uint32_t *)malloc(sizeof(uint32_t) * L1);
+    const size_t cb = orc_code_bytes(st, dim);
+    for (uint32_t t = 0; t < rl->n_nodes; ++t) {
+        if (failed_out) failed_out[t] = 0;
+        const uint32_t row = rl->row[t], md = rl->md_row[t];
+        orc_vector_data x;
+        x.code = (const uint8_t *)codes + (size_t)row * cb;
+        x.mag = mags[row];
+        x.has_id = 1;
+        x.id = rl->base_id[t];
+        x.md_bits = md == ORC_EMPTY ? NULL : md_bits + (size_t)md * md_dims;
+        x.md_mag = md == ORC_EMPTY ? 0.0f : md_mags[md];
+        /* IndexableEmbedding::node_kind / root_node_kind (vector_store.rs:461-483): metadata with mag != 0 -> pseudo root */
+        const int under_pseudo = x.md_bits && x.md_mag != 0.0f;
+        const uint32_t max_level = rl->max_level[t];
+        uint32_t entry = under_pseudo ? mg->pseudo_entry : g->entry, parent = ORC_EMPTY;
+        int failed = 0;
+        for (int level = (int)num_levels; level >= 0; --level) {
+            blevel *l = &b->lv[level];
+            md_refresh_view(b);
+            memset(fs, 0, sizeof(uint64_t) * l->nb);
+            fs_insert(fs, l->nb, rl->node_id[t]); /* skipm.insert(new_node_id), :803-807 */
+            mitem *zl = z + 64 * level;
+            uint32_t cnt = 0;
+            int rc = traverse_md(mg, (uint32_t)level, entry, &x, ef_construction, shortlist, 64, fs, zl, &cnt, NULL, NULL);
+            if (rc == ORC_OK && cnt == 0) { /* :829-851: the entry itself, fvec_data without an id */
+                orc_vector_data x0 = x, y;
+                x0.has_id = 0;
+                node_data(mg, (uint32_t)level, entry, &y);
+                float d = 0.0f;
+                rc = orc_distance_md(metric, st, dim, md_dims, &x0, &y, &d);
+                zl[0] = (mitem){mkey(mg, d, y.id), entry, d};
+                cnt = 1;
+            }
+            if (rc != ORC_OK) { failed = 1; break; } /* the reference returns Err (or panics on an unreachable arm): not indexed */
+            zn[level] = cnt;
+            const uint32_t next_entry = level > 0 ? l->child[zl[0].node] : 0;
+            if ((uint32_t)level <= max_level) {
+                lv_reserve(l, l->cnt + 1);
+                const uint32_t idx = l->cnt++;
+                lv_init_node(b->min_key, l, idx, row);
+                l->node_id[idx] = rl->node_id[t];
+                l->node_md[idx] = md;
+                if (parent != ORC_EMPTY) b->lv[level + 1].child[parent] = idx;
+                node_at[level] = idx;
+                parent = idx;
+            }
+            entry = next_entry;
+        }
+        if (failed) { /* nodes created on the way down stay unlinked, like a failed reference insert */
+            if (failed_out) failed_out[t] = 1;
+            continue;
+        }
+        const uint32_t top = max_level < num_levels ? max_level : num_levels;
+        for (uint32_t level = 0; level <= top; ++level)
+            md_create_node_edges(b, &b->lv[level], node_at[level], z + 64 * level, zn[level]);
+    }
+    md_refresh_view(b);
+    free(fs); free(z); free(zn); free(node_at);
+    return b;
+}
+
+const orc_md_graph *orc_md_built_graph(const orc_md_built *b) { return &b->mg; }
+
+void orc_md_built_free(orc_md_built *b) {
+    if (!b) return;
+    for (uint32_t L = 0; L < b->nlevels1; ++L) lv_free(&b->lv[L]);
+    free(b->lv); free(b->cnt_arr); free(b->node_row_arr); free(b->adj_arr); free(b->child_arr);
+    free(b->node_id_arr); free(b->node_md_arr);
+    free(b);
 }

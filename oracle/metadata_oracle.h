@@ -68,6 +68,35 @@ int orc_hnsw_search_batch_md(const orc_md_graph *mg, const float *raw, const flo
                              uint32_t ef_search, uint32_t shortlist_size, size_t k, int threads, uint32_t *out_ids,
                              float *out_scores, uint32_t *out_counts, uint8_t *err, uint64_t *evals, uint64_t *pops);
 
+/* ------------------------------------------------------------------ builder for collections with a metadata schema
+ * index_embeddings (src/vector_store.rs:714-780) over the flattened IndexableEmbeddings of preprocess_embedding
+ * (:629-712), single-threaded, in list order.  Each entry is one graph node to create:
+ *   row        vector row (pseudo replicas share the pseudo root's row, :661)
+ *   node_id    ProbNode::get_id(): the replica id, or prop_value.id without metadata (:803-806)
+ *   base_id    prop_value.id, the id fvec_data carries during the traversal (:812, 1131-1135)
+ *   md_row     metadata table row or ORC_EMPTY
+ *   max_level  the get_max_insert_level draw (levels_prob, or pseudo_level_probs for pseudo replicas; :749-753) -- drawn by
+ *              the caller, the reference uses rand::random
+ * Nodes whose metadata has mag != 0 (Pseudo and Metadata kinds) are indexed under the pseudo root, the others under the
+ * main root (IndexableEmbedding::root_node_kind, :480-483; types.rs:187-193).  create_node_edges applies the replica rules
+ * (:1014-1040): a Metadata node links to a Pseudo neighbour only on cs == 1.0, two Metadata nodes never on cs == -1.0.
+ * Layout of every level: [0] main root, [1] pseudo root, then the created nodes in list order. */
+typedef struct {
+    uint32_t n_nodes;
+    const uint32_t *row, *node_id, *base_id, *md_row;
+    const uint8_t *max_level;
+    uint32_t main_root_row, main_root_md;     /* create_root_node: id u32::MAX, base dimensions with mag 0 (vector_store.rs:79-93) */
+    uint32_t pseudo_root_row, pseudo_root_md; /* create_pseudo_root_node: id u32::MAX - 257 (vector_store.rs:160-200) */
+} orc_replica_list;
+
+typedef struct orc_md_built orc_md_built;
+orc_md_built *orc_hnsw_build_md(int metric, int storage_type, size_t dim, const void *codes, const float *mags, size_t md_dims,
+                                const int32_t *md_bits, const float *md_mags, const orc_replica_list *rl, uint32_t num_levels,
+                                uint32_t neighbors_count, uint32_t level0_neighbors_count, uint32_t ef_construction,
+                                uint32_t shortlist_size, uint8_t *failed /* [n_nodes] or NULL: insert returned Err */);
+const orc_md_graph *orc_md_built_graph(const orc_md_built *b);
+void orc_md_built_free(orc_md_built *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,12 @@ class _MdGraph(C.Structure):
                 ("node_id", C.c_void_p), ("node_md", C.c_void_p), ("pseudo_entry", C.c_uint32)]
 
 
+class _ReplicaList(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("row", C.c_void_p), ("node_id", C.c_void_p), ("base_id", C.c_void_p),
+                ("md_row", C.c_void_p), ("max_level", C.c_void_p), ("main_root_row", C.c_uint32), ("main_root_md", C.c_uint32),
+                ("pseudo_root_row", C.c_uint32), ("pseudo_root_md", C.c_uint32)]
+
+
 def _lib():
     L = po.lib()
     if not getattr(L, "_md_declared", False):
@@ -40,6 +46,13 @@ def _lib():
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
                                                C.POINTER(C.c_uint64)]
+        L.orc_hnsw_build_md.restype = C.c_void_p
+        L.orc_hnsw_build_md.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.POINTER(_ReplicaList), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_md_built_graph.restype = C.POINTER(_MdGraph)
+        L.orc_md_built_graph.argtypes = [C.c_void_p]
+        L.orc_md_built_free.restype = None
+        L.orc_md_built_free.argtypes = [C.c_void_p]
         L._md_declared = True
     return L
 
@@ -127,3 +140,56 @@ def search_batch_md(mg, raw, queries, filters, k, lo=-1.0, hi=1.0, ef_search=256
                                          _p(err), C.byref(ev), C.byref(pp))
     assert rc == 0
     return ids, scores, counts, err, ev.value, pp.value
+
+
+PSEUDO_ROOT_ID = 0xFFFFFFFF - 257
+
+
+class ReplicaList:
+    """the flattened IndexableEmbeddings of preprocess_embedding, in insertion order (see metadata_oracle.h)"""
+
+    def __init__(self, row, node_id, base_id, md_row, max_level, main_root_row, main_root_md, pseudo_root_row, pseudo_root_md):
+        self.row = np.ascontiguousarray(row, dtype=np.uint32)
+        self.node_id = np.ascontiguousarray(node_id, dtype=np.uint32)
+        self.base_id = np.ascontiguousarray(base_id, dtype=np.uint32)
+        self.md_row = np.ascontiguousarray(md_row, dtype=np.uint32)
+        self.max_level = np.ascontiguousarray(max_level, dtype=np.uint8)
+        self.main_root_row, self.main_root_md = int(main_root_row), int(main_root_md)
+        self.pseudo_root_row, self.pseudo_root_md = int(pseudo_root_row), int(pseudo_root_md)
+        n = self.row.size
+        assert self.node_id.size == n and self.base_id.size == n and self.md_row.size == n and self.max_level.size == n
+
+    def cstruct(self):
+        return _ReplicaList(self.row.size, _p(self.row), _p(self.node_id), _p(self.base_id), _p(self.md_row), _p(self.max_level),
+                            self.main_root_row, self.main_root_md, self.pseudo_root_row, self.pseudo_root_md)
+
+
+def build_md(metric, storage_type, dim, codes, mags, md_bits, md_mags, rl, num_levels=9, neighbors_count=32, level0_neighbors_count=64,
+             ef_construction=128, shortlist_size=64):
+    """single-threaded index_embeddings over a ReplicaList -> (MdGraph, failed u8[n_nodes])"""
+    L = _lib()
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    mags = np.ascontiguousarray(mags, dtype=np.float32)
+    md_bits = np.ascontiguousarray(md_bits, dtype=np.int32)
+    md_mags = np.ascontiguousarray(md_mags, dtype=np.float32)
+    failed = np.zeros(rl.row.size, dtype=np.uint8)
+    crl = rl.cstruct()
+    h = L.orc_hnsw_build_md(int(metric), int(storage_type), dim, _p(codes), _p(mags), md_bits.shape[1], _p(md_bits), _p(md_mags),
+                            C.byref(crl), num_levels, neighbors_count, level0_neighbors_count, ef_construction, shortlist_size,
+                            _p(failed))
+    g = L.orc_md_built_graph(h).contents
+    L1 = num_levels + 1
+
+    def arrs(tbl, per):
+        tp = C.cast(tbl, C.POINTER(C.c_void_p))
+        return [np.ctypeslib.as_array(C.cast(tp[lv], C.POINTER(C.c_uint32)), shape=(int(cnt[lv]) * per(lv),)).copy() for lv in range(L1)]
+    cnt = np.ctypeslib.as_array(C.cast(g.g.cnt, C.POINTER(C.c_uint32)), shape=(L1,)).copy()
+    one = lambda lv: 1
+    node_row, child = arrs(g.g.node_row, one), arrs(g.g.child, one)
+    adj = arrs(g.g.adj, lambda lv: level0_neighbors_count if lv == 0 else neighbors_count)
+    node_id, node_md = arrs(g.node_id, one), arrs(g.node_md, one)
+    fg = FlatGraph(metric, storage_type, dim, codes, mags, rl.main_root_row, num_levels, neighbors_count, level0_neighbors_count,
+                   g.g.entry, node_row, adj, child)
+    mg = MdGraph(fg, md_bits, md_mags, node_id, node_md, g.pseudo_entry)
+    L.orc_md_built_free(h)
+    return mg, failed

@@ -86,3 +86,40 @@ def make_queries(vecs, mg, nq, seed=2):
                 fs.append(rng.integers(-1, 2, mg.md_dims).astype(np.int8))
         filters.append(fs)
     return q, filters
+
+
+def replica_population(n=400, dim=24, md_dims=6, levels=4, n_patterns=7, seed=3, lo=-1.0, hi=1.0):
+    """The node list the reference would index for a collection with a metadata schema, in its insertion order
+    (vector_store.rs:629-712): pseudo replicas first (created with the collection), then per embedding its base replica
+    (base dimensions, mag 0 -> main root) and, for embeddings with metadata fields, one replica per field combination.
+    Dimension vectors are 0/1 (HIGH_WEIGHT = 1 binary encodings, metadata/mod.rs:19); pseudo replicas carry the same patterns
+    the metadata replicas use, so perfect matches (cs == 1.0) exist.
+    -> dict(vecs f32[n, dim], md_bits, md_mags, row, node_id, base_id, md_row, max_level, main_root_md, pseudo_root_md)"""
+    from cosdata_b200.api import level_probs, max_insert_level, pseudo_level_probs
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(size=(16, dim)).astype(np.float32)
+    v = (centres[rng.integers(0, 16, n)] + 0.35 * rng.normal(size=(n, dim))).astype(np.float32)
+    vecs = (v / (np.abs(v).max() * 1.01) * max(abs(lo), abs(hi))).astype(np.float32)
+    patterns = np.zeros((n_patterns, md_dims), np.int32)
+    for p in range(n_patterns):                                         # distinct non-zero binary codes
+        code = p + 1
+        patterns[p] = [(code >> b) & 1 for b in range(md_dims)]
+    md_bits = np.concatenate([np.zeros((1, md_dims), np.int32), np.ones((1, md_dims), np.int32), patterns])
+    md_mags = np.array([pymeta.metadata_mag(r) for r in md_bits], dtype=np.float32)
+    md_mags[0] = 0.0
+    row, node_id, base_id, md_row, max_level = [], [], [], [], []
+    plp = pseudo_level_probs(levels, n_patterns)
+    for j in range(n_patterns):                                         # pseudo_metadata_replicas: ids follow the pseudo root's
+        row.append(EMPTY); node_id.append(PSEUDO_ROOT_ID + 1 + j); base_id.append(PSEUDO_ROOT_ID); md_row.append(2 + j)
+        max_level.append(max_insert_level(float(np.float32(rng.random())), plp))
+    lp = level_probs(levels)
+    replicas = 4
+    for i in range(n):
+        fields = [] if i % 3 == 0 else sorted(set(int(x) for x in rng.integers(0, n_patterns, 1 + i % 2)))
+        # prop_metadata_replicas: replica 0 = base dimensions, then one per combination; ids base_id + j
+        for j, m in enumerate([0] + [2 + f for f in fields]):
+            row.append(i); node_id.append(i * replicas + j); base_id.append(i * replicas); md_row.append(m)
+            max_level.append(max_insert_level(float(np.float32(rng.random())), lp))
+    return dict(vecs=vecs, md_bits=md_bits, md_mags=md_mags, row=np.array(row, np.uint32), node_id=np.array(node_id, np.uint32),
+                base_id=np.array(base_id, np.uint32), md_row=np.array(md_row, np.uint32), max_level=np.array(max_level, np.uint8),
+                main_root_md=0, pseudo_root_md=1, n_pseudo=n_patterns)

@@ -59,8 +59,9 @@ def test_hnsw_search_matches_oracle(st, metric, ef):
     ix.close()
 
 
-@pytest.mark.parametrize("flags,name", [(0, "plain"), (2, "preload"), (4, "atomic fixed set"), (22, "pool + arg-max pops"), (8, "cta per query")])
-@pytest.mark.parametrize("st,ef,nb0", [(ST.HalfPrecisionFP, 128, 32), (ST.HalfPrecisionFP, 300, 64), (ST.UnsignedByte, 40, 32)])
+@pytest.mark.parametrize("flags,name", [(0, "plain"), (2, "preload"), (4, "atomic fixed set"), (22, "pool + arg-max pops"), (38, "speculative scoring"), (32, "speculative, plain"), (8, "cta per query")])
+@pytest.mark.parametrize("st,ef,nb0", [(ST.HalfPrecisionFP, 128, 32), (ST.HalfPrecisionFP, 300, 64), (ST.UnsignedByte, 40, 32),
+                                       (ST.BFloat16, 64, 64)])
 def test_hnsw_kernel_variants_walk_the_same_path(flags, name, st, ef, nb0):
     # every variant of the search kernel (cdb_debug_set_hnsw_flags) must pop the same nodes in the same order as the oracle
     n, dim, k = 3000, 40, 10
@@ -99,14 +100,23 @@ def test_hnsw_default_params_recall_and_shortlist():
     ix.close()
 
 
-def test_hnsw_zero_norm_row_fails_the_query_like_the_reference():
+@pytest.mark.parametrize("flags", [None, 38])
+def test_hnsw_zero_norm_row_fails_the_query_like_the_reference(flags):
+    # (flags 38: a zero-norm row scored ahead of time must fail only the queries whose traversal commits it)
     n, dim, k = 1500, 32, 5
     vecs = clustered(n, dim, 3)
     vecs[10] = 0.0                                                   # |v| = 0 -> CalculationError when scored
     fg, ix = build_both(vecs, ST.HalfPrecisionFP, MK.Cosine)
-    queries = vecs[[10, 11, 500]] + 0.01
-    ids, scores, counts, err = ix.batch_search(queries, k, cdb.SearchMode.HNSW, ef_search=64, shortlist_size=64)
+    rng = np.random.default_rng(5)
+    queries = np.concatenate([vecs[[10, 11, 500]] + 0.01, (vecs[rng.integers(0, n, 40)] + 0.02).astype(np.float32)])
+    try:
+        if flags is not None:
+            cdb.debug_set_hnsw_flags(flags)
+        ids, scores, counts, err = ix.batch_search(queries, k, cdb.SearchMode.HNSW, ef_search=64, shortlist_size=64)
+    finally:
+        cdb.debug_set_hnsw_flags()
     w = pyhnsw.search_batch(fg, vecs, queries, k, ef_search=64)
+    assert 0 < (w[3] != 0).sum() < len(queries)
     assert np.array_equal(err, w[3]) and np.array_equal(counts, w[2])
     assert np.array_equal(ids, w[0]) and np.array_equal(bits(scores), bits(w[1]))
     ix.close()

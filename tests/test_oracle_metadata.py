@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from oracle import pymeta
+from oracle import pyhnsw, pymeta
 from tests import f32emu, mdgraph
 
 EMPTY = 0xFFFFFFFF
@@ -219,3 +219,97 @@ def test_filtered_search_matches_python_restatement(st, metric):
     assert 0 in outcomes
     if metric == 0:
         assert 7 in outcomes                                            # the Some(empty) query
+
+
+# ----------------------------------------------------------------------------- builder with replica nodes
+def _oracle_replica_build(pop, st, metric, levels=4, nb=8, nb0=16, efc=32):
+    n, dim = pop["vecs"].shape
+    root = orc.synth_matrix(99, 1, dim)[0]
+    allv = np.concatenate([pop["vecs"], root[None], np.zeros((1, dim), np.float32)])     # rows n = main root, n+1 = pseudo root
+    codes, mags = orc.quantize_batch(st, allv)
+    rows = np.where(pop["row"] == mdgraph.EMPTY, n + 1, pop["row"]).astype(np.uint32)
+    rl = pymeta.ReplicaList(rows, pop["node_id"], pop["base_id"], pop["md_row"], pop["max_level"], n, pop["main_root_md"], n + 1,
+                            pop["pseudo_root_md"])
+    return pymeta.build_md(metric, st, dim, codes, mags, pop["md_bits"], pop["md_mags"], rl, num_levels=levels, neighbors_count=nb,
+                           level0_neighbors_count=nb0, ef_construction=efc), allv
+
+
+def _kinds(mg, lv):
+    ids, mds = mg.node_id[lv], mg.node_md[lv]
+    has = (mds != mdgraph.EMPTY) & (mg.md_mags[np.minimum(mds, mg.md_mags.size - 1)] != 0)
+    pseudo = (ids >= 0xFFFFFFFF - 257) & (ids <= 0xFFFFFFFF - 2)
+    return np.where(~has, pymeta.KIND_BASE, np.where(pseudo, pymeta.KIND_PSEUDO, pymeta.KIND_METADATA))
+
+
+def test_replica_builder_applies_the_edge_rules():
+    # create_node_edges, vector_store.rs:1014-1040: a Metadata node and a Pseudo node are linked only on a perfect match
+    # (identical dims -> cs == 1.0), two Metadata nodes never on cs == -1.0 (dims cosine <= 0.99), and the traversal arms keep
+    # Base nodes (main root) apart from the pseudo component.
+    pop = mdgraph.replica_population(n=300, levels=4)
+    (mg, failed), _ = _oracle_replica_build(pop, 4, 0)
+    assert failed.sum() == 0
+    seen = set()
+    for lv in range(5):
+        nbc = mg.fg.nbrs(lv)
+        adj = mg.fg.adj[lv].reshape(-1, nbc)
+        ks = _kinds(mg, lv)
+        assert mg.node_id[lv][0] == 0xFFFFFFFF and mg.node_id[lv][1] == pymeta.PSEUDO_ROOT_ID
+        for a in range(adj.shape[0]):
+            for b in adj[a][adj[a] != mdgraph.EMPTY]:
+                pair = (int(ks[a]), int(ks[b]))
+                seen.add(pair)
+                assert (pair[0] == pymeta.KIND_BASE) == (pair[1] == pymeta.KIND_BASE), (lv, a, b)
+                if pymeta.KIND_METADATA in pair and pair != (pymeta.KIND_BASE,) * 2:
+                    assert np.array_equal(mg.md_bits[mg.node_md[lv][a]], mg.md_bits[mg.node_md[lv][b]]), (lv, a, b, pair)
+        if lv:
+            assert np.array_equal(mg.fg.node_row[lv - 1][mg.fg.child[lv]], mg.fg.node_row[lv])
+            assert np.array_equal(mg.node_id[lv - 1][mg.fg.child[lv]], mg.node_id[lv])
+    assert seen == {(1, 1), (0, 0), (0, 2), (2, 0), (2, 2)}
+    # every created node is listed on levels 0..max_level, in list order behind the two roots
+    for lv in range(5):
+        want = pop["node_id"][pop["max_level"] >= lv]
+        assert np.array_equal(mg.node_id[lv][2:], want)
+
+
+@pytest.mark.parametrize("st,metric", [(4, 0), (0, 0), (2, 3)])
+def test_replica_builder_without_metadata_equals_the_plain_builder(st, metric):
+    # a replica list whose nodes carry no metadata is the plain collection: same level draws -> same graph as orc_hnsw_build,
+    # up to the layout (the replica builder lists an unused pseudo root at index 1 and level 0 in list order)
+    n, dim, levels, nb, nb0, efc, seed = 500, 24, 3, 8, 16, 24, 4
+    pop = mdgraph.replica_population(n=n, dim=dim, levels=levels)
+    vecs = pop["vecs"]
+    root = orc.synth_matrix(99, 1, dim)[0]
+    fg = pyhnsw.build(metric, st, vecs, root, num_levels=levels, neighbors_count=nb, level0_neighbors_count=nb0,
+                      ef_construction=efc, seed=seed)
+    max_level = np.zeros(n, np.uint8)
+    for lv in range(1, levels + 1):
+        max_level[fg.node_row[lv][1:]] = lv
+    allv = np.concatenate([vecs, root[None], np.zeros((1, dim), np.float32)])
+    codes, mags = orc.quantize_batch(st, allv)
+    ids = np.arange(n, dtype=np.uint32)
+    rl = pymeta.ReplicaList(ids, ids, ids, np.full(n, mdgraph.EMPTY, np.uint32), max_level, n, mdgraph.EMPTY, n + 1, 1)
+    mg, failed = pymeta.build_md(metric, st, dim, codes, mags, pop["md_bits"], pop["md_mags"], rl, num_levels=levels,
+                                 neighbors_count=nb, level0_neighbors_count=nb0, ef_construction=efc)
+    assert failed.sum() == 0
+    for lv in range(levels + 1):
+        nbc = nb0 if lv == 0 else nb
+        plain = fg.adj[lv].reshape(-1, nbc).astype(np.int64)
+        if lv == 0:     # plain level 0: node i = row i, root = n ; replica layout: root 0, pseudo root 1, row i -> 2 + i
+            to_new = np.concatenate([np.arange(n) + 2, [0]])
+        else:           # plain: root 0 then rows ; replica layout: root 0, pseudo root 1, rows shifted by one
+            to_new = np.concatenate([[0], np.arange(1, plain.shape[0]) + 1])
+        want = np.full((plain.shape[0] + 1, nbc), mdgraph.EMPTY, dtype=np.int64)
+        mapped = np.where(plain == mdgraph.EMPTY, mdgraph.EMPTY, to_new[np.minimum(plain, plain.shape[0] - 1)])
+        want[to_new] = mapped
+        assert np.array_equal(mg.fg.adj[lv].reshape(-1, nbc).astype(np.int64), want), lv
+
+
+def test_level_draw_helpers_match_the_reference_vectors():
+    from cosdata_b200.api import level_probs, max_insert_level, pseudo_level_probs
+    # src/metadata/mod.rs:286-301 (test_pseudo_level_probs)
+    assert pseudo_level_probs(9, 128) == [(0.999, 9), (0.99, 8), (0.9, 7), (0.0, 6), (0.0, 5), (0.0, 4), (0.0, 3), (0.0, 2),
+                                          (0.0, 1), (0.0, 0)]
+    assert pseudo_level_probs(2, 1000) == [(0.0, 2), (0.0, 1), (0.0, 0)]          # more higher levels than levels: all lower
+    lp = level_probs(9)                                                          # generate_level_probs(4.0, 9), common.rs:421-429
+    assert lp[0] == (1.0 - 4.0 ** -9, 9) and lp[-1] == (0.0, 0) and len(lp) == 10
+    assert max_insert_level(0.0, lp) == 0 and max_insert_level(0.75, lp) == 1 and max_insert_level(0.99999999, lp) == 9

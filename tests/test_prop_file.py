@@ -101,7 +101,7 @@ def test_writer_matches_known_serde_cbor_bytes():
     assert enc_f32(0.1) == b"\xfa" + struct.pack(">f", np.float32(0.1))     # not representable in half -> f32
 
 
-@pytest.mark.parametrize("st", list(ST))
+@pytest.mark.parametrize("st", [s for s in ST if s != ST.BFloat16])
 @pytest.mark.parametrize("dim", [8, 33, 100])
 def test_prop_file_round_trip(tmp_path, st, dim):
     n = 57
