@@ -53,6 +53,9 @@ def parse_args():
                          "hnsw: HNSW f16 search on a prebuilt graph (bench_data/, tools/build_hnsw_graph.py)")
     ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--hnsw-prof", action="store_true", help="c3: add the per-phase clock64 breakdown of one search (instrumented kernel variant)")
+    ap.add_argument("--storage", default="f16", choices=["f16", "bf16"],
+                    help="c3: f16 = the reference's HalfPrecisionFP (parity arm); bf16 = the labelled extension CDB_ST_BF16 (BASELINE.json's wording)")
+    ap.add_argument("--hnsw-flags", type=int, default=None, help="c3: kernel variant flags (cdb_debug_set_hnsw_flags) for the timed steps")
     ap.add_argument("--hnsw-variants", action="store_true", help="c3: time every kernel variant (cdb_debug_set_hnsw_flags) on the same graph")
     ap.add_argument("--dump-ids", default=None, help="c3: write the result ids/scores of the batch to this .npz (A/B runs)")
     ap.add_argument("--graph", default=os.path.join(ROOT, "bench_data", "hnsw_100k_128_f16.npz"))
@@ -488,7 +491,69 @@ def secondary_records(args, ix, cdb, torch, stream, dev, q_host):
                                  "kernel": "tensor_scan_u8_kernel (tcgen05 kind::i8, exact)", "tensor_path": st4}})
     except Exception as e:
         out.append({"name": "quaternary-quantized inner product (configs[3] shard)", "error": repr(e)})
+    # ---- BASELINE.json configs[2] at 1/10 size: HNSW f16, ef_search 128, batch 1024; graph built on the GPU (reference defaults)
+    try:
+        out.append(hnsw_record(cdb, torch, dev, stream, 1_000_000, 768, 1024, k, 128, hbm))
+    except Exception as e:
+        out.append({"name": "HNSW dense index (configs[2] at 1M rows)", "error": repr(e)})
     return out
+
+
+def hnsw_record(cdb, torch, dev, stream, rows, D, B, k, ef, hbm):
+    """clustered synthetic rows generated on device, graph built by cdb_index_build_graph (nbrs 32/64, ef_construction 128,
+    9 layers), search timed over 10 batches, recall@k against the exact scan of the same rows"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    ncent = 4096
+    centres = torch.randn((ncent, D), generator=g, device=dev)
+    scale = 1.0 / (4.5 * 1.06)
+    hx = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.HalfPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
+                        capacity=rows + 1, device=dev.index, keep_raw_f32=True)
+    for off in range(0, rows, 500_000):
+        m = min(500_000, rows - off)
+        idx = torch.randint(0, ncent, (m,), generator=g, device=dev)
+        x = ((centres[idx] + 0.35 * torch.randn((m, D), generator=g, device=dev)) * scale).clamp_(-0.999, 0.999).contiguous()
+        torch.cuda.synchronize()
+        hx.append_device(x.data_ptr(), m)
+        del x, idx
+    idx = torch.randint(0, ncent, (B,), generator=g, device=dev)
+    d_q = ((centres[idx] + 0.35 * torch.randn((B, D), generator=g, device=dev)) * scale).clamp_(-0.999, 0.999).contiguous()
+    q_host = d_q.cpu().numpy()
+    t0 = time.perf_counter()
+    hx.build_graph(9, 32, 64, 128, 64, 4096, 7)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
+    d_sc = torch.empty((B, k), dtype=torch.float32, device=dev)
+    d_cn = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def step():
+        hx.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_sc.data_ptr(), d_cn.data_ptr(), None, stream.cuda_stream,
+                               mode=cdb.SearchMode.HNSW, ef_search=ef, shortlist_size=64)
+    ev0, pp0 = hx.hnsw_counters()
+    step()
+    torch.cuda.synchronize()
+    ev1, pp1 = hx.hnsw_counters()
+    sam = ClockSampler(dev.index, period_ms=20)
+    sam.start()
+    ms = _timed_single(step, 20, 3, stream) / 20
+    clk = sam.stop()
+    kms = float(np.mean(hx.scan_ms_history(20)))
+    ids = d_ids.cpu().numpy().view(np.uint32)
+    gt = hx.batch_search(q_host, k + 1, cdb.SearchMode.BRUTE_RAW)[0]
+    gt = [[i for i in row if i != rows][:k] for row in gt]
+    recall = float(np.mean([len(set(ids[i]) & set(gt[i])) / k for i in range(B)]))
+    hx.close()
+    evals, pops = ev1 - ev0, pp1 - pp0
+    alg = evals * (D * 2 + 4) + pops * 64 * 4
+    return {"name": f"HNSW dense index {rows}x{D} f16, ef_search={ef}, batch={B} (BASELINE.json configs[2] at 1/10 of the rows; "
+                    "graph built on the GPU with the reference defaults)",
+            "value": B / (ms / 1000.0), "unit": "queries/s", "ms_per_step": ms, "clocks": clk, "recall_at_10": recall,
+            "build_seconds": t_build,
+            "roofline": {"bound": "hbm", "achieved": alg / (kms / 1000.0) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": alg / (kms / 1000.0) / 1e9 / hbm, "kernel_ms": kms, "alg_bytes_per_launch": alg,
+                         "evals_per_query": evals / B, "pops_per_query": pops / B,
+                         "kernel": "hnsw_search_warp_kernel (random row gathers; latency- not bandwidth-bound)"}}
 
 
 # ----------------------------------------------------------------------------- secondary workloads (reporting modes)
@@ -630,6 +695,8 @@ def run_hnsw(args):
         ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
                                stream.cuda_stream, mode=cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64)
 
+    if args.hnsw_flags is not None:
+        cdb.debug_set_hnsw_flags(args.hnsw_flags)
     ev0, pp0 = ix.hnsw_counters()
     step()
     torch.cuda.synchronize()
@@ -702,7 +769,8 @@ def run_c3(args):
     ncent = 4096
     centres = torch.randn((ncent, D), generator=g, device=dev)
     scale = 1.0 / (4.5 * 1.06)            # |x| < 1 with overwhelming probability; clamp below keeps the quantizer's domain
-    ix = cdb.DenseIndex(dim=D, storage_type=cdb.StorageType.HalfPrecisionFP, metric=cdb.DistanceMetricKind.Cosine,
+    st_ = cdb.StorageType.BFloat16 if args.storage == "bf16" else cdb.StorageType.HalfPrecisionFP
+    ix = cdb.DenseIndex(dim=D, storage_type=st_, metric=cdb.DistanceMetricKind.Cosine,
                         capacity=rows + 1, device=0, keep_raw_f32=True)
     chunk = 500_000
     t0 = time.perf_counter()
@@ -731,6 +799,8 @@ def run_c3(args):
         ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
                                stream.cuda_stream, mode=cdb.SearchMode.HNSW, ef_search=args.ef, shortlist_size=64)
 
+    if args.hnsw_flags is not None:
+        cdb.debug_set_hnsw_flags(args.hnsw_flags)
     ev0, pp0 = ix.hnsw_counters()
     step()
     torch.cuda.synchronize()
@@ -796,15 +866,15 @@ def run_c3(args):
             pr = ix.hnsw_profile(enable=False, read=True)
             pp_ = max(pr["pops"], 1)
             variants.append({"variant": name, "flags": fl, "batch": nb_, "kernel_ms": kms, "kernel_qps": nb_ / (kms / 1000.0),
-                             "ids_equal_default": same, "cycles_per_pop": {k_: round(v / pp_) for k_, v in pr.items() if k_ != "pops"}})
+                             "ids_equal_default": same, "cycles_per_pop": {k_: round(v / pp_, 2 if v < 20 * pp_ else None) for k_, v in pr.items() if k_ != "pops"}})
         cdb.debug_set_hnsw_flags()
     line = {
         "hnsw_variants": variants,
         "metric": "queries/sec + recall@10, HNSW f16", "value": args.steps * B / (ms / 1000.0), "unit": "queries/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f16 (f32 accumulate, reference order)", "data": "synthetic (4096 Gaussian clusters)",
+        "scaling": "strong", "vs_baseline": None, "dtype": f"{args.storage} (f32 accumulate, reference order)", "data": "synthetic (4096 Gaussian clusters)",
         "hnsw_phase_profile": prof,
-        "config": {"workload": f"HNSW dense index, {rows}x{D} f16, ef_search={args.ef}, batch={B} (BASELINE.json configs[2]); graph built on the GPU "
+        "config": {"workload": f"HNSW dense index, {rows}x{D} {args.storage}, ef_search={args.ef}, batch={B} (BASELINE.json configs[2]); graph built on the GPU "
                                "with the reference defaults", "rows": rows, "dim": D, "batch": B, "k": k},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": args.steps * B / (e2e_ms / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": B * D * 4,
@@ -826,7 +896,7 @@ def run_c5(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import cosdata_b200 as cdb
-    from cosdata_b200.sharding import cuda_merge_fn, gather_and_merge
+    from cosdata_b200.sharding import ShardGroup
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -863,19 +933,23 @@ def run_c5(args, rank, world, local_rank):
     d_ids = torch.empty((B, k), dtype=torch.int32, device=dev)
     d_scores = torch.empty((B, k), dtype=torch.float32, device=dev)
     d_counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    g_ids = torch.empty((world, B, k), dtype=torch.int32, device=dev)
-    g_scores = torch.empty((world, B, k), dtype=torch.float32, device=dev)
-    merge = cuda_merge_fn(ix._lib, local_rank, 0, stream.cuda_stream)
-
-    def all_gather(x):
-        out = g_ids if x.dtype == torch.int32 else g_scores
-        dist.all_gather_into_tensor(out.view(-1), x.view(-1))
-        return out
+    # the shard group behind the C ABI owns the NCCL communicator, the gather buffer and the merge (csrc/shard_group.cu):
+    # local HNSW search -> ONE ncclAllGather of packed keys -> merge, enqueued by one C call
+    group = None
+    if world > 1:
+        box = [ShardGroup.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        group = ShardGroup.rank(box[0], world, rank, local_rank)
+        group.attach(0, ix)
 
     def step(mode=cdb.SearchMode.HNSW):
-        ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
-                               stream.cuda_stream, mode=mode, ef_search=args.ef, shortlist_size=64)
-        return gather_and_merge(d_ids, d_scores, world, all_gather, merge)
+        if group is None:
+            ix.batch_search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                                   stream.cuda_stream, mode=mode, ef_search=args.ef, shortlist_size=64)
+        else:
+            group.search_device(d_q.data_ptr(), B, k, d_ids.data_ptr(), d_scores.data_ptr(), d_counts.data_ptr(), None,
+                                stream.cuda_stream, mode=mode, ef_search=args.ef, shortlist_size=64)
+        return d_ids, d_scores
 
     def barrier():
         if world > 1:
@@ -949,6 +1023,8 @@ def run_c5(args, rank, world, local_rank):
             "recall_at_10": recall, "build_seconds_max_over_ranks": float(tb.item()),
         }
         print(json.dumps(line), flush=True)
+    if group is not None:
+        group.close()
     ix.close()
     if world > 1:
         dist.destroy_process_group()

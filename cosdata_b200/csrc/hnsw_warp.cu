@@ -18,8 +18,9 @@
 //
 // f16 chain.  dot_product_f16 = sum_i f32(x_i) * f32(y_i), sequential, no FMA in the reference.  The product of two
 // halfs is exact in f32 (11 + 11 significand bits, exponent range far inside f32), so fma(x, y, s) rounds exactly once
-// at the same place as s + (x * y): one FFMA per element instead of FMUL + FADD, bit-identical.  The query is converted
-// to f32 once per warp; the chain then costs 1 conversion + 1 FFMA per element (+ 3 LDS.128 per 8 elements).
+// at the same place as s + (x * y): one fused multiply-add per element instead of FMUL + FADD, bit-identical.  On sm_100
+// that FMA is FHFMA (fma.rn.f32.f16: 16-bit operands read from packed registers, widened exactly, one f32 rounding), so the
+// chain costs 1 instruction per element (+ 2 LDS.128 per 8 elements) and needs neither conversions nor an f32 query copy.
 #include <cstdlib>
 
 #include "hnsw_traverse.cuh"
@@ -27,9 +28,11 @@
 namespace cdb {
 
 constexpr uint32_t HW_FINAL_LEN = 100;          // vector_store.rs:1194
-constexpr uint32_t HW_STAGE_BYTES = 12800;      // staged neighbour rows per group: 8 rows of f16 x 768, 4 of f32 x 768
-constexpr uint32_t HW_STAGE_BYTES_SPEC = 18700; // speculative form: 12 rows of f16 x 768 (7 warps/SM still fit in shared memory)
+// staged neighbour rows per group, sized so that 7 warps (queries) per SM still fit in shared memory at D = 768:
+constexpr uint32_t HW_STAGE_BYTES = 18700;      // 12 rows of f16 x 768, 6 of f32 x 768
+constexpr uint32_t HW_STAGE_BYTES_SPEC = 20200; // speculative form (score cache + work list added): 13 rows of f16 x 768
 constexpr uint32_t HW_CACHE = 256;              // speculative form: direct-mapped (node -> score key) cache entries per query
+constexpr int HW_NSRC = 3;                      // speculative form: upcoming heads examined per chain phase
 constexpr uint32_t HW_WORK = HN_MAX_TAKE + 32;  // speculative form: rows to score in one pop (misses of the head + fill)
 // clock64 sums per query (lane 0): [0] pop + adjacency (+ node_row) loads, [1] fixed-set walk + compaction + prefetches,
 // [2] issue of the row copies, [3] wait for the rows, [4] distance chains, [5] queue merge, [6] end-of-level result sort,
@@ -50,7 +53,7 @@ __host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, ui
     uint32_t r = (spec ? HW_STAGE_BYTES_SPEC : HW_STAGE_BYTES) / c.stage_pitch;
     c.stage_rows = r > 32 ? 32 : (r ? r : 1u);      // one lane scores one staged row
     uint32_t o = round_up(row_pitch, 16);
-    c.off_q32 = o;            o += f16fast ? round_up(dim * 4, 16) : 0;
+    c.off_q32 = o;            // (the f32 copy of the query is gone: FHFMA reads the f16 / bf16 code directly)
     c.off_qkeys = o;          o += 2 * c.EFP * 8;
     c.off_rkeys = o;          o += c.EFP * 8;
     c.off_nkeys = o;          o += HN_MAX_TAKE * 8;
@@ -64,9 +67,7 @@ __host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, ui
     if (spec) {
         o = round_up(o, 8);
         c.off_cache = o;      o += HW_CACHE * 8;
-        // the work list (node, row, destination) reuses the f16 copy of the query once the f32 copy exists
-        if (f16fast && round_up(row_pitch, 16) >= 3 * HW_WORK * 4) c.off_work = 0;
-        else { c.off_work = o; o += 3 * HW_WORK * 4; }
+        c.off_work = o;       o += 3 * HW_WORK * 4;
     }
     c.off_stage = round_up(o, 16);
     c.total = c.off_stage + c.stage_rows * c.stage_pitch;
@@ -112,34 +113,40 @@ __device__ __forceinline__ void hw_mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-// sum_i f32(q_i) * f32(row_i), sequential; q is the f32 copy of the (f16-quantized) query, row the staged f16 row.
-// The chain is latency bound (one dependent FFMA per element), so the shared-memory operands of the NEXT 16 elements
-// are loaded before the current 16 FFMAs issue (explicit double buffering: ptxas does not pipeline this loop itself).
-struct HwBlk16 { uint4 r0, r1; float4 q0, q1, q2, q3; };
-__device__ __forceinline__ HwBlk16 hw_ld16(const float *__restrict__ q, const uint8_t *__restrict__ row, uint32_t i) {
+// sum_i f32(q_i) * f32(row_i), sequential, on FHFMA: sm_100's mixed-precision FMA (PTX fma.rn.f32.f16 / .bf16) takes the two
+// 16-bit operands straight out of the packed registers (.H0/.H1 selectors), widens them exactly and rounds a*b + c once in
+// f32 -- the same single rounding as the FFMA of the converted values, and (the product of two halfs / two bf16 values being
+// exact in f32) the same result as the reference's multiply-then-add.  No conversion instructions, no f32 copy of the query:
+// 8 FHFMA + 2 LDS.128 per 8 elements instead of 8 FFMA + 8 conversions + 3 LDS.128.
+// The chain is latency bound (one dependent FMA per element), so the shared-memory operands of the NEXT 16 elements are
+// loaded before the current 16 FMAs issue (explicit double buffering: ptxas does not pipeline this loop itself).
+template <int FAST>
+__device__ __forceinline__ float hw_fhfma(float s, uint32_t q, uint32_t r, bool hi) {
+    const unsigned short a = (unsigned short)(hi ? q >> 16 : q & 0xFFFFu), b = (unsigned short)(hi ? r >> 16 : r & 0xFFFFu);
+    if (FAST == 1) asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(s) : "h"(a), "h"(b));
+    else asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(s) : "h"(a), "h"(b));
+    return s;
+}
+template <int FAST>
+__device__ __forceinline__ float hw_chain8(float s, const uint4 &q, const uint4 &r) {
+    s = hw_fhfma<FAST>(s, q.x, r.x, false); s = hw_fhfma<FAST>(s, q.x, r.x, true);
+    s = hw_fhfma<FAST>(s, q.y, r.y, false); s = hw_fhfma<FAST>(s, q.y, r.y, true);
+    s = hw_fhfma<FAST>(s, q.z, r.z, false); s = hw_fhfma<FAST>(s, q.z, r.z, true);
+    s = hw_fhfma<FAST>(s, q.w, r.w, false); s = hw_fhfma<FAST>(s, q.w, r.w, true);
+    return s;
+}
+struct HwBlk16 { uint4 r0, r1, q0, q1; };
+__device__ __forceinline__ HwBlk16 hw_ld16(const uint8_t *__restrict__ q, const uint8_t *__restrict__ row, uint32_t i) {
     HwBlk16 b;
     b.r0 = *reinterpret_cast<const uint4 *>(row + 2 * i);
     b.r1 = *reinterpret_cast<const uint4 *>(row + 2 * i + 16);
-    b.q0 = *reinterpret_cast<const float4 *>(q + i);
-    b.q1 = *reinterpret_cast<const float4 *>(q + i + 4);
-    b.q2 = *reinterpret_cast<const float4 *>(q + i + 8);
-    b.q3 = *reinterpret_cast<const float4 *>(q + i + 12);
+    b.q0 = *reinterpret_cast<const uint4 *>(q + 2 * i);
+    b.q1 = *reinterpret_cast<const uint4 *>(q + 2 * i + 16);
     return b;
 }
-__device__ __forceinline__ float hw_chain8(float s, const uint4 &vb, const float4 &qa, const float4 &qb) {
-    const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
-    const float2 f0 = __half22float2(hb[0]), f1 = __half22float2(hb[1]), f2 = __half22float2(hb[2]), f3 = __half22float2(hb[3]);
-    s = __fmaf_rn(qa.x, f0.x, s);
-    s = __fmaf_rn(qa.y, f0.y, s);
-    s = __fmaf_rn(qa.z, f1.x, s);
-    s = __fmaf_rn(qa.w, f1.y, s);
-    s = __fmaf_rn(qb.x, f2.x, s);
-    s = __fmaf_rn(qb.y, f2.y, s);
-    s = __fmaf_rn(qb.z, f3.x, s);
-    s = __fmaf_rn(qb.w, f3.y, s);
-    return s;
-}
-__device__ __forceinline__ float hw_dot_f16_q32(const float *__restrict__ q, const uint8_t *__restrict__ row, uint32_t n) {
+// q: the query's f16 / bf16 code in shared memory (16-byte aligned, like the staged row)
+template <int FAST>
+__device__ __forceinline__ float hw_dot16(const uint8_t *__restrict__ q, const uint8_t *__restrict__ row, uint32_t n) {
     float s = 0.0f;
     const uint32_t n16 = n & ~15u;
     uint32_t i = 0;
@@ -147,58 +154,22 @@ __device__ __forceinline__ float hw_dot_f16_q32(const float *__restrict__ q, con
         HwBlk16 cur = hw_ld16(q, row, 0);
         for (; i + 16 < n16; i += 16) {
             const HwBlk16 nxt = hw_ld16(q, row, i + 16);
-            s = hw_chain8(s, cur.r0, cur.q0, cur.q1);
-            s = hw_chain8(s, cur.r1, cur.q2, cur.q3);
+            s = hw_chain8<FAST>(s, cur.q0, cur.r0);
+            s = hw_chain8<FAST>(s, cur.q1, cur.r1);
             cur = nxt;
         }
-        s = hw_chain8(s, cur.r0, cur.q0, cur.q1);
-        s = hw_chain8(s, cur.r1, cur.q2, cur.q3);
+        s = hw_chain8<FAST>(s, cur.q0, cur.r0);
+        s = hw_chain8<FAST>(s, cur.q1, cur.r1);
         i = n16;
     }
     if (i + 8 <= n) {
-        s = hw_chain8(s, *reinterpret_cast<const uint4 *>(row + 2 * i), *reinterpret_cast<const float4 *>(q + i),
-                      *reinterpret_cast<const float4 *>(q + i + 4));
+        s = hw_chain8<FAST>(s, *reinterpret_cast<const uint4 *>(q + 2 * i), *reinterpret_cast<const uint4 *>(row + 2 * i));
         i += 8;
     }
-    for (; i < n; ++i) s = __fmaf_rn(q[i], __half2float(reinterpret_cast<const __half *>(row)[i]), s);
-    return s;
-}
-
-// bfloat16 rows (labelled extension CDB_ST_BF16): widening is a 16-bit shift / mask on the integer pipe, so the FMA pipe only
-// sees the one FFMA per element
-__device__ __forceinline__ float hw_chain8_bf16(float s, const uint4 &vb, const float4 &qa, const float4 &qb) {
-    s = __fmaf_rn(qa.x, bf16_lo(vb.x), s);
-    s = __fmaf_rn(qa.y, bf16_hi(vb.x), s);
-    s = __fmaf_rn(qa.z, bf16_lo(vb.y), s);
-    s = __fmaf_rn(qa.w, bf16_hi(vb.y), s);
-    s = __fmaf_rn(qb.x, bf16_lo(vb.z), s);
-    s = __fmaf_rn(qb.y, bf16_hi(vb.z), s);
-    s = __fmaf_rn(qb.z, bf16_lo(vb.w), s);
-    s = __fmaf_rn(qb.w, bf16_hi(vb.w), s);
-    return s;
-}
-__device__ __forceinline__ float hw_dot_bf16_q32(const float *__restrict__ q, const uint8_t *__restrict__ row, uint32_t n) {
-    float s = 0.0f;
-    const uint32_t n16 = n & ~15u;
-    uint32_t i = 0;
-    if (n16) {
-        HwBlk16 cur = hw_ld16(q, row, 0);
-        for (; i + 16 < n16; i += 16) {
-            const HwBlk16 nxt = hw_ld16(q, row, i + 16);
-            s = hw_chain8_bf16(s, cur.r0, cur.q0, cur.q1);
-            s = hw_chain8_bf16(s, cur.r1, cur.q2, cur.q3);
-            cur = nxt;
-        }
-        s = hw_chain8_bf16(s, cur.r0, cur.q0, cur.q1);
-        s = hw_chain8_bf16(s, cur.r1, cur.q2, cur.q3);
-        i = n16;
+    for (; i < n; ++i) {
+        const uint32_t qa = reinterpret_cast<const uint16_t *>(q)[i], ra = reinterpret_cast<const uint16_t *>(row)[i];
+        s = hw_fhfma<FAST>(s, qa, ra, false);
     }
-    if (i + 8 <= n) {
-        s = hw_chain8_bf16(s, *reinterpret_cast<const uint4 *>(row + 2 * i), *reinterpret_cast<const float4 *>(q + i),
-                           *reinterpret_cast<const float4 *>(q + i + 4));
-        i += 8;
-    }
-    for (; i < n; ++i) s = __fmaf_rn(q[i], __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(row)[i] << 16), s);
     return s;
 }
 
@@ -258,7 +229,7 @@ __device__ __forceinline__ uint32_t hw_score_group(const HnScoreCtx &sc, const H
             const uint8_t *code = m.stage + (size_t)lane * m.stage_pitch;
             float d = 0.0f;
             if (FAST) {
-                const float dot = FAST == 1 ? hw_dot_f16_q32(m.q32, code, sc.dim) : hw_dot_bf16_q32(m.q32, code, sc.dim);
+                const float dot = hw_dot16<FAST>(m.qs, code, sc.dim);
                 if (sc.metric == CDB_METRIC_COSINE) {
                     const float denom = __fmul_rn(qmag, rmag);
                     if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
@@ -315,7 +286,7 @@ __device__ __forceinline__ uint32_t hw_score_work(const HnScoreCtx &sc, const Hw
             const uint8_t *code = m.stage + (size_t)lane * m.stage_pitch;
             float d = 0.0f;
             if (FAST) {
-                const float dot = FAST == 1 ? hw_dot_f16_q32(m.q32, code, sc.dim) : hw_dot_bf16_q32(m.q32, code, sc.dim);
+                const float dot = hw_dot16<FAST>(m.qs, code, sc.dim);
                 if (sc.metric == CDB_METRIC_COSINE) {
                     const float denom = __fmul_rn(qmag, rmag);
                     if (denom == 0.0f) rc = CDB_CALCULATION_ERROR;   // cosine.rs:230-231
@@ -417,22 +388,6 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
         // lanes of this pop's chain phase score those rows ahead of time into a small cache; the later pop walks its fixed
         // set exactly as before (same order, same insertions, same evals count) and takes the keys from the cache, and a pop
         // whose accepted neighbours are all cached has no chain phase at all.
-        uint32_t ssrc[2] = {HN_EMPTY, HN_EMPTY}, snbl[2][2] = {{HN_EMPTY, HN_EMPTY}, {HN_EMPTY, HN_EMPTY}};
-        if (f_spec) {
-            for (uint32_t j = 1; j < qlen && j <= 5; ++j) {
-                const uint32_t nd = QN[j];
-                if (nd == sd0 || nd == sd1 || nd == sd2 || nd == sd3) continue;
-                if (ssrc[0] == HN_EMPTY) ssrc[0] = nd;
-                else { ssrc[1] = nd; break; }
-            }
-#pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t slot = (uint32_t)lane + 32u * h;
-                    if (ssrc[sidx] != HN_EMPTY && slot < take) snbl[sidx][h] = __ldg(adj + (size_t)ssrc[sidx] * nb + slot);
-                }
-        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             row[h] = 0;
@@ -442,6 +397,28 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                 const uint32_t id = hn_id(sc.root_row, row[h]);
                 bk[h] = (((id >> 6) & bmask) << 6) | (id & 0x3f);
             }
+        }
+        uint32_t ssrc[HW_NSRC], snbl[HW_NSRC][2];
+#pragma unroll
+        for (int sidx = 0; sidx < HW_NSRC; ++sidx) { ssrc[sidx] = HN_EMPTY; snbl[sidx][0] = snbl[sidx][1] = HN_EMPTY; }
+        if (f_spec) {
+            // the next queue entries whose neighbours are not all cached yet (lanes 1..6 look at one entry each); their
+            // adjacency slots are requested now -- AFTER the head's own slots were consumed above (loads share scoreboards:
+            // issued earlier, the head would wait for them too) -- and first looked at after the fixed-set walk
+            const uint32_t mine = (lane >= 1 && (uint32_t)lane < qlen && lane <= 2 * HW_NSRC) ? QN[lane] : HN_EMPTY;
+            uint32_t pick = __ballot_sync(0xFFFFFFFFu, mine != HN_EMPTY && mine != sd0 && mine != sd1 && mine != sd2 && mine != sd3);
+#pragma unroll
+            for (int sidx = 0; sidx < HW_NSRC; ++sidx)
+                if (pick) { ssrc[sidx] = __shfl_sync(0xFFFFFFFFu, mine, __ffs(pick) - 1); pick &= pick - 1; }
+            asm volatile("" :: "r"(bk[0]), "r"(bk[1]));
+#pragma unroll
+            for (int sidx = 0; sidx < HW_NSRC; ++sidx)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t slot = (uint32_t)lane + 32u * h;
+                    if (ssrc[sidx] != HN_EMPTY && slot < take)
+                        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(snbl[sidx][h]) : "l"(adj + (size_t)ssrc[sidx] * nb + slot));
+                }
         }
         if (PROF) t2 = clock64();
         // ---- the walk through the lossy fixed set, slot order: a slot is scored iff its bit is not yet set AND no
@@ -532,10 +509,13 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                     m.wnode[w] = m.nnodes[pos]; m.wrow[w] = m.nrow[pos]; m.wdst[w] = pos;
                 }
             uint32_t nt = nm;
+#pragma unroll
+            for (int sidx = 0; sidx < HW_NSRC; ++sidx)   // nothing below may be scheduled above the walk (the loads are still in flight there)
+                asm volatile("" : "+r"(snbl[sidx][0]), "+r"(snbl[sidx][1]));
             if (nm > 0 && nm < m.stage_rows) {
                 // one chain phase is due anyway: fill its free lanes with the uncached, not yet visited neighbours of the next heads
 #pragma unroll
-                for (int sidx = 0; sidx < 2; ++sidx) {
+                for (int sidx = 0; sidx < HW_NSRC; ++sidx) {
                     const uint32_t room = m.stage_rows - nt;
                     if (ssrc[sidx] == HN_EMPTY || room == 0) continue;
                     bool c[2];
@@ -784,10 +764,6 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarv
     for (uint32_t i = lane; i < a.row_pitch / 4; i += 32)
         reinterpret_cast<uint32_t *>(m.qs)[i] = reinterpret_cast<const uint32_t *>(a.q + (size_t)qi * a.row_pitch)[i];
     __syncwarp();
-    if (FAST == 1)
-        for (uint32_t i = lane; i < a.dim; i += 32) m.q32[i] = __half2float(reinterpret_cast<const __half *>(m.qs)[i]);
-    if (FAST == 2)
-        for (uint32_t i = lane; i < a.dim; i += 32) m.q32[i] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(m.qs)[i] << 16);
     const float qmag = a.qmags[qi];
     const HnScoreCtx sc{a.rows, a.row_pitch, a.mags, a.dim, a.st, a.metric, a.g.root_row};
     if (lane == 0) hw_mbar_init(m.bar, 1);

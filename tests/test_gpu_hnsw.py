@@ -102,21 +102,35 @@ def test_hnsw_default_params_recall_and_shortlist():
 
 @pytest.mark.parametrize("flags", [None, 38])
 def test_hnsw_zero_norm_row_fails_the_query_like_the_reference(flags):
-    # (flags 38: a zero-norm row scored ahead of time must fail only the queries whose traversal commits it)
+    # a row whose norm is 0 is a CalculationError the moment a traversal scores it (cosine.rs:230-231): exactly the queries that
+    # reach it fail.  The graph is built over normal vectors (an insert that errors is not indexed at all), then the stored vector
+    # of one well-connected node is replaced by zeros.  flags 38 = speculative scoring: a zero-norm row scored ahead of time must
+    # fail only the queries whose own traversal commits it.
     n, dim, k = 1500, 32, 5
     vecs = clustered(n, dim, 3)
-    vecs[10] = 0.0                                                   # |v| = 0 -> CalculationError when scored
-    fg, ix = build_both(vecs, ST.HalfPrecisionFP, MK.Cosine)
+    st, metric = ST.HalfPrecisionFP, MK.Cosine
+    root = orc.synth_matrix(31337, 1, dim)[0]
+    fg = pyhnsw.build(int(metric), int(st), vecs, root, num_levels=5, neighbors_count=16, level0_neighbors_count=32,
+                      ef_construction=64, seed=5)
+    hub = int(np.bincount(fg.adj[0][fg.adj[0] < n], minlength=n).argmax())      # the most linked-to data row
+    stored = vecs.copy()
+    stored[hub] = 0.0
+    ix = cdb.DenseIndex(dim=dim, storage_type=st, metric=metric, capacity=n + 1, keep_raw_f32=True)
+    ix.append(np.concatenate([stored, root[None]], axis=0))
+    ix.set_graph(5, 16, 32, fg.entry, n, fg.node_row, fg.adj, fg.child)
+    codes, mags = ix.read_codes(0, n + 1)
+    fz = pyhnsw.FlatGraph(int(metric), int(st), dim, codes, mags, n, 5, 16, 32, fg.entry, fg.node_row, fg.adj, fg.child)
     rng = np.random.default_rng(5)
-    queries = np.concatenate([vecs[[10, 11, 500]] + 0.01, (vecs[rng.integers(0, n, 40)] + 0.02).astype(np.float32)])
+    near = vecs[hub] + 0.02 * rng.normal(size=(6, dim)).astype(np.float32)
+    queries = np.concatenate([near, vecs[rng.integers(0, n, 60)] + 0.02]).astype(np.float32)
     try:
         if flags is not None:
             cdb.debug_set_hnsw_flags(flags)
-        ids, scores, counts, err = ix.batch_search(queries, k, cdb.SearchMode.HNSW, ef_search=64, shortlist_size=64)
+        ids, scores, counts, err = ix.batch_search(queries, k, cdb.SearchMode.HNSW, ef_search=24, shortlist_size=64)
     finally:
         cdb.debug_set_hnsw_flags()
-    w = pyhnsw.search_batch(fg, vecs, queries, k, ef_search=64)
-    assert 0 < (w[3] != 0).sum() < len(queries)
+    w = pyhnsw.search_batch(fz, stored, queries, k, ef_search=24)
+    assert 0 < (w[3] != 0).sum() < len(queries)                       # some traversals reach the zero row, others do not
     assert np.array_equal(err, w[3]) and np.array_equal(counts, w[2])
     assert np.array_equal(ids, w[0]) and np.array_equal(bits(scores), bits(w[1]))
     ix.close()
