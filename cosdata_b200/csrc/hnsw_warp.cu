@@ -43,7 +43,7 @@ constexpr int HW_PROF_SLOTS = 12;
 struct HwCarve {
     uint32_t EFP, stage_pitch, stage_rows;
     uint32_t off_q32, off_qkeys, off_rkeys, off_nkeys, off_fs, off_qnodes, off_rnodes, off_nnodes, off_nrow, off_bar, off_stage, total;
-    uint32_t off_cache, off_work;   // speculative form only
+    uint32_t off_cache, off_work, off_sadj;   // speculative form only
 };
 
 __host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, uint32_t ef, bool f16fast, bool spec = false) {
@@ -63,11 +63,12 @@ __host__ __device__ inline HwCarve hw_carve(uint32_t row_pitch, uint32_t dim, ui
     c.off_rnodes = o;         o += c.EFP * 4;
     c.off_nnodes = o;         o += HN_MAX_TAKE * 4;
     c.off_nrow = o;           o += HN_MAX_TAKE * 4;
-    c.off_cache = c.off_work = 0;
+    c.off_cache = c.off_work = c.off_sadj = 0;
     if (spec) {
         o = round_up(o, 8);
         c.off_cache = o;      o += HW_CACHE * 8;
         c.off_work = o;       o += 3 * HW_WORK * 4;
+        c.off_sadj = o;       o += HW_NSRC * HN_MAX_TAKE * 4;
     }
     c.off_stage = round_up(o, 16);
     c.total = c.off_stage + c.stage_rows * c.stage_pitch;
@@ -82,6 +83,7 @@ struct HwSmem {
     uint32_t *qnodes, *rnodes, *nnodes, *nrow;
     uint64_t *cache;         // speculative form: (node << 32 | score order key), tag 0xFFFFFFFF = empty
     uint32_t *wnode, *wrow, *wdst;
+    uint32_t *sadj;          // speculative form: adjacency slots of the next heads, [HW_NSRC][64], filled by cp.async
     uint8_t *stage;
     uint32_t bar;            // shared-space address of the warp's mbarrier (row copies complete on it)
     uint32_t EFP, stage_pitch, stage_rows;
@@ -398,26 +400,28 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                 bk[h] = (((id >> 6) & bmask) << 6) | (id & 0x3f);
             }
         }
-        uint32_t ssrc[HW_NSRC], snbl[HW_NSRC][2];
+        uint32_t ssrc[HW_NSRC];
 #pragma unroll
-        for (int sidx = 0; sidx < HW_NSRC; ++sidx) { ssrc[sidx] = HN_EMPTY; snbl[sidx][0] = snbl[sidx][1] = HN_EMPTY; }
+        for (int sidx = 0; sidx < HW_NSRC; ++sidx) ssrc[sidx] = HN_EMPTY;
         if (f_spec) {
-            // the next queue entries whose neighbours are not all cached yet (lanes 1..6 look at one entry each); their
-            // adjacency slots are requested now -- AFTER the head's own slots were consumed above (loads share scoreboards:
-            // issued earlier, the head would wait for them too) -- and first looked at after the fixed-set walk
+            // the next queue entries whose neighbours are not all cached yet (lanes 1..6 look at one entry each).  Their adjacency
+            // slots are copied to shared memory with cp.async: no registers and no scoreboard are held across the fixed-set walk
+            // (register loads issued here made the walk's own shared-memory waits stall on the same scoreboards), and the data is
+            // there when the chain phase of this pop -- if it has one -- chooses its fill
             const uint32_t mine = (lane >= 1 && (uint32_t)lane < qlen && lane <= 2 * HW_NSRC) ? QN[lane] : HN_EMPTY;
             uint32_t pick = __ballot_sync(0xFFFFFFFFu, mine != HN_EMPTY && mine != sd0 && mine != sd1 && mine != sd2 && mine != sd3);
 #pragma unroll
             for (int sidx = 0; sidx < HW_NSRC; ++sidx)
                 if (pick) { ssrc[sidx] = __shfl_sync(0xFFFFFFFFu, mine, __ffs(pick) - 1); pick &= pick - 1; }
-            asm volatile("" :: "r"(bk[0]), "r"(bk[1]));
+            asm volatile("cp.async.wait_all;" ::: "memory");   // copies of the previous pop (long finished)
 #pragma unroll
             for (int sidx = 0; sidx < HW_NSRC; ++sidx)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t slot = (uint32_t)lane + 32u * h;
                     if (ssrc[sidx] != HN_EMPTY && slot < take)
-                        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(snbl[sidx][h]) : "l"(adj + (size_t)ssrc[sidx] * nb + slot));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(hw_smem_u32(m.sadj + sidx * HN_MAX_TAKE + slot)),
+                                     "l"(adj + (size_t)ssrc[sidx] * nb + slot) : "memory");
                 }
         }
         if (PROF) t2 = clock64();
@@ -509,21 +513,21 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                     m.wnode[w] = m.nnodes[pos]; m.wrow[w] = m.nrow[pos]; m.wdst[w] = pos;
                 }
             uint32_t nt = nm;
-#pragma unroll
-            for (int sidx = 0; sidx < HW_NSRC; ++sidx)   // nothing below may be scheduled above the walk (the loads are still in flight there)
-                asm volatile("" : "+r"(snbl[sidx][0]), "+r"(snbl[sidx][1]));
             if (nm > 0 && nm < m.stage_rows) {
+                asm volatile("cp.async.wait_all;" ::: "memory");   // every lane reads back exactly the slots it copied
                 // one chain phase is due anyway: fill its free lanes with the uncached, not yet visited neighbours of the next heads
 #pragma unroll
                 for (int sidx = 0; sidx < HW_NSRC; ++sidx) {
                     const uint32_t room = m.stage_rows - nt;
                     if (ssrc[sidx] == HN_EMPTY || room == 0) continue;
                     bool c[2];
-                    uint32_t r[2];
+                    uint32_t r[2], snb[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         c[h] = false; r[h] = 0;
-                        const uint32_t nd = snbl[sidx][h];
+                        const uint32_t slot = (uint32_t)lane + 32u * h;
+                        const uint32_t nd = slot < take ? m.sadj[sidx * HN_MAX_TAKE + slot] : HN_EMPTY;
+                        snb[h] = nd;
                         if (nd != HN_EMPTY) {
                             r[h] = node_row ? __ldg(node_row + nd) : nd;
                             const uint32_t id = hn_id(sc.root_row, r[h]);
@@ -538,7 +542,7 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                     for (int h = 0; h < 2; ++h)
                         if (c[h]) {
                             const uint32_t pch = (h ? n0 : 0u) + (uint32_t)__popc((h ? c1 : c0) & lt);
-                            if (pch < room) { m.wnode[nt + pch] = snbl[sidx][h]; m.wrow[nt + pch] = r[h]; }
+                            if (pch < room) { m.wnode[nt + pch] = snb[h]; m.wrow[nt + pch] = r[h]; }
                         }
                     if (tot <= room) { sd3 = sd2; sd2 = sd1; sd1 = sd0; sd0 = ssrc[sidx]; }   // nothing left to score for this entry
                     nt += min(tot, room);
@@ -759,6 +763,7 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(HnswArgs a, HwCarv
     m.wnode = reinterpret_cast<uint32_t *>(smem + cv.off_work);
     m.wrow = m.wnode + HW_WORK;
     m.wdst = m.wrow + HW_WORK;
+    m.sadj = reinterpret_cast<uint32_t *>(smem + cv.off_sadj);
     m.EFP = cv.EFP; m.stage_pitch = cv.stage_pitch; m.stage_rows = cv.stage_rows;
 
     for (uint32_t i = lane; i < a.row_pitch / 4; i += 32)

@@ -89,69 +89,52 @@ __device__ inline float mag_f32_seq(const float *__restrict__ v, uint32_t n) {
     return __fsqrt_rn(s);
 }
 
-// ------------------------------------------------------------------ f16
-// rows are 16-byte pitched, so the operands are walked with 128-bit loads, 64 elements of the stored row in flight
-// at a time; the additions stay strictly in element order (the reference's `.sum()` is a sequential left fold)
-__device__ inline float dot_f16_seq(const __half *__restrict__ a, const __half *__restrict__ b, uint32_t n) {
+// ------------------------------------------------------------------ f16 / bf16 dot products
+// The reference's `.sum()` is a sequential left fold of f32(x_i) * f32(y_i).  The product of two halfs (11 + 11 significand
+// bits) or two bf16 values (8 + 8) is exact in f32, so s + x*y rounds once -- exactly what a fused multiply-add does.  sm_100
+// has that FMA with 16-bit operands: FHFMA (PTX fma.rn.f32.f16 / fma.rn.f32.bf16) reads the halves straight out of the packed
+// registers (.H0/.H1), widens them exactly (subnormals included) and rounds a*b + c once in f32.  One instruction per element
+// instead of two conversions + FMUL + FADD; bit-identical (tests: every f16 / bf16 arm against the oracle).
+// Rows are 16-byte pitched, so the operands are walked with 128-bit loads; the additions stay strictly in element order.
+template <bool BF16>
+__device__ __forceinline__ float fhfma16(float s, uint32_t x, uint32_t y, bool hi) {
+    const unsigned short a = (unsigned short)(hi ? x >> 16 : x & 0xFFFFu), b = (unsigned short)(hi ? y >> 16 : y & 0xFFFFu);
+    if (BF16) asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(s) : "h"(a), "h"(b));
+    else asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(s) : "h"(a), "h"(b));
+    return s;
+}
+template <bool BF16>
+__device__ __forceinline__ float fhfma16x8(float s, const uint4 &x, const uint4 &y) {
+    s = fhfma16<BF16>(s, x.x, y.x, false); s = fhfma16<BF16>(s, x.x, y.x, true);
+    s = fhfma16<BF16>(s, x.y, y.y, false); s = fhfma16<BF16>(s, x.y, y.y, true);
+    s = fhfma16<BF16>(s, x.z, y.z, false); s = fhfma16<BF16>(s, x.z, y.z, true);
+    s = fhfma16<BF16>(s, x.w, y.w, false); s = fhfma16<BF16>(s, x.w, y.w, true);
+    return s;
+}
+template <bool BF16>
+__device__ inline float dot16_seq(const uint16_t *__restrict__ a, const uint16_t *__restrict__ b, uint32_t n) {
     float s = 0.0f;
     uint32_t i = 0;
     if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
-        for (; i + 64 <= n; i += 64) {
+        for (; i + 64 <= n; i += 64) {   // 64 elements of the stored row in flight at a time
             uint4 vb[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) vb[t] = *reinterpret_cast<const uint4 *>(b + i + 8 * t);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const uint4 va = *reinterpret_cast<const uint4 *>(a + i + 8 * t);
-                const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
-                const __half2 *hb = reinterpret_cast<const __half2 *>(&vb[t]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
-                    s = __fadd_rn(s, __fmul_rn(fa.x, fb.x));
-                    s = __fadd_rn(s, __fmul_rn(fa.y, fb.y));
-                }
-            }
+            for (int t = 0; t < 8; ++t) s = fhfma16x8<BF16>(s, *reinterpret_cast<const uint4 *>(a + i + 8 * t), vb[t]);
         }
-        for (; i + 8 <= n; i += 8) {
-            const uint4 va = *reinterpret_cast<const uint4 *>(a + i);
-            const uint4 vb = *reinterpret_cast<const uint4 *>(b + i);
-            const __half2 *ha = reinterpret_cast<const __half2 *>(&va);
-            const __half2 *hb = reinterpret_cast<const __half2 *>(&vb);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
-                s = __fadd_rn(s, __fmul_rn(fa.x, fb.x));
-                s = __fadd_rn(s, __fmul_rn(fa.y, fb.y));
-            }
-        }
+        for (; i + 8 <= n; i += 8)
+            s = fhfma16x8<BF16>(s, *reinterpret_cast<const uint4 *>(a + i), *reinterpret_cast<const uint4 *>(b + i));
     }
-    for (; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__half2float(a[i]), __half2float(b[i])));
+    for (; i < n; ++i) s = fhfma16<BF16>(s, a[i], b[i], false);
     return s;
 }
-
-// ------------------------------------------------------------------ bf16 (labelled extension)
-// same sequential fold as dot_f16_seq; a bf16 widens to f32 by a 16-bit shift, products of two bf16 are exact in f32
-// (PRMT keeps the widening on the integer pipe; ptxas turns `w << 16` into an IMAD on the FMA pipe)
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(__byte_perm(w, 0u, 0x1044)); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ inline float dot_f16_seq(const __half *__restrict__ a, const __half *__restrict__ b, uint32_t n) {
+    return dot16_seq<false>(reinterpret_cast<const uint16_t *>(a), reinterpret_cast<const uint16_t *>(b), n);
+}
+// bf16 (labelled extension): same fold
 __device__ inline float dot_bf16_seq(const uint16_t *__restrict__ a, const uint16_t *__restrict__ b, uint32_t n) {
-    float s = 0.0f;
-    uint32_t i = 0;
-    if ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) {
-        for (; i + 8 <= n; i += 8) {
-            const uint4 va = *reinterpret_cast<const uint4 *>(a + i);
-            const uint4 vb = *reinterpret_cast<const uint4 *>(b + i);
-            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                s = __fadd_rn(s, __fmul_rn(bf16_lo(wa[e]), bf16_lo(wb[e])));
-                s = __fadd_rn(s, __fmul_rn(bf16_hi(wa[e]), bf16_hi(wb[e])));
-            }
-        }
-    }
-    for (; i < n; ++i) s = __fadd_rn(s, __fmul_rn(__uint_as_float((uint32_t)a[i] << 16), __uint_as_float((uint32_t)b[i] << 16)));
-    return s;
+    return dot16_seq<true>(a, b, n);
 }
 __device__ inline float euclid_bf16_seq(const uint16_t *a, const uint16_t *b, uint32_t n) {
     float s = 0.0f;

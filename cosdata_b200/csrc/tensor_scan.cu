@@ -284,7 +284,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             sort_desc<NG>(g2);
 #pragma unroll
             for (int i = 0; i < NG; ++i) if ((uint32_t)i == a.k - 1) bound = g2[i];
-            thr = KIND == 1 ? bound * a.rel : bound - a.two_eps;
+            thr = KIND == 1 ? (cosine ? bound * a.rel : bound) : bound - a.two_eps;
         }
         uint32_t as = 0, aphase = 0, t = 0;
         for (uint32_t nt = g; nt < a.ntiles; nt += G, ++t) {
@@ -325,9 +325,15 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float v0, v1;
-                        if (KIND == 1) {      // exact integer dot -> f32 (dot product) or -> f32 / |row| (cosine filter value)
-                            v0 = __int2float_rn((int)r0[j]); v1 = __int2float_rn((int)r1[j]);
-                            if (cosine) { v0 *= rs[c * 64 + j]; v1 *= rs[c * 64 + 32 + j]; }
+                        if (KIND == 1) {
+                            // dot product: u8 x u8 sums are >= 0, and non-negative s32 bit patterns order like non-negative floats
+                            // (FMNMX and the compare keep denormals), so the raw accumulator IS the filter value -- no I2F.
+                            // cosine: f32(dp) / |row| through the staged reciprocals
+                            if (cosine) {
+                                v0 = __int2float_rn((int)r0[j]) * rs[c * 64 + j]; v1 = __int2float_rn((int)r1[j]) * rs[c * 64 + 32 + j];
+                            } else {
+                                v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
+                            }
                         } else {
                             v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
                         }
@@ -346,9 +352,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float v0, v1;
-                            if (KIND == 1) {
-                                v0 = __int2float_rn((int)r0[j]); v1 = __int2float_rn((int)r1[j]);
-                                if (cosine) { v0 *= rs[c * 64 + j]; v1 *= rs[c * 64 + 32 + j]; }
+                            if (KIND == 1 && cosine) {
+                                v0 = __int2float_rn((int)r0[j]) * rs[c * 64 + j]; v1 = __int2float_rn((int)r1[j]) * rs[c * 64 + 32 + j];
                             } else {
                                 v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
                             }
@@ -361,9 +366,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float v0, v1;
-                        if (KIND == 1) {
-                            v0 = __int2float_rn((int)r0[j]); v1 = __int2float_rn((int)r1[j]);
-                            if (cosine) { v0 *= rs[c * 64 + j]; v1 *= rs[c * 64 + 32 + j]; }
+                        if (KIND == 1 && cosine) {
+                            v0 = __int2float_rn((int)r0[j]) * rs[c * 64 + j]; v1 = __int2float_rn((int)r1[j]) * rs[c * 64 + 32 + j];
                         } else {
                             v0 = __uint_as_float(r0[j]); v1 = __uint_as_float(r1[j]);
                         }
@@ -408,7 +412,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 float nb = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < NG; ++i) if ((uint32_t)i == a.k - 1) nb = g2[i];
-                if (nb > bound) { bound = nb; thr = KIND == 1 ? bound * a.rel : bound - a.two_eps; }
+                if (nb > bound) { bound = nb; thr = KIND == 1 ? (cosine ? bound * a.rel : bound) : bound - a.two_eps; }
             }
         }
         if (qvalid) {  // final publish + flush of the staged candidates
