@@ -542,7 +542,14 @@ __device__ void hw_traverse_level(const uint32_t *__restrict__ node_row /* null:
                     for (int h = 0; h < 2; ++h)
                         if (c[h]) {
                             const uint32_t pch = (h ? n0 : 0u) + (uint32_t)__popc((h ? c1 : c0) & lt);
-                            if (pch < room) { m.wnode[nt + pch] = snb[h]; m.wrow[nt + pch] = r[h]; }
+                            if (pch < room) {
+                                m.wnode[nt + pch] = snb[h]; m.wrow[nt + pch] = r[h];
+                                // a row scored ahead of time is accepted later WITHOUT a chain phase and may be the very next
+                                // head: its adjacency slots must be on their way to L2 now, not when it is accepted
+                                const uint8_t *ap = reinterpret_cast<const uint8_t *>(adj + (size_t)snb[h] * nb);
+                                hw_prefetch_l2(ap);
+                                if (nb > 32) hw_prefetch_l2(ap + 128);
+                            }
                         }
                     if (tot <= room) { sd3 = sd2; sd2 = sd1; sd1 = sd0; sd0 = ssrc[sidx]; }   // nothing left to score for this entry
                     nt += min(tot, room);
