@@ -307,12 +307,15 @@ def run_ours(args, rank, world, local_rank):
     total_ms, launches_timed = timed(step_device, args.steps, max(args.warmup, 3))
     # nvidia-smi delivers a sample every 20 ms: a timed region shorter than ~0.2 s is followed by UNTIMED repeats of the
     # same step so that the clock record still comes from this load (the timing above is not affected)
-    while time.perf_counter() - t_from < 0.25:
+    # (the number of repeats is derived from the max-reduced step time, so every rank issues the same number of collectives)
+    per_step = max(total_ms / max(args.steps, 1), 1e-3)
+    extra = int(min(2000, max(0.0, 250.0 - (args.steps + max(args.warmup, 3)) * per_step) / per_step + 0.999))
+    for _ in range(extra):
         step_device()
-        torch.cuda.synchronize(dev)
+    barrier()
     t_to = time.perf_counter()
     clocks = sampler.stop(t_from, t_to)
-    clocks["window"] = "warm-up + timed steps" + (" + untimed repeats up to 0.25 s" if total_ms < 200.0 else "")
+    clocks["window"] = "warm-up + timed steps" + (f" + {extra} untimed repeats (~0.25 s of load)" if extra else "")
     scan_ms = ix.scan_ms_history(args.steps)
     e2e_ms = timed_host(step_e2e, args.steps, 2)
 
