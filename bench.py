@@ -119,6 +119,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def clock_sampling_repeats(total_ms, steps, warmup, min_load_ms=250.0, cap=2000):
+    """untimed repeats of the step after the timed region so that warm-up + timed steps + repeats last ~min_load_ms
+    (nvidia-smi delivers a sample every 20 ms).  A pure function of the MAX-REDUCED time of the timed region, i.e. the same
+    integer on every rank: the repeats contain collectives, so a time-based loop per rank would deadlock."""
+    per_step = max(float(total_ms) / max(int(steps), 1), 1e-3)
+    missing = max(0.0, float(min_load_ms) - (int(steps) + int(warmup)) * per_step)
+    return int(min(cap, missing / per_step + 0.999))
+
+
 # ----------------------------------------------------------------------------- CPU baseline (oracle)
 def cpu_queries(args):
     """the reference runs one query per rayon worker (indexes/mod.rs:268): give every host core a query"""
@@ -308,15 +317,14 @@ def run_ours(args, rank, world, local_rank):
     # nvidia-smi delivers a sample every 20 ms: a timed region shorter than ~0.2 s is followed by UNTIMED repeats of the
     # same step so that the clock record still comes from this load (the timing above is not affected)
     # (the number of repeats is derived from the max-reduced step time, so every rank issues the same number of collectives)
-    per_step = max(total_ms / max(args.steps, 1), 1e-3)
-    extra = int(min(2000, max(0.0, 250.0 - (args.steps + max(args.warmup, 3)) * per_step) / per_step + 0.999))
+    scan_ms = ix.scan_ms_history(args.steps)      # the dominant kernel's launches of the TIMED steps
+    extra = clock_sampling_repeats(total_ms, args.steps, max(args.warmup, 3))
     for _ in range(extra):
         step_device()
     barrier()
     t_to = time.perf_counter()
     clocks = sampler.stop(t_from, t_to)
     clocks["window"] = "warm-up + timed steps" + (f" + {extra} untimed repeats (~0.25 s of load)" if extra else "")
-    scan_ms = ix.scan_ms_history(args.steps)
     e2e_ms = timed_host(step_e2e, args.steps, 2)
 
     value = args.steps * B / (total_ms / 1000.0)

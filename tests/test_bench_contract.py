@@ -33,3 +33,18 @@ def test_reference_arm_other_ranks_do_nothing():
     r = run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29571"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+def test_clock_sampling_repeats_are_a_pure_function_of_the_reduced_time():
+    # the untimed repeats contain NCCL collectives: every rank must derive the same count (a time-based loop per rank hung the
+    # 8-GPU run of round 2).  The count only depends on values that are identical on all ranks.
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f = bench.clock_sampling_repeats
+    assert f(120.0, 10, 3) == 8                      # 12 ms steps: 156 ms of load so far, 94 ms missing -> 8 more steps
+    assert f(16.0, 10, 3) == 144                     # 1.6 ms steps (8 GPUs): 20.8 ms so far -> 144 more
+    assert f(5000.0, 10, 3) == 0                     # long steps: nothing to add
+    assert f(0.0, 10, 3) == 2000 and f(1e-9, 1, 0) == 2000      # degenerate timings are capped
+    assert all(f(t, 5, 3) == f(t, 5, 3) for t in (1.0, 33.3, 250.0))
