@@ -150,7 +150,17 @@ def cpu_baseline(rows_full, dim, k, sample_rows, sample_queries, threads):
     busy = min(threads, sample_queries)
     desc = (f"oracle port (C/AVX2+FMA), one query per thread like rayon: {sample_queries} queries on {busy} of {threads} host threads, "
             f"{sample_rows}x{dim} rows (1/{max(1, rows_full // sample_rows)} of the corpus) in {dt:.2f}s, scaled linearly in rows")
-    return qps_full, dt, desc, (ids, scores), busy
+    # the 1-thread figure SURVEY 8d asks for: one query, one thread, a quarter of the sample rows (scaled like the rest)
+    one = None
+    try:
+        r1 = max(1, sample_rows // 4)
+        t1 = time.perf_counter()
+        orc.brute_topk_f32(corpus[:r1], queries[:1], k, threads=1)
+        d1 = time.perf_counter() - t1
+        one = {"value": (1.0 / d1) * (r1 / rows_full), "unit": "queries/s", "sample": f"1 query on 1 thread, {r1}x{dim} rows in {d1:.2f}s"}
+    except Exception:
+        pass
+    return qps_full, dt, desc, (ids, scores), busy, one
 
 
 def run_reference(args, rank, world):
@@ -380,8 +390,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         nqs = cpu_queries(args)
-        v, dt, sample, (o_ids, o_scores), busy = cpu_baseline(args.rows, D, k, args.cpu_sample_rows, nqs, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": busy, "host_threads": threads, "kind": "port", "sample": sample}
+        v, dt, sample, (o_ids, o_scores), busy, one = cpu_baseline(args.rows, D, k, args.cpu_sample_rows, nqs, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": busy, "host_threads": threads, "kind": "port", "sample": sample,
+                                "one_thread": one}
         # oracle leg of the parity gate: the same sample (rows [0, sample_rows) x nqs queries) through the CUDA path
         srows = min(args.cpu_sample_rows, args.rows)
         sm = cdb.DenseIndex(dim=D, capacity=srows, device=local_rank)
