@@ -381,3 +381,47 @@ def test_bf16_extension_conversion_and_dot_against_independent_restatements():
     assert rc == orc.OK and bits(np.array([d], np.float32))[0] == bits(np.array([s], np.float32))[0]
     rc, c = orc.distance(orc.METRIC_COSINE, orc.ST_BF16, 333, ac[0], am[0], bc[0], bm[0])
     assert rc == orc.OK and bits(np.array([c], np.float32))[0] == bits(np.array([s / np.float32(am[0] * bm[0])], np.float32))[0]
+
+
+def test_fused_multiply_add_of_16_bit_operands_equals_the_reference_fold():
+    """The CUDA kernels fold f16 / bf16 dot products with ONE fused multiply-add per element (sm_100 FHFMA, PTX fma.rn.f32.f16 /
+    .bf16: operands widened exactly, a*b + c rounded once).  The reference rounds twice (f32 multiply, then f32 add).  Both
+    agree because the product of two halfs (11-bit significands) or two bf16 values (8-bit) is exact in f32 -- checked here
+    with the exact-integer binary32 emulation over operands that include subnormals, the largest finite values and sign
+    mixes, against the oracle's dot_product_f16 / bf16 arm."""
+    r = rng(66)
+    L = lib()
+    # halfs: random normals, subnormals (|x| < 2^-14), the extremes
+    raw = np.concatenate([r.uniform(-1, 1, 400), r.uniform(-6e-5, 6e-5, 120), r.uniform(-6e-8, 6e-8, 40),
+                          [65504.0, -65504.0, 6.1e-5, -6.1e-5, 5.96e-8, 0.0, -0.0, 1.0, -1.0, 0.333251953125]])
+    a = raw.astype(np.float16)
+    b = r.permutation(raw).astype(np.float16)
+    assert (np.abs(a.astype(np.float32)) < 6.1e-5).sum() > 100              # subnormal halfs present
+    fused = two = 0.0
+    for x, y in zip(a.astype(np.float32), b.astype(np.float32)):
+        p = f32emu.mul32(float(x), float(y))
+        assert p == float(np.float64(x) * np.float64(y))                    # exact product, also for subnormal operands
+        fused = f32emu.fma32(float(x), float(y), fused)
+        two = f32emu.add32(two, p)
+        assert fused == two
+    got = np.float32(L.orc_dot_f16(_p(a.view(np.uint16)), _p(b.view(np.uint16)), a.size))
+    assert got == np.float32(fused)
+    # bf16: same statement with 8-bit significands and the f32 exponent range (products can overflow / underflow like any f32 product)
+    v = np.concatenate([r.normal(size=300).astype(np.float32), np.array([3.0e38, -3.0e38, 1e-38, -1e-38, 1e-40, 1.0, -0.0], np.float32)])
+    ca, ma = orc.quantize_batch(orc.ST_BF16, v[None])
+    cb, mb = orc.quantize_batch(orc.ST_BF16, r.permutation(v)[None])
+    fa = (ca.view(np.uint16)[0].astype(np.uint32) << 16).view(np.float32)
+    fb = (cb.view(np.uint16)[0].astype(np.uint32) << 16).view(np.float32)
+    fused = two = 0.0
+    finite = True
+    for x, y in zip(fa, fb):
+        if not (np.isfinite(fused) and np.isfinite(two)):
+            finite = False
+            break
+        p64 = np.float64(x) * np.float64(y)
+        if abs(p64) >= 2.0 ** 128 or (p64 != 0 and abs(p64) < 2.0 ** -126):
+            continue                                                        # products outside the normal f32 range round in both forms; skipped
+        fused = f32emu.fma32(float(x), float(y), fused)
+        two = f32emu.add32(two, f32emu.mul32(float(x), float(y)))
+        assert fused == two
+    assert finite
