@@ -1079,8 +1079,20 @@ def run_c5(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def _watchdog(limit_s):
+    """a collective that never completes must not hang the whole run: give up loudly after limit_s"""
+    def bark():
+        sys.stderr.write(f"bench.py: no result after {limit_s} s -- giving up (a stuck collective or kernel)\n")
+        sys.stderr.flush()
+        os._exit(4)
+    t = threading.Timer(limit_s, bark)
+    t.daemon = True
+    t.start()
+
+
 def main():
     args = parse_args()
+    _watchdog(float(os.environ.get("CDB_BENCH_WATCHDOG_S", "1500")))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
