@@ -13,11 +13,11 @@ PICK = [
     ("tensor_scan_kernel<6 stages, NG=16, no degenerate rows, CTA pair, kind::f16>  (C2 headline prefilter)", r"tensor_scan_kernelILi6ELi16ELb0ELi2ELi0E"),
     ("tensor_scan_kernel<4 stages, NG=16, single CTA, kind::f16>", r"tensor_scan_kernelILi4ELi16ELb0ELi1ELi0E"),
     ("tensor_scan_kernel<6 stages, NG=16, CTA pair, kind::i8>  (C4 exact integer scores)", r"tensor_scan_kernelILi6ELi16ELb0ELi2ELi1E"),
-    ("hnsw_search_warp_kernel<f16 chain, no profiling>  (C3/C5)", r"hnsw_search_warp_kernelILi1ELb0E"),
+    ("hnsw_search_warp_kernel<f16 FHFMA chain, no profiling>  (C3/C5)", r"hnsw_search_warp_kernelILi1ELb0E"),
     ("scan_f32_kernel<QB=1>  (exact f32 scan, B=1)", r"scan_f32_kernelILi1ELi2E"),
     ("tc_probe_kernel<kind::i8>  (measured integer tensor peak)", r"tc_probe_kernelILb1E"),
 ]
-WANT = re.compile(r"\b(UTC[A-Z]+MMA|UTCBAR|UTMALDG|UTMACCTL|UTMAPF|UBLKCP|UBLKPF|LDTM|STTM|UTCATOMSWS|SYNCS|REDUX|CREDUX|UCGABAR|FMNMX3?|LDG|LDS|ATOMS|ATOMG|RED|CCTL|PREFETCH|F2FP|HADD2|HFMA2|FFMA|I2FP|I2F|IDP|POPC|SHFL|VOTE|MATCH|NANOSLEEP|BAR|WARPSYNC|MEMBAR|FENCE|ELECT|PLOP3|UCLEA|ACQBULK|ARRIVES)(\.[A-Z0-9_.]+)?")
+WANT = re.compile(r"\b(UTC[A-Z]+MMA|UTCBAR|UTMALDG|UTMACCTL|UTMAPF|UBLKCP|UBLKPF|LDTM|STTM|UTCATOMSWS|SYNCS|REDUX|CREDUX|UCGABAR|FHFMA|FMNMX3?|LDG|LDS|ATOMS|ATOMG|RED|CCTL|PREFETCH|F2FP|HADD2|HFMA2|FFMA|I2FP|I2F|IDP|POPC|SHFL|VOTE|MATCH|NANOSLEEP|BAR|WARPSYNC|MEMBAR|FENCE|ELECT|PLOP3|UCLEA|ACQBULK|ARRIVES)(\.[A-Z0-9_.]+)?")
 
 sass = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
 funcs = collections.OrderedDict()
