@@ -313,3 +313,156 @@ def test_level_draw_helpers_match_the_reference_vectors():
     lp = level_probs(9)                                                          # generate_level_probs(4.0, 9), common.rs:421-429
     assert lp[0] == (1.0 - 4.0 ** -9, 9) and lp[-1] == (0.0, 0) and len(lp) == 10
     assert max_insert_level(0.0, lp) == 0 and max_insert_level(0.75, lp) == 1 and max_insert_level(0.99999999, lp) == 9
+
+
+# ------------------------------------------------------------------ index_embeddings with replica nodes, pure Python
+def py_build_md(pop, codes, mags, st, metric, levels, nb, nb0, efc, shortlist=64):
+    """index_embeddings / index_embedding / create_node_edges / ProbNode::add_neighbor (vector_store.rs:714-1070,
+    prob_node.rs:210-283) for a replica list, written independently of oracle/metadata_oracle.c: dict-free lists, a heap as a
+    sorted list, floats compared through the order key.  Level layout as the oracle's: [0] main root, [1] pseudo root."""
+    n, dim = pop["vecs"].shape
+    md_bits, md_mags = pop["md_bits"], pop["md_mags"]
+    okey = lambda v: orc.order_key(metric, v)
+    min_key, max_key = (okey(np.float32(-1.0)), okey(np.float32(2.0))) if metric == 0 else (okey(np.float32(-np.inf)), okey(np.float32(np.inf)))
+    L1 = levels + 1
+    nbs = [nb0 if lv == 0 else nb for lv in range(L1)]
+    # per level: parallel lists
+    rows = [[n, n + 1] for _ in range(L1)]
+    ids = [[0xFFFFFFFF, pymeta.PSEUDO_ROOT_ID] for _ in range(L1)]
+    mds = [[pop["main_root_md"], pop["pseudo_root_md"]] for _ in range(L1)]
+    adj = [[[EMPTY] * nbs[lv] for _ in range(2)] for lv in range(L1)]
+    sim = [[[0] * nbs[lv] for _ in range(2)] for lv in range(L1)]
+    low = [[[0, min_key] for _ in range(2)] for lv in range(L1)]
+    child = [[(0 if lv else EMPTY), (1 if lv else EMPTY)] for lv in range(L1)]
+
+    def vd(lv, i):
+        m = mds[lv][i]
+        return (codes[rows[lv][i]], mags[rows[lv][i]], ids[lv][i], None if m == EMPTY else md_bits[m], 0.0 if m == EMPTY else md_mags[m])
+
+    def kind_of(lv, i):
+        y = vd(lv, i)
+        return py_kind(y[2], y[3], y[4])
+
+    def add_neighbor(lv, node, nbr, dkey):
+        lidx, lkey = low[lv][node]
+        if dkey <= lkey:
+            return -1
+        ok, old = False, EMPTY
+        if adj[lv][node][lidx] == EMPTY:
+            adj[lv][node][lidx], sim[lv][node][lidx], ok = nbr, dkey, True
+        elif dkey > sim[lv][node][lidx]:
+            old = adj[lv][node][lidx]
+            adj[lv][node][lidx], sim[lv][node][lidx], ok = nbr, dkey, True
+        nidx, nkey = 0, max_key
+        for s in range(nbs[lv]):
+            if adj[lv][node][s] == EMPTY:
+                nidx, nkey = s, min_key
+                break
+            if sim[lv][node][s] < nkey:
+                nidx, nkey = s, sim[lv][node][s]
+        low[lv][node] = [nidx, nkey]
+        if not ok:
+            return -1
+        if old != EMPTY:
+            for s in range(nbs[lv]):
+                if adj[lv][old][s] == node:
+                    adj[lv][old][s] = EMPTY
+                    break
+        return lidx
+
+    def traverse(lv, entry, x, self_id):
+        nbv = nbs[lv]
+        take = min(shortlist, nbv)
+        fs = {((self_id >> 6) & (nbv - 1), self_id & 63)}
+        y = vd(lv, entry)
+        rc, d = py_distance(metric, st, dim, x, y)
+        if rc:
+            return rc, []
+        fs.add(((y[2] >> 6) & (nbv - 1), y[2] & 63))
+        heap, res, visited = [((okey(d) << 32) | (~y[2] & 0xFFFFFFFF), entry, d)], [], 0
+        while heap:
+            heap.sort(reverse=True)
+            cur = heap.pop(0)
+            if visited >= efc:
+                break
+            visited += 1
+            res.append(cur)
+            for s in range(take):
+                nbl = adj[lv][cur[1]][s]
+                if nbl == EMPTY:
+                    continue
+                y = vd(lv, nbl)
+                bit = ((y[2] >> 6) & (nbv - 1), y[2] & 63)
+                if bit in fs:
+                    continue
+                rc, d = py_distance(metric, st, dim, x, y)
+                if rc:
+                    return rc, []
+                fs.add(bit)
+                heap.append(((okey(d) << 32) | (~y[2] & 0xFFFFFFFF), nbl, d))
+        res.sort(reverse=True)
+        return 0, res[:64]
+
+    failed = []
+    for t in range(len(pop["row"])):
+        row = n + 1 if pop["row"][t] == EMPTY else int(pop["row"][t])
+        m = int(pop["md_row"][t])
+        x = (codes[row], mags[row], int(pop["base_id"][t]), None if m == EMPTY else md_bits[m], 0.0 if m == EMPTY else md_mags[m])
+        under_pseudo = x[3] is not None and x[4] != 0.0
+        entry, parent, node_at, zs, bad = (1 if under_pseudo else 0), EMPTY, {}, {}, False
+        max_level = int(pop["max_level"][t])
+        for lv in range(levels, -1, -1):
+            rc, z = traverse(lv, entry, x, int(pop["node_id"][t]))
+            if rc:
+                bad = True
+                break
+            zs[lv] = z
+            nxt = child[lv][z[0][1]] if lv else 0
+            if lv <= max_level:
+                idx = len(rows[lv])
+                rows[lv].append(row); ids[lv].append(int(pop["node_id"][t])); mds[lv].append(m)
+                adj[lv].append([EMPTY] * nbs[lv]); sim[lv].append([0] * nbs[lv]); low[lv].append([0, min_key]); child[lv].append(EMPTY)
+                if parent != EMPTY:
+                    child[lv + 1][parent] = idx
+                node_at[lv], parent = idx, idx
+            entry = nxt
+        failed.append(1 if bad else 0)
+        if bad:
+            continue
+        for lv in range(0, min(max_level, levels) + 1):
+            node, good = node_at[lv], 0
+            nk = kind_of(lv, node)
+            for _, nbr, d in zs[lv]:
+                if good >= nbs[lv]:
+                    break
+                if metric == 0:
+                    bk = kind_of(lv, nbr)
+                    if bk == "pseudo" and nk == "metadata" and d != np.float32(1.0):
+                        continue
+                    if bk == "metadata" and nk == "metadata" and d == np.float32(-1.0):
+                        continue
+                i = add_neighbor(lv, node, nbr, okey(d))
+                if i >= 0:
+                    if add_neighbor(lv, nbr, node, okey(d)) >= 0:
+                        good += 1
+                    elif adj[lv][node][i] == nbr:
+                        adj[lv][node][i] = EMPTY
+    return rows, ids, mds, adj, child, failed
+
+
+@pytest.mark.parametrize("st,metric", [(4, 0), (0, 0)])
+def test_replica_builder_matches_python_restatement(st, metric):
+    levels, nb, nb0, efc = 3, 4, 8, 12
+    pop = mdgraph.replica_population(n=90, dim=16, md_dims=5, levels=levels, n_patterns=5, seed=41)
+    (mg, failed), allv = _oracle_replica_build(pop, st, metric, levels=levels, nb=nb, nb0=nb0, efc=efc)
+    codes, mags = orc.quantize_batch(st, allv)
+    rows, ids, mds, adj, child, pfailed = py_build_md(pop, codes, mags, st, metric, levels, nb, nb0, efc)
+    assert failed.tolist() == pfailed
+    edges = 0
+    for lv in range(levels + 1):
+        assert mg.fg.node_row[lv].tolist() == rows[lv] and mg.node_id[lv].tolist() == ids[lv] and mg.node_md[lv].tolist() == mds[lv], lv
+        assert mg.fg.adj[lv].reshape(-1, nb0 if lv == 0 else nb).tolist() == adj[lv], lv
+        if lv:
+            assert mg.fg.child[lv].tolist() == child[lv], lv
+        edges += sum(v != EMPTY for r in adj[lv] for v in r)
+    assert edges > 3 * len(pop["row"])
