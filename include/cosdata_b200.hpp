@@ -18,7 +18,8 @@
 
 namespace cosdata {
 
-enum class StorageType : int32_t { UnsignedByte = 0, SubByte1 = 1, SubByte2 = 2, SubByte3 = 3, HalfPrecisionFP = 4, FullPrecisionFP = 5 };
+enum class StorageType : int32_t { UnsignedByte = 0, SubByte1 = 1, SubByte2 = 2, SubByte3 = 3, HalfPrecisionFP = 4, FullPrecisionFP = 5,
+                                   BFloat16 = 6 /* labelled extension, no reference variant */ };
 enum class DistanceMetricKind : int32_t { Cosine = 0, Euclidean = 1, Hamming = 2, DotProduct = 3 };
 enum class SearchMode : int32_t { BruteRaw = 0, BruteCodes = 1, Hnsw = 2 };
 
@@ -151,11 +152,65 @@ class DenseIndex {
         for (uint32_t i = 0; i < n; ++i) out.emplace_back(ids[i], sc[i]);
         return out;
     }
+    // index_embeddings on the device (reference defaults: config.toml:19-25); appends the root row
+    void build_graph(uint32_t num_levels = 9, uint32_t nbrs = 32, uint32_t nbrs0 = 64, uint32_t ef_construction = 128,
+                     uint32_t shortlist_size = 64, uint32_t max_batch = 4096, uint64_t seed = 1) {
+        cdb_build_params bp{num_levels, nbrs, nbrs0, ef_construction, shortlist_size, max_batch, seed};
+        check(cdb_index_build_graph(h_, &bp));
+    }
+    // the same for a collection with a metadata schema: preprocess_embedding's flattened IndexableEmbeddings (one entry per
+    // node to create); returns the per-entry "insert would have failed" flags
+    std::vector<uint8_t> build_graph_replicas(const cdb_replica_build &rb, const cdb_build_params &bp) {
+        std::vector<uint8_t> failed(rb.n_nodes ? rb.n_nodes : 1);
+        check(cdb_index_build_graph_replicas(h_, &bp, &rb, failed.data()));
+        failed.resize(rb.n_nodes);
+        return failed;
+    }
+    // raw f32 rows for rows appended as codes (cold start of a quantized index)
+    void set_raw(uint64_t first_row, const float *vecs, uint64_t n) { check(cdb_index_set_raw_f32(h_, first_row, vecs, n)); }
+    uint64_t raw_missing() const { return cdb_index_raw_missing(h_); }
     cdb_index *handle() const { return h_; }
 
   private:
     cdb_index *h_ = nullptr;
     uint32_t dim_ = 0;
+};
+
+// row-sharded search over the GPUs of one box: the library owns the NCCL communicator
+class ShardGroup {
+  public:
+    // one process drives every device (a device listed twice selects the copy-based loopback gather)
+    explicit ShardGroup(const std::vector<int32_t> &devices) { check(cdb_shard_group_create(devices.data(), (uint32_t)devices.size(), &g_)); }
+    // one process per GPU: every rank passes the id rank 0 made with unique_id()
+    ShardGroup(const std::vector<uint8_t> &id128, uint32_t world, uint32_t rank, int32_t device) {
+        check(cdb_shard_group_create_rank(id128.data(), world, rank, device, &g_));
+    }
+    ~ShardGroup() { if (g_) cdb_shard_group_destroy(g_); }
+    ShardGroup(const ShardGroup &) = delete;
+    ShardGroup &operator=(const ShardGroup &) = delete;
+    static std::vector<uint8_t> unique_id() {
+        std::vector<uint8_t> id(CDB_NCCL_UNIQUE_ID_BYTES);
+        check(cdb_nccl_unique_id(id.data()));
+        return id;
+    }
+    void attach(uint32_t local_slot, DenseIndex &shard) { check(cdb_shard_group_attach(g_, local_slot, shard.handle())); }
+    uint32_t world() const { return cdb_shard_group_world(g_); }
+    // IndexOps::batch_search over all shards: one all-gather of packed keys, merged with "better score, then smaller id"
+    SearchResults batch_search(const float *queries, uint32_t b, uint32_t k, SearchMode mode = SearchMode::BruteRaw,
+                               uint32_t ef_search = 256, uint32_t shortlist_size = 64) const {
+        SearchResults r;
+        r.k = k;
+        r.ids.resize((size_t)b * k);
+        r.scores.resize((size_t)b * k);
+        r.counts.resize(b);
+        r.err.resize(b);
+        cdb_search_params p{k, (int32_t)mode, ef_search, shortlist_size, 0, 0, 0, 0};
+        check(cdb_search_batch_sharded(g_, queries, b, &p, r.ids.data(), r.scores.data(), r.counts.data(), r.err.data()));
+        return r;
+    }
+
+  private:
+    cdb_shard_group *g_ = nullptr;
 };
 
 }  // namespace cosdata

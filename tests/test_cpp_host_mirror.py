@@ -6,14 +6,14 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_and_run(tmp_path):
+def _build_and_run(tmp_path, name="abi_smoke"):
     from cosdata_b200 import _lib
     _lib.load()
-    exe = str(tmp_path / "abi_smoke")
+    exe = str(tmp_path / name)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     libdir = os.path.join(ROOT, "cosdata_b200")
     subprocess.run([cxx, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "tests", "cpp", "abi_smoke.cpp"), "-o", exe, "-L", libdir, "-lcosdata_b200",
+                    os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", libdir, "-lcosdata_b200",
                     f"-Wl,-rpath,{libdir}"], check=True)
     return subprocess.run([exe], capture_output=True, text=True)
 
@@ -32,3 +32,10 @@ def test_cpp_mirror_computes_on_gpu(tmp_path):
     r = _build_and_run(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "cosine=" in r.stdout and "top=1 count=2" in r.stdout
+
+
+def test_cpp_mirror_round2_surface_builds_and_fails_loudly_without_a_device(tmp_path):
+    r = _build_and_run(tmp_path, "mirror_round2")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "devices=" in r.stdout
+
