@@ -64,3 +64,20 @@ def test_header_is_plain_c11(tmp_path):
     r = subprocess.run([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_integration_extern_block_covers_the_header():
+    """INTEGRATION.md's `extern "C"` block (what the Rust shim binds) + the listed helper functions == every function of the header"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "cosdata_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(cdb_[a-z0-9_]+)\s*\(", hdr))
+    bound = set(re.findall(r"pub fn (cdb_[a-z0-9_]+)", doc))
+    helpers = {"cdb_synth_fill_host", "cdb_index_append_synthetic", "cdb_index_read_codes", "cdb_index_stats",
+               "cdb_index_last_candidate_counts", "cdb_index_last_kernel_ms", "cdb_index_scan_ms_history", "cdb_kernel_launch_count",
+               "cdb_index_hnsw_profile", "cdb_debug_set_hnsw_flags", "cdb_debug_tensor_peak"}
+    assert bound <= declared, sorted(bound - declared)
+    assert declared - bound == helpers, (sorted(declared - bound - helpers), sorted(helpers - (declared - bound)))
+    for h in helpers:
+        assert h in doc, h
